@@ -1,0 +1,190 @@
+// emcid_b200 — host-side plumbing for the C ABI: error reporting, TMA tensor-map encoding and
+// launch helpers for the generic 3xTF32 GEMM.  No exceptions cross the C boundary.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "gemm3x.cuh"
+
+namespace emcid {
+
+// ----------------------------------------------------------------------------------------------
+// last-error string (thread local), returned by emcid_last_error()
+// ----------------------------------------------------------------------------------------------
+inline char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+inline int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define EMCID_CUDA_CHECK(expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      return ::emcid::set_error(EMCID_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,    \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);                \
+    }                                                                                       \
+  } while (0)
+
+#define EMCID_CHECK(cond, code, ...)                                  \
+  do {                                                                \
+    if (!(cond)) return ::emcid::set_error((code), __VA_ARGS__);      \
+  } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// device properties
+// ----------------------------------------------------------------------------------------------
+struct DeviceInfo {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  int l2_bytes = 0;
+};
+
+inline int get_device_info(DeviceInfo* out) {
+  static thread_local DeviceInfo cache[16];
+  int dev = 0;
+  EMCID_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 16 && cache[dev].device == dev) {
+    *out = cache[dev];
+    return EMCID_OK;
+  }
+  DeviceInfo info;
+  info.device = dev;
+  EMCID_CUDA_CHECK(cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  EMCID_CUDA_CHECK(cudaDeviceGetAttribute(&info.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  EMCID_CUDA_CHECK(cudaDeviceGetAttribute(&info.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  EMCID_CUDA_CHECK(cudaDeviceGetAttribute(&info.l2_bytes, cudaDevAttrL2CacheSize, dev));
+  EMCID_CHECK(info.cc_major == 10, EMCID_ERR_UNSUPPORTED,
+              "emcid_b200 kernels are built for sm_100a only; device %d is sm_%d%d", dev,
+              info.cc_major, info.cc_minor);
+  if (dev >= 0 && dev < 16) cache[dev] = info;
+  *out = info;
+  return EMCID_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA tensor maps.  cuTensorMapEncodeTiled is resolved through the runtime so the library has
+// no link-time dependency on libcuda (it must load on GPU-less build hosts).
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+  }
+  return fn;
+}
+
+// Row-major fp32 matrix [rows x cols] with row pitch `ld` elements; boxes of 32 cols x box_rows,
+// written to shared memory with the 128-byte swizzle the UMMA descriptors expect.
+inline int make_tmap_2d(CUtensorMap* out, const float* base, long long rows, long long cols,
+                        long long ld, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  EMCID_CHECK(fn != nullptr, EMCID_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  EMCID_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, EMCID_ERR_INVALID,
+              "TMA base pointer must be 16-byte aligned");
+  EMCID_CHECK(ld % 4 == 0 && ld >= cols, EMCID_ERR_INVALID,
+              "TMA row pitch must be a multiple of 4 floats and >= cols (ld=%lld cols=%lld)", ld, cols);
+  EMCID_CHECK(rows > 0 && cols > 0, EMCID_ERR_INVALID, "empty TMA tensor");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(GEMM_BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EMCID_CHECK(r == CUDA_SUCCESS, EMCID_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d",
+              static_cast<int>(r));
+  return EMCID_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// GEMM launch
+// ----------------------------------------------------------------------------------------------
+struct GemmOperands {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+template <int BLOCK_N, int STAGES, int EPI>
+inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, STAGES>;
+  auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI>;
+  static thread_local bool configured[16] = {false};
+  int dev = 0;
+  EMCID_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16 || !configured[dev]) {
+    EMCID_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    if (dev >= 0 && dev < 16) configured[dev] = true;
+  }
+  if (grid < 1) grid = 1;
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo, p);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  return EMCID_OK;
+}
+
+inline int gemm_num_tiles(int M, int N, int block_n, int lower) {
+  const int mt = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int nt = (N + block_n - 1) / block_n;
+  if (!lower) return mt * nt;
+  int t = 0;
+  const int R = block_n / GEMM_BLOCK_M;
+  for (int j = 0; j < nt; ++j) {
+    int c = mt - j * R;
+    if (c > 0) t += c;
+  }
+  return t;
+}
+
+// ----------------------------------------------------------------------------------------------
+// elementwise helpers
+// ----------------------------------------------------------------------------------------------
+// planes = split(scale * src); rows x cols, zero-filling the pitch padding [cols, ldp).
+__global__ void split_planes_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
+                                    float scale, float* __restrict__ hi, float* __restrict__ lo,
+                                    long long ldp) {
+  const long long total = static_cast<long long>(rows) * ldp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / ldp);
+    const int c = static_cast<int>(i - static_cast<long long>(r) * ldp);
+    float h = 0.f, l = 0.f;
+    if (c < cols) split_tf32(scale * src[static_cast<long long>(r) * ld + c], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+inline int launch_split_planes(const float* src, long long ld, int rows, int cols, float scale,
+                               float* hi, float* lo, long long ldp, cudaStream_t stream) {
+  const long long total = static_cast<long long>(rows) * ldp;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split_planes_kernel<<<blocks, 256, 0, stream>>>(src, ld, rows, cols, scale, hi, lo, ldp);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  return EMCID_OK;
+}
+
+}  // namespace emcid

@@ -1,0 +1,286 @@
+"""TEST INFRASTRUCTURE ONLY — runs the *unmodified* reference (SilentView/EMCID, /root/reference)
+on CPU with synthetic inputs so that golden vectors for the hot path can be generated here.
+
+Nothing under emcid_b200/ may import this module.  It only works in the build container, where
+/root/reference exists; on the GPU box tests use the committed fixtures under tests/golden/ and
+the independent restatement in oracle/emcid_oracle.py.
+
+Recipe: the reference opens globals.yml relative to the CWD (util/globals.py:8)
+and imports diffusers / matplotlib only for type hints and isinstance checks on this path
+(util/nethook.py:19,83; emcid/layer_stats.py:12; emcid/compute_z.py:12-15), so those two packages
+are replaced by stub modules.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+REFERENCE_ROOT = os.environ.get("EMCID_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "emcid"))
+
+
+class _Dummy:
+    def __init__(self, *a, **k):
+        pass
+
+
+def _stub_module(name: str) -> types.ModuleType:
+    m = types.ModuleType(name)
+    m.__path__ = []  # behave like a package
+
+    def __getattr__(attr):
+        if attr.startswith("__"):
+            raise AttributeError(attr)
+        return type(attr, (_Dummy,), {})
+
+    m.__getattr__ = __getattr__
+    return m
+
+
+_imported = None
+
+
+def import_reference():
+    """Import the reference's hot-path modules; returns a namespace with them."""
+    global _imported
+    if _imported is not None:
+        return _imported
+    if not reference_available():
+        raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
+    for name in ("diffusers", "diffusers.models", "diffusers.models.attention_processor",
+                 "diffusers.models.attention", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = _stub_module(name)
+    cwd = os.getcwd()
+    sys.path.insert(0, REFERENCE_ROOT)
+    os.chdir(REFERENCE_ROOT)
+    try:
+        import util.runningstats as runningstats
+        import util.nethook as nethook
+        import dsets.stat_dataset as stat_dataset
+        import emcid.layer_stats as layer_stats
+        import emcid.emcid_main as emcid_main
+        import emcid.emcid_hparams as emcid_hparams
+    finally:
+        os.chdir(cwd)
+    _imported = SimpleNamespace(runningstats=runningstats, nethook=nethook, stat_dataset=stat_dataset,
+                                layer_stats=layer_stats, emcid_main=emcid_main, emcid_hparams=emcid_hparams)
+    return _imported
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic model / data / tokenizer shared by the harness, the oracle tests and bench.py
+# ---------------------------------------------------------------------------------------------
+BOS, EOS = 49406, 49407
+
+
+def make_clip_text_model(kind: str = "clip-l", seed: int = 0, **overrides):
+    """Random-init HF CLIPTextModel of the shapes in SURVEY.md Appendix B."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+
+    presets = {
+        "clip-l": dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                       num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu"),
+        "bigg": dict(vocab_size=49408, hidden_size=1280, intermediate_size=5120, num_hidden_layers=32,
+                     num_attention_heads=20, max_position_embeddings=77, hidden_act="gelu"),
+        "tiny": dict(vocab_size=1000, hidden_size=64, intermediate_size=256, num_hidden_layers=2,
+                     num_attention_heads=4, max_position_embeddings=77, hidden_act="quick_gelu"),
+        "tiny-gelu": dict(vocab_size=1000, hidden_size=64, intermediate_size=256, num_hidden_layers=2,
+                          num_attention_heads=4, max_position_embeddings=77, hidden_act="gelu"),
+    }
+    cfg = dict(presets[kind])
+    cfg.update(overrides)
+    vocab = cfg["vocab_size"]
+    cfg.setdefault("bos_token_id", vocab - 2)
+    cfg.setdefault("eos_token_id", vocab - 1)
+    torch.manual_seed(seed)
+    model = CLIPTextModel(CLIPTextConfig(**cfg)).eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    model.config._name_or_path = f"synthetic/{kind}-seed{seed}"
+    return model
+
+
+def make_captions(n: int, vocab: int, seed: int = 0, min_len: int = 8, max_len: int = 77, full: bool = False):
+    """Synthetic token-id captions: BOS first, EOS last, ids ~ U{0..vocab-3}."""
+    g = torch.Generator().manual_seed(seed)
+    bos, eos = vocab - 2, vocab - 1
+    lens = torch.full((n,), max_len) if full else torch.randint(min_len, max_len + 1, (n,), generator=g)
+    ids = torch.randint(0, vocab - 2, (n, max_len), generator=g)
+    out = []
+    for i in range(n):
+        L = int(lens[i])
+        row = ids[i, :L].clone()
+        row[0] = bos
+        row[L - 1] = eos
+        out.append(row)
+    return out
+
+
+class SynthTokenDataset(torch.utils.data.Dataset):
+    """Drop-in for dsets/stat_dataset.py::TokenizedDataset items (:99-110)."""
+
+    def __init__(self, captions):
+        self.captions = captions
+
+    def __len__(self):
+        return len(self.captions)
+
+    def __getitem__(self, i):
+        ids = self.captions[i]
+        return dict(input_ids=ids.clone(), position_ids=torch.arange(len(ids)),
+                    attention_mask=torch.ones(len(ids), dtype=torch.long))
+
+
+class FakeTokenizer:
+    """Whitespace tokenizer with a hashed vocabulary, enough for find_token_range
+    (experiments/causal_trace.py:1057-1103) and tokenize_prompts (emcid/compute_z.py:56-74)."""
+
+    model_max_length = 77
+
+    def __init__(self, vocab_size: int):
+        self.vocab_size = vocab_size
+        self.bos, self.eos = vocab_size - 2, vocab_size - 1
+        self._words = {}
+
+    def _id(self, w: str) -> int:
+        import zlib
+
+        i = zlib.crc32(w.encode()) % (self.vocab_size - 2)
+        self._words.setdefault(i, w)
+        return i
+
+    def encode(self, text, truncation=True, max_length=None):
+        ids = [self.bos] + [self._id(w) for w in text.split()] + [self.eos]
+        max_length = max_length or self.model_max_length
+        if len(ids) > max_length:
+            ids = ids[: max_length - 1] + [self.eos]
+        return ids
+
+    def __call__(self, prompts, return_tensors="pt", padding=True, truncation=True, max_length=None):
+        if isinstance(prompts, str):
+            prompts = [prompts]
+        enc = [self.encode(p, max_length=max_length if truncation else None) for p in prompts]
+        width = max(len(e) for e in enc) if padding is True else (max_length or self.model_max_length)
+        ids = torch.full((len(enc), width), self.eos, dtype=torch.long)
+        mask = torch.zeros((len(enc), width), dtype=torch.long)
+        for i, e in enumerate(enc):
+            ids[i, : len(e)] = torch.tensor(e)
+            mask[i, : len(e)] = 1
+        return {"input_ids": ids, "attention_mask": mask}
+
+    def decode(self, ids):
+        if torch.is_tensor(ids):
+            ids = ids.tolist()
+        if isinstance(ids, int):
+            ids = [ids]
+        toks = []
+        for i in ids:
+            if i == self.bos:
+                toks.append("<|startoftext|>")
+            elif i == self.eos:
+                toks.append("<|endoftext|>")
+            else:
+                toks.append(self._words.get(i, f"w{i}"))
+        return " ".join(toks)
+
+
+def make_requests(n: int, seed: int = 0):
+    """ICEB-style edit requests (dsets/iceb_dataset.py:325-329 templates)."""
+    return [
+        {"source": f"artist{i} name{i}", "dest": "art", "seed_train": seed,
+         "prompts": ["An image of {}", "A photo of {}", "{}"]}
+        for i in range(n)
+    ]
+
+
+@contextlib.contextmanager
+def cpu_cuda_patches():
+    """emcid_main.py:1072-1073 calls torch.cuda.device / empty_cache unconditionally."""
+    dev, ec = torch.cuda.device, torch.cuda.empty_cache
+    torch.cuda.device = lambda *_a, **_k: contextlib.nullcontext()
+    torch.cuda.empty_cache = lambda: None
+    try:
+        yield
+    finally:
+        torch.cuda.device, torch.cuda.empty_cache = dev, ec
+
+
+def run_reference_layer_stats(model, captions, layer: int, stats_dir: str, sample_size: int,
+                              batch_tokens: int = 3072):
+    """Reference emcid/layer_stats.py::layer_stats_text_encoder (:140-220), unmodified."""
+    ref = import_reference()
+    ref.layer_stats.get_ccs_filtered_ds = lambda tokenizer: SynthTokenDataset(captions)
+    layer_name = f"text_model.encoder.layers.{layer}.mlp.fc2"
+    stat = ref.layer_stats.layer_stats_text_encoder(
+        model, None, layer_name, stats_dir=stats_dir, sample_size=sample_size, precision="float32",
+        batch_tokens=batch_tokens, progress=lambda x, total=None: x)
+    return stat
+
+
+def write_vstar_cache(cache_name: str, requests, h: int, seed: int = 2):
+    g = torch.Generator().manual_seed(seed)
+    os.makedirs(os.path.dirname(cache_name) or ".", exist_ok=True)
+    vs = []
+    for r in requests:
+        v = torch.randn(h, generator=g)
+        np.savez(cache_name + f"source_{r['source']}_dest_{r['dest']}.npz", v_star=v.numpy())
+        vs.append(v)
+    return torch.stack(vs, dim=1)  # [h, n]
+
+
+def make_hparams(layers, mom2_n_samples: int, mom2_update_weight: float = 4000, edit_weight: float = 0.5):
+    """Minimal stand-in for emcid/emcid_hparams.py::EMCIDHyperParams (:55-163) with exactly the
+    fields the stage-2 loop reads (emcid_main.py:846-1065)."""
+    return SimpleNamespace(
+        layers=list(layers), mom2_update_weight=mom2_update_weight, edit_weight=edit_weight,
+        rewrite_module_tmp="text_model.encoder.layers.{}.mlp.fc2", mom2_dataset="ccs_filtered",
+        mom2_n_samples=mom2_n_samples, mom2_dtype="float32", num_edit_tokens=1, objective="ori",
+        sld_supervision=False, use_new_compute_z=False, txt_img_align_scale_factor=0)
+
+
+def run_reference_execute(model, tokenizer, requests, hparams, cache_name: str, stat_dir: str,
+                          capture: list | None = None):
+    """Reference emcid/emcid_main.py::execute_emcid_text_encoder (:818-1082), unmodified, on CPU.
+    When `capture` is a list, the (M, Ks) operands of every torch.linalg.solve call are appended."""
+    ref = import_reference()
+    ref.emcid_main.COV_CACHE.clear()
+    pipe = SimpleNamespace(text_encoder=model, tokenizer=tokenizer, device=next(model.parameters()).device)
+    orig_solve = torch.linalg.solve
+
+    def spy(A, B, *a, **k):
+        if capture is not None:
+            capture.append((A.detach().clone(), B.detach().clone()))
+        return orig_solve(A, B, *a, **k)
+
+    torch.linalg.solve = spy
+    try:
+        with cpu_cuda_patches():
+            deltas = ref.emcid_main.execute_emcid_text_encoder(
+                pipe, requests, hparams, cache_name=cache_name, verbose=False, stat_dir=stat_dir)
+    finally:
+        torch.linalg.solve = orig_solve
+    return deltas
+
+
+def run_reference_apply(model, tokenizer, requests, hparams, cache_name: str, stat_dir: str):
+    """Reference apply_emcid_to_text_encoder (:769-815); mutates `model` in place."""
+    ref = import_reference()
+    ref.emcid_main.COV_CACHE.clear()
+    pipe = SimpleNamespace(text_encoder=model, tokenizer=tokenizer, device=next(model.parameters()).device)
+    with cpu_cuda_patches():
+        ref.emcid_main.apply_emcid_to_text_encoder(
+            pipe, requests, hparams, device=pipe.device, cache_name=cache_name, stats_dir=stat_dir, verbose=False)
+    return model
