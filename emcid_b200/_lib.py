@@ -39,6 +39,14 @@ SIGNATURES = {
         [c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
          c_float, c_float, c_int, c_void_p, c_size_t, c_void_p],
     ),
+    "emcid_mom2_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "emcid_mom2_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
+    "emcid_mom2_set_chunks": (c_int, [c_void_p, c_int, c_int]),
+    "emcid_mom2_set_weights": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
+    "emcid_mom2_accumulate": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p]),
+    "emcid_mom2_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emcid_mom2_reset": (c_int, [c_void_p, c_void_p]),
+    "emcid_mom2_destroy": (c_int, [c_void_p]),
 }
 
 _lib = None
@@ -91,7 +99,7 @@ def ptr(t) -> int:
 
 
 def gemm3x_nt(A, B, C=None, alpha: float = 1.0, beta: float = 0.0, lower: bool = False,
-              streamk: bool = False, n128: bool = False):
+              streamk: bool = False, n128: bool = False, chunk: int = 0):
     """C = alpha * A @ B.T + beta * C on tcgen05 with the 3xTF32 split (fp32 CUDA tensors)."""
     import torch
 
@@ -105,7 +113,7 @@ def gemm3x_nt(A, B, C=None, alpha: float = 1.0, beta: float = 0.0, lower: bool =
     assert C.stride(1) == 1
     ws_bytes = lib().emcid_gemm3x_workspace_bytes(M, N, K)
     ws = torch.empty(ws_bytes, device=A.device, dtype=torch.uint8)
-    flags = (1 if lower else 0) | (2 if streamk else 0) | (4 if n128 else 0)
+    flags = (1 if lower else 0) | (2 if streamk else 0) | (4 if n128 else 0) | ((chunk & 0xFF) << 8)
     with torch.cuda.device(A.device):
         check(lib().emcid_gemm3x_nt(M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0),
                                     alpha, beta, flags, ptr(ws), ws_bytes, current_stream_ptr()))

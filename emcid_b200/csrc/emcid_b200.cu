@@ -6,6 +6,7 @@
 #include "../../include/emcid_b200.h"
 
 #include "gemm_api.cuh"
+#include "mom2.cuh"
 
 using namespace emcid;
 
@@ -37,5 +38,47 @@ int emcid_gemm3x_nt(int M, int N, int K, const float* A, long long lda, const fl
   return gemm3x_nt(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, flags, workspace, workspace_bytes,
                    static_cast<cudaStream_t>(stream));
 }
+
+// ---------------------------------------------------------------------------------------------
+// mom2 statistics pass
+// ---------------------------------------------------------------------------------------------
+size_t emcid_mom2_workspace_bytes(int d, int h, int slab_tokens) {
+  if (slab_tokens <= 0) slab_tokens = MOM2_DEFAULT_SLAB;
+  return mom2_workspace_bytes(d, h, slab_tokens);
+}
+
+int emcid_mom2_create(emcid_mom2_t** out, int device, int d, int h, int act, int slab_tokens,
+                      void* workspace, size_t workspace_bytes) {
+  return mom2_create(reinterpret_cast<Mom2Handle**>(out), device, d, h, act, slab_tokens, workspace,
+                     workspace_bytes);
+}
+
+int emcid_mom2_set_chunks(emcid_mom2_t* h, int fc1_kblocks, int syrk_kblocks) {
+  Mom2Handle* H = reinterpret_cast<Mom2Handle*>(h);
+  EMCID_CHECK(H && fc1_kblocks > 0 && syrk_kblocks > 0 && fc1_kblocks < 256 && syrk_kblocks < 256,
+              EMCID_ERR_INVALID, "emcid_mom2_set_chunks: bad argument");
+  H->chunk_fc1 = fc1_kblocks;
+  H->chunk_syrk = syrk_kblocks;
+  return EMCID_OK;
+}
+
+int emcid_mom2_set_weights(emcid_mom2_t* h, const float* W1, long long ldw, const float* b1, void* stream) {
+  return mom2_set_weights(reinterpret_cast<Mom2Handle*>(h), W1, ldw, b1, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_mom2_accumulate(emcid_mom2_t* h, const float* X, long long ldx, const uint8_t* valid,
+                          long long T, void* stream) {
+  return mom2_accumulate(reinterpret_cast<Mom2Handle*>(h), X, ldx, valid, T, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_mom2_finalize(emcid_mom2_t* h, float* mom2_full, long long* count_dev, void* stream) {
+  return mom2_finalize(reinterpret_cast<Mom2Handle*>(h), mom2_full, count_dev, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_mom2_reset(emcid_mom2_t* h, void* stream) {
+  return mom2_reset(reinterpret_cast<Mom2Handle*>(h), static_cast<cudaStream_t>(stream));
+}
+
+int emcid_mom2_destroy(emcid_mom2_t* h) { return mom2_destroy(reinterpret_cast<Mom2Handle*>(h)); }
 
 }  // extern "C"

@@ -16,7 +16,8 @@ inline size_t gemm3x_workspace_bytes(int M, int N, int K, bool same_ab) {
 }
 
 // C = alpha * A B^T + beta * C  (fp32 in/out, 3xTF32 on tcgen05).  flags: bit0 = lower tiles only,
-// bit1 = stream-K with red.add epilogue (requires beta == 1, alpha == 1), bit2 = BLOCK_N 128.
+// bit1 = stream-K with red.add epilogue (requires beta == 1, alpha == 1), bit2 = BLOCK_N 128,
+// bits 8-15 = k-blocks per TMEM chunk (0 = default).
 inline int gemm3x_nt(int M, int N, int K, const float* A, long long lda, const float* B,
                      long long ldb, float* C, long long ldc, float alpha, float beta, int flags,
                      void* workspace, size_t ws_bytes, cudaStream_t stream) {
@@ -54,8 +55,9 @@ inline int gemm3x_nt(int M, int N, int K, const float* A, long long lda, const f
   p.M = M; p.N = N; p.K = K;
   p.lower = flags & 1;
   p.streamk = (flags >> 1) & 1;
-  p.chunk_kblocks = 0;
+  p.chunk_kblocks = (flags >> 8) & 0xff;  // 0 = library default
   p.C = C; p.ldc = ldc; p.alpha = alpha; p.beta = beta;
+  if (beta != 0.f) { p.Cin = C; p.ldcin = ldc; }
   const bool n128 = (flags >> 2) & 1;
   const int block_n = n128 ? 128 : 256;
   const int tiles = gemm_num_tiles(M, N, block_n, p.lower);
@@ -66,8 +68,8 @@ inline int gemm3x_nt(int M, int N, int K, const float* A, long long lda, const f
     return n128 ? launch_gemm3x<128, 3, EPI_RED>(ops, p, grid, stream)
                 : launch_gemm3x<256, 2, EPI_RED>(ops, p, grid, stream);
   }
-  return n128 ? launch_gemm3x<128, 3, EPI_STORE>(ops, p, grid, stream)
-              : launch_gemm3x<256, 2, EPI_STORE>(ops, p, grid, stream);
+  return n128 ? launch_gemm3x<128, 3, EPI_GENERIC>(ops, p, grid, stream)
+              : launch_gemm3x<256, 2, EPI_GENERIC>(ops, p, grid, stream);
 }
 
 }  // namespace emcid

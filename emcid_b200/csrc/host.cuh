@@ -127,7 +127,8 @@ struct GemmOperands {
 };
 
 template <int BLOCK_N, int STAGES, int EPI>
-inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid, cudaStream_t stream) {
+inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid, cudaStream_t stream,
+                         int batches = 1) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
   auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI>;
   static thread_local bool configured[16] = {false};
@@ -139,7 +140,7 @@ inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid,
     if (dev >= 0 && dev < 16) configured[dev] = true;
   }
   if (grid < 1) grid = 1;
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo, p);
+  kern<<<dim3(grid, batches), GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo, p);
   EMCID_CUDA_CHECK(cudaGetLastError());
   return EMCID_OK;
 }

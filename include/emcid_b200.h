@@ -46,6 +46,36 @@ int emcid_gemm3x_nt(int M, int N, int K, const float* A, long long lda, const fl
                     long long ldb, float* C, long long ldc, float alpha, float beta, int flags,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- mom2 statistics pass (one handle per edited layer) ---------------------------------------
+ * Replaces, per sub-batch, the reference's
+ *     feats = flatten_masked_batch(tr.input, batch["attention_mask"])   dsets/stat_dataset.py:166-172
+ *     stat.add(feats)  ->  count += T; mom2 += feats.t().mm(feats)      util/runningstats.py:483-493
+ * (called from emcid/layer_stats.py:208-219), where tr.input = act(fc1(X)) is recomputed on-chip
+ * from X = LN2 output, the argument of the CLIP MLP (transformers modeling_clip.py CLIPMLP.forward).
+ *
+ * workspace: scratch of emcid_mom2_workspace_bytes() bytes on `device`, owned by the caller; it may
+ * be shared by several handles that are only ever used on the same stream.  slab_tokens: rows
+ * processed per fc1/SYRK launch pair (multiple of 256, <= 4096; 0 = default 1536).
+ * act: EMCID_ACT_*.  The library allocates the handle-private accumulators (fp32 + fp64 [d x d],
+ * tf32 planes of W1) with cudaMalloc; emcid_mom2_destroy frees them. */
+typedef struct emcid_mom2 emcid_mom2_t;
+size_t emcid_mom2_workspace_bytes(int d, int h, int slab_tokens);
+int emcid_mom2_create(emcid_mom2_t** out, int device, int d, int h, int act, int slab_tokens,
+                      void* workspace, size_t workspace_bytes);
+/* k-blocks (32 tokens / 32 features each) accumulated in TMEM between round-to-nearest folds. */
+int emcid_mom2_set_chunks(emcid_mom2_t* h, int fc1_kblocks, int syrk_kblocks);
+/* W1 [d x h] row-major (pitch ldw floats) and b1 [d] (may be NULL): fc1.weight / fc1.bias. */
+int emcid_mom2_set_weights(emcid_mom2_t* h, const float* W1, long long ldw, const float* b1, void* stream);
+/* X [T x h] fp32 (pitch ldx), valid [T] bytes (non-zero = attended token; NULL = all rows).
+ * count += #valid ; mom2 += sum over valid rows of a a^T with a = act(W1 x + b1). */
+int emcid_mom2_accumulate(emcid_mom2_t* h, const float* X, long long ldx, const uint8_t* valid,
+                          long long T, void* stream);
+/* mom2_full [d x d] fp32 device (full symmetric matrix, the layout SecondMoment.state_dict saves,
+ * util/runningstats.py:502-507); count_dev: device int64 scalar (may be NULL).  Does not reset. */
+int emcid_mom2_finalize(emcid_mom2_t* h, float* mom2_full, long long* count_dev, void* stream);
+int emcid_mom2_reset(emcid_mom2_t* h, void* stream);
+int emcid_mom2_destroy(emcid_mom2_t* h);
+
 #ifdef __cplusplus
 }
 #endif

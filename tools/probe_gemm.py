@@ -63,17 +63,24 @@ check("streamk_full", 640, 512, 4096, streamk=True, alpha=1.0, beta=1.0)
 # ---- accumulation rounding probe: positive terms, growing K.  Linear growth of the relative
 # error with K means round-toward-zero accumulation in the tensor core; sqrt growth means RN.
 probe = []
-for K in (256, 1024, 4096, 16384, 65536):
-    g = torch.Generator(device="cuda").manual_seed(K)
-    A = torch.rand(128, K, device="cuda", generator=g) + 0.5
-    B = torch.rand(256, K, device="cuda", generator=g) + 0.5
-    ref = A.double() @ B.double().T
-    C = _lib.gemm3x_nt(A, B)
-    torch.cuda.synchronize()
-    d = (C.double() - ref) / ref
-    probe.append({"K": K, "mean_rel": float(d.mean()), "rms_rel": float(d.pow(2).mean().sqrt()),
-                  "torch_fp32_mean_rel": float((((A @ B.T).double() - ref) / ref).mean())})
-    print(json.dumps(probe[-1]), flush=True)
+for chunk in (1, 2, 4, 8, 32):
+    for K in (256, 1024, 4096, 16384):
+        g = torch.Generator(device="cuda").manual_seed(K)
+        A = torch.rand(128, K, device="cuda", generator=g) + 0.5
+        B = torch.rand(256, K, device="cuda", generator=g) + 0.5
+        ref = A.double() @ B.double().T
+        C = _lib.gemm3x_nt(A, B, chunk=chunk)
+        torch.cuda.synchronize()
+        d = (C.double() - ref) / ref
+        A2 = torch.randn(128, K, device="cuda", generator=g)
+        B2 = torch.randn(256, K, device="cuda", generator=g)
+        ref2 = A2.double() @ B2.double().T
+        C2 = _lib.gemm3x_nt(A2, B2, chunk=chunk)
+        probe.append({"chunk_kblocks": chunk, "K": K, "pos_mean_rel": float(d.mean()),
+                      "pos_rms_rel": float(d.pow(2).mean().sqrt()),
+                      "randn_rel_fro": rel(C2, ref2), "torch_fp32_randn_rel_fro": rel(A2 @ B2.T, ref2),
+                      "torch_fp32_pos_mean_rel": float((((A @ B.T).double() - ref) / ref).mean())})
+        print(json.dumps(probe[-1]), flush=True)
 out["rounding_probe"] = probe
 
 
@@ -94,19 +101,25 @@ def timeit(fn, iters=10):
 timings = []
 lib = _lib.lib()
 for (M, N, K, kw) in [
-    (3072, 3072, 1536, dict(lower=True, streamk=True, alpha=1.0, beta=1.0)),
+    (3072, 3072, 1536, dict(lower=True, streamk=True, alpha=1.0, beta=1.0, chunk=1)),
+    (3072, 3072, 1536, dict(lower=True, streamk=True, alpha=1.0, beta=1.0, chunk=2)),
+    (3072, 3072, 1536, dict(lower=True, streamk=True, alpha=1.0, beta=1.0, chunk=4)),
+    (3072, 3072, 1536, dict(lower=True, streamk=True, alpha=1.0, beta=1.0, chunk=48)),
     (3072, 3072, 1536, dict(lower=True)),
     (3072, 3072, 1536, dict()),
     (3072, 1536, 768, dict()),
     (3072, 3072, 4096, dict(lower=True, streamk=True, alpha=1.0, beta=1.0)),
-    (8192, 8192, 8192, dict()),
+    (8192, 8192, 8192, dict(chunk=1)),
+    (8192, 8192, 8192, dict(chunk=2)),
+    (8192, 8192, 8192, dict(chunk=4)),
+    (8192, 8192, 8192, dict(chunk=255)),
 ]:
     A = torch.randn(M, K, device="cuda")
     B = A if (M == N) else torch.randn(N, K, device="cuda")
     C = torch.zeros(M, N, device="cuda")
     ws_bytes = lib.emcid_gemm3x_workspace_bytes(M, N, K)
     ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
-    flags = (1 if kw.get("lower") else 0) | (2 if kw.get("streamk") else 0)
+    flags = (1 if kw.get("lower") else 0) | (2 if kw.get("streamk") else 0) | (kw.get("chunk", 0) << 8)
     alpha, beta = kw.get("alpha", 1.0), kw.get("beta", 0.0)
 
     def run():
