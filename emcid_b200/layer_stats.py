@@ -1,0 +1,253 @@
+"""Load-or-compute cached second-moment statistics of CLIP text-encoder MLP layers on B200.
+
+Drop-in for emcid/layer_stats.py::layer_stats_text_encoder (:140-220) of SilentView/EMCID: same
+signature, same cache file names and npz layout, same return type (a CombinedStat whose `.mom2`
+holds the raw fp32 [d, d] sum on the CPU and the integer token count).  What changes is how the
+numbers are produced:
+
+  * ONE forward pass serves every requested layer (`layer_stats_text_encoder_multi`); the
+    reference runs a full pass over the dataset per layer (emcid/layer_stats.py:112-134).
+  * The fc2 input is never materialised: a forward pre-hook on each edited layer's MLP hands the
+    h-wide LN2 output and the attention mask to `Mom2Accumulator`, whose sm_100a kernels do
+    fc1 -> activation -> pad masking -> lower-triangular SYRK (see csrc/mom2.cuh).  The forward is
+    abandoned at the deepest edited layer, like `Trace(stop=True)` (util/nethook.py:112-113).
+  * Captions are sharded `subset[rank::world]` across the GPUs of a torch.distributed job and the
+    per-rank sums meet in one NCCL reduce per layer; counts are reduced as int64 (bit exact).
+
+There is no CPU path: a model that is not on a CUDA (sm_100) device is an error.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from . import nethook
+from .runningstats import (CombinedStat, FixedSubsetSampler, Mean, NormMean, SecondMoment, load_cached_state,
+                           save_cached_state, subset_indices)
+from .stat_dataset import TokenizedDataset, dict_to_, fixed_width_collation
+
+try:  # the reference's default progress bar
+    from tqdm.auto import tqdm
+except Exception:  # pragma: no cover
+    tqdm = None
+
+STAT_TYPES = {"mom2": SecondMoment, "mean": Mean, "norm_mean": NormMean}
+
+
+def get_ccs_filtered_ds(tokenizer):
+    """Dataset factory (reference :137-138); the patch point for synthetic data."""
+    return TokenizedDataset("./data/ccs_filtered.json", tokenizer)
+
+
+def stats_filename(stats_dir, model_name, ds_name, layer_name, precision, to_collect, batch_tokens, sample_size):
+    """Cache path, reference :166-174."""
+    size_suffix = "" if sample_size is None else f"_{sample_size}"
+    size_suffix = f"_t{batch_tokens}" + size_suffix
+    return Path(stats_dir) / (f"{model_name}/{ds_name}_stats/{layer_name}_{precision}_"
+                              f"{'-'.join(sorted(to_collect))}{size_suffix}.npz")
+
+
+def _mlp_of(model, layer_name: str):
+    """The CLIP MLP that owns `layer_name` (= "...mlp.fc2"): its argument is the fc1 input."""
+    if not layer_name.endswith(".fc2"):
+        raise NotImplementedError(
+            f"emcid_b200 computes mom2 for CLIP MLP fc2 inputs (…mlp.fc2); got {layer_name!r}")
+    nethook.get_module(model, layer_name)  # LookupError for unknown names, like the reference
+    mlp = nethook.get_module(model, layer_name[: -len(".fc2")])
+    if not hasattr(mlp, "fc1") or not isinstance(mlp.fc1, torch.nn.Linear):
+        raise NotImplementedError(f"{layer_name}: parent module has no fc1 Linear")
+    return mlp
+
+
+class TextEncoderMom2Pass:
+    """Streams padded caption blocks through the HF CLIP text model and accumulates mom2/count for
+    a set of MLP layers in the same pass."""
+
+    def __init__(self, model, layer_names: Sequence[str], slab_tokens: int = 0, accumulator_factory=None):
+        from .mom2 import Mom2Accumulator
+
+        self.model = model
+        self.layer_names = list(layer_names)
+        device = next(model.parameters()).device
+        if accumulator_factory is None:
+            if device.type != "cuda":
+                raise RuntimeError(
+                    "emcid_b200.layer_stats needs the model on a CUDA sm_100 device (no CPU fallback); "
+                    f"model is on {device}")
+            accumulator_factory = lambda d, h, act: Mom2Accumulator(device, d, h, act, slab_tokens=slab_tokens)
+        act = getattr(model.config, "hidden_act", None)
+        if act not in ("quick_gelu", "gelu"):
+            raise NotImplementedError(f"unsupported CLIP MLP activation {act!r}")
+        self.accs: Dict[str, object] = {}
+        self._mlps = []
+        order = {n: i for i, (n, _) in enumerate(model.named_modules())}
+        deepest = max(self.layer_names, key=lambda n: order[n])
+        for name in self.layer_names:
+            mlp = _mlp_of(model, name)
+            W1, b1 = mlp.fc1.weight, mlp.fc1.bias
+            if W1.dtype != torch.float32:
+                raise NotImplementedError("the statistics pass runs on fp32 weights (reference precision float32)")
+            acc = accumulator_factory(W1.shape[0], W1.shape[1], act)
+            acc.set_weights(W1, b1)
+            self.accs[name] = acc
+            self._mlps.append((name, mlp, name == deepest))
+        self._mask = None
+
+    def _hook(self, name, stop):
+        def pre_hook(_module, args):
+            self.accs[name].add(args[0], self._mask)
+            if stop:
+                raise nethook.StopForward()
+        return pre_hook
+
+    @torch.no_grad()
+    def run_batch(self, batch: Dict[str, torch.Tensor]) -> None:
+        """batch: input_ids / position_ids / attention_mask [B, L] on the model's device."""
+        self._mask = batch["attention_mask"]
+        handles = [mlp.register_forward_pre_hook(self._hook(name, stop)) for name, mlp, stop in self._mlps]
+        try:
+            self.model(**batch)
+        except nethook.StopForward:
+            pass
+        finally:
+            for h in handles:
+                h.remove()
+            self._mask = None
+
+    def finalize(self):
+        """{layer_name: (mom2 [d,d] fp32 on device, count 0-d int64 on device)}."""
+        return {name: acc.finalize() for name, acc in self.accs.items()}
+
+    def close(self):
+        for acc in self.accs.values():
+            acc.close()
+
+
+def _dist_info(distributed):
+    import torch.distributed as dist
+
+    if distributed is False or not (dist.is_available() and dist.is_initialized()):
+        return None, 0, 1
+    return dist, dist.get_rank(), dist.get_world_size()
+
+
+def layer_stats_text_encoder_multi(
+    model,
+    tokenizer,
+    layer_names: Sequence[str],
+    stats_dir="data/stats",
+    ds_name="ccs_filtered",
+    to_collect=["mom2"],
+    model_name="text_encoder",
+    sample_size=None,
+    precision=None,
+    batch_tokens=3 * 1024,
+    download=False,
+    progress=tqdm,
+    force_recompute=False,
+    captions_per_batch: int = 256,
+    num_workers: int = 2,
+    slab_tokens: int = 0,
+    distributed: Optional[bool] = None,
+    keep_on_device: bool = False,
+    _accumulator_factory: Optional[Callable] = None,
+) -> Dict[str, CombinedStat]:
+    """All `layer_names` in one pass.  Arguments up to `force_recompute` mean exactly what they mean
+    in the reference's layer_stats_text_encoder; the rest tune the B200 driver."""
+    device = model.device
+    if precision is None:
+        precision = "float64"  # reference default (:161-162); every EMCID caller passes "float32"
+    if precision != "float32":
+        raise NotImplementedError("emcid_b200 accumulates mom2 in fp32 (hparams.mom2_dtype == 'float32')")
+    if sorted(to_collect) != ["mom2"]:
+        raise NotImplementedError(
+            f"only to_collect=['mom2'] is on the accelerated path (got {to_collect}); "
+            "mean / norm_mean are not used by the EMCID edit")
+    layer_names = list(layer_names)
+    stats_dir = Path(stats_dir)
+    stats_dir.mkdir(exist_ok=True, parents=True)
+    files = {n: stats_filename(stats_dir, model_name, ds_name, n, precision, to_collect, batch_tokens, sample_size)
+             for n in layer_names}
+    for f in files.values():
+        if not f.exists() and download:
+            raise NotImplementedError("Downloading stats from remote is not implemented yet.")  # reference :176-178
+
+    args = {"sample_size": sample_size}  # tally forwards it even when None (boxed as a null NaN in the npz)
+    stats: Dict[str, CombinedStat] = {}
+    todo: List[str] = []
+    for n in layer_names:
+        stat = CombinedStat(**{k: STAT_TYPES[k]() for k in to_collect})
+        cached = None if force_recompute else load_cached_state(files[n], args)
+        if cached is not None:
+            stat.load_state_dict(cached)
+            if keep_on_device:
+                stat.to_(device)
+        else:
+            todo.append(n)
+        stats[n] = stat
+    if not todo:
+        return stats
+
+    dist, rank, world = _dist_info(distributed)
+    ds = get_ccs_filtered_ds(tokenizer=tokenizer)
+    indices = subset_indices(len(ds), sample_size, random_sample=1)  # tally(..., random_sample=1), reference :204
+    my_indices = indices[rank::world]
+    loader = torch.utils.data.DataLoader(
+        ds, sampler=FixedSubsetSampler(my_indices), batch_size=captions_per_batch,
+        collate_fn=fixed_width_collation(), num_workers=num_workers, pin_memory=(device.type == "cuda"))
+    batch_count = -(-len(my_indices) // captions_per_batch)
+    if progress is None:
+        progress = lambda x, total=None: x
+
+    runner = TextEncoderMom2Pass(model, todo, slab_tokens=slab_tokens, accumulator_factory=_accumulator_factory)
+    try:
+        for batch in progress(loader, total=batch_count):
+            if batch["input_ids"].numel() == 0:
+                continue
+            batch = {k: v.to(device, non_blocking=True) for k, v in batch.items()}
+            runner.run_batch(batch)
+        results = runner.finalize()
+        for i, n in enumerate(todo):
+            mom2, count = results[n]
+            root = i % world
+            if dist is not None and world > 1:
+                # the one exchange step of the pass: per-rank partial sums -> one matrix per layer
+                dist.reduce(mom2, dst=root, op=dist.ReduceOp.SUM)
+                dist.reduce(count, dst=root, op=dist.ReduceOp.SUM)
+                dist.broadcast(mom2, src=root)
+                dist.broadcast(count, src=root)
+            sm = stats[n].mom2
+            sm.count = int(count.item())
+            sm.mom2 = mom2 if keep_on_device else mom2.to("cpu")
+            if not force_recompute and rank == root:
+                save_cached_state(files[n], stats[n], args)
+        if dist is not None and world > 1:
+            dist.barrier()
+    finally:
+        runner.close()
+    return stats
+
+
+def layer_stats_text_encoder(
+    model,
+    tokenizer,
+    layer_name,
+    stats_dir="data/stats",
+    ds_name="ccs_filtered",
+    to_collect=["mom2"],
+    model_name="text_encoder",
+    sample_size=None,
+    precision=None,
+    batch_tokens=3 * 1024,
+    download=False,
+    progress=tqdm,
+    force_recompute=False,
+    **b200_options,
+) -> CombinedStat:
+    """Function to load or compute cached stats (signature of emcid/layer_stats.py:140-154)."""
+    return layer_stats_text_encoder_multi(
+        model, tokenizer, [layer_name], stats_dir=stats_dir, ds_name=ds_name, to_collect=to_collect,
+        model_name=model_name, sample_size=sample_size, precision=precision, batch_tokens=batch_tokens,
+        download=download, progress=progress, force_recompute=force_recompute, **b200_options)[layer_name]

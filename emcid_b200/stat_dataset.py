@@ -1,0 +1,108 @@
+"""Caption batching for the statistics pass (host logic).
+
+Mirrors the observable behaviour of dsets/stat_dataset.py in SilentView/EMCID — item layout
+(:99-110), length-sorted sub-batching (:122-150), right padding with 0 (:153-163) and the masked
+flatten (:166-172) — because those four pieces define WHICH token rows enter mom2 and `count`.
+The B200 driver itself (`layer_stats.py`) re-batches captions into fixed-width blocks: with right
+padding and CLIP's causal attention the fc2 input of a valid token does not depend on how captions
+are batched, so only the *set* of valid tokens has to match, and it does.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, List, Sequence
+
+import torch
+from torch.utils.data import Dataset
+
+
+class TokenizedDataset(Dataset):
+    """Caption json -> {input_ids, position_ids, attention_mask} 1-D int64 tensors per item."""
+
+    def __init__(self, data_path, tokenizer=None, maxlen=None):
+        if not os.path.exists(data_path):
+            raise FileNotFoundError(
+                f"{data_path} not found (the reference downloads ccs_filtered.json here; this build has no network)")
+        with open(data_path, "r") as f:
+            records = json.load(f)
+        self.data = [rec["caption"] for rec in records]
+        self.tokenizer = tokenizer
+        self.maxlen = maxlen
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        ids = self.tokenizer.encode(self.data[idx], truncation=True, max_length=self.maxlen)
+        n = len(ids)
+        return dict(input_ids=torch.tensor(ids), position_ids=torch.arange(n),
+                    attention_mask=torch.ones(n, dtype=torch.long))
+
+
+def dict_to_(data: Dict[str, torch.Tensor], device):
+    for k in data:
+        data[k] = data[k].to(device)
+    return data
+
+
+def make_padded_batch(items: Sequence[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
+    """Right-pad every field with zeros to the longest sequence; empty sequences are dropped."""
+    keep = [it for it in items if len(it["input_ids"])]
+    if not keep:
+        return {k: torch.zeros((0, 0), dtype=torch.long) for k in items[0]}
+    width = max(len(it["input_ids"]) for it in keep)
+    out = {}
+    for k in items[0]:
+        buf = torch.zeros((len(keep), width), dtype=keep[0][k].dtype)
+        for r, it in enumerate(keep):
+            buf[r, : len(it[k])] = it[k]
+        out[k] = buf
+    return out
+
+
+def length_collation(token_size: int):
+    """collate_fn factory: sort by decreasing length, cut a new sub-batch whenever
+    width * (rows + 1) would exceed token_size, pad each sub-batch (reference :122-150)."""
+
+    def collate_fn(items):
+        ordered = sorted(items, key=lambda it: -len(it["input_ids"]))
+        groups: List[List[Dict[str, torch.Tensor]]] = []
+        cur: List[Dict[str, torch.Tensor]] = []
+        width = 0
+        for it in ordered:
+            n = len(it["input_ids"])
+            if n == 0:
+                break
+            if width * (len(cur) + 1) > token_size:
+                groups.append(cur)
+                cur, width = [], 0
+            if not cur:
+                width = n
+            cur.append(it)
+        if cur:
+            groups.append(cur)
+        return [make_padded_batch(g) for g in groups]
+
+    return collate_fn
+
+
+def flatten_masked_batch(data: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Rows of data.view(-1, d) whose attention mask is non-zero (reference :166-172).  The fused
+    kernels never call this (they mask on the h-wide MLP input); it exists for API parity."""
+    flat = data.reshape(-1, data.size(-1))
+    return flat[mask.reshape(-1).nonzero()[:, 0]]
+
+
+def fixed_width_collation(width: int = 0):
+    """collate_fn of the B200 driver: one right-padded block per DataLoader batch (`width` = 0 pads
+    to the longest caption of the block)."""
+
+    def collate_fn(items):
+        batch = make_padded_batch(items)
+        if width and batch["input_ids"].shape[1] < width:
+            pad = width - batch["input_ids"].shape[1]
+            batch = {k: torch.nn.functional.pad(v, (0, pad)) for k, v in batch.items()}
+        return batch
+
+    return collate_fn

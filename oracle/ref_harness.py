@@ -188,6 +188,7 @@ class FakeTokenizer:
             ids = [ids]
         toks = []
         for i in ids:
+            i = int(i)  # the reference passes lists of 0-d tensors (experiments/causal_trace.py:1046-1049)
             if i == self.bos:
                 toks.append("<|startoftext|>")
             elif i == self.eos:

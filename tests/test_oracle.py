@@ -1,0 +1,120 @@
+"""Pins oracle/emcid_oracle.py (the CPU restatement) against the reference: committed fixtures made
+by the unmodified reference (oracle/gen_golden.py), the reference's own known-answer test, and —
+in the build container — the live reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import model_from_golden, rel_fro, rh, unpack_captions
+from oracle import emcid_oracle as orc
+
+
+@pytest.mark.parametrize("name", ["tiny_stats.npz", "tiny_gelu_stats.npz"])
+def test_stats_oracle_matches_reference_fixture(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name), allow_pickle=False)
+    model = model_from_golden(g)
+    caps = unpack_captions(g)
+    ss = None if int(g["sample_size"]) < 0 else int(g["sample_size"])
+    stat = orc.layer_stats_oracle(model, [c.numpy() for c in caps], int(g["layer"]), ss, int(g["batch_tokens"]))
+    assert stat.count == int(g["npz.mom2.count"])                      # bit exact
+    assert rel_fro(stat.mom2, g["npz.mom2.mom2"]) < 1e-6               # same arithmetic, fp32 noise only
+    assert stat.mom2.dtype == np.float32 and g["npz.mom2.mom2"].dtype == np.float32
+
+
+def test_npz_layout_of_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny_stats.npz"))
+    assert str(g["npz.mom2.constructor"]) == "util.runningstats.SecondMoment()"
+    assert g["npz.mom2.count"].dtype == np.int64 and g["npz.mom2.count"].shape == ()
+    assert g["npz.sample_size"].dtype == np.int64
+    assert str(g["rel_path"]) == orc.stats_filename("", "text_encoder", "ccs_filtered",
+                                                    "text_model.encoder.layers.1.mlp.fc2", "float32", ["mom2"],
+                                                    3072, 120).lstrip("/")
+    st = orc.SecondMomentOracle()
+    st.count, st.mom2 = 5, np.eye(3, dtype=np.float32)
+    assert set(orc.combined_state(st, 7)) == {"mom2.constructor", "mom2.count", "mom2.mom2", "sample_size"}
+
+
+def test_second_moment_known_answer():
+    """The reference's own check (util/runningstats.py:1787-1789): moment() == X^T X / n."""
+    rng = np.random.RandomState(0)
+    data = rng.randn(5000, 24).astype(np.float32)
+    st = orc.SecondMomentOracle()
+    for i in range(0, 5000, 617):
+        st.add(data[i: i + 617])
+    st.add(data[:0])
+    assert st.count == 5000
+    np.testing.assert_allclose(st.moment(), data.T @ data / 5000, rtol=1e-2, atol=1e-4)
+    assert rel_fro(st.moment(), data.astype(np.float64).T @ data.astype(np.float64) / 5000) < 1e-6
+
+
+def test_length_collation_matches_survey_examples():
+    # 100 full-length captions -> [(39,77),(39,77),(22,77)]
+    subs = orc.length_collation([77] * 100, 3072)
+    assert [len(s) for s in subs] == [39, 39, 22]
+    lens = [77] * 39 + [49] * 61
+    subs = orc.length_collation(lens, 3072)
+    assert [(len(s), max(lens[i] for i in s)) for s in subs] == [(39, 77), (61, 49)]
+    assert orc.length_collation([0, 0], 3072) == []
+    assert orc.length_collation([5000], 3072) == [[0]]  # a single over-long sequence stays alone
+
+
+@pytest.mark.parametrize("name", ["tiny_solve_ew05.npz", "tiny_solve_ew06.npz"])
+def test_solve_block_matches_reference_fixture(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    lam, ew = float(g["lam"]), float(g["edit_weight"])
+    layers = [int(l) for l in g["layers"]]
+    for i, l in enumerate(layers):
+        C = orc.cov_from_state(g[f"mom2.{l}"], int(g[f"count.{l}"]))
+        Ks = g[f"solveK.{l}"]                       # already scaled by sqrt(ew/0.5), fp64
+        K = (Ks / (ew / 0.5) ** 0.5).astype(np.float32)
+        # M as the reference formed it
+        C32 = (C * np.float32(1 - ew) / np.float32(0.5)).astype(np.float32)
+        M = lam * C32.astype(np.float64) + Ks @ Ks.T
+        assert rel_fro(M, g[f"solveM.{l}"]) < 1e-12
+        resid = g[f"resid.{l}"]
+        S = (resid * (len(layers) - i) / (ew / 0.5) ** 0.5).astype(np.float32)
+        adj_k, resid_o, upd = orc.solve_layer(C, K, S, lam, ew, len(layers) - i)
+        assert rel_fro(adj_k, g[f"adj_k.{l}"]) < 1e-7
+        assert rel_fro(resid_o, resid) < 1e-6
+        w_after = orc.apply_delta(g[f"w_before.{l}"], g[f"adj_k.{l}"], resid)
+        assert rel_fro(w_after, g[f"w_after.{l}"]) < 1e-7
+
+
+def test_execute_oracle_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny_solve_ew05.npz"))
+    model = rh.make_clip_text_model("tiny", seed=0)
+    layers = [int(l) for l in g["layers"]]
+    for l in layers:  # same weights as when the fixture was made
+        assert np.array_equal(model.text_model.encoder.layers[l].mlp.fc2.weight.numpy(), g[f"w_before.{l}"])
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    reqs = rh.make_requests(int(g["n_req"]))
+    covs = {l: orc.cov_from_state(g[f"mom2.{l}"], int(g[f"count.{l}"])) for l in layers}
+    deltas = orc.execute_oracle(model, tok, reqs, layers, g["zs"], covs, float(g["lam"]), float(g["edit_weight"]))
+    for l in layers:
+        assert rel_fro(deltas[l][0], g[f"adj_k.{l}"]) < 1e-5
+        assert rel_fro(deltas[l][1], g[f"resid.{l}"]) < 1e-5
+        upd = deltas[l][1] @ deltas[l][0].T
+        assert rel_fro(upd, g[f"resid.{l}"] @ g[f"adj_k.{l}"].T) < 1e-5
+        assert np.array_equal(model.text_model.encoder.layers[l].mlp.fc2.weight.numpy(), g[f"w_before.{l}"])
+
+
+def test_exact_spd_matrix_is_reproducible():
+    a = orc.exact_spd_matrix(64, 128, seed=3)
+    b = orc.exact_spd_matrix(64, 128, seed=3)
+    assert np.array_equal(a, b) and np.array_equal(a, a.T)
+    assert np.linalg.eigvalsh(a.astype(np.float64)).min() > 0
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not rh.reference_available(), reason="needs /root/reference")
+def test_find_token_range_matches_live_reference():
+    import sys
+    rh.import_reference()
+    from experiments.causal_trace import find_token_range as ref_ftr
+    tok = rh.FakeTokenizer(1000)
+    for prompt, word in [("An image of artist3 name3", "artist3 name3"), ("artist7 name7", "artist7 name7"),
+                         ("A photo of artist1 name1", "artist1 name1")]:
+        ids = tok([prompt])["input_ids"][0]
+        assert tuple(ref_ftr(tok, ids, word)) == tuple(orc.find_token_range(tok, ids, word))
