@@ -47,6 +47,12 @@ SIGNATURES = {
     "emcid_mom2_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "emcid_mom2_reset": (c_int, [c_void_p, c_void_p]),
     "emcid_mom2_destroy": (c_int, [c_void_p]),
+    "emcid_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "emcid_solve_layers": (
+        c_int,
+        [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_double, c_double,
+         ctypes.POINTER(c_double), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p],
+    ),
 }
 
 _lib = None

@@ -1,0 +1,129 @@
+// emcid_b200 — fp64 "NT" GEMM on the DMMA tensor path (mma.sync.m8n8k4.f64), sm_100a.
+//
+//   C[M x N] = alpha * A[M x K] * B[N x K]^T + beta * Cin          (row-major, K contiguous)
+//
+// Used where the reference demands true double precision and 3xTF32 cannot deliver it:
+//   * M64 = lambda * double(C32) + Ks Ks^T            emcid/emcid_main.py:1046
+//   * the iterative-refinement residual  R^T = Ks^T - X^T M64   (fp64 accumulate is what makes
+//     one refinement step worth ~3 digits; SURVEY.md §7 hard part 3)
+//   * upd_matrix = resid @ adj_k.T                     emcid/emcid_main.py:1050
+// Block tile 128x128x16, 8 warps (2x4), warp tile 64x32, register-staged prefetch.
+#pragma once
+
+#include "host.cuh"
+
+namespace emcid {
+
+constexpr int DG_BM = 128, DG_BN = 128, DG_BK = 16, DG_THREADS = 256;
+constexpr int DG_LD = DG_BM + 4;  // smem pitch (doubles): k-stride == 32 B mod 128 B -> conflict-free frags
+
+struct DgemmParams {
+  int M, N, K;
+  const double* A; long long lda, a_batch;
+  const double* B; long long ldb, b_batch;
+  double alpha, beta;
+  const double* Cin; long long ldcin, cin_batch;   // fp64 addend (or null)
+  const float* Cin32; long long ldcin32, cin32_batch;  // fp32 addend, promoted (or null)
+  double* C; long long ldc, c_batch;               // fp64 result (or null)
+  float* C32; long long ldc32, c32_batch;          // fp32 copy of the result (or null)
+  int lower;                                       // skip tiles strictly above the diagonal
+};
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(DG_THREADS) dgemm_nt_kernel(const DgemmParams p) {
+  __shared__ double As[DG_BK][DG_LD];
+  __shared__ double Bs[DG_BK][DG_LD];
+  const int bm = blockIdx.y * DG_BM, bn = blockIdx.x * DG_BN;
+  if (p.lower && bn > bm + DG_BM - 1) return;
+  const int batch = blockIdx.z;
+  const double* A = p.A + batch * p.a_batch;
+  const double* B = p.B + batch * p.b_batch;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+
+  // global->register staging: tile is 128 rows x 16 k; thread owns (row = tid/2 [+0], k8 = (tid&1)*8 .. +8)
+  const int lrow = tid >> 1, lk = (tid & 1) * 8;
+  double ra[8], rb[8];
+  auto load_tiles = [&](int k0) {
+    const int ar = bm + lrow, br = bn + lrow;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + lk + j;
+      ra[j] = (ar < p.M && k < p.K) ? A[static_cast<long long>(ar) * p.lda + k] : 0.0;
+      rb[j] = (br < p.N && k < p.K) ? B[static_cast<long long>(br) * p.ldb + k] : 0.0;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      As[lk + j][lrow] = ra[j];
+      Bs[lk + j][lrow] = rb[j];
+    }
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nk = (p.K + DG_BK - 1) / DG_BK;
+  load_tiles(0);
+  store_tiles();
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + 1 < nk) load_tiles((kt + 1) * DG_BK);  // global loads in flight during the MMAs
+#pragma unroll
+    for (int ks = 0; ks < DG_BK; ks += 4) {
+      double af[8], bf[4];
+      const int kk = ks + (lane & 3), r = lane >> 2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = As[kk][wm + i * 8 + r];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[kk][wn + j * 8 + r];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+    if (kt + 1 < nk) store_tiles();
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = bm + wm + i * 8 + (lane >> 2);
+    if (row >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = bn + wn + j * 8 + 2 * (lane & 3);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = col + e;
+        if (c >= p.N) continue;
+        double v = p.alpha * acc[i][j][e];
+        if (p.Cin) v += p.beta * p.Cin[batch * p.cin_batch + static_cast<long long>(row) * p.ldcin + c];
+        if (p.Cin32)
+          v += p.beta * static_cast<double>(p.Cin32[batch * p.cin32_batch + static_cast<long long>(row) * p.ldcin32 + c]);
+        if (p.C) p.C[batch * p.c_batch + static_cast<long long>(row) * p.ldc + c] = v;
+        if (p.C32) p.C32[batch * p.c32_batch + static_cast<long long>(row) * p.ldc32 + c] = static_cast<float>(v);
+      }
+    }
+  }
+}
+
+inline int launch_dgemm_nt(const DgemmParams& p, int batches, cudaStream_t stream) {
+  dim3 grid((p.N + DG_BN - 1) / DG_BN, (p.M + DG_BM - 1) / DG_BM, batches);
+  dgemm_nt_kernel<<<grid, DG_THREADS, 0, stream>>>(p);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  return EMCID_OK;
+}
+
+}  // namespace emcid

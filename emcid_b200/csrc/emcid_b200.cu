@@ -7,6 +7,7 @@
 
 #include "gemm_api.cuh"
 #include "mom2.cuh"
+#include "solve.cuh"
 
 using namespace emcid;
 
@@ -80,5 +81,18 @@ int emcid_mom2_reset(emcid_mom2_t* h, void* stream) {
 }
 
 int emcid_mom2_destroy(emcid_mom2_t* h) { return mom2_destroy(reinterpret_cast<Mom2Handle*>(h)); }
+
+// ---------------------------------------------------------------------------------------------
+// closed-form update
+// ---------------------------------------------------------------------------------------------
+size_t emcid_solve_workspace_bytes(int batch, int d, int h, int n) { return solve_workspace_bytes(batch, d, h, n); }
+
+int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* C32, const float* Kt,
+                       long long ldk, const float* St, long long lds, double lambda, double scale,
+                       const double* inv_layers_left, double* adj_k, double* resid, float* dW,
+                       int refine_steps, void* workspace, size_t workspace_bytes, int* status_dev, void* stream) {
+  return solve_layers(device, batch, d, h, n, C32, Kt, ldk, St, lds, lambda, scale, inv_layers_left, adj_k, resid,
+                      dW, refine_steps, workspace, workspace_bytes, status_dev, static_cast<cudaStream_t>(stream));
+}
 
 }  // extern "C"

@@ -1,0 +1,533 @@
+// emcid_b200 — the closed-form update  adj_k = (lambda*C + Ks Ks^T)^-1 Ks,  dW = resid adj_k^T.
+//
+// Replaces the solve block of execute_emcid_text_encoder (emcid/emcid_main.py:1037-1050; identical
+// copies at :1265-1312, :1365-1414, :2016-2042), which is fp64 LU (`torch.linalg.solve`).  Here:
+//
+//   M32 = lambda*C32 + Ks Ks^T                 3xTF32 tcgen05 SYRK, lower tiles, planes kept
+//   M32 = L L^T                                blocked right-looking Cholesky, nb = 128:
+//        diag block   fp64 potrf + triangular inverse in shared memory (one CTA per layer)
+//        panel        L_ik = M_ik Linv_kk^T            tcgen05 GEMM (K = 128)
+//        trailing     M_ij -= L_ik L_jk^T  (i>=j>k)    tcgen05 GEMM, lower tiles
+//   L Y = Ks, L^T X = Y                        blocked right-looking TRSM on the transposed
+//                                              right-hand side [n x d]; every block product is a
+//                                              tcgen05 GEMM against L / L^T / Linv_kk planes
+//   refinement (fp64 residual on DMMA):        R^T = Ks^T - X^T M64 ; X += solve(R)
+//   dW = resid adj_k^T                         fp64 DMMA GEMM, rounded once to fp32
+//
+// Everything is batched over independent layers (grid.y / grid.z = layer): the benchmark form of
+// SURVEY.md §8d solves the 5 edited layers in one call; the faithful sequential loop calls it with
+// batch = 1 per layer because K_{i+1} depends on dW_i (emcid_main.py:1061).
+// All right-hand-side / solution matrices are held TRANSPOSED ([n x d], d contiguous) so that every
+// operand of every product is K-major, the only layout the TMA/UMMA descriptors here describe.
+#pragma once
+
+#include "dgemm.cuh"
+#include "gemm_api.cuh"
+
+namespace emcid {
+
+constexpr int SOLVE_NB = 128;
+constexpr int SOLVE_ADAPT_MAX = 8;
+constexpr double SOLVE_ADAPT_TOL = 1e-4;
+
+// ---- diagonal block: potrf + inverse, fp64 in shared memory ---------------------------------------
+// M32: [B][d x d] fp32.  Writes L_kk (symmetric fill) into the LL planes' diagonal block and
+// Linv_kk / Linv_kk^T planes into row-block k of the [B*d x 128] Linv / LinvT arrays.
+__global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict__ M32, int d, int k,
+                                                         float* __restrict__ LL_hi, float* __restrict__ LL_lo,
+                                                         float* __restrict__ Li_hi, float* __restrict__ Li_lo,
+                                                         float* __restrict__ LiT_hi, float* __restrict__ LiT_lo,
+                                                         int* __restrict__ status) {
+  extern __shared__ double sm[];
+  constexpr int LD = SOLVE_NB + 1;
+  double* A = sm;                    // [128][129]
+  double* colbuf = sm + SOLVE_NB * LD;  // [128]
+  const int b = blockIdx.x;
+  const long long base = static_cast<long long>(b) * d * d + static_cast<long long>(k) * SOLVE_NB * d + k * SOLVE_NB;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
+    const int r = e / SOLVE_NB, c = e % SOLVE_NB;
+    A[r * LD + c] = (c <= r) ? static_cast<double>(M32[base + static_cast<long long>(r) * d + c]) : 0.0;
+  }
+  __syncthreads();
+  // right-looking Cholesky
+  for (int j = 0; j < SOLVE_NB; ++j) {
+    if (tid == 0) {
+      double ajj = A[j * LD + j];
+      if (!(ajj > 0.0)) {  // also catches NaN
+        atomicOr(status, 1);
+        ajj = 1.0;
+      }
+      A[j * LD + j] = sqrt(ajj);
+    }
+    __syncthreads();
+    const double inv = 1.0 / A[j * LD + j];
+    for (int i = j + 1 + tid; i < SOLVE_NB; i += blockDim.x) A[i * LD + j] *= inv;
+    __syncthreads();
+    const int rem = SOLVE_NB - 1 - j;
+    for (int e = tid; e < rem * rem; e += blockDim.x) {
+      const int i = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= i) A[i * LD + c] -= A[i * LD + j] * A[c * LD + j];
+    }
+    __syncthreads();
+  }
+  // L_kk -> LL planes (lower = L, upper = L^T)
+  for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
+    const int r = e / SOLVE_NB, c = e % SOLVE_NB;
+    const double v = (c <= r) ? A[r * LD + c] : A[c * LD + r];
+    float hi, lo;
+    split_tf32(static_cast<float>(v), hi, lo);
+    LL_hi[base + static_cast<long long>(r) * d + c] = hi;
+    LL_lo[base + static_cast<long long>(r) * d + c] = lo;
+  }
+  __syncthreads();
+  // in-place inverse of the lower-triangular A (column sweep from the right)
+  for (int j = SOLVE_NB - 1; j >= 0; --j) {
+    for (int i = j + 1 + tid; i < SOLVE_NB; i += blockDim.x) colbuf[i] = A[i * LD + j];
+    __syncthreads();
+    const double ajj = 1.0 / A[j * LD + j];
+    for (int i = j + 1 + tid; i < SOLVE_NB; i += blockDim.x) {
+      double s0 = 0.0, s1 = 0.0;
+      int kk = j + 1;
+      for (; kk + 1 <= i; kk += 2) {
+        s0 += A[i * LD + kk] * colbuf[kk];
+        s1 += A[i * LD + kk + 1] * colbuf[kk + 1];
+      }
+      if (kk <= i) s0 += A[i * LD + kk] * colbuf[kk];
+      A[i * LD + j] = -(s0 + s1) * ajj;
+    }
+    __syncthreads();
+    if (tid == 0) A[j * LD + j] = ajj;
+    __syncthreads();
+  }
+  const long long ibase = (static_cast<long long>(b) * d + static_cast<long long>(k) * SOLVE_NB) * SOLVE_NB;
+  for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
+    const int r = e / SOLVE_NB, c = e % SOLVE_NB;
+    float hi, lo;
+    split_tf32(static_cast<float>((c <= r) ? A[r * LD + c] : 0.0), hi, lo);
+    Li_hi[ibase + r * SOLVE_NB + c] = hi;
+    Li_lo[ibase + r * SOLVE_NB + c] = lo;
+    split_tf32(static_cast<float>((r <= c) ? A[c * LD + r] : 0.0), hi, lo);
+    LiT_hi[ibase + r * SOLVE_NB + c] = hi;
+    LiT_lo[ibase + r * SOLVE_NB + c] = lo;
+  }
+}
+
+// ---- operand preparation ----------------------------------------------------------------------------
+// Kt [B][n x d] fp32 -> Ks64t [B][n_pad x d] (= s*K, zero pad rows), W / Wp (fp32 + planes of the
+// same), Kd64 [B][d x n_pad] and Kd planes (transposes).  32x32 tiles through shared memory.
+__global__ void solve_prep_kernel(const float* __restrict__ Kt, long long ldk, long long k_batch, int n, int n_pad,
+                                  int d, double s, double* __restrict__ Ks64t, float* __restrict__ W,
+                                  float* __restrict__ Wp_hi, float* __restrict__ Wp_lo, double* __restrict__ Kd64,
+                                  float* __restrict__ Kd_hi, float* __restrict__ Kd_lo) {
+  __shared__ double tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, i0 = blockIdx.x * 32;  // c: concept row, i: feature column
+  const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, i = i0 + tx;
+    double v = 0.0;
+    if (c < n && i < d) v = s * static_cast<double>(Kt[b * k_batch + static_cast<long long>(c) * ldk + i]);
+    tile[r][tx] = v;
+    if (c < n_pad && i < d) {
+      const long long o = (static_cast<long long>(b) * n_pad + c) * d + i;
+      Ks64t[o] = v;
+      const float f = static_cast<float>(v);
+      float hi, lo;
+      split_tf32(f, hi, lo);
+      W[o] = f; Wp_hi[o] = hi; Wp_lo[o] = lo;
+    }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, c = c0 + tx;
+    if (i < d && c < n_pad) {
+      const double v = tile[tx][r];
+      const long long o = (static_cast<long long>(b) * d + i) * n_pad + c;
+      Kd64[o] = v;
+      float hi, lo;
+      split_tf32(static_cast<float>(v), hi, lo);
+      Kd_hi[o] = hi; Kd_lo[o] = lo;
+    }
+  }
+}
+
+// X64t (+)= double(W)
+__global__ void solve_axpy_kernel(const float* __restrict__ W, double* __restrict__ X, long long total, int accumulate) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double w = static_cast<double>(W[i]);
+    X[i] = accumulate ? X[i] + w : w;
+  }
+}
+
+// out[0] += sum(W^2), out[1] += sum(X^2)   (convergence monitor of the refinement)
+__global__ void solve_norms_kernel(const float* __restrict__ W, const double* __restrict__ X, long long total,
+                                   double* __restrict__ out) {
+  double sw = 0.0, sx = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double w = static_cast<double>(W[i]);
+    const double x = X[i];
+    sw += w * w;
+    sx += x * x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, sw);
+    atomicAdd(out + 1, sx);
+  }
+}
+
+// in-place mirror of the lower triangle of [B][d x d] fp64
+__global__ void mirror64_kernel(double* __restrict__ M, int d) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj >= bi && !(bj == bi)) return;
+  double* Mb = M + static_cast<long long>(blockIdx.z) * d * d;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = Mb[static_cast<long long>(bi * 32 + r) * d + bj * 32 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int row = bj * 32 + r, col = bi * 32 + tx;  // transposed position
+    if (bi != bj || col > row) Mb[static_cast<long long>(row) * d + col] = tile[tx][r];
+  }
+}
+
+// adj_k [B][d x n] = X64t[B][:n, :]^T
+__global__ void transpose_out_kernel(const double* __restrict__ Xt, int n, int n_pad, int d, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, i = i0 + tx;
+    tile[r][tx] = (c < n && i < d) ? Xt[(static_cast<long long>(b) * n_pad + c) * d + i] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, c = c0 + tx;
+    if (i < d && c < n) out[(static_cast<long long>(b) * d + i) * n + c] = tile[tx][r];
+  }
+}
+
+// resid [B][h x n] = s * inv_left[b] * double(St[B][n x h])^T
+__global__ void resid_kernel(const float* __restrict__ St, long long lds, long long s_batch, int n, int h, double s,
+                             const double* __restrict__ inv_left, double* __restrict__ resid) {
+  __shared__ double tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const double f = s * inv_left[b];
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, j = j0 + tx;
+    // reference order: (S.double() * s) / (L - i)
+    tile[r][tx] = (c < n && j < h) ? static_cast<double>(St[b * s_batch + static_cast<long long>(c) * lds + j]) : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + r, c = c0 + tx;
+    if (j < h && c < n) resid[(static_cast<long long>(b) * h + j) * n + c] = tile[tx][r] * f;
+  }
+}
+
+// ---- workspace --------------------------------------------------------------------------------------
+struct SolveWs {
+  // fp32
+  float *M32, *Mp_hi, *Mp_lo, *LL_hi, *LL_lo, *Li_hi, *Li_lo, *LiT_hi, *LiT_lo, *W, *Wp_hi, *Wp_lo, *Kd_hi, *Kd_lo;
+  // fp64
+  double *M64, *Ks64t, *X64t, *Kd64, *inv_left, *norms;
+  size_t bytes;
+};
+
+inline SolveWs solve_carve(void* base, int B, int d, int h, int n) {
+  (void)h;
+  const long long n_pad = round_up_ll(n, 128);
+  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* p0 = p;
+  auto take = [&](size_t bytes) { uint8_t* r = p; p += (bytes + 1023) & ~static_cast<size_t>(1023); return r; };
+  SolveWs w;
+  const size_t dd = static_cast<size_t>(B) * d * d, nd = static_cast<size_t>(B) * n_pad * d,
+               d128 = static_cast<size_t>(B) * d * SOLVE_NB;
+  w.M64 = reinterpret_cast<double*>(take(dd * 8));
+  w.Ks64t = reinterpret_cast<double*>(take(nd * 8));
+  w.X64t = reinterpret_cast<double*>(take(nd * 8));
+  w.Kd64 = reinterpret_cast<double*>(take(nd * 8));
+  w.inv_left = reinterpret_cast<double*>(take(static_cast<size_t>(B) * 8));
+  w.norms = reinterpret_cast<double*>(take(2 * 8));
+  w.M32 = reinterpret_cast<float*>(take(dd * 4));
+  w.Mp_hi = reinterpret_cast<float*>(take(dd * 4));
+  w.Mp_lo = reinterpret_cast<float*>(take(dd * 4));
+  w.LL_hi = reinterpret_cast<float*>(take(dd * 4));
+  w.LL_lo = reinterpret_cast<float*>(take(dd * 4));
+  w.Li_hi = reinterpret_cast<float*>(take(d128 * 4));
+  w.Li_lo = reinterpret_cast<float*>(take(d128 * 4));
+  w.LiT_hi = reinterpret_cast<float*>(take(d128 * 4));
+  w.LiT_lo = reinterpret_cast<float*>(take(d128 * 4));
+  w.W = reinterpret_cast<float*>(take(nd * 4));
+  w.Wp_hi = reinterpret_cast<float*>(take(nd * 4));
+  w.Wp_lo = reinterpret_cast<float*>(take(nd * 4));
+  w.Kd_hi = reinterpret_cast<float*>(take(nd * 4));
+  w.Kd_lo = reinterpret_cast<float*>(take(nd * 4));
+  w.bytes = static_cast<size_t>(p - p0) + 1024;
+  return w;
+}
+
+inline size_t solve_workspace_bytes(int B, int d, int h, int n) { return solve_carve(nullptr, B, d, h, n).bytes; }
+
+// ---- 3xTF32 GEMM helper on sub-matrices of stacked batched tensors --------------------------------------
+struct PlaneMaps {
+  CUtensorMap hi, lo;
+};
+
+inline int make_plane_maps(PlaneMaps* m, const float* hi, const float* lo, long long rows, long long cols, long long ld) {
+  int rc;
+  if ((rc = make_tmap_2d(&m->hi, hi, rows, cols, ld, 128))) return rc;
+  return make_tmap_2d(&m->lo, lo, rows, cols, ld, 128);
+}
+
+struct SubGemm {
+  const PlaneMaps* A; int a_row0, a_col0, a_batch_rows;
+  const PlaneMaps* B; int b_row0, b_col0, b_batch_rows;
+  int M, N, K, lower;
+  float alpha, beta;
+  const float* Cin; long long ldcin, cin_batch;
+  float* C; long long ldc, c_batch;
+  float* P_hi; float* P_lo; long long ldp, p_batch;
+  float* Pt_hi; float* Pt_lo; long long ldpt, pt_batch;
+};
+
+inline int run_subgemm(const SubGemm& g, int batches, int sm_count, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return EMCID_OK;
+  GemmOperands ops;
+  ops.a_hi = g.A->hi; ops.a_lo = g.A->lo; ops.b_hi = g.B->hi; ops.b_lo = g.B->lo;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.a_row0 = g.a_row0; p.a_col0 = g.a_col0; p.a_batch_rows = g.a_batch_rows;
+  p.b_row0 = g.b_row0; p.b_col0 = g.b_col0; p.b_batch_rows = g.b_batch_rows;
+  p.lower = g.lower;
+  p.chunk_kblocks = 1;  // shortest TMEM chains: the factorisation wants every bit 3xTF32 can give
+  p.alpha = g.alpha; p.beta = g.beta;
+  p.Cin = g.Cin; p.ldcin = g.ldcin; p.cin_batch = g.cin_batch;
+  p.C = g.C; p.ldc = g.ldc; p.c_batch = g.c_batch;
+  p.P_hi = g.P_hi; p.P_lo = g.P_lo; p.ldp = g.ldp; p.p_batch = g.p_batch;
+  p.Pt_hi = g.Pt_hi; p.Pt_lo = g.Pt_lo; p.ldpt = g.ldpt; p.pt_batch = g.pt_batch;
+  const int tiles = gemm_num_tiles(g.M, g.N, 128, g.lower);
+  int grid = tiles;
+  const int cap = sm_count / (batches > 0 ? batches : 1);
+  if (grid > cap) grid = cap > 0 ? cap : 1;
+  return launch_gemm3x<128, 3, EPI_GENERIC>(ops, p, grid, stream, batches);
+}
+
+// ---- the solve -----------------------------------------------------------------------------------------
+inline int solve_layers(int device, int B, int d, int h, int n, const float* C32, const float* Kt, long long ldk,
+                        const float* St, long long lds, double lambda, double scale, const double* inv_left_host,
+                        double* adj_k, double* resid, float* dW, int refine_steps, void* workspace, size_t ws_bytes,
+                        int* status_dev, cudaStream_t stream) {
+  EMCID_CHECK(B > 0 && d > 0 && h > 0 && n > 0, EMCID_ERR_INVALID, "solve: empty problem");
+  EMCID_CHECK(d % SOLVE_NB == 0, EMCID_ERR_UNSUPPORTED, "solve: d must be a multiple of %d (got %d)", SOLVE_NB, d);
+  EMCID_CHECK(C32 && Kt && St && adj_k && resid && dW && status_dev && inv_left_host, EMCID_ERR_INVALID,
+              "solve: null argument");
+  EMCID_CHECK(ldk >= d && lds >= h, EMCID_ERR_INVALID, "solve: bad leading dimensions");
+  EMCID_CHECK(refine_steps >= -1 && refine_steps <= 8, EMCID_ERR_INVALID, "solve: refine_steps out of range");
+  EMCID_CHECK(ws_bytes >= solve_workspace_bytes(B, d, h, n), EMCID_ERR_WORKSPACE,
+              "solve: workspace too small (%zu < %zu)", ws_bytes, solve_workspace_bytes(B, d, h, n));
+  EMCID_CUDA_CHECK(cudaSetDevice(device));
+  DeviceInfo info;
+  int rc = get_device_info(&info);
+  if (rc) return rc;
+  const int sms = info.sm_count;
+  const int n_pad = static_cast<int>(round_up_ll(n, 128));
+  const int nblk = d / SOLVE_NB;
+  SolveWs w = solve_carve(workspace, B, d, h, n);
+  const long long dd = static_cast<long long>(d) * d, nd = static_cast<long long>(n_pad) * d;
+
+  static thread_local bool potrf_configured[16] = {false};
+  const int potrf_smem = (SOLVE_NB * (SOLVE_NB + 1) + SOLVE_NB) * sizeof(double);
+  if (device < 0 || device >= 16 || !potrf_configured[device]) {
+    EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem));
+    if (device >= 0 && device < 16) potrf_configured[device] = true;
+  }
+
+  EMCID_CUDA_CHECK(cudaMemsetAsync(status_dev, 0, sizeof(int), stream));
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(w.inv_left, inv_left_host, B * sizeof(double), cudaMemcpyHostToDevice, stream));
+  // LL planes' never-written upper/lower halves must not hold NaN patterns (TMA reads whole boxes)
+  EMCID_CUDA_CHECK(cudaMemsetAsync(w.LL_hi, 0, B * dd * sizeof(float), stream));
+  EMCID_CUDA_CHECK(cudaMemsetAsync(w.LL_lo, 0, B * dd * sizeof(float), stream));
+  EMCID_CUDA_CHECK(cudaMemsetAsync(w.Mp_hi, 0, B * dd * sizeof(float), stream));
+  EMCID_CUDA_CHECK(cudaMemsetAsync(w.Mp_lo, 0, B * dd * sizeof(float), stream));
+
+  // 1. operands
+  {
+    dim3 grid((d + 31) / 32, (n_pad + 31) / 32, B);
+    solve_prep_kernel<<<grid, dim3(32, 8), 0, stream>>>(Kt, ldk, static_cast<long long>(n) * ldk, n, n_pad, d, scale,
+                                                        w.Ks64t, w.W, w.Wp_hi, w.Wp_lo, w.Kd64, w.Kd_hi, w.Kd_lo);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+  }
+  PlaneMaps mKd, mMp, mLL, mLi, mLiT, mW;
+  if ((rc = make_plane_maps(&mKd, w.Kd_hi, w.Kd_lo, static_cast<long long>(B) * d, n_pad, n_pad)) ||
+      (rc = make_plane_maps(&mMp, w.Mp_hi, w.Mp_lo, static_cast<long long>(B) * d, d, d)) ||
+      (rc = make_plane_maps(&mLL, w.LL_hi, w.LL_lo, static_cast<long long>(B) * d, d, d)) ||
+      (rc = make_plane_maps(&mLi, w.Li_hi, w.Li_lo, static_cast<long long>(B) * d, SOLVE_NB, SOLVE_NB)) ||
+      (rc = make_plane_maps(&mLiT, w.LiT_hi, w.LiT_lo, static_cast<long long>(B) * d, SOLVE_NB, SOLVE_NB)) ||
+      (rc = make_plane_maps(&mW, w.Wp_hi, w.Wp_lo, static_cast<long long>(B) * n_pad, d, d)))
+    return rc;
+
+  // 2. M32 = lambda*C32 + Ks Ks^T (lower tiles; fp32 + planes)   and   M64 (fp64, full)
+  {
+    SubGemm g;
+    memset(&g, 0, sizeof(g));
+    g.A = &mKd; g.a_batch_rows = d; g.B = &mKd; g.b_batch_rows = d;
+    g.M = d; g.N = d; g.K = n_pad; g.lower = 1;
+    g.alpha = 1.0f; g.beta = static_cast<float>(lambda);
+    g.Cin = C32; g.ldcin = d; g.cin_batch = dd;
+    g.C = w.M32; g.ldc = d; g.c_batch = dd;
+    g.P_hi = w.Mp_hi; g.P_lo = w.Mp_lo; g.ldp = d; g.p_batch = dd;
+    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+    DgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = d; p.N = d; p.K = n;
+    p.A = w.Kd64; p.lda = n_pad; p.a_batch = static_cast<long long>(d) * n_pad;
+    p.B = w.Kd64; p.ldb = n_pad; p.b_batch = static_cast<long long>(d) * n_pad;
+    p.alpha = 1.0; p.beta = lambda;
+    p.Cin32 = C32; p.ldcin32 = d; p.cin32_batch = dd;
+    p.C = w.M64; p.ldc = d; p.c_batch = dd;
+    p.lower = 1;
+    if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
+    mirror64_kernel<<<dim3(d / 32, d / 32, B), dim3(32, 8), 0, stream>>>(w.M64, d);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // 3. blocked right-looking Cholesky of M32
+  for (int k = 0; k < nblk; ++k) {
+    potrf_diag_kernel<<<B, 256, potrf_smem, stream>>>(w.M32, d, k, w.LL_hi, w.LL_lo, w.Li_hi, w.Li_lo, w.LiT_hi,
+                                                      w.LiT_lo, status_dev);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    const int rem = d - (k + 1) * SOLVE_NB;
+    if (rem <= 0) break;
+    const long long off_panel = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k) * SOLVE_NB;
+    const long long off_panel_t = static_cast<long long>(k) * SOLVE_NB * d + static_cast<long long>(k + 1) * SOLVE_NB;
+    const long long off_trail = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k + 1) * SOLVE_NB;
+    SubGemm g;
+    memset(&g, 0, sizeof(g));  // panel: L_ik = M_ik Linv_kk^T
+    g.A = &mMp; g.a_row0 = (k + 1) * SOLVE_NB; g.a_col0 = k * SOLVE_NB; g.a_batch_rows = d;
+    g.B = &mLi; g.b_row0 = k * SOLVE_NB; g.b_col0 = 0; g.b_batch_rows = d;
+    g.M = rem; g.N = SOLVE_NB; g.K = SOLVE_NB;
+    g.alpha = 1.0f; g.beta = 0.0f;
+    g.P_hi = w.LL_hi + off_panel; g.P_lo = w.LL_lo + off_panel; g.ldp = d; g.p_batch = dd;
+    g.Pt_hi = w.LL_hi + off_panel_t; g.Pt_lo = w.LL_lo + off_panel_t; g.ldpt = d; g.pt_batch = dd;
+    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+    memset(&g, 0, sizeof(g));  // trailing: M_ij -= L_ik L_jk^T
+    g.A = &mLL; g.a_row0 = (k + 1) * SOLVE_NB; g.a_col0 = k * SOLVE_NB; g.a_batch_rows = d;
+    g.B = &mLL; g.b_row0 = (k + 1) * SOLVE_NB; g.b_col0 = k * SOLVE_NB; g.b_batch_rows = d;
+    g.M = rem; g.N = rem; g.K = SOLVE_NB; g.lower = 1;
+    g.alpha = -1.0f; g.beta = 1.0f;
+    g.Cin = w.M32 + off_trail; g.ldcin = d; g.cin_batch = dd;
+    g.C = w.M32 + off_trail; g.ldc = d; g.c_batch = dd;
+    g.P_hi = w.Mp_hi + off_trail; g.P_lo = w.Mp_lo + off_trail; g.ldp = d; g.p_batch = dd;
+    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+  }
+
+  // 4./5. solve + refinement; W holds the current right-hand side (transposed), then the solution
+  auto trsm_both = [&]() -> int {
+    SubGemm g;
+    for (int i = 0; i < nblk; ++i) {  // forward: Y^T L^T = W
+      memset(&g, 0, sizeof(g));
+      g.A = &mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
+      g.B = &mLi; g.b_row0 = i * SOLVE_NB; g.b_batch_rows = d;
+      g.M = n_pad; g.N = SOLVE_NB; g.K = SOLVE_NB; g.alpha = 1.0f;
+      g.C = w.W + i * SOLVE_NB; g.ldc = d; g.c_batch = nd;
+      g.P_hi = w.Wp_hi + i * SOLVE_NB; g.P_lo = w.Wp_lo + i * SOLVE_NB; g.ldp = d; g.p_batch = nd;
+      if (int r = run_subgemm(g, B, sms, stream)) return r;
+      const int rem = d - (i + 1) * SOLVE_NB;
+      if (rem <= 0) break;
+      memset(&g, 0, sizeof(g));
+      g.A = &mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
+      g.B = &mLL; g.b_row0 = (i + 1) * SOLVE_NB; g.b_col0 = i * SOLVE_NB; g.b_batch_rows = d;
+      g.M = n_pad; g.N = rem; g.K = SOLVE_NB; g.alpha = -1.0f; g.beta = 1.0f;
+      const long long off = static_cast<long long>(i + 1) * SOLVE_NB;
+      g.Cin = w.W + off; g.ldcin = d; g.cin_batch = nd;
+      g.C = w.W + off; g.ldc = d; g.c_batch = nd;
+      g.P_hi = w.Wp_hi + off; g.P_lo = w.Wp_lo + off; g.ldp = d; g.p_batch = nd;
+      if (int r = run_subgemm(g, B, sms, stream)) return r;
+    }
+    for (int i = nblk - 1; i >= 0; --i) {  // backward: X^T L = Y^T
+      memset(&g, 0, sizeof(g));
+      g.A = &mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
+      g.B = &mLiT; g.b_row0 = i * SOLVE_NB; g.b_batch_rows = d;
+      g.M = n_pad; g.N = SOLVE_NB; g.K = SOLVE_NB; g.alpha = 1.0f;
+      g.C = w.W + i * SOLVE_NB; g.ldc = d; g.c_batch = nd;
+      g.P_hi = w.Wp_hi + i * SOLVE_NB; g.P_lo = w.Wp_lo + i * SOLVE_NB; g.ldp = d; g.p_batch = nd;
+      if (int r = run_subgemm(g, B, sms, stream)) return r;
+      if (i == 0) break;
+      memset(&g, 0, sizeof(g));
+      g.A = &mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
+      g.B = &mLL; g.b_row0 = 0; g.b_col0 = i * SOLVE_NB; g.b_batch_rows = d;  // upper blocks hold L^T
+      g.M = n_pad; g.N = i * SOLVE_NB; g.K = SOLVE_NB; g.alpha = -1.0f; g.beta = 1.0f;
+      g.Cin = w.W; g.ldcin = d; g.cin_batch = nd;
+      g.C = w.W; g.ldc = d; g.c_batch = nd;
+      g.P_hi = w.Wp_hi; g.P_lo = w.Wp_lo; g.ldp = d; g.p_batch = nd;
+      if (int r = run_subgemm(g, B, sms, stream)) return r;
+    }
+    return EMCID_OK;
+  };
+
+  const long long tot = static_cast<long long>(B) * nd;
+  // refine_steps >= 0: exactly that many sweeps.  -1: adaptive — stop once the last correction is below
+  // SOLVE_ADAPT_TOL relative to the solution (each sweep contracts the error by ~1e-2 at cond ~1e7, so the
+  // error left after applying a correction of that size is orders of magnitude under the 1e-4 dW tolerance).
+  const bool adaptive = refine_steps < 0;
+  const int max_steps = adaptive ? SOLVE_ADAPT_MAX : refine_steps;
+  for (int it = 0; it <= max_steps; ++it) {
+    if (it > 0) {
+      // R^T = Ks^T - X^T M64  (fp64), rounded to fp32 into W, then re-split
+      DgemmParams p;
+      memset(&p, 0, sizeof(p));
+      p.M = n; p.N = d; p.K = d;
+      p.A = w.X64t; p.lda = d; p.a_batch = nd;
+      p.B = w.M64; p.ldb = d; p.b_batch = dd;
+      p.alpha = -1.0; p.beta = 1.0;
+      p.Cin = w.Ks64t; p.ldcin = d; p.cin_batch = nd;
+      p.C32 = w.W; p.ldc32 = d; p.c32_batch = nd;
+      if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
+      if ((rc = launch_split_planes(w.W, d, B * n_pad, d, 1.0f, w.Wp_hi, w.Wp_lo, d, stream))) return rc;
+    }
+    if ((rc = trsm_both())) return rc;
+    solve_axpy_kernel<<<sms * 8, 256, 0, stream>>>(w.W, w.X64t, tot, it > 0 ? 1 : 0);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    if (adaptive && it > 0) {
+      double hn[2] = {0.0, 0.0};
+      EMCID_CUDA_CHECK(cudaMemsetAsync(w.norms, 0, 2 * sizeof(double), stream));
+      solve_norms_kernel<<<sms * 4, 256, 0, stream>>>(w.W, w.X64t, tot, w.norms);
+      EMCID_CUDA_CHECK(cudaGetLastError());
+      EMCID_CUDA_CHECK(cudaMemcpyAsync(hn, w.norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      EMCID_CUDA_CHECK(cudaStreamSynchronize(stream));
+      if (!(hn[1] > 0.0) || hn[0] <= SOLVE_ADAPT_TOL * SOLVE_ADAPT_TOL * hn[1]) break;
+    }
+  }
+
+  // 6. outputs
+  transpose_out_kernel<<<dim3((d + 31) / 32, (n + 31) / 32, B), dim3(32, 8), 0, stream>>>(w.X64t, n, n_pad, d, adj_k);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  resid_kernel<<<dim3((h + 31) / 32, (n + 31) / 32, B), dim3(32, 8), 0, stream>>>(
+      St, lds, static_cast<long long>(n) * lds, n, h, scale, w.inv_left, resid);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  {
+    DgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = h; p.N = d; p.K = n;
+    p.A = resid; p.lda = n; p.a_batch = static_cast<long long>(h) * n;
+    p.B = adj_k; p.ldb = n; p.b_batch = static_cast<long long>(d) * n;
+    p.alpha = 1.0;
+    p.C32 = dW; p.ldc32 = d; p.c32_batch = static_cast<long long>(h) * d;
+    if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
+  }
+  return EMCID_OK;
+}
+
+}  // namespace emcid

@@ -1,0 +1,219 @@
+"""The EMCID text-encoder edit on B200: drop-in for the hot-path entry points of
+emcid/emcid_main.py in SilentView/EMCID —
+
+    get_cov_text_encoder                 :2239-2276
+    execute_emcid_text_encoder           :818-1082     (stage 2, the insert loop :980-1073)
+    apply_emcid_to_text_encoder          :769-815
+    execute_emcid_sd_xl_text_encoders    :1085-1425
+    apply_emcid_to_sdxl_text_encoders    :38-106
+    upd_matrix_match_shape               :2279-2298
+
+Same signatures, same return values (adj_k / resid as fp64 CPU tensors, weights restored on return
+of execute_*, fc2 weights updated in place by apply_*).  The statistics come from
+`emcid_b200.layer_stats` and the per-layer solve runs in `libemcid_b200.so` (csrc/solve.cuh):
+3xTF32 tcgen05 Cholesky + TRSM with fp64-residual refinement instead of fp64 LU.
+
+Stage 1 (the v* optimisation through UNet/VAE, emcid/compute_z.py) is outside this path: requests
+must come with their `v_star` cached at `cache_name + "source_{src}_dest_{dst}.npz"` exactly as the
+reference caches them (:873-969); a miss raises NotImplementedError.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import nethook
+from .compute_ks import get_module_input_output_at_words
+from .globals import STATS_DIR, XL_STATS_DIR1, XL_STATS_DIR2
+from .layer_stats import layer_stats_text_encoder
+from .solve import DEFAULT_REFINE_STEPS, solve_layers
+
+COV_CACHE: Dict[Tuple[str, str], torch.Tensor] = {}
+
+
+def get_cov_text_encoder(model, tok, layer_name: str, mom2_dataset: str, mom2_n_samples: int, mom2_dtype: str,
+                         inv: bool = False, force_recompute: bool = False, verbose: bool = True,
+                         stat_dir: str = STATS_DIR) -> torch.Tensor:
+    """C = mom2 / count as fp32 on model.device; cached per (model name, layer) like the reference,
+    but the cached copy already lives on the device (no 37.7 MB H2D per layer per edit)."""
+    model_name = model.config._name_or_path.replace("/", "_")
+    key = (model_name, layer_name)
+    if verbose:
+        print(f"Retrieving covariance statistics for {model_name} @ {layer_name}.")
+    if key not in COV_CACHE or force_recompute:
+        stat = layer_stats_text_encoder(model, tok, layer_name, stat_dir, mom2_dataset, to_collect=["mom2"],
+                                        sample_size=mom2_n_samples, precision=mom2_dtype,
+                                        force_recompute=force_recompute)
+        COV_CACHE[key] = stat.mom2.moment().float().to(model.device)
+    cov = COV_CACHE[key].to(model.device)
+    return torch.inverse(cov) if inv else cov
+
+
+def upd_matrix_match_shape(matrix: torch.Tensor, shape: torch.Size) -> torch.Tensor:
+    if matrix.shape == shape:
+        return matrix
+    if matrix.T.shape == shape:
+        return matrix.T
+    if len(matrix.shape) == 2 and len(shape) == 4:
+        return matrix.reshape(shape[0], shape[1], *shape[2:])
+    print(f"matrix shape: {matrix.shape}")
+    print(f"desired shape: {shape}")
+    raise ValueError("Update matrix computed by EMCIDdoes not match original weight shape. "
+                     "Check for bugs in the code?")
+
+
+def _load_vstars(requests, hparams, cache_name, device, suffix=""):
+    zs = []
+    for idx, request in enumerate(requests):
+        if "esd" in getattr(hparams, "objective", ""):
+            stem = f"source_{request['source']}"
+        elif getattr(hparams, "sld_supervision", False):
+            stem = f"source_{request['source_cat']}_{idx}"
+        else:
+            stem = f"source_{request['source']}_dest_{request['dest']}"
+        path = Path(cache_name + stem + suffix + ".npz") if cache_name is not None else None
+        if path is None or not path.exists():
+            raise NotImplementedError(
+                f"v_star cache miss for request {request['source']!r} ({path}): stage 1 (compute_z, UNet/VAE "
+                "optimisation) is outside the B200 hot path — precompute v_star with the reference")
+        zs.append(torch.from_numpy(np.load(path)["v_star"]).to(device))
+    if getattr(hparams, "use_new_compute_z", False):
+        z = torch.stack(zs, dim=0)                      # [rq, num, h]
+        return z.permute(2, 0, 1).reshape(z.shape[2], -1)
+    return torch.stack(zs, dim=1)                       # [h, n]
+
+
+def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_update_weight, stat_dir, verbose,
+                 refine_steps):
+    """The stage-2 loop of the reference (:980-1073) for one encoder."""
+    device = text_encoder.device
+    names = [f"{hparams.rewrite_module_tmp.format(l)}.weight" for l in layers]
+    weights = {n: nethook.get_parameter(text_encoder, n) for n in names}
+    weights_copy = {n: w.detach().clone() for n, w in weights.items()}
+    deltas = {}
+    ew = hparams.edit_weight
+    try:
+        with torch.no_grad():
+            for i, layer in enumerate(layers):
+                module_name = hparams.rewrite_module_tmp.format(layer)
+                # one forward gives both the keys (:987-996) and the current outputs (:1004-1014)
+                layer_ks, cur_zs = get_module_input_output_at_words(
+                    text_encoder, tokenizer, requests, module_name, num_fact_token=hparams.num_edit_tokens)
+                if hparams.num_edit_tokens > 1:
+                    layer_ks = layer_ks.reshape(-1, layer_ks.shape[-1])
+                    cur_zs = cur_zs.reshape(-1, cur_zs.shape[-1])
+                if verbose:
+                    print(f"\n\nLAYER {layer}\n")
+                    print(f"Writing {layer_ks.size(0)} key/value pair(s) into layer {layer}")
+                sources_t = zs.T.to(cur_zs.dtype) - cur_zs                       # (zs - cur_zs)^T, [n, h]
+                if verbose:
+                    print("z error", torch.linalg.norm(sources_t, dim=1).mean())
+                cov = get_cov_text_encoder(text_encoder, tokenizer, module_name, hparams.mom2_dataset,
+                                           hparams.mom2_n_samples, hparams.mom2_dtype, stat_dir=stat_dir,
+                                           force_recompute=False, verbose=verbose) * (1 - ew) / 0.5   # fp32, :1037
+                adj_k, resid, dW = solve_layers(cov, layer_ks.float(), sources_t.float(), mom2_update_weight,
+                                                (ew / 0.5) ** 0.5, [len(layers) - i], refine_steps=refine_steps)
+                adj_k, resid, dW = adj_k[0], resid[0], dW[0]
+                name = names[i]
+                upd = upd_matrix_match_shape(dW, weights[name].shape)
+                if verbose:
+                    print("orig norm", torch.linalg.norm(weights[name]))
+                    print("upd norm", torch.linalg.norm(upd))
+                weights[name][...] = weights_copy[name] + upd                     # :1061 — next layer sees it
+                deltas[name] = (adj_k.detach().cpu(), resid.detach().cpu())
+    finally:
+        with torch.no_grad():
+            for n, w in weights.items():
+                w[...] = weights_copy[n]                                          # :1075-1078
+    return deltas
+
+
+def execute_emcid_text_encoder(pipe, requests: List[Dict], hparams, cache_name: Optional[str] = None,
+                               mom2_weight: Optional[int] = None, edit_weight: Optional[float] = None,
+                               verbose: bool = True, stat_dir=STATS_DIR,
+                               refine_steps: int = DEFAULT_REFINE_STEPS) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+    """Executes the EMCID update algorithm; invariant: model weights at return == at entry."""
+    device = pipe.device
+    hparams.mom2_update_weight = mom2_weight if mom2_weight is not None else hparams.mom2_update_weight
+    hparams.edit_weight = edit_weight if edit_weight is not None else hparams.edit_weight
+    requests = deepcopy(requests)
+    if verbose:
+        for request in requests:
+            print(f"EMCID request sample: [{request['source']}] -> [{request['dest']}]")
+    zs = _load_vstars(requests, hparams, cache_name, device)
+    deltas = _insert_loop(pipe.text_encoder, pipe.tokenizer, requests, hparams, hparams.layers, zs,
+                          hparams.mom2_update_weight, stat_dir, verbose, refine_steps)
+    print(f"Deltas successfully computed for {list(deltas.keys())}")
+    return deltas
+
+
+def _apply_deltas(model, deltas, device):
+    with torch.no_grad():
+        for w_name, (key_mat, val_mat) in deltas.items():
+            key_mat, val_mat = key_mat.to(device), val_mat.to(device)
+            upd_matrix = key_mat @ val_mat.T                                      # :805, fp64 on the device
+            w = nethook.get_parameter(model, w_name)
+            w[...] += upd_matrix_match_shape(upd_matrix, w.shape).float()
+
+
+def apply_emcid_to_text_encoder(pipe, requests: List[Dict], hparams, device: str, mom2_weight: Optional[int] = None,
+                                edit_weight: Optional[float] = None, return_orig_text_encoder=False,
+                                cache_name: Optional[str] = None, stats_dir: Optional[str] = STATS_DIR,
+                                verbose: bool = True):
+    """Returns (pipe with edited text encoder, original text encoder or None)."""
+    origin_text_encoder = None
+    if return_orig_text_encoder:
+        origin_text_encoder = deepcopy(pipe.text_encoder).to("cpu")
+    deltas = execute_emcid_text_encoder(pipe, requests, hparams, cache_name=cache_name, mom2_weight=mom2_weight,
+                                        edit_weight=edit_weight, verbose=verbose, stat_dir=stats_dir)
+    _apply_deltas(pipe.text_encoder, deltas, device)
+    print(f"New weights successfully inserted into {list(deltas.keys())}")
+    if return_orig_text_encoder:
+        origin_text_encoder = origin_text_encoder.to(device)
+    return pipe, origin_text_encoder
+
+
+def execute_emcid_sd_xl_text_encoders(pipe, requests: List[Dict], hparams, cache_name: Optional[str] = None,
+                                      mom2_weight: Optional[int] = None, mom2_weight_2: Optional[int] = None,
+                                      edit_weight: Optional[float] = None, verbose: bool = True,
+                                      stat_dir="data/stats/sdxl/text1", stat_dir_2="data/stats/sdxl/text2",
+                                      refine_steps: int = DEFAULT_REFINE_STEPS):
+    """Both SDXL text encoders: `layers` / `mom2_update_weight` / stat_dir for text_encoder,
+    `layers_2` / `mom2_update_weight_2` / stat_dir_2 for text_encoder_2 (v_star files end in _2)."""
+    device = pipe.device
+    hparams.mom2_update_weight = mom2_weight if mom2_weight is not None else hparams.mom2_update_weight
+    hparams.mom2_update_weight_2 = mom2_weight_2 if mom2_weight_2 is not None else hparams.mom2_update_weight_2
+    hparams.edit_weight = edit_weight if edit_weight is not None else hparams.edit_weight
+    requests = deepcopy(requests)
+    zs = _load_vstars(requests, hparams, cache_name, device)
+    zs_2 = _load_vstars(requests, hparams, cache_name, device, suffix="_2")
+    deltas = _insert_loop(pipe.text_encoder, pipe.tokenizer, requests, hparams, hparams.layers, zs,
+                          hparams.mom2_update_weight, stat_dir, verbose, refine_steps)
+    deltas_2 = _insert_loop(pipe.text_encoder_2, pipe.tokenizer_2, requests, hparams, hparams.layers_2, zs_2,
+                            hparams.mom2_update_weight_2, stat_dir_2, verbose, refine_steps)
+    print(f"Deltas successfully computed for {list(deltas.keys())} and {list(deltas_2.keys())}")
+    return deltas, deltas_2
+
+
+def apply_emcid_to_sdxl_text_encoders(pipe, requests: List[Dict], hparams, device: str,
+                                      mom2_weight: Optional[int] = None, mom2_weight_2: Optional[int] = None,
+                                      edit_weight: Optional[float] = None, return_orig_text_encoder=False,
+                                      cache_name: Optional[str] = None, stat_dir: Optional[str] = XL_STATS_DIR1,
+                                      stat_dir_2: Optional[str] = XL_STATS_DIR2, verbose: bool = True):
+    origin_1 = origin_2 = None
+    if return_orig_text_encoder:
+        origin_1 = deepcopy(pipe.text_encoder).to("cpu")
+        origin_2 = deepcopy(pipe.text_encoder_2).to("cpu")
+    deltas, deltas_2 = execute_emcid_sd_xl_text_encoders(
+        pipe, requests, hparams, cache_name=cache_name, mom2_weight=mom2_weight, mom2_weight_2=mom2_weight_2,
+        edit_weight=edit_weight, verbose=verbose, stat_dir=stat_dir, stat_dir_2=stat_dir_2)
+    _apply_deltas(pipe.text_encoder, deltas, device)
+    _apply_deltas(pipe.text_encoder_2, deltas_2, device)
+    print(f"New weights successfully inserted into {list(deltas.keys())}")
+    if return_orig_text_encoder:
+        origin_1, origin_2 = origin_1.to(device), origin_2.to(device)
+    return pipe, origin_1, origin_2

@@ -70,6 +70,7 @@ class TextEncoderMom2Pass:
 
         self.model = model
         self.layer_names = list(layer_names)
+        mlps = {name: _mlp_of(model, name) for name in self.layer_names}  # LookupError before anything else
         device = next(model.parameters()).device
         if accumulator_factory is None:
             if device.type != "cuda":
@@ -85,7 +86,7 @@ class TextEncoderMom2Pass:
         order = {n: i for i, (n, _) in enumerate(model.named_modules())}
         deepest = max(self.layer_names, key=lambda n: order[n])
         for name in self.layer_names:
-            mlp = _mlp_of(model, name)
+            mlp = mlps[name]
             W1, b1 = mlp.fc1.weight, mlp.fc1.bias
             if W1.dtype != torch.float32:
                 raise NotImplementedError("the statistics pass runs on fp32 weights (reference precision float32)")

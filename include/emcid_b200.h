@@ -76,6 +76,28 @@ int emcid_mom2_finalize(emcid_mom2_t* h, float* mom2_full, long long* count_dev,
 int emcid_mom2_reset(emcid_mom2_t* h, void* stream);
 int emcid_mom2_destroy(emcid_mom2_t* h);
 
+/* ---- closed-form multi-layer update ---------------------------------------------------------------
+ * Replaces the solve block of execute_emcid_text_encoder, emcid/emcid_main.py:1037-1050 (byte-identical
+ * copies at :1265-1312, :1365-1414 for SDXL and :2016-2042 in cal_insert_deltas):
+ *     M      = lambda * C32.double() + Ks @ Ks.T          Ks = K.double() * scale
+ *     adj_k  = torch.linalg.solve(M, Ks)                  [d, n] fp64
+ *     resid  = (S.double() * scale) / (L - i)             [h, n] fp64
+ *     upd    = resid @ adj_k.T                            [h, d] fp64 -> dW = upd.float()
+ * `batch` independent layers are solved in one call (stacked inputs/outputs).  Per layer b:
+ *   C32 [d, d] fp32  = cov * (1 - edit_weight) / 0.5 as the reference forms it in fp32 (:1037)
+ *   Kt  [n, d] fp32 (row pitch ldk)  = layer_ks BEFORE the "rq c_i -> c_i rq" rearrange (:993-996)
+ *   St  [n, h] fp32 (row pitch lds)  = (zs - cur_zs)^T  (:1016)
+ *   scale = sqrt(edit_weight / 0.5)  (:1041-1042);  inv_layers_left[b] = 1 / (L - i) (host array)
+ * refine_steps: fp64-residual iterative-refinement sweeps after the fp32-class Cholesky solve; -1 = adaptive
+ * (sweeps until the last correction is < 1e-4 of the solution, at most 8; synchronises the stream per sweep).
+ * status_dev: device int, 0 on success, bit0 = a pivot was not positive (matrix not SPD).
+ * d must be a multiple of 128.  Blackwell-only; asynchronous on `stream`. */
+size_t emcid_solve_workspace_bytes(int batch, int d, int h, int n);
+int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* C32, const float* Kt,
+                       long long ldk, const float* St, long long lds, double lambda, double scale,
+                       const double* inv_layers_left, double* adj_k, double* resid, float* dW,
+                       int refine_steps, void* workspace, size_t workspace_bytes, int* status_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

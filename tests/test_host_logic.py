@@ -1,0 +1,173 @@
+"""Host-side behaviour of the drop-in boundary (runs on CPU): npz layout and cache semantics, batching
+rules, subset selection, key extraction, error behaviour."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import model_from_golden, rel_fro, rh, unpack_captions
+from emcid_b200 import compute_ks, emcid_main, layer_stats, runningstats, stat_dataset
+from oracle import emcid_oracle as orc
+
+
+def _write_reference_npz(g, stats_dir):
+    path = os.path.join(stats_dir, str(g["rel_path"]))
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez(path, **{k[4:]: g[k] for k in g.files if k.startswith("npz.")})
+    return path
+
+
+def test_npz_roundtrip_layout(tmp_path):
+    sm = runningstats.SecondMoment()
+    sm.count = 7
+    sm.mom2 = torch.arange(9, dtype=torch.float32).reshape(3, 3)
+    cs = runningstats.CombinedStat(mom2=sm)
+    f = tmp_path / "a" / "s.npz"
+    runningstats.save_cached_state(f, cs, {"sample_size": 5})
+    dat = np.load(f)
+    assert sorted(dat.files) == ["mom2.constructor", "mom2.count", "mom2.mom2", "sample_size"]
+    assert str(dat["mom2.constructor"]) == "util.runningstats.SecondMoment()"
+    assert dat["mom2.count"].dtype == np.int64 and dat["mom2.count"].shape == ()
+    assert dat["mom2.mom2"].dtype == np.float32 and dat["sample_size"].dtype == np.int64
+    assert runningstats.load_cached_state(f, {"sample_size": 6}, quiet=True) is None     # size mismatch -> miss
+    assert runningstats.load_cached_state(tmp_path / "nope.npz", {}, quiet=True) is None
+    cs2 = runningstats.CombinedStat(mom2=runningstats.SecondMoment())
+    cs2.load_state_dict(runningstats.load_cached_state(f, {"sample_size": 5}, quiet=True))
+    assert cs2.mom2.count == 7 and torch.equal(cs2.mom2.mom2, sm.mom2)
+    np.testing.assert_allclose(cs2.mom2.moment().numpy(), sm.mom2.numpy() / 7)
+
+
+def test_null_boxing_of_missing_sample_size(tmp_path):
+    cs = runningstats.CombinedStat(mom2=runningstats.SecondMoment())
+    cs.mom2.count, cs.mom2.mom2 = 1, torch.zeros(2, 2)
+    f = tmp_path / "n.npz"
+    runningstats.save_cached_state(f, cs, {"sample_size": None})
+    raw = np.load(f)["sample_size"]
+    assert raw.dtype == np.float64 and runningstats.is_null_numpy_value(raw)
+    assert runningstats.load_cached_state(f, {"sample_size": None}, quiet=True) is not None
+    assert runningstats.load_cached_state(f, {"sample_size": 3}, quiet=True) is None
+
+
+def test_second_moment_rejects_cpu_batches():
+    with pytest.raises(RuntimeError):
+        runningstats.SecondMoment().add(torch.randn(4, 8))
+    runningstats.SecondMoment().add(torch.randn(0, 8))  # empty batch is a no-op, like the reference
+
+
+def test_subset_selection_matches_oracle():
+    for n, ss in [(150, 120), (10, 10), (7, None), (5, 9)]:
+        assert runningstats.subset_indices(n, ss, 1) == orc.fixed_random_subset(n, ss, 1)
+    assert runningstats.subset_indices(9, 4, None) == [0, 1, 2, 3]
+    s = runningstats.FixedRandomSubsetSampler(range(50), end=20, seed=1)
+    assert list(s) == orc.fixed_random_subset(50, 20, 1)
+
+
+def test_length_collation_matches_oracle():
+    rng = random.Random(0)
+    for trial in range(20):
+        lens = [rng.randint(0 if trial % 5 == 0 else 1, 77) for _ in range(rng.randint(1, 100))]
+        items = [dict(input_ids=torch.arange(L), position_ids=torch.arange(L),
+                      attention_mask=torch.ones(L, dtype=torch.long)) for L in lens]
+        tok = rng.choice([256, 512, 3072])
+        ours = stat_dataset.length_collation(tok)(items)
+        ref = orc.length_collation(lens, tok)
+        assert [tuple(b["input_ids"].shape) for b in ours] == [(len(s), max(lens[i] for i in s)) for s in ref]
+        for b in ours:
+            assert torch.equal(b["attention_mask"].sum(1), (b["position_ids"].max(1).values + 1))
+    data = torch.arange(24.0).reshape(2, 3, 4)
+    mask = torch.tensor([[1, 1, 0], [1, 0, 0]])
+    assert torch.equal(stat_dataset.flatten_masked_batch(data, mask), data.reshape(6, 4)[[0, 1, 3]])
+
+
+def test_layer_stats_cache_hit_needs_no_gpu(golden_dir, tmp_path):
+    """A cached file written by the reference is a hit: no dataset, no compute, CPU tensors returned."""
+    g = np.load(os.path.join(golden_dir, "tiny_stats.npz"))
+    _write_reference_npz(g, tmp_path)
+    model = model_from_golden(g)
+    calls = []
+    layer_stats.get_ccs_filtered_ds, saved = (lambda tokenizer: calls.append(1)), layer_stats.get_ccs_filtered_ds
+    try:
+        stat = layer_stats.layer_stats_text_encoder(
+            model, None, f"text_model.encoder.layers.{int(g['layer'])}.mlp.fc2", stats_dir=tmp_path,
+            sample_size=int(g["sample_size"]), precision="float32", progress=None)
+    finally:
+        layer_stats.get_ccs_filtered_ds = saved
+    assert not calls
+    assert stat.mom2.count == int(g["npz.mom2.count"])
+    assert stat.mom2.mom2.device.type == "cpu" and np.array_equal(stat.mom2.mom2.numpy(), g["npz.mom2.mom2"])
+
+
+def test_layer_stats_has_no_cpu_fallback(tmp_path):
+    model = rh.make_clip_text_model("tiny", seed=0)
+    caps = rh.make_captions(8, 1000, seed=1)
+    layer_stats.get_ccs_filtered_ds, saved = (lambda tokenizer: rh.SynthTokenDataset(caps)), layer_stats.get_ccs_filtered_ds
+    try:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            layer_stats.layer_stats_text_encoder(model, None, "text_model.encoder.layers.1.mlp.fc2",
+                                                 stats_dir=tmp_path, sample_size=8, precision="float32",
+                                                 progress=None, num_workers=0)
+        with pytest.raises(LookupError):
+            layer_stats.layer_stats_text_encoder(model, None, "text_model.encoder.layers.9.mlp.fc2",
+                                                 stats_dir=tmp_path, sample_size=8, precision="float32",
+                                                 progress=None, num_workers=0)
+        with pytest.raises(NotImplementedError):
+            layer_stats.layer_stats_text_encoder(model, None, "text_model.encoder.layers.1.mlp.fc2",
+                                                 stats_dir=tmp_path, sample_size=8, precision="float32",
+                                                 download=True, progress=None)
+    finally:
+        layer_stats.get_ccs_filtered_ds = saved
+
+
+def test_key_extraction_matches_oracle():
+    model = rh.make_clip_text_model("tiny", seed=0)
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    reqs = rh.make_requests(6)
+    for layer in (0, 1):
+        K, Z = compute_ks.get_module_input_output_at_words(model, tok, reqs, f"text_model.encoder.layers.{layer}.mlp.fc2")
+        Ko, Zo = orc.module_io_at_words(model, tok, reqs, layer)
+        assert K.shape == (6, 256) and Z.shape == (6, 64)
+        assert rel_fro(K.numpy(), Ko) < 1e-6 and rel_fro(Z.numpy(), Zo) < 1e-6
+    ids = tok(["An image of artist3 name3"])["input_ids"][0]
+    assert compute_ks.find_token_range(tok, ids, "artist3 name3") == orc.find_token_range(tok, ids, "artist3 name3") == (4, 6)
+    assert compute_ks.find_token_range(tok, ids, "[CLS]") == (0, 1)
+    assert compute_ks.find_token_range(tok, ids, "") == (len(ids) - 1, len(ids))
+    with pytest.raises(ValueError):
+        compute_ks.find_token_range(tok, ids, "absent")
+
+
+def test_edit_api_error_behaviour(tmp_path):
+    a = torch.zeros(3, 5)
+    assert emcid_main.upd_matrix_match_shape(a, torch.Size([3, 5])) is a
+    assert emcid_main.upd_matrix_match_shape(a, torch.Size([5, 3])).shape == (5, 3)
+    with pytest.raises(ValueError):
+        emcid_main.upd_matrix_match_shape(a, torch.Size([4, 4]))
+    hp = rh.make_hparams([0, 1], 8)
+    with pytest.raises(NotImplementedError, match="v_star cache miss"):
+        emcid_main._load_vstars(rh.make_requests(1), hp, str(tmp_path / "c_"), "cpu")
+    zs = rh.write_vstar_cache(str(tmp_path / "c_"), rh.make_requests(3), 64)
+    got = emcid_main._load_vstars(rh.make_requests(3), hp, str(tmp_path / "c_"), "cpu")
+    assert torch.equal(got, zs) and got.shape == (64, 3)
+    emcid_main.COV_CACHE[("m", "l")] = torch.zeros(1)
+    emcid_main.COV_CACHE.clear()
+    assert not emcid_main.COV_CACHE
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not rh.reference_available(), reason="needs /root/reference")
+def test_our_npz_loads_in_the_live_reference(tmp_path):
+    ref = rh.import_reference()
+    sm = runningstats.SecondMoment()
+    sm.count, sm.mom2 = 11, torch.eye(4)
+    f = str(tmp_path / "x.npz")
+    runningstats.save_cached_state(f, runningstats.CombinedStat(mom2=sm), {"sample_size": 9})
+    dat = ref.runningstats.load_cached_state(f, {"sample_size": 9}, quiet=True)
+    cs = ref.runningstats.CombinedStat(mom2=ref.runningstats.SecondMoment())
+    cs.load_state_dict(dat)
+    assert cs.mom2.count == 11 and torch.equal(cs.mom2.mom2, torch.eye(4))
+    items = [dict(input_ids=torch.arange(L), position_ids=torch.arange(L), attention_mask=torch.ones(L, dtype=torch.long))
+             for L in [5, 77, 30, 30, 2, 64] * 9]
+    a = ref.stat_dataset.length_collation(256)(items)
+    b = stat_dataset.length_collation(256)(items)
+    assert len(a) == len(b) and all(torch.equal(x["input_ids"], y["input_ids"]) for x, y in zip(a, b))
