@@ -46,6 +46,8 @@ SIGNATURES = {
     "emcid_mom2_accumulate": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p]),
     "emcid_mom2_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "emcid_mom2_reset": (c_int, [c_void_p, c_void_p]),
+    "emcid_mom2_profile": (c_int, [c_void_p, c_int]),
+    "emcid_mom2_get_profile": (c_int, [c_void_p, ctypes.POINTER(c_double)]),
     "emcid_mom2_destroy": (c_int, [c_void_p]),
     "emcid_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "emcid_solve_layers": (

@@ -80,6 +80,15 @@ int emcid_mom2_reset(emcid_mom2_t* h, void* stream) {
   return mom2_reset(reinterpret_cast<Mom2Handle*>(h), static_cast<cudaStream_t>(stream));
 }
 
+int emcid_mom2_profile(emcid_mom2_t* h, int enable) {
+  Mom2Handle* H = reinterpret_cast<Mom2Handle*>(h);
+  EMCID_CHECK(H, EMCID_ERR_INVALID, "emcid_mom2_profile: null handle");
+  H->profile = enable != 0;
+  return EMCID_OK;
+}
+
+int emcid_mom2_get_profile(emcid_mom2_t* h, double* out8) { return mom2_get_profile(reinterpret_cast<Mom2Handle*>(h), out8); }
+
 int emcid_mom2_destroy(emcid_mom2_t* h) { return mom2_destroy(reinterpret_cast<Mom2Handle*>(h)); }
 
 // ---------------------------------------------------------------------------------------------

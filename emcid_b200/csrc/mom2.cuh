@@ -16,6 +16,8 @@
 //   finalize: full[i][j] = full[j][i] = (float) acc64[max(i,j)][min(i,j)]
 #pragma once
 
+#include <vector>
+
 #include "host.cuh"
 
 namespace emcid {
@@ -39,6 +41,12 @@ struct Mom2Handle {
   int* dest; int* n_valid;
   GemmOperands fc1_ops, syrk_ops;
   DeviceInfo info;
+  // optional per-launch timing (bench.py's roofline block): event pairs around fc1 / SYRK launches
+  bool profile;
+  std::vector<cudaEvent_t>* ev_fc1;   // begin,end,begin,end,...
+  std::vector<cudaEvent_t>* ev_syrk;
+  double rows_fc1, rows_syrk;         // slab rows covered by the timed launches
+  long long launches;                 // every kernel this handle has launched
 };
 
 inline size_t mom2_workspace_bytes(int d, int h, int slab) {
@@ -191,6 +199,8 @@ inline int mom2_create(Mom2Handle** out, int device, int d, int h, int act, int 
   EMCID_CUDA_CHECK(cudaSetDevice(device));
   Mom2Handle* H = new Mom2Handle();
   memset(H, 0, sizeof(*H));
+  H->ev_fc1 = new std::vector<cudaEvent_t>();
+  H->ev_syrk = new std::vector<cudaEvent_t>();
   int rc = get_device_info(&H->info);
   if (rc) { delete H; return rc; }
   H->device = device; H->d = d; H->h = h; H->act = act; H->slab = slab;
@@ -255,6 +265,7 @@ fail:
 fail_rc:
   cudaFree(H->w_hi); cudaFree(H->w_lo); cudaFree(H->bias); cudaFree(H->acc32); cudaFree(H->acc64);
   cudaFree(H->count);
+  delete H->ev_fc1; delete H->ev_syrk;
   delete H;
   return rc;
 }
@@ -264,6 +275,9 @@ inline int mom2_destroy(Mom2Handle* H) {
   cudaSetDevice(H->device);
   cudaFree(H->w_hi); cudaFree(H->w_lo); cudaFree(H->bias); cudaFree(H->acc32); cudaFree(H->acc64);
   cudaFree(H->count);
+  for (cudaEvent_t e : *H->ev_fc1) cudaEventDestroy(e);
+  for (cudaEvent_t e : *H->ev_syrk) cudaEventDestroy(e);
+  delete H->ev_fc1; delete H->ev_syrk;
   delete H;
   return EMCID_OK;
 }
@@ -286,6 +300,7 @@ inline int mom2_fold(Mom2Handle* H, cudaStream_t stream) {
   const int nb = (H->d + 127) / 128;
   mom2_fold_kernel<<<nb * (nb + 1) / 2, 256, 0, stream>>>(H->acc32, H->acc64, H->d);
   EMCID_CUDA_CHECK(cudaGetLastError());
+  H->launches += 1;
   H->slabs_since_fold = 0;
   return EMCID_OK;
 }
@@ -309,6 +324,7 @@ inline int mom2_accumulate(Mom2Handle* H, const float* X, long long ldx, const u
     const int t = static_cast<int>(T - r0 < per ? T - r0 : per);
     mom2_scan_kernel<<<1, 1024, 0, stream>>>(valid ? valid + r0 : nullptr, t, H->dest, H->n_valid, H->count);
     EMCID_CUDA_CHECK(cudaGetLastError());
+    H->launches += 4;  // scan, gather, fc1, syrk
     {
       int blocks = (t + 7) / 8;
       mom2_gather_split_kernel<<<blocks, 256, 0, stream>>>(X + r0 * ldx, ldx, t, H->h, H->hp, H->dest,
@@ -325,8 +341,17 @@ inline int mom2_accumulate(Mom2Handle* H, const float* X, long long ldx, const u
       p.P_hi = H->at_hi; p.P_lo = H->at_lo; p.ldp = H->slab;
       p.bias = H->bias; p.act = H->act;
       const int tiles = gemm_num_tiles(H->d, t, 256, 0);
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (H->profile) {
+        EMCID_CUDA_CHECK(cudaEventCreate(&e0)); EMCID_CUDA_CHECK(cudaEventCreate(&e1));
+        EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
+      }
       rc = launch_gemm3x<256, 2, EPI_FC1>(H->fc1_ops, p, tiles < sms ? tiles : sms, stream);
       if (rc) return rc;
+      if (H->profile) {
+        EMCID_CUDA_CHECK(cudaEventRecord(e1, stream));
+        H->ev_fc1->push_back(e0); H->ev_fc1->push_back(e1); H->rows_fc1 += t;
+      }
     }
     {
       GemmParams p;
@@ -336,8 +361,17 @@ inline int mom2_accumulate(Mom2Handle* H, const float* X, long long ldx, const u
       p.lower = 1; p.streamk = 1;
       p.chunk_kblocks = H->chunk_syrk;
       p.C = H->acc32; p.ldc = H->d;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (H->profile) {
+        EMCID_CUDA_CHECK(cudaEventCreate(&e0)); EMCID_CUDA_CHECK(cudaEventCreate(&e1));
+        EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
+      }
       rc = launch_gemm3x<256, 2, EPI_RED>(H->syrk_ops, p, sms, stream);
       if (rc) return rc;
+      if (H->profile) {
+        EMCID_CUDA_CHECK(cudaEventRecord(e1, stream));
+        H->ev_syrk->push_back(e0); H->ev_syrk->push_back(e1); H->rows_syrk += t;
+      }
     }
     if (++H->slabs_since_fold >= MOM2_FOLD_EVERY) {
       rc = mom2_fold(H, stream);
@@ -355,6 +389,7 @@ inline int mom2_finalize(Mom2Handle* H, float* mom2_full, long long* count_dev, 
   const int nb = (H->d + 31) / 32;
   mom2_mirror_kernel<<<dim3(nb, nb), dim3(32, 8), 0, stream>>>(H->acc64, mom2_full, H->d);
   EMCID_CUDA_CHECK(cudaGetLastError());
+  H->launches += 1;
   if (count_dev) {
     EMCID_CUDA_CHECK(cudaMemcpyAsync(count_dev, H->count, sizeof(long long), cudaMemcpyDeviceToDevice, stream));
   }
@@ -369,6 +404,36 @@ inline int mom2_reset(Mom2Handle* H, cudaStream_t stream) {
   EMCID_CUDA_CHECK(cudaMemsetAsync(H->acc64, 0, dd * sizeof(double), stream));
   EMCID_CUDA_CHECK(cudaMemsetAsync(H->count, 0, sizeof(long long), stream));
   H->slabs_since_fold = 0;
+  return EMCID_OK;
+}
+
+// out[0..7] = {fc1 ms total, fc1 launches, fc1 rows, syrk ms total, syrk launches, syrk rows, all launches, 0};
+// waits for the recorded events, then clears them.
+inline int mom2_get_profile(Mom2Handle* H, double* out) {
+  EMCID_CHECK(H && out, EMCID_ERR_INVALID, "mom2_get_profile: null argument");
+  EMCID_CUDA_CHECK(cudaSetDevice(H->device));
+  auto drain = [](std::vector<cudaEvent_t>* v, double* ms_total) -> cudaError_t {
+    *ms_total = 0.0;
+    for (size_t i = 0; i + 1 < v->size(); i += 2) {
+      cudaError_t e = cudaEventSynchronize((*v)[i + 1]);
+      if (e != cudaSuccess) return e;
+      float ms = 0.f;
+      e = cudaEventElapsedTime(&ms, (*v)[i], (*v)[i + 1]);
+      if (e != cudaSuccess) return e;
+      *ms_total += ms;
+      cudaEventDestroy((*v)[i]); cudaEventDestroy((*v)[i + 1]);
+    }
+    return cudaSuccess;
+  };
+  out[1] = static_cast<double>(H->ev_fc1->size() / 2);
+  out[4] = static_cast<double>(H->ev_syrk->size() / 2);
+  EMCID_CUDA_CHECK(drain(H->ev_fc1, &out[0]));
+  EMCID_CUDA_CHECK(drain(H->ev_syrk, &out[3]));
+  H->ev_fc1->clear(); H->ev_syrk->clear();
+  out[2] = H->rows_fc1; out[5] = H->rows_syrk;
+  out[6] = static_cast<double>(H->launches);
+  out[7] = 0.0;
+  H->rows_fc1 = H->rows_syrk = 0.0;
   return EMCID_OK;
 }
 

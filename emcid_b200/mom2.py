@@ -87,6 +87,16 @@ class Mom2Accumulator:
             _lib.check(_lib.lib().emcid_mom2_finalize(self._h, _lib.ptr(out), _lib.ptr(count), self._stream()))
         return out, count
 
+    def profile(self, enable: bool = True) -> None:
+        _lib.check(_lib.lib().emcid_mom2_profile(self._h, 1 if enable else 0))
+
+    def get_profile(self) -> dict:
+        out = (ctypes.c_double * 8)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().emcid_mom2_get_profile(self._h, out))
+        keys = ("fc1_ms", "fc1_launches", "fc1_rows", "syrk_ms", "syrk_launches", "syrk_rows", "launches")
+        return {k: float(out[i]) for i, k in enumerate(keys)}
+
     def reset(self) -> None:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().emcid_mom2_reset(self._h, self._stream()))

@@ -74,6 +74,11 @@ int emcid_mom2_accumulate(emcid_mom2_t* h, const float* X, long long ldx, const 
  * util/runningstats.py:502-507); count_dev: device int64 scalar (may be NULL).  Does not reset. */
 int emcid_mom2_finalize(emcid_mom2_t* h, float* mom2_full, long long* count_dev, void* stream);
 int emcid_mom2_reset(emcid_mom2_t* h, void* stream);
+/* Measurement aid: when enabled, every fc1 / SYRK launch is bracketed by CUDA events on the caller's
+ * stream.  emcid_mom2_get_profile waits for them and fills out8 = {fc1 ms total, fc1 launches, fc1 slab
+ * rows, syrk ms total, syrk launches, syrk slab rows, kernels launched by this handle so far, 0}. */
+int emcid_mom2_profile(emcid_mom2_t* h, int enable);
+int emcid_mom2_get_profile(emcid_mom2_t* h, double* out8);
 int emcid_mom2_destroy(emcid_mom2_t* h);
 
 /* ---- closed-form multi-layer update ---------------------------------------------------------------

@@ -1,0 +1,290 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: committed fixtures produced by
+the unmodified reference, the CPU oracle on seeded inputs, and size-independent properties at
+CLIP-L / bigG sizes.  Tolerances are BASELINE.json's: token counts bit exact, mom2 <= 1e-5 and
+dW <= 1e-4 relative Frobenius error."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import model_from_golden, rel_fro, rh, unpack_captions, weight_checksum
+from oracle import emcid_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+MOM2_TOL = 1e-5
+DW_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from emcid_b200 import _lib
+    _lib.check(_lib.lib().emcid_device_check(0))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _patch_ds(caps):
+    from emcid_b200 import layer_stats
+    layer_stats.get_ccs_filtered_ds = lambda tokenizer: rh.SynthTokenDataset(caps)
+    return layer_stats
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K,kw", [
+    (128, 256, 32, {}), (200, 260, 72, {}), (130, 132, 40, dict(n128=True)),
+    (512, 768, 256, dict(chunk=1)), (1024, 1024, 2048, dict(lower=True, streamk=True, beta=1.0)),
+])
+def test_gemm3x_matches_fp64(dev, M, N, K, kw):
+    from emcid_b200 import _lib
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=dev, generator=g)
+    B = torch.randn(N, K, device=dev, generator=g)
+    beta = kw.pop("beta", 0.0)
+    C0 = torch.randn(M, N, device=dev, generator=g) if beta else None
+    ref = A.double() @ B.double().T + (beta * C0.double() if beta else 0)
+    C = _lib.gemm3x_nt(A, B, C0.clone() if beta else None, beta=beta, **kw)
+    if kw.get("lower"):
+        mask = torch.tril(torch.ones(M, N, device=dev))
+        assert float(((C.double() - ref) * mask).norm() / (ref * mask).norm()) < 2e-6
+    else:
+        assert float((C.double() - ref).norm() / ref.norm()) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------ mom2 kernel vs oracle
+@pytest.mark.parametrize("d,h,T,act,frac", [
+    (256, 64, 300, "quick_gelu", 1.0), (256, 64, 1000, "gelu", 0.6), (200, 80, 513, "quick_gelu", 0.5),
+    (3072, 768, 2000, "quick_gelu", 0.7), (5120, 1280, 1100, "gelu", 0.9),
+])
+def test_mom2_accumulator_matches_oracle(dev, d, h, T, act, frac):
+    from emcid_b200.mom2 import Mom2Accumulator
+    g = torch.Generator().manual_seed(d + T)
+    W = torch.randn(d, h, generator=g) * (0.7 / h ** 0.5)
+    b = torch.randn(d, generator=g) * 0.1
+    X = torch.randn(T, h, generator=g)
+    valid = (torch.rand(T, generator=g) < frac) if frac < 1 else None
+    acc = Mom2Accumulator(dev, d, h, act)
+    acc.set_weights(W.to(dev), b.to(dev))
+    acc.add(X[: T // 3].to(dev), None if valid is None else valid[: T // 3].to(dev))
+    acc.add(X[T // 3:].to(dev), None if valid is None else valid[T // 3:].to(dev))
+    acc.add(X[:0].to(dev))                                              # empty batch: no-op
+    mom2, count = acc.finalize()
+    Xv = X.numpy() if valid is None else X.numpy()[valid.numpy()]
+    A = orc.fc2_input(Xv, W.numpy(), b.numpy(), act, dtype=np.float64)
+    assert int(count) == Xv.shape[0]
+    m = mom2.cpu().numpy()
+    assert np.array_equal(m, m.T)
+    assert rel_fro(m, A.T @ A) < MOM2_TOL
+    acc.reset()
+    acc.add(X.to(dev), torch.zeros(T, dtype=torch.bool, device=dev))    # everything masked
+    mom2, count = acc.finalize()
+    assert int(count) == 0 and float(mom2.abs().max()) == 0.0
+    acc.close()
+
+
+# ------------------------------------------------------------------------------------------ layer_stats vs reference fixtures
+@pytest.mark.parametrize("name", ["tiny_stats.npz", "tiny_gelu_stats.npz"])
+def test_layer_stats_matches_reference_fixture(dev, golden_dir, tmp_path, name):
+    g = np.load(os.path.join(golden_dir, name))
+    model = model_from_golden(g).to(dev)
+    caps = unpack_captions(g)
+    ls = _patch_ds(caps)
+    ss = None if int(g["sample_size"]) < 0 else int(g["sample_size"])
+    layer_name = f"text_model.encoder.layers.{int(g['layer'])}.mlp.fc2"
+    stat = ls.layer_stats_text_encoder(model, None, layer_name, stats_dir=tmp_path, sample_size=ss,
+                                       precision="float32", batch_tokens=int(g["batch_tokens"]), progress=None,
+                                       captions_per_batch=32, num_workers=0)
+    assert stat.mom2.count == int(g["npz.mom2.count"])                       # bit exact
+    assert stat.mom2.mom2.device.type == "cpu" and stat.mom2.mom2.dtype == torch.float32
+    assert rel_fro(stat.mom2.mom2.numpy(), g["npz.mom2.mom2"]) < MOM2_TOL
+    f = tmp_path / str(g["rel_path"])                                        # same file name as the reference
+    dat = np.load(f)
+    assert sorted(dat.files) == sorted(k[4:] for k in g.files if k.startswith("npz."))
+    for k in dat.files:
+        assert dat[k].dtype == g["npz." + k].dtype and dat[k].shape == g["npz." + k].shape, k
+    # second call is a cache hit: no dataset access, identical numbers
+    ls.get_ccs_filtered_ds = lambda tokenizer: (_ for _ in ()).throw(AssertionError("cache miss"))
+    again = ls.layer_stats_text_encoder(model, None, layer_name, stats_dir=tmp_path, sample_size=ss,
+                                        precision="float32", batch_tokens=int(g["batch_tokens"]), progress=None)
+    assert again.mom2.count == stat.mom2.count and torch.equal(again.mom2.mom2, stat.mom2.mom2)
+
+
+def test_clipl_layer_stats_matches_reference_digest(dev, golden_dir, tmp_path):
+    g = np.load(os.path.join(golden_dir, "clipl_stats_digest.npz"))
+    model = rh.make_clip_text_model("clip-l", seed=0)
+    if not np.allclose(weight_checksum(model), g["weight_checksum"], rtol=1e-12):
+        pytest.skip("random-init CLIP-L differs from the fixture's (torch RNG stream changed)")
+    model = model.to(dev)
+    caps = rh.make_captions(int(g["n_caps"]), model.config.vocab_size, seed=int(g["seed_caps"]))
+    ls = _patch_ds(caps)
+    layer = int(g["layer"])
+    names = [f"text_model.encoder.layers.{l}.mlp.fc2" for l in (layer - 1, layer)]
+    stats = ls.layer_stats_text_encoder_multi(model, None, names, stats_dir=tmp_path, sample_size=int(g["sample_size"]),
+                                              precision="float32", progress=None, captions_per_batch=64, num_workers=0)
+    m = stats[names[1]].mom2.mom2.numpy()
+    assert stats[names[1]].mom2.count == int(g["count"]) == stats[names[0]].mom2.count
+    assert rel_fro(m[:, g["cols"]], g["mom2_cols"]) < MOM2_TOL
+    assert rel_fro(np.diag(m), g["diag"]) < MOM2_TOL
+    assert rel_fro(m.astype(np.float64) @ g["probe_v"], g["probe_mv"]) < MOM2_TOL
+    assert abs(np.linalg.norm(m.astype(np.float64)) / float(g["fro"]) - 1) < MOM2_TOL
+    # the multi-layer pass equals a single-layer pass of the other layer
+    single = ls.layer_stats_text_encoder(model, None, names[0], stats_dir=tmp_path / "s", sample_size=int(g["sample_size"]),
+                                         precision="float32", progress=None, captions_per_batch=50, num_workers=0)
+    assert single.mom2.count == stats[names[0]].mom2.count
+    assert rel_fro(single.mom2.mom2.numpy(), stats[names[0]].mom2.mom2.numpy()) < 2e-6
+
+
+def test_stats_properties_at_clipl_size(dev, tmp_path):
+    """Linearity over caption sets, batching invariance, count = sum of lengths (CLIP-L, layers 7-11)."""
+    model = rh.make_clip_text_model("clip-l", seed=0).to(dev)
+    caps = rh.make_captions(768, model.config.vocab_size, seed=11)
+    names = [f"text_model.encoder.layers.{l}.mlp.fc2" for l in range(7, 12)]
+
+    def run(subset, per_batch, tag):
+        ls = _patch_ds(subset)
+        st = ls.layer_stats_text_encoder_multi(model, None, names, stats_dir=tmp_path / tag, sample_size=None,
+                                               precision="float32", progress=None, captions_per_batch=per_batch,
+                                               num_workers=0, keep_on_device=True)
+        return {n: (st[n].mom2.count, st[n].mom2.mom2.double()) for n in names}
+
+    full = run(caps, 128, "full")
+    a, b = run(caps[:300], 77, "a"), run(caps[300:], 201, "b")
+    total = sum(len(c) for c in caps)
+    for n in names:
+        assert full[n][0] == total == a[n][0] + b[n][0]
+        s = a[n][1] + b[n][1]
+        assert float((full[n][1] - s).norm() / s.norm()) < 3e-6
+        assert float(torch.diagonal(full[n][1]).min()) > 0
+        assert torch.equal(full[n][1], full[n][1].T)
+
+
+# ------------------------------------------------------------------------------------------ closed-form update
+@pytest.mark.parametrize("name", ["tiny_solve_ew05.npz", "tiny_solve_ew06.npz"])
+def test_solve_matches_reference_fixture(dev, golden_dir, name):
+    from emcid_b200.solve import solve_layers
+    g = np.load(os.path.join(golden_dir, name))
+    lam, ew = float(g["lam"]), float(g["edit_weight"])
+    layers = [int(l) for l in g["layers"]]
+    s = (ew / 0.5) ** 0.5
+    for i, l in enumerate(layers):
+        C = torch.from_numpy(orc.cov_from_state(g[f"mom2.{l}"], int(g[f"count.{l}"]))).to(dev)
+        C32 = C * (1 - ew) / 0.5
+        Kt = torch.from_numpy((g[f"solveK.{l}"] / s).astype(np.float32).T.copy()).to(dev)
+        St = torch.from_numpy((g[f"resid.{l}"] * (len(layers) - i) / s).astype(np.float32).T.copy()).to(dev)
+        adj, resid, dW = solve_layers(C32, Kt, St, lam, s, [len(layers) - i])
+        ref_upd = g[f"resid.{l}"] @ g[f"adj_k.{l}"].T
+        assert rel_fro(dW[0].cpu().numpy(), ref_upd) < DW_TOL
+        assert rel_fro(adj[0].cpu().numpy(), g[f"adj_k.{l}"]) < DW_TOL
+        assert rel_fro(resid[0].cpu().numpy(), g[f"resid.{l}"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["tiny_solve_ew05.npz", "tiny_solve_ew06.npz"])
+def test_execute_and_apply_match_reference_fixture(dev, golden_dir, tmp_path, name):
+    """Whole edit through the reference-shaped API on the tiny model: deltas, restored weights, applied weights."""
+    from emcid_b200 import emcid_main
+    from types import SimpleNamespace
+    g = np.load(os.path.join(golden_dir, name))
+    layers = [int(l) for l in g["layers"]]
+    ss = int(g["sample_size"])
+    model = rh.make_clip_text_model("tiny", seed=0)
+    for l in layers:
+        assert np.array_equal(model.text_model.encoder.layers[l].mlp.fc2.weight.numpy(), g[f"w_before.{l}"])
+    model = model.to(dev)
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    reqs = rh.make_requests(int(g["n_req"]))
+    stats_dir = tmp_path / "stats"
+    for l in layers:  # the reference's own statistics files -> identical C on both sides
+        f = orc.stats_filename(str(stats_dir), "text_encoder", "ccs_filtered", f"text_model.encoder.layers.{l}.mlp.fc2",
+                               "float32", ["mom2"], 3072, ss)
+        os.makedirs(os.path.dirname(f), exist_ok=True)
+        np.savez(f, **{"mom2.constructor": "util.runningstats.SecondMoment()", "mom2.count": int(g[f"count.{l}"]),
+                       "mom2.mom2": g[f"mom2.{l}"], "sample_size": ss})
+    cache = str(tmp_path / "v" / "c_")
+    rh.write_vstar_cache(cache, reqs, model.config.hidden_size, seed=2)
+    hp = rh.make_hparams(layers, ss, mom2_update_weight=float(g["lam"]), edit_weight=float(g["edit_weight"]))
+    pipe = SimpleNamespace(text_encoder=model, tokenizer=tok, device=dev)
+    emcid_main.COV_CACHE.clear()
+    deltas = emcid_main.execute_emcid_text_encoder(pipe, reqs, hp, cache_name=cache, verbose=False, stat_dir=stats_dir)
+    assert list(deltas) == [f"text_model.encoder.layers.{l}.mlp.fc2.weight" for l in layers]
+    for l in layers:
+        adj, resid = deltas[f"text_model.encoder.layers.{l}.mlp.fc2.weight"]
+        assert adj.dtype == torch.float64 and adj.device.type == "cpu" and tuple(adj.shape) == g[f"adj_k.{l}"].shape
+        assert rel_fro(resid.numpy(), g[f"resid.{l}"]) < 1e-5
+        assert rel_fro(resid.numpy() @ adj.numpy().T, g[f"resid.{l}"] @ g[f"adj_k.{l}"].T) < DW_TOL
+        w = model.text_model.encoder.layers[l].mlp.fc2.weight.detach().cpu().numpy()
+        assert np.array_equal(w, g[f"w_before.{l}"])                       # invariant: restored
+    emcid_main.apply_emcid_to_text_encoder(pipe, reqs, hp, device=dev, cache_name=cache, stats_dir=stats_dir, verbose=False)
+    for l in layers:
+        w = model.text_model.encoder.layers[l].mlp.fc2.weight.detach().cpu().numpy()
+        dw_ref = g[f"w_after.{l}"].astype(np.float64) - g[f"w_before.{l}"]
+        assert rel_fro(w.astype(np.float64) - g[f"w_before.{l}"], dw_ref) < DW_TOL
+
+
+@pytest.mark.parametrize("d,h,n,B", [(3072, 768, 96, 1), (3072, 768, 1000, 2), (5120, 1280, 64, 1)])
+def test_solve_full_size_matches_oracle(dev, d, h, n, B):
+    """CLIP-L / bigG sized systems with cond ~1e6, bit-reproducible inputs, oracle = fp64 LU on CPU."""
+    from emcid_b200.solve import solve_layers
+    Cs, Ks, Ss = [], [], []
+    for b in range(B):
+        Cs.append(orc.exact_spd_matrix(d, d + 1024, seed=b))
+        g = torch.Generator().manual_seed(100 + b)
+        Ks.append((torch.randn(n, d, generator=g) * 0.3 + 0.1).numpy())
+        Ss.append(torch.randn(n, h, generator=g).numpy())
+    lam, ew = 4000.0, 0.5
+    left = list(range(B, 0, -1))
+    adj, resid, dW = solve_layers(torch.from_numpy(np.stack(Cs)).to(dev), torch.from_numpy(np.stack(Ks)).to(dev),
+                                  torch.from_numpy(np.stack(Ss)).to(dev), lam, 1.0, left)
+    for b in range(B):
+        a_ref, r_ref, u_ref = orc.solve_layer(Cs[b], Ks[b].T, Ss[b].T, lam, ew, left[b])
+        assert rel_fro(dW[b].cpu().numpy(), u_ref) < DW_TOL
+        assert rel_fro(adj[b].cpu().numpy(), a_ref) < DW_TOL
+        assert rel_fro(resid[b].cpu().numpy(), r_ref) < 1e-6
+
+
+def test_solve_reports_breakdown(dev):
+    from emcid_b200 import _lib
+    from emcid_b200.solve import solve_layers
+    C = -torch.eye(256, device=dev)
+    with pytest.raises(_lib.EmcidError):
+        solve_layers(C, torch.zeros(4, 256, device=dev), torch.zeros(4, 64, device=dev), 4000.0, 1.0, [1])
+
+
+def test_sequential_editing_matches_oracle(dev, tmp_path):
+    """Config-5 pattern (experiments/sequential_editing.py): successive edits on the same model reuse the
+    cached C and re-solve on the already-edited weights."""
+    from emcid_b200 import emcid_main
+    from types import SimpleNamespace
+    layers, ss = [0, 1], 60
+    caps = rh.make_captions(80, 1000, seed=21)
+    m_gpu = rh.make_clip_text_model("tiny", seed=3).to(dev)
+    m_cpu = rh.make_clip_text_model("tiny", seed=3)
+    tok = rh.FakeTokenizer(1000)
+    ls = _patch_ds(caps)
+    names = [f"text_model.encoder.layers.{l}.mlp.fc2" for l in layers]
+    stats = ls.layer_stats_text_encoder_multi(m_gpu, None, names, stats_dir=tmp_path, sample_size=ss, precision="float32",
+                                              progress=None, num_workers=0)
+    covs = {l: orc.cov_from_state(stats[n].mom2.mom2.numpy(), stats[n].mom2.count) for l, n in zip(layers, names)}
+    pipe = SimpleNamespace(text_encoder=m_gpu, tokenizer=tok, device=dev)
+    emcid_main.COV_CACHE.clear()
+    for e in range(3):
+        reqs = [dict(r, source=f"edit{e} {r['source']}") for r in rh.make_requests(5)]
+        cache = str(tmp_path / f"v{e}" / "c_")
+        zs = rh.write_vstar_cache(cache, reqs, 64, seed=10 + e)
+        hp = rh.make_hparams(layers, ss)
+        emcid_main.apply_emcid_to_text_encoder(pipe, reqs, hp, device=dev, cache_name=cache, stats_dir=tmp_path, verbose=False)
+        deltas = orc.execute_oracle(m_cpu, tok, reqs, layers, zs.numpy(), covs, 4000.0, 0.5)
+        for l in layers:
+            w = m_cpu.text_model.encoder.layers[l].mlp.fc2.weight
+            with torch.no_grad():
+                w[...] = torch.from_numpy(orc.apply_delta(w.numpy(), *deltas[l]))
+    for l in layers:
+        w0 = rh.make_clip_text_model("tiny", seed=3).text_model.encoder.layers[l].mlp.fc2.weight.numpy().astype(np.float64)
+        got = m_gpu.text_model.encoder.layers[l].mlp.fc2.weight.detach().cpu().numpy().astype(np.float64) - w0
+        want = m_cpu.text_model.encoder.layers[l].mlp.fc2.weight.numpy().astype(np.float64) - w0
+        assert rel_fro(got, want) < DW_TOL
+
+
+def test_smoke_entry(dev):
+    import __graft_entry__
+    __graft_entry__.smoke()
