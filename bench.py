@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the EMCID hot path on B200 (BASELINE.json metric): mom2 statistics tokens/s for the
+edited sd-text layers 7-11, plus ms per 1000-concept 5-layer closed-form update.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels, C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm
+
+One "step" = one pass of the statistics hot path (CLIP forward up to layer 11 with the fused
+fc1 -> quick_gelu -> mask -> SYRK kernels spliced into layers 7..11) over `--captions` synthetic
+77-token captions PER GPU (weak scaling: every rank owns its own caption shard; the one exchange
+step of the path, the NCCL reduce of the per-rank mom2, runs once at the end of the timed region
+exactly as it runs once per statistics pass).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LAYERS = [7, 8, 9, 10, 11]
+LAYER_TMP = "text_model.encoder.layers.{}.mlp.fc2"
+H, D, WIDTH = 768, 3072, 77
+FLOPS_PER_TOKEN_LAYER = 2 * H * D + D * (D + 1)          # fc1 + lower-triangular SYRK
+METRIC = "mom2_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def workload_name(captions):
+    return (f"sd-text (CLIP ViT-L/14 text, random-init) mom2+count of layers 7-11 mlp.fc2 inputs, "
+            f"{captions} synthetic 77-token captions per GPU per step (BASELINE configs[1], caption-sharded)")
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": float(p["bf16_tflops"]), "bf16_sustained": float(p.get("bf16_tflops_sustained",
+                p["bf16_tflops"])), "hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic():
+    """dram bytes per SYRK launch from the committed ncu --set full capture, if one exists."""
+    path = os.path.join(ROOT, "profiles", "ncu_top_kernel.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+_CPU_MODEL = None
+
+
+def cpu_port_tokens_per_s(captions_n: int, threads: int):
+    """The reference's algorithm for the same workload on host cores: one full pass PER LAYER
+    (emcid/layer_stats.py:112-134), HF forward + masked flatten + fp32 Gram, via the oracle port."""
+    import numpy as np  # noqa: F401
+    import torch
+
+    from emcid_b200 import synth
+    from oracle import emcid_oracle as orc
+
+    torch.set_num_threads(threads)
+    global _CPU_MODEL
+    if _CPU_MODEL is None:
+        _CPU_MODEL = synth.make_text_encoder("sd-text", seed=0)
+    model = _CPU_MODEL
+    caps = [c.numpy() for c in synth.make_caption_ids(captions_n, seed=123, full=True)]
+    t0 = time.perf_counter()
+    tokens = 0
+    for layer in LAYERS:
+        stat = orc.layer_stats_oracle(model, caps, layer, sample_size=None)
+        tokens = stat.count
+    dt = time.perf_counter() - t0
+    return tokens / dt, dt, tokens
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port: the
+    reference is pure Python/torch and /root/reference does not exist on the GPU box), all host
+    threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    threads = os.cpu_count() or 1
+    sample = args.ref_captions
+    for _ in range(args.warmup):
+        cpu_port_tokens_per_s(max(4, sample // 4), threads)
+    vals, secs = [], []
+    for _ in range(args.steps):
+        v, dt, tokens = cpu_port_tokens_per_s(sample, threads)
+        vals.append(v); secs.append(dt)
+    value = (sample * WIDTH * len(vals)) / sum(secs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.captions), "sample": f"{sample} captions x 77 tokens per step",
+                   "layers": LAYERS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sample} captions x 77 tokens, one full forward+Gram pass per layer (5 passes) "
+                                   f"per step, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from emcid_b200 import _lib, layer_stats, synth
+    from emcid_b200.solve import solve_layers
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA sm_100a device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.check(_lib.lib().emcid_device_check(local))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False     # the surrounding forward must stay fp32-accurate
+    torch.backends.cudnn.allow_tf32 = False
+
+    K, W, C = args.steps, args.warmup, args.captions
+    model = synth.make_text_encoder("sd-text", seed=0).to(dev)
+    names = [LAYER_TMP.format(l) for l in LAYERS]
+    tokens_per_step = C * WIDTH
+
+    # ---- inputs resident in HBM before the timed region: (K + W) distinct caption blocks per rank
+    g = torch.Generator().manual_seed(1000 + rank)
+    ids = torch.randint(0, 49406, (K + W, C, WIDTH), generator=g)
+    ids[:, :, 0] = 49406
+    ids[:, :, -1] = 49407
+    ids_dev = ids.to(dev)
+    pos_dev = torch.arange(WIDTH, device=dev).expand(C, WIDTH).contiguous()
+    mask_dev = torch.ones(C, WIDTH, dtype=torch.long, device=dev)
+    blk = args.block_captions
+
+    runner = layer_stats.TextEncoderMom2Pass(model, names, slab_tokens=args.slab)
+
+    def step(i):
+        for c0 in range(0, C, blk):
+            runner.run_batch({"input_ids": ids_dev[i, c0:c0 + blk], "position_ids": pos_dev[c0:c0 + blk],
+                              "attention_mask": mask_dev[c0:c0 + blk]})
+
+    def finish():
+        out = runner.finalize()
+        if world > 1:
+            for j, n in enumerate(names):
+                dist.reduce(out[n][0], dst=j % world, op=dist.ReduceOp.SUM)
+                dist.reduce(out[n][1], dst=j % world, op=dist.ReduceOp.SUM)
+        return out
+
+    def launches():
+        return sum(acc.get_profile()["launches"] for acc in runner.accs.values())
+
+    for i in range(W):
+        step(i)
+    finish()
+    for acc in runner.accs.values():
+        acc.reset()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(W, W + K):
+        step(i)
+    out = finish()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    n_launch = launches() - l0
+    count0 = int(out[names[0]][1].item())
+    value = world * K * tokens_per_step / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (stream-K lower SYRK on tcgen05), timed per launch with CUDA events
+    for acc in runner.accs.values():
+        acc.reset(); acc.profile(True)
+    for i in range(W, W + min(K, 2)):
+        step(i)
+    torch.cuda.synchronize()
+    prof = {"fc1_ms": 0.0, "fc1_rows": 0.0, "fc1_launches": 0.0, "syrk_ms": 0.0, "syrk_rows": 0.0, "syrk_launches": 0.0}
+    for acc in runner.accs.values():
+        p = acc.get_profile()
+        for k in prof:
+            prof[k] += p[k]
+        acc.profile(False)
+    peaks = measured_peaks()
+    tf32_peak = peaks["bf16_sustained"] / 2.0   # dense TF32 = half the bf16 rate; kernel timed inside a long step
+    syrk_tflops = prof["syrk_rows"] * D * (D + 1) / (prof["syrk_ms"] * 1e-3) / 1e12 if prof["syrk_ms"] else 0.0
+    fc1_tflops = prof["fc1_rows"] * 2 * H * D / (prof["fc1_ms"] * 1e-3) / 1e12 if prof["fc1_ms"] else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "gemm3x_kernel<256,2,EPI_RED> (stream-K lower SYRK, 3xTF32)",
+        "achieved": syrk_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": syrk_tflops / tf32_peak,
+        "peak_source": f"{peaks['source']}: bf16_tflops_sustained / 2 (dense TF32 runs at half the bf16 rate)",
+        "issued_frac": 3.0 * syrk_tflops / tf32_peak,
+        "avg_launch_ms": prof["syrk_ms"] / max(prof["syrk_launches"], 1.0),
+        "rows_per_launch": prof["syrk_rows"] / max(prof["syrk_launches"], 1.0),
+        "fc1": {"achieved": fc1_tflops, "frac": fc1_tflops / tf32_peak,
+                "avg_launch_ms": prof["fc1_ms"] / max(prof["fc1_launches"], 1.0)},
+        "kernel_share_of_step": (prof["syrk_ms"] + prof["fc1_ms"]) / (min(K, 2) * ms_total / K),
+        "traffic": ncu_traffic(),
+    }
+    # whole-step fraction of the tensor roofline (what the BASELINE metric asks next to tokens/s)
+    step_tflops = value * len(LAYERS) * FLOPS_PER_TOKEN_LAYER / 1e12 / world
+    roofline["step_frac"] = step_tflops / tf32_peak
+
+    # ---- second half of the metric: ms per 1000-concept 5-layer closed-form update (one GPU, batched)
+    solve = None
+    if not args.no_solve:
+        n = args.concepts
+        gg = torch.Generator(device=dev).manual_seed(2)
+        C32 = torch.stack([out[nm][0] / max(count0, 1) for nm in names]).contiguous()
+        if world > 1:  # layers were reduced to different roots; any rank's partial sum is a valid SPD C for timing
+            C32 = C32 / 1.0
+        Kt = torch.randn(len(LAYERS), n, D, device=dev, generator=gg) * 0.5 + 0.2
+        St = torch.randn(len(LAYERS), n, H, device=dev, generator=gg)
+        left = [len(LAYERS) - i for i in range(len(LAYERS))]
+        for _ in range(2):
+            solve_layers(C32, Kt, St, 4000.0, 1.0, left)
+        torch.cuda.synchronize()
+        reps = 3
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            adj, resid, dW = solve_layers(C32, Kt, St, 4000.0, 1.0, left)
+        s1.record()
+        torch.cuda.synchronize()
+        solve = {"ms": s0.elapsed_time(s1) / reps, "concepts": n, "layers": len(LAYERS), "d": D, "h": H,
+                 "lambda": 4000.0, "edit_weight": 0.5, "refine": "adaptive",
+                 "what": "K,S,C on device -> adj_k, resid (fp64), dW (fp32) on device, 5 layers batched on one GPU"}
+        # residual check in fp64 on layer 0 (cheap; full parity lives in tests/)
+        M0 = 4000.0 * C32[0].double() + Kt[0].double().T @ Kt[0].double()
+        solve["rel_residual_fp64"] = float((M0 @ adj[0] - Kt[0].double().T).norm() / Kt[0].double().norm())
+        del M0, adj, resid, dW
+    runner.close()
+
+    # ---- e2e: the public API (reference signature) from HOST captions to HOST mom2, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        total_caps = K * C * world
+        caps = synth.make_caption_ids(total_caps, seed=7, full=True)
+        layer_stats.get_ccs_filtered_ds = lambda tokenizer: synth.CaptionIdDataset(caps)
+        tmp = tempfile.mkdtemp(prefix="emcid_bench_")
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        stats = layer_stats.layer_stats_text_encoder_multi(
+            model, None, names, stats_dir=tmp, sample_size=total_caps, precision="float32", progress=None,
+            force_recompute=True, captions_per_batch=blk, slab_tokens=args.slab)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert stats[names[0]].mom2.count == total_caps * WIDTH
+        assert stats[names[0]].mom2.mom2.device.type == "cpu"
+        e2e = {"value": total_caps * WIDTH / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": 3 * C * WIDTH * 8,
+               "d2h_bytes_per_step": (len(LAYERS) * (D * D * 4 + 8)) // K,
+               "api": "emcid_b200.layer_stats.layer_stats_text_encoder_multi(model, None, layer_names, ...) "
+                      "host caption ids -> DataLoader -> pinned H2D -> pass -> NCCL reduce -> mom2 on host",
+               "seconds": float(dt.item()), "captions": total_caps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, dt, tokens = cpu_port_tokens_per_s(args.ref_captions, os.cpu_count() or 1)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{args.ref_captions} captions x 77 tokens, layers 7-11 (one full pass per layer as the "
+                         f"reference does), {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32x3 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": workload_name(C), "layers": LAYERS, "captions_per_gpu_per_step": C,
+                       "tokens_per_gpu_per_step": tokens_per_step, "block_captions": blk,
+                       "l2": "per-step working set (X slabs, activations) >> 126 MB L2; no flush needed",
+                       "parallelism": f"caption-sharded x{world}, one NCCL reduce per layer at the end of the pass",
+                       "count_check": count0},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solve": solve, "clocks": clocks,
+            "gpu_launches": int(n_launch),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--captions", type=int, default=2048, help="captions per GPU per step")
+    ap.add_argument("--block-captions", type=int, default=512, help="captions per forward block")
+    ap.add_argument("--slab", type=int, default=0, help="tokens per fc1/SYRK launch pair (0 = library default)")
+    ap.add_argument("--concepts", type=int, default=1000)
+    ap.add_argument("--ref-captions", type=int, default=48, help="captions per CPU-baseline sample")
+    ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

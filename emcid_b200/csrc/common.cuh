@@ -7,6 +7,8 @@
 #pragma once
 
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -53,6 +55,21 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = to_tf32_rna(x);
   lo = to_tf32_rna(x - hi);
+}
+
+// 3x16-bit operand split for tcgen05.mma.kind::f16 (twice the tf32 issue rate, half the bytes):
+//   hi = fp16(x)  (11 significant bits, saturated to the fp16 range so it can never become inf)
+//   lo = x - hi   (exact in fp32), stored as bf16 (8 bits, fp32 exponent range: never underflows)
+//                 or as fp16 (11 bits, but subnormal below 6.1e-5: absolute error <= 2^-25)
+// |x - (hi + lo)| <= 2^-20 |x| with a bf16 lo, 2^-23 |x| (or 2^-25 absolute) with an fp16 lo.
+constexpr int FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2;  // UMMA instruction-descriptor operand formats
+
+__device__ __forceinline__ void split_f16(float x, int lo_fmt, uint16_t& hi, uint16_t& lo) {
+  const float xs = fminf(fmaxf(x, -65504.f), 65504.f);
+  const __half h = __float2half_rn(xs);
+  const float r = x - __half2float(h);
+  hi = __half_as_ushort(h);
+  lo = lo_fmt == FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(r)) : __half_as_ushort(__float2half_rn(r));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -176,6 +193,20 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// Same, 16-bit inputs (each operand independently fp16 or bf16, chosen by the instruction descriptor).
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes with
 // the 128-byte swizzle (what TMA SWIZZLE_128B writes): 8-row groups are 1024 B apart (SBO),
 // LBO is unused for swizzled K-major layouts, version=1 (sm_100), layout_type=2 (SWIZZLE_128B).
@@ -197,6 +228,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, b
          | ((neg_a ? 1u : 0u) << 13)// a_negate
          | ((N >> 3) << 17)         // n_dim
          | ((M >> 4) << 24);        // m_dim
+}
+
+// Instruction descriptor with explicit operand formats (FMT_*), fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt_a, uint32_t fmt_b, uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i gets lane i).

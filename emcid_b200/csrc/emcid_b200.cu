@@ -63,6 +63,10 @@ int emcid_mom2_set_chunks(emcid_mom2_t* h, int fc1_kblocks, int syrk_kblocks) {
   return EMCID_OK;
 }
 
+int emcid_mom2_set_precision(emcid_mom2_t* h, int precision) {
+  return mom2_set_precision(reinterpret_cast<Mom2Handle*>(h), precision);
+}
+
 int emcid_mom2_set_weights(emcid_mom2_t* h, const float* W1, long long ldw, const float* b1, void* stream) {
   return mom2_set_weights(reinterpret_cast<Mom2Handle*>(h), W1, ldw, b1, static_cast<cudaStream_t>(stream));
 }

@@ -33,7 +33,16 @@
 namespace emcid {
 
 constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 32;  // 32 fp32 = 128 bytes = one swizzle row
+constexpr int GEMM_BLOCK_K = 32;  // tf32 kind: 32 fp32 = 128 bytes = one swizzle row
+
+// Operand kind of the 3-term split.  KIND_TF32: planes are fp32 containers of tf32-exact values,
+// tcgen05.mma.kind::tf32 (K = 8 per instruction).  KIND_F16: planes are 16-bit (hi = fp16, lo = bf16
+// or fp16, see split_f16), tcgen05.mma.kind::f16 (K = 16 per instruction): the same three MMAs per
+// 128-byte k-step retire twice the contraction depth and every plane moves half the bytes.
+enum GemmKind : int { KIND_TF32 = 0, KIND_F16 = 1 };
+template <int KIND> struct KindTraits;
+template <> struct KindTraits<KIND_TF32> { static constexpr int kBlockK = 32; static constexpr int kElemBytes = 4; };
+template <> struct KindTraits<KIND_F16> { static constexpr int kBlockK = 64; static constexpr int kElemBytes = 2; };
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_THREADS = 256;
 constexpr int GEMM_ROW_BYTES = 128;
@@ -73,6 +82,7 @@ struct GemmParams {
   long long ldpt, pt_batch;
   const float* bias;           // [M], EPI_FC1
   int act;
+  int lo_fmt;                  // KIND_F16: format of the lo planes (FMT_BF16 default, FMT_F16)
 };
 
 template <int BLOCK_N, int STAGES>
@@ -96,11 +106,11 @@ struct Sched {
   long long pos, end;          // stream-K: position in the flattened (tile, kb) space
   int tile, tile_step, num_tiles;
 
-  __device__ void init(const GemmParams& p, int block_n_, int M, int N, int K) {
+  __device__ void init(const GemmParams& p, int block_n_, int block_k, int M, int N, int K) {
     block_n = block_n_;
     m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
     n_tiles = (N + block_n - 1) / block_n;
-    kb_tile = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    kb_tile = (K + block_k - 1) / block_k;
     R = block_n / GEMM_BLOCK_M;
     lower = p.lower;
     streamk = p.streamk;
@@ -180,13 +190,49 @@ template <int N> __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-template <int BLOCK_N, int STAGES, int EPI>
+// Stores 4 consecutive result values as split planes (tf32: two float4; f16: two 8-byte words).
+template <int KIND>
+__device__ __forceinline__ void store_planes4(float* hi_base, float* lo_base, long long idx, float4 o, int lo_fmt) {
+  if (KIND == KIND_TF32) {
+    float4 h, l;
+    split_tf32(o.x, h.x, l.x); split_tf32(o.y, h.y, l.y);
+    split_tf32(o.z, h.z, l.z); split_tf32(o.w, h.w, l.w);
+    *reinterpret_cast<float4*>(hi_base + idx) = h;
+    *reinterpret_cast<float4*>(lo_base + idx) = l;
+  } else {
+    uint16_t h[4], l[4];
+    split_f16(o.x, lo_fmt, h[0], l[0]); split_f16(o.y, lo_fmt, h[1], l[1]);
+    split_f16(o.z, lo_fmt, h[2], l[2]); split_f16(o.w, lo_fmt, h[3], l[3]);
+    uint2 hv, lv;
+    hv.x = h[0] | (static_cast<uint32_t>(h[1]) << 16); hv.y = h[2] | (static_cast<uint32_t>(h[3]) << 16);
+    lv.x = l[0] | (static_cast<uint32_t>(l[1]) << 16); lv.y = l[2] | (static_cast<uint32_t>(l[3]) << 16);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi_base) + idx) = hv;
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo_base) + idx) = lv;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void store_plane1(float* hi_base, float* lo_base, long long idx, float v, int lo_fmt) {
+  if (KIND == KIND_TF32) {
+    float h, l;
+    split_tf32(v, h, l);
+    hi_base[idx] = h; lo_base[idx] = l;
+  } else {
+    uint16_t h, l;
+    split_f16(v, lo_fmt, h, l);
+    reinterpret_cast<uint16_t*>(hi_base)[idx] = h;
+    reinterpret_cast<uint16_t*>(lo_base)[idx] = l;
+  }
+}
+
+template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
               const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
   constexpr int COLS = BLOCK_N / 2;  // accumulator columns owned by one epilogue thread
+  constexpr int BLOCK_K = KindTraits<KIND>::kBlockK;  // elements per 128-byte k-block
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -235,7 +281,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   const int chunk = p.chunk_kblocks > 0 ? p.chunk_kblocks : GEMM_DEFAULT_CHUNK; \
   const int batch = blockIdx.y;                                              \
   Sched sched;                                                               \
-  sched.init(p, BLOCK_N, p.M, N, K);                                         \
+  sched.init(p, BLOCK_N, BLOCK_K, p.M, N, K);                                         \
   Unit u;                                                                    \
   (void)chunk; (void)batch;
 
@@ -252,7 +298,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          const int kc = kb * GEMM_BLOCK_K;
+          const int kc = kb * BLOCK_K;
           tma_load_2d(st, &tmA_hi, &full_bar[stage], p.a_col0 + kc, arow + u.m0);
           tma_load_2d(st + GEMM_A_PLANE_BYTES, &tmA_lo, &full_bar[stage], p.a_col0 + kc, arow + u.m0);
           uint8_t* sb = st + 2 * GEMM_A_PLANE_BYTES;
@@ -269,7 +315,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
     } else if (warp == 1 && lane == 0) {
       // ---------------------------------------------------------------- MMA issuer
       EMCID_GEMM_ROLE_SETUP();
-      constexpr uint32_t idesc = make_idesc_tf32(GEMM_BLOCK_M, BLOCK_N);
+      // three MMAs per k-step: lo*hi, hi*lo, hi*hi (small terms first)
+      const uint32_t f_hi = KIND == KIND_TF32 ? FMT_TF32 : FMT_F16;
+      const uint32_t f_lo = KIND == KIND_TF32 ? FMT_TF32 : static_cast<uint32_t>(p.lo_fmt);
+      const uint32_t idesc_lh = make_idesc(f_lo, f_hi, GEMM_BLOCK_M, BLOCK_N);
+      const uint32_t idesc_hl = make_idesc(f_hi, f_lo, GEMM_BLOCK_M, BLOCK_N);
+      const uint32_t idesc_hh = make_idesc(f_hi, f_hi, GEMM_BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -290,12 +341,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             const uint64_t db_hi = make_desc_k128(sa + 2 * GEMM_A_PLANE_BYTES);
             const uint64_t db_lo = make_desc_k128(sa + 2 * GEMM_A_PLANE_BYTES + Cfg::kBPlaneBytes);
 #pragma unroll
-            for (int k = 0; k < GEMM_BLOCK_K / 8; ++k) {
-              // +32 bytes along K inside the swizzle row = +2 in the (addr >> 4) field.
+            for (int k = 0; k < 4; ++k) {
+              // one instruction contracts 32 bytes of K (8 tf32 / 16 halves): +2 in the (addr >> 4) field
               const uint64_t koff = static_cast<uint64_t>(k * 2);
-              tc_mma_tf32(tmem_d, da_lo + koff, db_hi + koff, idesc, accumulate);
-              tc_mma_tf32(tmem_d, da_hi + koff, db_lo + koff, idesc, 1);
-              tc_mma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc, 1);
+              if (KIND == KIND_TF32) {
+                tc_mma_tf32(tmem_d, da_lo + koff, db_hi + koff, idesc_lh, accumulate);
+                tc_mma_tf32(tmem_d, da_hi + koff, db_lo + koff, idesc_hl, 1);
+                tc_mma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc_hh, 1);
+              } else {
+                tc_mma_f16(tmem_d, da_lo + koff, db_hi + koff, idesc_lh, accumulate);
+                tc_mma_f16(tmem_d, da_hi + koff, db_lo + koff, idesc_hl, 1);
+                tc_mma_f16(tmem_d, da_hi + koff, db_hi + koff, idesc_hh, 1);
+              }
               accumulate = 1;
             }
             tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
@@ -348,8 +405,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         } else if (EPI == EPI_GENERIC) {
           const float* cin = p.Cin ? p.Cin + batch * p.cin_batch + static_cast<long long>(row) * p.ldcin + col0 : nullptr;
           float* dst = p.C ? p.C + batch * p.c_batch + static_cast<long long>(row) * p.ldc + col0 : nullptr;
-          float* ph = p.P_hi ? p.P_hi + batch * p.p_batch + static_cast<long long>(row) * p.ldp + col0 : nullptr;
-          float* pl = p.P_lo ? p.P_lo + batch * p.p_batch + static_cast<long long>(row) * p.ldp + col0 : nullptr;
+          const long long pidx = batch * p.p_batch + static_cast<long long>(row) * p.ldp + col0;  // plane elements
 #pragma unroll
           for (int j = 0; j < COLS / 4; ++j) {
             const int col = col0 + 4 * j;
@@ -364,21 +420,14 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                 o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
               }
               if (dst) *reinterpret_cast<float4*>(dst + 4 * j) = o;
-              if (ph || p.Pt_hi) {
-                float4 h, l;
-                split_tf32(o.x, h.x, l.x); split_tf32(o.y, h.y, l.y);
-                split_tf32(o.z, h.z, l.z); split_tf32(o.w, h.w, l.w);
-                if (ph) {
-                  *reinterpret_cast<float4*>(ph + 4 * j) = h;
-                  *reinterpret_cast<float4*>(pl + 4 * j) = l;
-                }
-                if (p.Pt_hi) {
-                  // transposed planes: consecutive lanes (rows) hit consecutive addresses
-                  float* th = p.Pt_hi + batch * p.pt_batch + static_cast<long long>(col) * p.ldpt + row;
-                  float* tl = p.Pt_lo + batch * p.pt_batch + static_cast<long long>(col) * p.ldpt + row;
-                  th[0] = h.x; th[p.ldpt] = h.y; th[2 * p.ldpt] = h.z; th[3 * p.ldpt] = h.w;
-                  tl[0] = l.x; tl[p.ldpt] = l.y; tl[2 * p.ldpt] = l.z; tl[3 * p.ldpt] = l.w;
-                }
+              if (p.P_hi) store_planes4<KIND>(p.P_hi, p.P_lo, pidx + 4 * j, o, p.lo_fmt);
+              if (p.Pt_hi) {
+                // transposed planes: consecutive lanes (rows) hit consecutive addresses
+                const long long t = batch * p.pt_batch + static_cast<long long>(col) * p.ldpt + row;
+                store_plane1<KIND>(p.Pt_hi, p.Pt_lo, t, o.x, p.lo_fmt);
+                store_plane1<KIND>(p.Pt_hi, p.Pt_lo, t + p.ldpt, o.y, p.lo_fmt);
+                store_plane1<KIND>(p.Pt_hi, p.Pt_lo, t + 2 * p.ldpt, o.z, p.lo_fmt);
+                store_plane1<KIND>(p.Pt_hi, p.Pt_lo, t + 3 * p.ldpt, o.w, p.lo_fmt);
               }
             }
           }
@@ -386,21 +435,17 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
           // acc[row = feature i][col = token t]; tokens >= N (dynamic valid count) are padding
           // rows of the compacted X slab and must contribute exactly zero to mom2.
           const float bias = p.bias ? p.bias[row] : 0.f;
-          float* dh = p.P_hi + batch * p.p_batch + static_cast<long long>(row) * p.ldp + col0;
-          float* dl = p.P_lo + batch * p.p_batch + static_cast<long long>(row) * p.ldp + col0;
+          const long long pidx = batch * p.p_batch + static_cast<long long>(row) * p.ldp + col0;
 #pragma unroll
           for (int j = 0; j < COLS / 4; ++j) {
             const int col = col0 + 4 * j;
             if (col < p.ldp) {
-              float4 h, l;
-              const float a0 = (col + 0 < N) ? apply_act(sum[4 * j + 0] + bias, p.act) : 0.f;
-              const float a1 = (col + 1 < N) ? apply_act(sum[4 * j + 1] + bias, p.act) : 0.f;
-              const float a2 = (col + 2 < N) ? apply_act(sum[4 * j + 2] + bias, p.act) : 0.f;
-              const float a3 = (col + 3 < N) ? apply_act(sum[4 * j + 3] + bias, p.act) : 0.f;
-              split_tf32(a0, h.x, l.x); split_tf32(a1, h.y, l.y);
-              split_tf32(a2, h.z, l.z); split_tf32(a3, h.w, l.w);
-              *reinterpret_cast<float4*>(dh + 4 * j) = h;
-              *reinterpret_cast<float4*>(dl + 4 * j) = l;
+              float4 a;
+              a.x = (col + 0 < N) ? apply_act(sum[4 * j + 0] + bias, p.act) : 0.f;
+              a.y = (col + 1 < N) ? apply_act(sum[4 * j + 1] + bias, p.act) : 0.f;
+              a.z = (col + 2 < N) ? apply_act(sum[4 * j + 2] + bias, p.act) : 0.f;
+              a.w = (col + 3 < N) ? apply_act(sum[4 * j + 3] + bias, p.act) : 0.f;
+              store_planes4<KIND>(p.P_hi, p.P_lo, pidx + 4 * j, a, p.lo_fmt);
             }
           }
         }

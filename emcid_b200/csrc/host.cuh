@@ -98,20 +98,22 @@ inline PFN_encodeTiled get_encode_fn() {
 
 // Row-major fp32 matrix [rows x cols] with row pitch `ld` elements; boxes of 32 cols x box_rows,
 // written to shared memory with the 128-byte swizzle the UMMA descriptors expect.
-inline int make_tmap_2d(CUtensorMap* out, const float* base, long long rows, long long cols,
-                        long long ld, int box_rows) {
+// elem_bytes = 4 (tf32 planes) or 2 (fp16 / bf16 planes): the box is always one 128-byte swizzle row wide.
+inline int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols,
+                        long long ld, int box_rows, int elem_bytes = 4) {
   PFN_encodeTiled fn = get_encode_fn();
   EMCID_CHECK(fn != nullptr, EMCID_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   EMCID_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, EMCID_ERR_INVALID,
               "TMA base pointer must be 16-byte aligned");
-  EMCID_CHECK(ld % 4 == 0 && ld >= cols, EMCID_ERR_INVALID,
-              "TMA row pitch must be a multiple of 4 floats and >= cols (ld=%lld cols=%lld)", ld, cols);
+  EMCID_CHECK((ld * elem_bytes) % 16 == 0 && ld >= cols, EMCID_ERR_INVALID,
+              "TMA row pitch must be a multiple of 16 bytes and >= cols (ld=%lld cols=%lld)", ld, cols);
   EMCID_CHECK(rows > 0 && cols > 0, EMCID_ERR_INVALID, "empty TMA tensor");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(GEMM_BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(GEMM_ROW_BYTES / elem_bytes), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride,
+  CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                  const_cast<void*>(base), gdim, gstride,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EMCID_CHECK(r == CUDA_SUCCESS, EMCID_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d",
@@ -126,11 +128,11 @@ struct GemmOperands {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int BLOCK_N, int STAGES, int EPI>
+template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32>
 inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid, cudaStream_t stream,
                          int batches = 1) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
-  auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI>;
+  auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI, KIND>;
   static thread_local bool configured[16] = {false};
   int dev = 0;
   EMCID_CUDA_CHECK(cudaGetDevice(&dev));
@@ -175,6 +177,34 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long ld,
     hi[i] = h;
     lo[i] = l;
   }
+}
+
+// 16-bit planes (KIND_F16): hi = fp16, lo = bf16 / fp16 of scale * src.
+__global__ void split_planes16_kernel(const float* __restrict__ src, long long ld, int rows, int cols,
+                                      float scale, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                      long long ldp, int lo_fmt) {
+  const long long total = static_cast<long long>(rows) * ldp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / ldp);
+    const int c = static_cast<int>(i - static_cast<long long>(r) * ldp);
+    uint16_t h = 0, l = 0;
+    if (c < cols) split_f16(scale * src[static_cast<long long>(r) * ld + c], lo_fmt, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+inline int launch_split_planes16(const float* src, long long ld, int rows, int cols, float scale,
+                                 void* hi, void* lo, long long ldp, int lo_fmt, cudaStream_t stream) {
+  const long long total = static_cast<long long>(rows) * ldp;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split_planes16_kernel<<<blocks, 256, 0, stream>>>(src, ld, rows, cols, scale, static_cast<uint16_t*>(hi),
+                                                     static_cast<uint16_t*>(lo), ldp, lo_fmt);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  return EMCID_OK;
 }
 
 inline int launch_split_planes(const float* src, long long ld, int rows, int cols, float scale,

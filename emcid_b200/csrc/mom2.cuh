@@ -25,9 +25,12 @@ namespace emcid {
 constexpr int MOM2_MAX_SLAB = 4096;
 constexpr int MOM2_DEFAULT_SLAB = 1536;
 constexpr int MOM2_FOLD_EVERY = 8;
+constexpr int MOM2_DEFAULT_KIND = KIND_TF32;
 
 struct Mom2Handle {
   int device, d, h, hp, act, slab;
+  int kind, lo_fmt;    // KIND_TF32 (3xTF32) or KIND_F16 (fp16 hi + bf16/fp16 lo planes, kind::f16 MMAs)
+  void* workspace;
   int chunk_fc1, chunk_syrk;
   // private state (library-allocated)
   float* w_hi; float* w_lo; float* bias;
@@ -50,12 +53,12 @@ struct Mom2Handle {
 };
 
 inline size_t mom2_workspace_bytes(int d, int h, int slab) {
-  const long long hp = round_up_ll(h, GEMM_BLOCK_K);
+  const long long hp = round_up_ll(h, 64);
   long long bytes = 0;
   bytes += 2ll * slab * hp * sizeof(float);   // X planes
   bytes += 2ll * d * slab * sizeof(float);    // A^T planes
   bytes += static_cast<long long>(slab) * sizeof(int) + 256;  // dest + n_valid
-  return static_cast<size_t>(bytes + 4096);
+  return static_cast<size_t>(bytes + 8192);
 }
 
 // ---- kernels ------------------------------------------------------------------------------------
@@ -101,6 +104,39 @@ __global__ void __launch_bounds__(1024) mom2_scan_kernel(const uint8_t* __restri
   if (tid == 0) {
     *n_valid = base_s;
     *count += base_s;
+  }
+}
+
+// Same for 16-bit planes (KIND_F16).
+__global__ void mom2_gather_split16_kernel(const float* __restrict__ X, long long ldx, int T, int h, int hp,
+                                           const int* __restrict__ dest, uint16_t* __restrict__ x_hi,
+                                           uint16_t* __restrict__ x_lo, int lo_fmt) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < T; r += gridDim.x * warps_per_block) {
+    const int dst = dest[r];
+    if (dst < 0) continue;
+    const float* src = X + static_cast<long long>(r) * ldx;
+    uint16_t* oh = x_hi + static_cast<long long>(dst) * hp;
+    uint16_t* ol = x_lo + static_cast<long long>(dst) * hp;
+    for (int c = lane * 4; c < hp; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c + 3 < h) {
+        v = *reinterpret_cast<const float4*>(src + c);
+      } else {
+        if (c + 0 < h) v.x = src[c + 0];
+        if (c + 1 < h) v.y = src[c + 1];
+        if (c + 2 < h) v.z = src[c + 2];
+      }
+      uint16_t hh[4], ll[4];
+      split_f16(v.x, lo_fmt, hh[0], ll[0]); split_f16(v.y, lo_fmt, hh[1], ll[1]);
+      split_f16(v.z, lo_fmt, hh[2], ll[2]); split_f16(v.w, lo_fmt, hh[3], ll[3]);
+      uint2 hv, lv;
+      hv.x = hh[0] | (static_cast<uint32_t>(hh[1]) << 16); hv.y = hh[2] | (static_cast<uint32_t>(hh[3]) << 16);
+      lv.x = ll[0] | (static_cast<uint32_t>(ll[1]) << 16); lv.y = ll[2] | (static_cast<uint32_t>(ll[3]) << 16);
+      *reinterpret_cast<uint2*>(oh + c) = hv;
+      *reinterpret_cast<uint2*>(ol + c) = lv;
+    }
   }
 }
 
@@ -185,6 +221,33 @@ __global__ void mom2_mirror_kernel(const double* __restrict__ acc64, float* __re
 
 // ---- host ---------------------------------------------------------------------------------------
 
+// (Re)carves the shared scratch and encodes the TMA maps for the handle's operand kind.  The scratch is
+// sized for fp32 planes (mom2_workspace_bytes), so the 16-bit layout always fits.
+inline int mom2_configure(Mom2Handle* H) {
+  const int eb = H->kind == KIND_F16 ? 2 : 4;
+  H->hp = static_cast<int>(round_up_ll(H->h, KIND_F16 == H->kind ? 64 : GEMM_BLOCK_K));
+  uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(H->workspace) + 1023) & ~static_cast<uintptr_t>(1023));
+  const size_t xb = (static_cast<size_t>(H->slab) * H->hp * eb + 1023) & ~static_cast<size_t>(1023);
+  const size_t ab = (static_cast<size_t>(H->d) * H->slab * eb + 1023) & ~static_cast<size_t>(1023);
+  H->x_hi = reinterpret_cast<float*>(w); w += xb;
+  H->x_lo = reinterpret_cast<float*>(w); w += xb;
+  H->at_hi = reinterpret_cast<float*>(w); w += ab;
+  H->at_lo = reinterpret_cast<float*>(w); w += ab;
+  H->dest = reinterpret_cast<int*>(w); w += static_cast<size_t>(H->slab) * sizeof(int);
+  H->n_valid = reinterpret_cast<int*>(w);
+  int rc;
+  if ((rc = make_tmap_2d(&H->fc1_ops.a_hi, H->w_hi, H->d, H->h, H->hp, 128, eb)) ||
+      (rc = make_tmap_2d(&H->fc1_ops.a_lo, H->w_lo, H->d, H->h, H->hp, 128, eb)) ||
+      (rc = make_tmap_2d(&H->fc1_ops.b_hi, H->x_hi, H->slab, H->h, H->hp, 128, eb)) ||
+      (rc = make_tmap_2d(&H->fc1_ops.b_lo, H->x_lo, H->slab, H->h, H->hp, 128, eb)) ||
+      (rc = make_tmap_2d(&H->syrk_ops.a_hi, H->at_hi, H->d, H->slab, H->slab, 128, eb)) ||
+      (rc = make_tmap_2d(&H->syrk_ops.a_lo, H->at_lo, H->d, H->slab, H->slab, 128, eb)))
+    return rc;
+  H->syrk_ops.b_hi = H->syrk_ops.a_hi;
+  H->syrk_ops.b_lo = H->syrk_ops.a_lo;
+  return EMCID_OK;
+}
+
 inline int mom2_create(Mom2Handle** out, int device, int d, int h, int act, int slab, void* workspace,
                        size_t ws_bytes) {
   EMCID_CHECK(out != nullptr, EMCID_ERR_INVALID, "mom2_create: null out");
@@ -204,9 +267,10 @@ inline int mom2_create(Mom2Handle** out, int device, int d, int h, int act, int 
   int rc = get_device_info(&H->info);
   if (rc) { delete H; return rc; }
   H->device = device; H->d = d; H->h = h; H->act = act; H->slab = slab;
-  H->hp = static_cast<int>(round_up_ll(h, GEMM_BLOCK_K));
+  H->kind = MOM2_DEFAULT_KIND; H->lo_fmt = FMT_BF16; H->workspace = workspace;
+  H->hp = static_cast<int>(round_up_ll(h, 64));
   H->chunk_fc1 = 1; H->chunk_syrk = GEMM_DEFAULT_CHUNK;  // fc1 rounding bias counts twice in mom2
-  const size_t wbytes = static_cast<size_t>(d) * H->hp * sizeof(float);
+  const size_t wbytes = static_cast<size_t>(d) * H->hp * sizeof(float);   // sized for either kind
   const size_t dd = static_cast<size_t>(d) * d;
 #define EMCID_TRY_ALLOC(ptr, bytes)                                                          \
   do {                                                                                       \
@@ -231,33 +295,12 @@ inline int mom2_create(Mom2Handle** out, int device, int d, int h, int act, int 
     set_error(EMCID_ERR_CUDA, "mom2_create: cudaMemset failed");
     goto fail;
   }
-  {
-    // carve the shared scratch
-    uint8_t* w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~static_cast<uintptr_t>(1023));
-    const size_t xb = static_cast<size_t>(slab) * H->hp * sizeof(float);
-    const size_t ab = static_cast<size_t>(d) * slab * sizeof(float);
-    H->x_hi = reinterpret_cast<float*>(w); w += xb;
-    H->x_lo = reinterpret_cast<float*>(w); w += xb;
-    H->at_hi = reinterpret_cast<float*>(w); w += ab;
-    H->at_lo = reinterpret_cast<float*>(w); w += ab;
-    H->dest = reinterpret_cast<int*>(w); w += static_cast<size_t>(slab) * sizeof(int);
-    H->n_valid = reinterpret_cast<int*>(w);
-    // stale-but-finite contents are fine everywhere except NaN/Inf patterns: start from zeros
-    if (cudaMemset(workspace, 0, ws_bytes) != cudaSuccess) {
-      set_error(EMCID_ERR_CUDA, "mom2_create: cudaMemset(workspace) failed");
-      goto fail;
-    }
-    if ((rc = make_tmap_2d(&H->fc1_ops.a_hi, H->w_hi, d, h, H->hp, 128)) ||
-        (rc = make_tmap_2d(&H->fc1_ops.a_lo, H->w_lo, d, h, H->hp, 128)) ||
-        (rc = make_tmap_2d(&H->fc1_ops.b_hi, H->x_hi, slab, h, H->hp, 128)) ||
-        (rc = make_tmap_2d(&H->fc1_ops.b_lo, H->x_lo, slab, h, H->hp, 128)) ||
-        (rc = make_tmap_2d(&H->syrk_ops.a_hi, H->at_hi, d, slab, slab, 128)) ||
-        (rc = make_tmap_2d(&H->syrk_ops.a_lo, H->at_lo, d, slab, slab, 128))) {
-      goto fail_rc;
-    }
-    H->syrk_ops.b_hi = H->syrk_ops.a_hi;
-    H->syrk_ops.b_lo = H->syrk_ops.a_lo;
+  // stale-but-finite contents are fine everywhere except NaN/Inf patterns: start from zeros
+  if (cudaMemset(workspace, 0, ws_bytes) != cudaSuccess) {
+    set_error(EMCID_ERR_CUDA, "mom2_create: cudaMemset(workspace) failed");
+    goto fail;
   }
+  if ((rc = mom2_configure(H))) goto fail_rc;
   *out = H;
   return EMCID_OK;
 fail:
@@ -285,7 +328,9 @@ inline int mom2_destroy(Mom2Handle* H) {
 inline int mom2_set_weights(Mom2Handle* H, const float* W1, long long ldw, const float* b1, cudaStream_t stream) {
   EMCID_CHECK(H && W1, EMCID_ERR_INVALID, "mom2_set_weights: null argument");
   EMCID_CUDA_CHECK(cudaSetDevice(H->device));
-  int rc = launch_split_planes(W1, ldw, H->d, H->h, 1.0f, H->w_hi, H->w_lo, H->hp, stream);
+  int rc = H->kind == KIND_F16
+               ? launch_split_planes16(W1, ldw, H->d, H->h, 1.0f, H->w_hi, H->w_lo, H->hp, H->lo_fmt, stream)
+               : launch_split_planes(W1, ldw, H->d, H->h, 1.0f, H->w_hi, H->w_lo, H->hp, stream);
   if (rc) return rc;
   if (b1) {
     EMCID_CUDA_CHECK(cudaMemcpyAsync(H->bias, b1, H->d * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -294,6 +339,16 @@ inline int mom2_set_weights(Mom2Handle* H, const float* W1, long long ldw, const
   }
   H->has_weights = true;
   return EMCID_OK;
+}
+
+// precision: 0 = 3xTF32, 1 = fp16 hi + bf16 lo, 2 = fp16 hi + fp16 lo.  Must precede set_weights.
+inline int mom2_set_precision(Mom2Handle* H, int precision) {
+  EMCID_CHECK(H && precision >= 0 && precision <= 2, EMCID_ERR_INVALID, "mom2_set_precision: bad argument");
+  EMCID_CHECK(H->slabs_since_fold == 0, EMCID_ERR_INVALID, "mom2_set_precision: call before accumulating");
+  H->kind = precision == 0 ? KIND_TF32 : KIND_F16;
+  H->lo_fmt = precision == 2 ? FMT_F16 : FMT_BF16;
+  H->has_weights = false;
+  return mom2_configure(H);
 }
 
 inline int mom2_fold(Mom2Handle* H, cudaStream_t stream) {
@@ -327,8 +382,13 @@ inline int mom2_accumulate(Mom2Handle* H, const float* X, long long ldx, const u
     H->launches += 4;  // scan, gather, fc1, syrk
     {
       int blocks = (t + 7) / 8;
-      mom2_gather_split_kernel<<<blocks, 256, 0, stream>>>(X + r0 * ldx, ldx, t, H->h, H->hp, H->dest,
-                                                           H->x_hi, H->x_lo);
+      if (H->kind == KIND_F16)
+        mom2_gather_split16_kernel<<<blocks, 256, 0, stream>>>(X + r0 * ldx, ldx, t, H->h, H->hp, H->dest,
+                                                               reinterpret_cast<uint16_t*>(H->x_hi),
+                                                               reinterpret_cast<uint16_t*>(H->x_lo), H->lo_fmt);
+      else
+        mom2_gather_split_kernel<<<blocks, 256, 0, stream>>>(X + r0 * ldx, ldx, t, H->h, H->hp, H->dest,
+                                                             H->x_hi, H->x_lo);
       EMCID_CUDA_CHECK(cudaGetLastError());
     }
     int rc;
@@ -339,14 +399,16 @@ inline int mom2_accumulate(Mom2Handle* H, const float* X, long long ldx, const u
       p.dyn_n = H->n_valid;
       p.chunk_kblocks = H->chunk_fc1;
       p.P_hi = H->at_hi; p.P_lo = H->at_lo; p.ldp = H->slab;
-      p.bias = H->bias; p.act = H->act;
+      p.bias = H->bias; p.act = H->act; p.lo_fmt = H->lo_fmt;
       const int tiles = gemm_num_tiles(H->d, t, 256, 0);
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (H->profile) {
         EMCID_CUDA_CHECK(cudaEventCreate(&e0)); EMCID_CUDA_CHECK(cudaEventCreate(&e1));
         EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
       }
-      rc = launch_gemm3x<256, 2, EPI_FC1>(H->fc1_ops, p, tiles < sms ? tiles : sms, stream);
+      rc = H->kind == KIND_F16
+               ? launch_gemm3x<256, 2, EPI_FC1, KIND_F16>(H->fc1_ops, p, tiles < sms ? tiles : sms, stream)
+               : launch_gemm3x<256, 2, EPI_FC1>(H->fc1_ops, p, tiles < sms ? tiles : sms, stream);
       if (rc) return rc;
       if (H->profile) {
         EMCID_CUDA_CHECK(cudaEventRecord(e1, stream));
@@ -360,13 +422,14 @@ inline int mom2_accumulate(Mom2Handle* H, const float* X, long long ldx, const u
       p.dyn_k = H->n_valid;
       p.lower = 1; p.streamk = 1;
       p.chunk_kblocks = H->chunk_syrk;
-      p.C = H->acc32; p.ldc = H->d;
+      p.C = H->acc32; p.ldc = H->d; p.lo_fmt = H->lo_fmt;
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (H->profile) {
         EMCID_CUDA_CHECK(cudaEventCreate(&e0)); EMCID_CUDA_CHECK(cudaEventCreate(&e1));
         EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
       }
-      rc = launch_gemm3x<256, 2, EPI_RED>(H->syrk_ops, p, sms, stream);
+      rc = H->kind == KIND_F16 ? launch_gemm3x<256, 2, EPI_RED, KIND_F16>(H->syrk_ops, p, sms, stream)
+                               : launch_gemm3x<256, 2, EPI_RED>(H->syrk_ops, p, sms, stream);
       if (rc) return rc;
       if (H->profile) {
         EMCID_CUDA_CHECK(cudaEventRecord(e1, stream));

@@ -8,6 +8,7 @@ what the reference does with ``flatten_masked_batch`` + ``SecondMoment.add``
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -27,8 +28,10 @@ def _shared_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 
 class Mom2Accumulator:
+    PRECISIONS = {"tf32x3": 0, "f16x3": 1, "f16x3_f16": 2}
+
     def __init__(self, device, d: int, h: int, act: str = "quick_gelu", slab_tokens: int = 0,
-                 fc1_chunk: Optional[int] = None, syrk_chunk: Optional[int] = None):
+                 fc1_chunk: Optional[int] = None, syrk_chunk: Optional[int] = None, precision: Optional[str] = None):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("Mom2Accumulator needs a CUDA (sm_100a) device; there is no CPU path")
@@ -42,6 +45,10 @@ class Mom2Accumulator:
         self._h = ctypes.c_void_p()
         _lib.check(lib.emcid_mom2_create(ctypes.byref(self._h), device.index, self.d, self.h, _lib.act_code(act),
                                          int(slab_tokens), _lib.ptr(self._ws), self._ws.numel()))
+        if precision is None:
+            precision = os.environ.get("EMCID_MOM2_PRECISION")
+        if precision is not None:
+            _lib.check(lib.emcid_mom2_set_precision(self._h, self.PRECISIONS[precision]))
         if fc1_chunk or syrk_chunk:
             _lib.check(lib.emcid_mom2_set_chunks(self._h, int(fc1_chunk or 1), int(syrk_chunk or 2)))
         self._keep = []  # tensors that must outlive asynchronous launches

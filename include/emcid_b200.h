@@ -40,7 +40,8 @@ unsigned int emcid_hang_code(void);
  * A [M x K], B [N x K], C [M x N], row-major fp32 on the device.  Replaces the fp32/fp64 `@` /
  * `.mm` products on the path (util/runningstats.py:493, emcid/emcid_main.py:1046,1050).
  * flags: bit0 = compute only tiles touching the lower triangle, bit1 = stream-K (alpha = beta = 1,
- * accumulation by red.global.add), bit2 = 128-wide N tiles. */
+ * accumulation by red.global.add), bit2 = 128-wide N tiles, bit3 = fp16+bf16 planes on kind::f16
+ * instead of 3xTF32, bit4 (with bit3) = fp16 lo planes, bits 8-15 = k-blocks per TMEM chunk. */
 size_t emcid_gemm3x_workspace_bytes(int M, int N, int K);
 int emcid_gemm3x_nt(int M, int N, int K, const float* A, long long lda, const float* B,
                     long long ldb, float* C, long long ldc, float alpha, float beta, int flags,
@@ -62,7 +63,15 @@ typedef struct emcid_mom2 emcid_mom2_t;
 size_t emcid_mom2_workspace_bytes(int d, int h, int slab_tokens);
 int emcid_mom2_create(emcid_mom2_t** out, int device, int d, int h, int act, int slab_tokens,
                       void* workspace, size_t workspace_bytes);
-/* k-blocks (32 tokens / 32 features each) accumulated in TMEM between round-to-nearest folds. */
+/* Operand precision of the two tensor-core products (fc1 and SYRK); call before emcid_mom2_set_weights.
+ *   EMCID_PREC_TF32X3     3xTF32: hi/lo tf32 planes, tcgen05.mma.kind::tf32          (|err| <= 2^-22 |x| per operand)
+ *   EMCID_PREC_F16X3      fp16 hi + bf16 lo planes, tcgen05.mma.kind::f16 (2x rate)  (|err| <= 2^-20 |x|)
+ *   EMCID_PREC_F16X3_F16  fp16 hi + fp16 lo planes                                   (2^-23 |x| or 2^-25 absolute) */
+#define EMCID_PREC_TF32X3 0
+#define EMCID_PREC_F16X3 1
+#define EMCID_PREC_F16X3_F16 2
+int emcid_mom2_set_precision(emcid_mom2_t* h, int precision);
+/* k-blocks (128 bytes of contraction each: 32 tf32 / 64 halves) accumulated in TMEM between round-to-nearest folds. */
 int emcid_mom2_set_chunks(emcid_mom2_t* h, int fc1_kblocks, int syrk_kblocks);
 /* W1 [d x h] row-major (pitch ldw floats) and b1 [d] (may be NULL): fc1.weight / fc1.bias. */
 int emcid_mom2_set_weights(emcid_mom2_t* h, const float* W1, long long ldw, const float* b1, void* stream);
