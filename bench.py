@@ -232,7 +232,7 @@ def run_ours(args):
         return out
 
     def launches():
-        return sum(acc.get_profile()["launches"] for acc in runner.accs.values())
+        return runner.launches()
 
     for i in range(W):
         step(i)
@@ -278,18 +278,24 @@ def run_ours(args):
             prof[k] += p[k]
         acc.profile(False)
     peaks = measured_peaks()
-    tf32_peak = peaks["bf16_sustained"] / 2.0   # dense TF32 = half the bf16 rate; kernel timed inside a long step
+    native = runner._native is not None
+    # the 3xFP16 kernels issue kind::f16 MMAs: the denominator is the measured dense bf16/fp16 GEMM rate
+    # (sustained figure: the kernel is timed inside a long step)
+    tc_peak = peaks["bf16_sustained"]
+    tf32_peak = tc_peak
     syrk_tflops = prof["syrk_rows"] * D * (D + 1) / (prof["syrk_ms"] * 1e-3) / 1e12 if prof["syrk_ms"] else 0.0
     fc1_tflops = prof["fc1_rows"] * 2 * H * D / (prof["fc1_ms"] * 1e-3) / 1e12 if prof["fc1_ms"] else 0.0
     roofline = {
-        "bound": "tensor", "kernel": "gemm3x_kernel<256,2,EPI_RED> (stream-K lower SYRK, 3xTF32)",
+        "bound": "tensor", "kernel": "gemm3x_kernel<256,2,EPI_RED,KIND_F16> (stream-K lower SYRK, 3xFP16 split on tcgen05 kind::f16)",
         "achieved": syrk_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": syrk_tflops / tf32_peak,
-        "peak_source": f"{peaks['source']}: bf16_tflops_sustained / 2 (dense TF32 runs at half the bf16 rate)",
+        "peak_source": f"{peaks['source']}: bf16_tflops_sustained (cuBLAS dense 16-bit GEMM); achieved counts "
+                       "ALGORITHMIC flops d(d+1) per token, the 3-term split issues 3x that",
         "issued_frac": 3.0 * syrk_tflops / tf32_peak,
         "avg_launch_ms": prof["syrk_ms"] / max(prof["syrk_launches"], 1.0),
         "rows_per_launch": prof["syrk_rows"] / max(prof["syrk_launches"], 1.0),
-        "fc1": {"achieved": fc1_tflops, "frac": fc1_tflops / tf32_peak,
-                "avg_launch_ms": prof["fc1_ms"] / max(prof["fc1_launches"], 1.0)},
+        "fc1": ({"achieved": fc1_tflops, "frac": fc1_tflops / tf32_peak,
+                 "avg_launch_ms": prof["fc1_ms"] / max(prof["fc1_launches"], 1.0)} if prof["fc1_ms"] else
+                "part of the native forward (EPI_LINEAR GEMM), not timed separately"),
         "kernel_share_of_step": (prof["syrk_ms"] + prof["fc1_ms"]) / (min(K, 2) * ms_total / K),
         "traffic": ncu_traffic(),
     }
@@ -365,11 +371,13 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32x3 (fp32 accumulate)", "data": "synthetic",
+            "dtype": "f16x3 (3-term fp16 split, fp32 accumulate; fp32-class accuracy)", "data": "synthetic",
             "config": {"workload": workload_name(C), "layers": LAYERS, "captions_per_gpu_per_step": C,
                        "tokens_per_gpu_per_step": tokens_per_step, "block_captions": blk,
                        "l2": "per-step working set (X slabs, activations) >> 126 MB L2; no flush needed",
                        "parallelism": f"caption-sharded x{world}, one NCCL reduce per layer at the end of the pass",
+                       "forward": "native (csrc/clip.cuh, packed tokens, 3xFP16 GEMMs)" if native else
+                                  "HF torch fp32 forward with fused kernels hooked in",
                        "count_check": count0},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solve": solve, "clocks": clocks,
             "gpu_launches": int(n_launch),

@@ -50,6 +50,14 @@ SIGNATURES = {
     "emcid_mom2_profile": (c_int, [c_void_p, c_int]),
     "emcid_mom2_get_profile": (c_int, [c_void_p, ctypes.POINTER(c_double)]),
     "emcid_mom2_destroy": (c_int, [c_void_p]),
+    "emcid_clip_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                  c_longlong, c_int]),
+    "emcid_clip_set_embeddings": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emcid_clip_set_layer": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p), c_void_p]),
+    "emcid_clip_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   ctypes.POINTER(c_int), ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
+    "emcid_clip_launches": (c_longlong, [c_void_p]),
+    "emcid_clip_destroy": (c_int, [c_void_p]),
     "emcid_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "emcid_solve_layers": (
         c_int,
@@ -108,7 +116,7 @@ def ptr(t) -> int:
 
 
 def gemm3x_nt(A, B, C=None, alpha: float = 1.0, beta: float = 0.0, lower: bool = False,
-              streamk: bool = False, n128: bool = False, chunk: int = 0, f16: bool = False, lo_f16: bool = False):
+              streamk: bool = False, n128: bool = False, chunk: int = 0, f16: bool = False):
     """C = alpha * A @ B.T + beta * C on tcgen05 with the 3xTF32 split (fp32 CUDA tensors)."""
     import torch
 
@@ -122,8 +130,7 @@ def gemm3x_nt(A, B, C=None, alpha: float = 1.0, beta: float = 0.0, lower: bool =
     assert C.stride(1) == 1
     ws_bytes = lib().emcid_gemm3x_workspace_bytes(M, N, K)
     ws = torch.empty(ws_bytes, device=A.device, dtype=torch.uint8)
-    flags = ((1 if lower else 0) | (2 if streamk else 0) | (4 if n128 else 0) | (8 if f16 else 0) |
-             (16 if lo_f16 else 0) | ((chunk & 0xFF) << 8))
+    flags = (1 if lower else 0) | (2 if streamk else 0) | (4 if n128 else 0) | (8 if f16 else 0) | ((chunk & 0xFF) << 8)
     with torch.cuda.device(A.device):
         check(lib().emcid_gemm3x_nt(M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0),
                                     alpha, beta, flags, ptr(ws), ws_bytes, current_stream_ptr()))

@@ -1,0 +1,147 @@
+"""Native text-encoder forward for the statistics pass: thin wrapper over the ``emcid_clip_*`` C ABI.
+
+The reference runs ``model(**batch)`` under ``Trace(..., stop=True)`` for every sub-batch
+(emcid/layer_stats.py:210-216); with a HF ``CLIPTextModel`` that forward is the dominant cost of the
+pass on a GPU.  ``NativeClipTextEncoder`` copies the weights of such a model into the library once
+and then runs embeddings -> [LN1, causal attention, LN2, fc1, act, fc2] on the 3xFP16 tcgen05 GEMM over
+packed valid tokens, handing act(fc1) of every edited layer to its ``Mom2Accumulator`` on the device.
+Anything that is not a plain fp32 CLIP text tower keeps using the HF forward with the fused kernels
+spliced in by hooks (``layer_stats.TextEncoderMom2Pass``) — still no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _text_model(model):
+    return getattr(model, "text_model", model)
+
+
+def supports(model) -> bool:
+    """True for an fp32 HF CLIP text tower (CLIPTextModel / CLIPTextModelWithProjection layout)."""
+    try:
+        tm = _text_model(model)
+        emb, layers = tm.embeddings, tm.encoder.layers
+        cfg = model.config
+        if getattr(cfg, "hidden_act", None) not in ("quick_gelu", "gelu"):
+            return False
+        if cfg.hidden_size % cfg.num_attention_heads or cfg.hidden_size > 2048 or cfg.max_position_embeddings > 128:
+            return False
+        if cfg.hidden_size % 4 or cfg.intermediate_size % 4:
+            return False
+        ly = layers[0]
+        for mod in (ly.self_attn.q_proj, ly.self_attn.k_proj, ly.self_attn.v_proj, ly.self_attn.out_proj, ly.mlp.fc1,
+                    ly.mlp.fc2):
+            if not isinstance(mod, torch.nn.Linear) or mod.weight.dtype != torch.float32:
+                return False
+        if not isinstance(ly.layer_norm1, torch.nn.LayerNorm) or not isinstance(ly.layer_norm2, torch.nn.LayerNorm):
+            return False
+        return (isinstance(emb.token_embedding, torch.nn.Embedding) and isinstance(emb.position_embedding, torch.nn.Embedding)
+                and emb.token_embedding.weight.is_cuda)
+    except AttributeError:
+        return False
+
+
+def pack_batch(batch: Dict[str, torch.Tensor], max_positions: int):
+    """Right-padded [B, L] input_ids / position_ids / attention_mask -> packed int32 ids, positions,
+    cu_seqlens (on the tensors' device) plus host-side (n_captions, n_tokens).  Returns None when the mask
+    is not a right-padding mask (the packed causal forward would then differ from the reference)."""
+    ids, mask = batch["input_ids"], batch["attention_mask"]
+    pos = batch.get("position_ids")
+    if ids.dim() != 2 or ids.numel() == 0:
+        return None
+    keep = mask != 0
+    lengths = keep.sum(dim=1)
+    B, L = ids.shape
+    right_padded = keep == (torch.arange(L, device=ids.device)[None, :] < lengths[:, None])
+    info = torch.stack([right_padded.all().to(torch.int64), lengths.sum(), lengths.max()]).cpu()
+    ok, T, longest = bool(info[0]), int(info[1]), int(info[2])
+    if not ok or longest > max_positions:
+        return None
+    cu = torch.zeros(B + 1, dtype=torch.int32, device=ids.device)
+    cu[1:] = torch.cumsum(lengths, 0).to(torch.int32)
+    if pos is None:
+        pos = torch.arange(L, device=ids.device)[None, :].expand(B, L)
+    return ids[keep].to(torch.int32), pos[keep].to(torch.int32), cu, B, T
+
+
+class NativeClipTextEncoder:
+    def __init__(self, model, max_tokens: int, max_captions: int):
+        if not supports(model):
+            raise NotImplementedError("not a plain fp32 HF CLIP text encoder on a CUDA device")
+        tm, cfg = _text_model(model), model.config
+        self.device = tm.embeddings.token_embedding.weight.device
+        self.n_layers = len(tm.encoder.layers)
+        self.hidden, self.inter = cfg.hidden_size, cfg.intermediate_size
+        self.max_positions = tm.embeddings.position_embedding.weight.shape[0]
+        self.max_tokens, self.max_captions = int(max_tokens), int(max_captions)
+        lib = _lib.lib()
+        self._h = ctypes.c_void_p()
+        eps = float(tm.encoder.layers[0].layer_norm1.eps)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.emcid_clip_create(
+                ctypes.byref(self._h), self.device.index, self.n_layers, self.hidden, cfg.num_attention_heads, self.inter,
+                _lib.act_code(cfg.hidden_act), self.max_positions, tm.embeddings.token_embedding.weight.shape[0], eps,
+                self.max_tokens, self.max_captions))
+            stream = _lib.current_stream_ptr()
+            tok = tm.embeddings.token_embedding.weight.detach().contiguous()
+            pos = tm.embeddings.position_embedding.weight.detach().contiguous()
+            _lib.check(lib.emcid_clip_set_embeddings(self._h, _lib.ptr(tok), _lib.ptr(pos), stream))
+            for i, ly in enumerate(tm.encoder.layers):
+                a = ly.self_attn
+                mods = [ly.layer_norm1, a.q_proj, a.k_proj, a.v_proj, a.out_proj, ly.layer_norm2, ly.mlp.fc1, ly.mlp.fc2]
+                tensors = []
+                for m in mods:
+                    tensors.append(m.weight.detach().contiguous())
+                    tensors.append(None if m.bias is None else m.bias.detach().contiguous())
+                arr = (ctypes.c_void_p * 16)(*[_lib.ptr(t) or None for t in tensors])
+                _lib.check(lib.emcid_clip_set_layer(self._h, i, arr, stream))
+            torch.cuda.synchronize(self.device)  # the library copied / split everything: sources may change now
+
+    def _stream(self) -> int:
+        return int(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _run(self, ids, pos, cu, S, T, n_layers, stat_layers, accs, hidden_out):
+        ids = ids.to(self.device, non_blocking=True)
+        pos = pos.to(self.device, non_blocking=True)
+        cu = cu.to(self.device, non_blocking=True)
+        n_stat = len(stat_layers)
+        layers_arr = (ctypes.c_int * max(n_stat, 1))(*stat_layers)
+        accs_arr = (ctypes.c_void_p * max(n_stat, 1))(*[a._h for a in accs])
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().emcid_clip_forward(self._h, _lib.ptr(ids), _lib.ptr(pos), _lib.ptr(cu), S, T, n_layers, n_stat,
+                                                     layers_arr, accs_arr, _lib.ptr(hidden_out), self._stream()))
+        s = torch.cuda.current_stream(self.device)
+        for t in (ids, pos, cu):
+            t.record_stream(s)
+
+    def forward_stats(self, ids, pos, cu, S: int, T: int, stat_layers: Sequence[int], accs) -> None:
+        """mom2 / count of every layer in `stat_layers` (ascending) += statistics of the packed tokens."""
+        order = sorted(range(len(stat_layers)), key=lambda i: stat_layers[i])
+        self._run(ids, pos, cu, S, T, 0, [int(stat_layers[i]) for i in order], [accs[i] for i in order], None)
+
+    def forward_hidden(self, ids, pos, cu, S: int, T: int, n_layers: Optional[int] = None) -> torch.Tensor:
+        """Residual stream [T, hidden] after `n_layers` full layers (== HF hidden_states[n_layers], packed)."""
+        n_layers = self.n_layers if n_layers is None else n_layers
+        out = torch.empty(T, self.hidden, dtype=torch.float32, device=self.device)
+        self._run(ids, pos, cu, S, T, n_layers, [], [], out)
+        return out
+
+    def launches(self) -> int:
+        return int(_lib.lib().emcid_clip_launches(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().emcid_clip_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,510 @@
+// emcid_b200 — native CLIP text-encoder forward for the statistics pass.
+//
+// The reference runs the HF `CLIPTextModel` in fp32 up to the traced layer for every sub-batch
+// (emcid/layer_stats.py:208-219 -> transformers modeling_clip.py: embeddings, 12 x [LN1, causal
+// self-attention, residual, LN2, fc1, act, fc2, residual]); on a GPU that forward is cuBLAS SIMT sgemm
+// and costs 6x what the fused mom2 kernels cost.  Here the same arithmetic runs on the 3xFP16
+// tcgen05 GEMM of gemm3x.cuh (fp32-class accuracy, see common.cuh::split_f16), over PACKED valid
+// tokens only: with right padding and causal attention a valid token never attends a pad token
+// (SURVEY.md §6), so pad rows are dropped before the first layer and `count` is the packed length.
+//
+//   embed            hres[t] = tok_emb[ids[t]] + pos_emb[pos[t]]                       (fp32 residual stream)
+//   per layer        x  = split(LN1(hres))                      warp per token
+//                    qkv = x Wqkv^T + b                          3xFP16 GEMM (q, k, v fused, N = 3h)
+//                    a  = split(softmax(q k^T * dh^-1/2, causal) v)   fp32, one CTA per (caption, head)
+//                    hres += a Wo^T + bo                         GEMM with residual epilogue
+//                    x  = split(LN2(hres))
+//                    f  = split(act(x W1^T + b1))                GEMM; edited layers also emit f^T planes
+//                    [edited layer]  mom2 += f^T f               stream-K lower SYRK per L2-sized token slab
+//                    hres += f W2^T + b2                         (skipped after the deepest edited layer,
+//                                                                 like Trace(stop=True), util/nethook.py:112)
+// Every GEMM operand is K-major 16-bit hi/lo planes; static weights are pre-scaled by an exact power
+// of two (host.cuh::f16_prescale) and the scale is undone by `alpha` in the epilogue.
+#pragma once
+
+#include <vector>
+
+#include "mom2.cuh"
+
+namespace emcid {
+
+struct ClipWeight {
+  uint16_t* hi = nullptr; uint16_t* lo = nullptr;  // [N x Kp] planes
+  float* bias = nullptr;                           // [N]
+  float scale = 1.f;
+  int N = 0, K = 0, Kp = 0;
+  CUtensorMap m_hi, m_lo;
+};
+
+struct ClipLayer {
+  ClipWeight qkv, o, fc1, fc2;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+  bool set = false;
+};
+
+struct ClipHandle {
+  int device, L, h, heads, dh, d, act, max_pos, vocab;
+  float eps;
+  int hp, dp;                  // K extents padded to 64
+  long long cap_tokens, tp;    // token capacity, padded to 256 (pitch of the transposed planes)
+  int cap_seqs;
+  float *tok_emb, *pos_emb;
+  std::vector<ClipLayer>* layers;
+  float* hres;                 // [cap x h]
+  float* qkv;                  // [cap x 3h]
+  uint16_t *x_hi, *x_lo;       // [cap x hp]   LN output
+  uint16_t *a_hi, *a_lo;       // [cap x hp]   attention output
+  uint16_t *f_hi, *f_lo;       // [cap x dp]   act(fc1)
+  uint16_t *ft_hi, *ft_lo;     // [d x tp]     act(fc1)^T (edited layers)
+  unsigned int* scratch;
+  std::vector<void*>* allocs;
+  DeviceInfo info;
+  long long launches;
+  int attn_smem;
+};
+
+// ---- kernels ------------------------------------------------------------------------------------
+
+__global__ void clip_embed_kernel(const int* __restrict__ ids, const int* __restrict__ pos, int T, int h, int vocab,
+                                  int max_pos, const float* __restrict__ tok, const float* __restrict__ pe,
+                                  float* __restrict__ out) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
+    int id = ids[t], p = pos[t];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
+    const float* a = tok + static_cast<long long>(id) * h;
+    const float* b = pe + static_cast<long long>(p) * h;
+    float* o = out + static_cast<long long>(t) * h;
+    for (int c = lane; c < h; c += 32) o[c] = a[c] + b[c];
+  }
+}
+
+// One warp per token: y = (x - mean) * rsqrt(var + eps) * w + b (biased variance, like torch.nn.LayerNorm),
+// written as fp16 hi/lo planes.  NV = ceil(h / 32) values per lane stay in registers between the passes.
+template <int NV>
+__global__ void clip_layernorm_kernel(const float* __restrict__ x, int T, int h, const float* __restrict__ w,
+                                      const float* __restrict__ b, float eps, uint16_t* __restrict__ o_hi,
+                                      uint16_t* __restrict__ o_lo, int ldo) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const float inv_h = 1.0f / static_cast<float>(h);
+  for (int t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
+    const float* src = x + static_cast<long long>(t) * h;
+    float v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < h ? src[c] : 0.f;
+      s += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_h;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      const float dlt = c < h ? v[i] - mean : 0.f;
+      q += dlt * dlt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_h + eps);
+    uint16_t* oh = o_hi + static_cast<long long>(t) * ldo;
+    uint16_t* ol = o_lo + static_cast<long long>(t) * ldo;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < h) {
+        const float y = (v[i] - mean) * rstd * w[c] + b[c];
+        uint16_t hh, ll;
+        split_f16(y, FMT_F16, hh, ll);
+        oh[c] = hh;
+        ol[c] = ll;
+      }
+    }
+  }
+}
+
+// Causal softmax attention of one (caption, head): fp32, K/V of the caption staged in shared memory,
+// one warp per query row.  qkv: [T x 3h] (q | k | v), output planes [T x ldo] at columns head*dh...
+__global__ void __launch_bounds__(128) clip_attention_kernel(const float* __restrict__ qkv, const int* __restrict__ cu,
+                                                             int h, int dh, int lmax, float scale,
+                                                             uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo,
+                                                             int ldo) {
+  extern __shared__ float attn_sm[];
+  const int ldk = dh + 1;
+  float* Ks = attn_sm;                        // [lmax][dh + 1]
+  float* Vs = Ks + lmax * ldk;            // [lmax][dh + 1]
+  float* Qs = Vs + lmax * ldk;            // [4][dh]
+  float* Ps = Qs + 4 * dh;                // [4][lmax]
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int t0 = cu[seq];
+  int Ls = cu[seq + 1] - t0;
+  if (Ls > lmax) Ls = lmax;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long ld = 3ll * h;
+  const float* base = qkv + static_cast<long long>(t0) * ld + head * dh;
+  for (int e = tid; e < Ls * dh; e += blockDim.x) {
+    const int j = e / dh, c = e - j * dh;
+    Ks[j * ldk + c] = base[j * ld + h + c];
+    Vs[j * ldk + c] = base[j * ld + 2 * h + c];
+  }
+  __syncthreads();
+  float* q = Qs + warp * dh;
+  float* pr = Ps + warp * lmax;
+  for (int i = warp; i < Ls; i += 4) {
+    for (int c = lane; c < dh; c += 32) q[c] = base[i * ld + c];
+    __syncwarp();
+    float sc[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      float dot = -INFINITY;
+      if (j <= i) {
+        dot = 0.f;
+        const float* kr = Ks + j * ldk;
+        for (int c = 0; c < dh; ++c) dot = fmaf(q[c], kr[c], dot);
+        dot *= scale;
+      }
+      sc[m] = dot;
+      mx = fmaxf(mx, dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      const float e = j <= i ? expf(sc[m] - mx) : 0.f;
+      sc[m] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      if (j <= i) pr[j] = sc[m] * inv;
+    }
+    __syncwarp();
+    uint16_t* oh = o_hi + static_cast<long long>(t0 + i) * ldo + head * dh;
+    uint16_t* ol = o_lo + static_cast<long long>(t0 + i) * ldo + head * dh;
+    for (int c = lane; c < dh; c += 32) {
+      float acc = 0.f;
+      for (int j = 0; j <= i; ++j) acc = fmaf(pr[j], Vs[j * ldk + c], acc);
+      uint16_t hh, ll;
+      split_f16(acc, FMT_F16, hh, ll);
+      oh[c] = hh;
+      ol[c] = ll;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void clip_add_count_kernel(long long* count, long long n) { *count += n; }
+
+// ---- host ---------------------------------------------------------------------------------------
+
+template <typename T>
+inline int clip_alloc(ClipHandle* H, T** p, size_t elems) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, elems * sizeof(T) + 256);
+  if (e != cudaSuccess)
+    return set_error(EMCID_ERR_CUDA, "clip: cudaMalloc(%zu) failed: %s", elems * sizeof(T), cudaGetErrorString(e));
+  H->allocs->push_back(q);
+  *p = static_cast<T*>(q);
+  return EMCID_OK;
+}
+
+inline int clip_destroy(ClipHandle* H) {
+  if (!H) return EMCID_OK;
+  cudaSetDevice(H->device);
+  cudaDeviceSynchronize();
+  for (void* p : *H->allocs) cudaFree(p);
+  delete H->allocs;
+  delete H->layers;
+  delete H;
+  return EMCID_OK;
+}
+
+inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, int d, int act, int max_pos, int vocab,
+                       float eps, long long cap_tokens, int cap_seqs) {
+  EMCID_CHECK(out, EMCID_ERR_INVALID, "clip_create: null out");
+  EMCID_CHECK(L > 0 && h > 0 && heads > 0 && h % heads == 0 && d > 0 && max_pos > 0 && vocab > 0 && cap_tokens > 0 &&
+                  cap_seqs > 0,
+              EMCID_ERR_INVALID, "clip_create: bad shape");
+  EMCID_CHECK(h % 4 == 0 && d % 4 == 0, EMCID_ERR_INVALID, "clip_create: hidden and intermediate sizes must be multiples of 4");
+  EMCID_CHECK(h <= 2048, EMCID_ERR_UNSUPPORTED, "clip_create: hidden size %d > 2048", h);
+  EMCID_CHECK(max_pos <= 128, EMCID_ERR_UNSUPPORTED, "clip_create: max_position_embeddings %d > 128", max_pos);
+  EMCID_CHECK(act == ACT_QUICK_GELU || act == ACT_GELU_ERF, EMCID_ERR_INVALID, "clip_create: unknown activation %d", act);
+  EMCID_CUDA_CHECK(cudaSetDevice(device));
+  ClipHandle* H = new ClipHandle();
+  memset(H, 0, sizeof(*H));
+  H->allocs = new std::vector<void*>();
+  H->layers = new std::vector<ClipLayer>(L);
+  int rc = get_device_info(&H->info);
+  if (rc) { clip_destroy(H); return rc; }
+  H->device = device; H->L = L; H->h = h; H->heads = heads; H->dh = h / heads; H->d = d; H->act = act;
+  H->max_pos = max_pos; H->vocab = vocab; H->eps = eps;
+  H->hp = static_cast<int>(round_up_ll(h, 64));
+  H->dp = static_cast<int>(round_up_ll(d, 64));
+  H->cap_tokens = cap_tokens; H->cap_seqs = cap_seqs;
+  H->tp = round_up_ll(cap_tokens, 256);
+  const size_t cap = static_cast<size_t>(cap_tokens);
+  if ((rc = clip_alloc(H, &H->tok_emb, static_cast<size_t>(vocab) * h)) ||
+      (rc = clip_alloc(H, &H->pos_emb, static_cast<size_t>(max_pos) * h)) ||
+      (rc = clip_alloc(H, &H->hres, cap * h)) || (rc = clip_alloc(H, &H->qkv, cap * 3 * h)) ||
+      (rc = clip_alloc(H, &H->x_hi, cap * H->hp)) || (rc = clip_alloc(H, &H->x_lo, cap * H->hp)) ||
+      (rc = clip_alloc(H, &H->a_hi, cap * H->hp)) || (rc = clip_alloc(H, &H->a_lo, cap * H->hp)) ||
+      (rc = clip_alloc(H, &H->f_hi, cap * H->dp)) || (rc = clip_alloc(H, &H->f_lo, cap * H->dp)) ||
+      (rc = clip_alloc(H, &H->ft_hi, static_cast<size_t>(d) * H->tp)) ||
+      (rc = clip_alloc(H, &H->ft_lo, static_cast<size_t>(d) * H->tp)) || (rc = clip_alloc(H, &H->scratch, 64))) {
+    clip_destroy(H);
+    return rc;
+  }
+  // pad columns [h, hp) / [d, dp) of the activation planes are never written: they must read as zeros
+  if (cudaMemset(H->x_hi, 0, cap * H->hp * 2) != cudaSuccess || cudaMemset(H->x_lo, 0, cap * H->hp * 2) != cudaSuccess ||
+      cudaMemset(H->a_hi, 0, cap * H->hp * 2) != cudaSuccess || cudaMemset(H->a_lo, 0, cap * H->hp * 2) != cudaSuccess ||
+      cudaMemset(H->f_hi, 0, cap * H->dp * 2) != cudaSuccess || cudaMemset(H->f_lo, 0, cap * H->dp * 2) != cudaSuccess ||
+      cudaMemset(H->ft_hi, 0, static_cast<size_t>(d) * H->tp * 2) != cudaSuccess ||
+      cudaMemset(H->ft_lo, 0, static_cast<size_t>(d) * H->tp * 2) != cudaSuccess) {
+    clip_destroy(H);
+    return set_error(EMCID_ERR_CUDA, "clip_create: cudaMemset failed");
+  }
+  H->attn_smem = (2 * max_pos * (H->dh + 1) + 4 * H->dh + 4 * max_pos) * static_cast<int>(sizeof(float));
+  if (H->attn_smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(clip_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
+    if (e != cudaSuccess) {
+      clip_destroy(H);
+      return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", H->attn_smem, cudaGetErrorString(e));
+    }
+  }
+  *out = H;
+  return EMCID_OK;
+}
+
+inline int clip_set_embeddings(ClipHandle* H, const float* tok, const float* pos, cudaStream_t stream) {
+  EMCID_CHECK(H && tok && pos, EMCID_ERR_INVALID, "clip_set_embeddings: null argument");
+  EMCID_CUDA_CHECK(cudaSetDevice(H->device));
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(H->tok_emb, tok, static_cast<size_t>(H->vocab) * H->h * 4, cudaMemcpyDeviceToDevice, stream));
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(H->pos_emb, pos, static_cast<size_t>(H->max_pos) * H->h * 4, cudaMemcpyDeviceToDevice, stream));
+  return EMCID_OK;
+}
+
+// Splits `parts` stacked row blocks (each [rows_each x K], row pitch K) into one [parts*rows_each x Kp] plane pair.
+inline int clip_prepare_weight(ClipHandle* H, ClipWeight* W, int parts, const float* const* w, const float* const* b,
+                               int rows_each, int K, cudaStream_t stream) {
+  const int N = parts * rows_each;
+  const int Kp = static_cast<int>(round_up_ll(K, 64));
+  int rc;
+  if (!W->hi) {
+    if ((rc = clip_alloc(H, &W->hi, static_cast<size_t>(N) * Kp)) || (rc = clip_alloc(H, &W->lo, static_cast<size_t>(N) * Kp)) ||
+        (rc = clip_alloc(H, &W->bias, static_cast<size_t>(N))))
+      return rc;
+  }
+  W->N = N; W->K = K; W->Kp = Kp;
+  // one scale for the stacked tensor: max over the parts
+  float mx_scale = 0.f;
+  for (int i = 0; i < parts; ++i) {
+    float s;
+    if ((rc = f16_prescale(w[i], K, rows_each, K, H->scratch, &s, stream))) return rc;
+    if (i == 0 || s < mx_scale) mx_scale = s;   // the smallest scale belongs to the largest |w|
+  }
+  W->scale = mx_scale;
+  for (int i = 0; i < parts; ++i) {
+    const size_t off = static_cast<size_t>(i) * rows_each * Kp;
+    if ((rc = launch_split_planes16(w[i], K, rows_each, K, W->scale, W->hi + off, W->lo + off, Kp, FMT_F16, stream))) return rc;
+    if (b && b[i]) {
+      EMCID_CUDA_CHECK(cudaMemcpyAsync(W->bias + static_cast<size_t>(i) * rows_each, b[i], rows_each * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, stream));
+    } else {
+      EMCID_CUDA_CHECK(cudaMemsetAsync(W->bias + static_cast<size_t>(i) * rows_each, 0, rows_each * sizeof(float), stream));
+    }
+  }
+  if ((rc = make_tmap_2d(&W->m_hi, W->hi, N, K, Kp, 128, 2)) || (rc = make_tmap_2d(&W->m_lo, W->lo, N, K, Kp, 128, 2))) return rc;
+  return EMCID_OK;
+}
+
+// tensors: ln1.w ln1.b q.w q.b k.w k.b v.w v.b o.w o.b ln2.w ln2.b fc1.w fc1.b fc2.w fc2.b (fp32, device, contiguous)
+inline int clip_set_layer(ClipHandle* H, int layer, const float* const* t, cudaStream_t stream) {
+  EMCID_CHECK(H && t && layer >= 0 && layer < H->L, EMCID_ERR_INVALID, "clip_set_layer: bad argument");
+  for (int i = 0; i < 16; ++i)
+    EMCID_CHECK(t[i] != nullptr || i == 3 || i == 5 || i == 7 || i == 9 || i == 13 || i == 15, EMCID_ERR_INVALID,
+                "clip_set_layer: tensor %d is null", i);
+  EMCID_CUDA_CHECK(cudaSetDevice(H->device));
+  ClipLayer& Ly = (*H->layers)[layer];
+  int rc;
+  if (!Ly.ln1_w) {
+    if ((rc = clip_alloc(H, &Ly.ln1_w, static_cast<size_t>(H->h))) || (rc = clip_alloc(H, &Ly.ln1_b, static_cast<size_t>(H->h))) ||
+        (rc = clip_alloc(H, &Ly.ln2_w, static_cast<size_t>(H->h))) || (rc = clip_alloc(H, &Ly.ln2_b, static_cast<size_t>(H->h))))
+      return rc;
+  }
+  const size_t hb = static_cast<size_t>(H->h) * sizeof(float);
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln1_w, t[0], hb, cudaMemcpyDeviceToDevice, stream));
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln1_b, t[1], hb, cudaMemcpyDeviceToDevice, stream));
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln2_w, t[10], hb, cudaMemcpyDeviceToDevice, stream));
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln2_b, t[11], hb, cudaMemcpyDeviceToDevice, stream));
+  const float* wq[3] = {t[2], t[4], t[6]};
+  const float* bq[3] = {t[3], t[5], t[7]};
+  if ((rc = clip_prepare_weight(H, &Ly.qkv, 3, wq, bq, H->h, H->h, stream))) return rc;
+  if ((rc = clip_prepare_weight(H, &Ly.o, 1, &t[8], &t[9], H->h, H->h, stream))) return rc;
+  if ((rc = clip_prepare_weight(H, &Ly.fc1, 1, &t[12], &t[13], H->d, H->h, stream))) return rc;
+  if ((rc = clip_prepare_weight(H, &Ly.fc2, 1, &t[14], &t[15], H->h, H->d, stream))) return rc;
+  Ly.set = true;
+  return EMCID_OK;
+}
+
+struct ClipActMaps {
+  GemmOperands x, a, f;   // a_hi / a_lo of each hold the activation planes (rows = tokens of this call)
+};
+
+// out[T x N] = act(X[T x K] W^T / scale + bias) (+ residual), optionally as fp32 / planes / transposed planes.
+inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap& x_lo, const ClipWeight& W, int T,
+                       int act, const float* Cin, float* C, long long ldc, uint16_t* P_hi, uint16_t* P_lo, long long ldp,
+                       uint16_t* Pt_hi, uint16_t* Pt_lo, long long ldpt, cudaStream_t stream) {
+  GemmOperands ops;
+  ops.a_hi = x_hi; ops.a_lo = x_lo; ops.b_hi = W.m_hi; ops.b_lo = W.m_lo;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = T; p.N = W.N; p.K = W.K;
+  p.chunk_kblocks = 2;
+  p.alpha = 1.0f / W.scale; p.beta = Cin ? 1.0f : 0.0f;
+  p.bias_col = W.bias; p.act = act; p.lo_fmt = FMT_F16;
+  p.Cin = Cin; p.ldcin = ldc;
+  p.C = C; p.ldc = ldc;
+  p.P_hi = reinterpret_cast<float*>(P_hi); p.P_lo = reinterpret_cast<float*>(P_lo); p.ldp = ldp;
+  p.Pt_hi = reinterpret_cast<float*>(Pt_hi); p.Pt_lo = reinterpret_cast<float*>(Pt_lo); p.ldpt = ldpt;
+  const int tiles = gemm_num_tiles(T, W.N, 256, 0);
+  const int grid = tiles < H->info.sm_count ? tiles : H->info.sm_count;
+  H->launches += 1;
+  // the epilogue variant is a compile-time option (see EF_* in gemm3x.cuh): only the combinations the forward uses
+  const int ef = act | (C ? EF_C : 0) | (Cin ? EF_CIN : 0) | (P_hi ? EF_P : 0) | (Pt_hi ? EF_PT : 0);
+#define EMCID_LIN_CASE(F) \
+  if (ef == (F)) return launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream);
+  EMCID_LIN_CASE(ACT_NONE | EF_C)                       // q/k/v projection
+  EMCID_LIN_CASE(ACT_NONE | EF_C | EF_CIN)              // out projection / fc2 with residual
+  EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P)                 // fc1
+  EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P | EF_PT)         // fc1 of an edited layer
+  EMCID_LIN_CASE(ACT_QUICK_GELU | EF_PT)                // fc1 of the deepest edited layer
+  EMCID_LIN_CASE(ACT_GELU_ERF | EF_P)
+  EMCID_LIN_CASE(ACT_GELU_ERF | EF_P | EF_PT)
+  EMCID_LIN_CASE(ACT_GELU_ERF | EF_PT)
+#undef EMCID_LIN_CASE
+  return set_error(EMCID_ERR_UNSUPPORTED, "clip_linear: epilogue variant %d is not instantiated", ef);
+}
+
+inline int clip_layernorm(ClipHandle* H, const float* x, int T, const float* w, const float* b, uint16_t* o_hi,
+                          uint16_t* o_lo, cudaStream_t stream) {
+  const int nv = (H->h + 31) / 32;
+  int blocks = (T + 7) / 8;
+  if (blocks > H->info.sm_count * 16) blocks = H->info.sm_count * 16;
+  H->launches += 1;
+#define EMCID_LN_CASE(NV)                                                                                         \
+  if (nv <= NV) {                                                                                                 \
+    clip_layernorm_kernel<NV><<<blocks, 256, 0, stream>>>(x, T, H->h, w, b, H->eps, o_hi, o_lo, H->hp);          \
+    EMCID_CUDA_CHECK(cudaGetLastError());                                                                         \
+    return EMCID_OK;                                                                                              \
+  }
+  EMCID_LN_CASE(2) EMCID_LN_CASE(4) EMCID_LN_CASE(8) EMCID_LN_CASE(16) EMCID_LN_CASE(24) EMCID_LN_CASE(32)
+  EMCID_LN_CASE(40) EMCID_LN_CASE(64)
+#undef EMCID_LN_CASE
+  return set_error(EMCID_ERR_UNSUPPORTED, "clip_layernorm: hidden size %d too large", H->h);
+}
+
+// Runs layers [0, n_layers) (full layers) — or, when stats are requested, up to fc1 of the deepest edited
+// layer — over `T` packed tokens of `S` captions.  stat_layers / accs: edited layers (ascending) and their
+// accumulators.  hidden_out (optional, [T x h] fp32): the residual stream after the last executed FULL layer.
+inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int* cu_seqlens, int S, int T,
+                        int n_layers, int n_stat, const int* stat_layers, Mom2Handle* const* accs, float* hidden_out,
+                        cudaStream_t stream) {
+  EMCID_CHECK(H && ids && pos && cu_seqlens, EMCID_ERR_INVALID, "clip_forward: null argument");
+  EMCID_CHECK(T >= 0 && T <= H->cap_tokens && S >= 0 && S <= H->cap_seqs, EMCID_ERR_INVALID,
+              "clip_forward: %d tokens / %d captions exceed the handle capacity (%lld / %d)", T, S, H->cap_tokens, H->cap_seqs);
+  EMCID_CHECK(n_layers >= 0 && n_layers <= H->L, EMCID_ERR_INVALID, "clip_forward: bad layer count");
+  int last_stat = -1;
+  for (int i = 0; i < n_stat; ++i) {
+    EMCID_CHECK(stat_layers[i] >= 0 && stat_layers[i] < H->L && accs[i] && (i == 0 || stat_layers[i] > stat_layers[i - 1]),
+                EMCID_ERR_INVALID, "clip_forward: edited layers must be ascending, in range and have accumulators");
+    EMCID_CHECK(accs[i]->d == H->d && accs[i]->device == H->device, EMCID_ERR_INVALID,
+                "clip_forward: accumulator %d does not match the encoder (d=%d vs %d)", i, accs[i]->d, H->d);
+    last_stat = stat_layers[i];
+  }
+  const int run_layers = n_stat > 0 ? last_stat + 1 : n_layers;
+  for (int l = 0; l < run_layers; ++l)
+    EMCID_CHECK((*H->layers)[l].set, EMCID_ERR_INVALID, "clip_forward: weights of layer %d were never set", l);
+  if (T == 0) return EMCID_OK;
+  EMCID_CUDA_CHECK(cudaSetDevice(H->device));
+  const int sms = H->info.sm_count;
+  int rc;
+  // per-call TMA maps over exactly T rows: out-of-range rows of the last tile read as zeros
+  CUtensorMap mx_hi, mx_lo, ma_hi, ma_lo, mf_hi, mf_lo;
+  GemmOperands ft;
+  if ((rc = make_tmap_2d(&mx_hi, H->x_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&mx_lo, H->x_lo, T, H->h, H->hp, 128, 2)) ||
+      (rc = make_tmap_2d(&ma_hi, H->a_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&ma_lo, H->a_lo, T, H->h, H->hp, 128, 2)) ||
+      (rc = make_tmap_2d(&mf_hi, H->f_hi, T, H->d, H->dp, 128, 2)) || (rc = make_tmap_2d(&mf_lo, H->f_lo, T, H->d, H->dp, 128, 2)) ||
+      (rc = make_tmap_2d(&ft.a_hi, H->ft_hi, H->d, T, H->tp, 128, 2)) || (rc = make_tmap_2d(&ft.a_lo, H->ft_lo, H->d, T, H->tp, 128, 2)))
+    return rc;
+  ft.b_hi = ft.a_hi; ft.b_lo = ft.a_lo;
+
+  {
+    int blocks = (T + 7) / 8;
+    if (blocks > sms * 16) blocks = sms * 16;
+    clip_embed_kernel<<<blocks, 256, 0, stream>>>(ids, pos, T, H->h, H->vocab, H->max_pos, H->tok_emb, H->pos_emb, H->hres);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    H->launches += 1;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(H->dh));
+  int si = 0;
+  for (int l = 0; l < run_layers; ++l) {
+    const ClipLayer& Ly = (*H->layers)[l];
+    if ((rc = clip_layernorm(H, H->hres, T, Ly.ln1_w, Ly.ln1_b, H->x_hi, H->x_lo, stream))) return rc;
+    if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, nullptr,
+                          nullptr, 0, stream)))
+      return rc;
+    clip_attention_kernel<<<dim3(H->heads, S), 128, H->attn_smem, stream>>>(H->qkv, cu_seqlens, H->h, H->dh, H->max_pos,
+                                                                            scale, H->a_hi, H->a_lo, H->hp);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    H->launches += 1;
+    if ((rc = clip_linear(H, ma_hi, ma_lo, Ly.o, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                          stream)))
+      return rc;
+    if ((rc = clip_layernorm(H, H->hres, T, Ly.ln2_w, Ly.ln2_b, H->x_hi, H->x_lo, stream))) return rc;
+    const bool is_stat = si < n_stat && stat_layers[si] == l;
+    const bool is_last = n_stat > 0 && l == last_stat;
+    // the deepest edited layer needs only f^T (no fc2 follows); other edited layers need both orientations
+    if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.fc1, T, H->act, nullptr, nullptr, 0, is_last ? nullptr : H->f_hi,
+                          is_last ? nullptr : H->f_lo, H->dp, is_stat ? H->ft_hi : nullptr, is_stat ? H->ft_lo : nullptr,
+                          H->tp, stream)))
+      return rc;
+    if (is_stat) {
+      Mom2Handle* A = accs[si++];
+      const int slab = A->slab;
+      const long long nslabs = (T + slab - 1) / slab;
+      long long per = round_up_ll((T + nslabs - 1) / nslabs, 64);
+      if (per > slab) per = slab;
+      for (long long c0 = 0; c0 < T; c0 += per) {
+        const int t = static_cast<int>(T - c0 < per ? T - c0 : per);
+        if ((rc = mom2_syrk_slab(A, ft, KIND_F16, static_cast<int>(c0), t, nullptr, stream))) return rc;
+        if (++A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
+      }
+      clip_add_count_kernel<<<1, 1, 0, stream>>>(A->count, static_cast<long long>(T));
+      EMCID_CUDA_CHECK(cudaGetLastError());
+      A->launches += 1;
+    }
+    if (is_last) break;
+    if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                          stream)))
+      return rc;
+  }
+  if (hidden_out) {
+    EMCID_CUDA_CHECK(cudaMemcpyAsync(hidden_out, H->hres, static_cast<size_t>(T) * H->h * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, stream));
+  }
+  return EMCID_OK;
+}
+
+}  // namespace emcid

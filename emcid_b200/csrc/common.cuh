@@ -57,11 +57,13 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = to_tf32_rna(x - hi);
 }
 
-// 3x16-bit operand split for tcgen05.mma.kind::f16 (twice the tf32 issue rate, half the bytes):
+// 3xFP16 operand split for tcgen05.mma.kind::f16 (twice the tf32 issue rate, half the bytes):
 //   hi = fp16(x)  (11 significant bits, saturated to the fp16 range so it can never become inf)
-//   lo = x - hi   (exact in fp32), stored as bf16 (8 bits, fp32 exponent range: never underflows)
-//                 or as fp16 (11 bits, but subnormal below 6.1e-5: absolute error <= 2^-25)
-// |x - (hi + lo)| <= 2^-20 |x| with a bf16 lo, 2^-23 |x| (or 2^-25 absolute) with an fp16 lo.
+//   lo = fp16(x - hi)   (x - hi is exact in fp32; 11 more bits, subnormal below 6.1e-5)
+// |x - (hi + lo)| <= max(2^-23 |x|, 2^-25): the same 22 bits as the tf32 split for |x| in [2^-3, 65504],
+// an absolute 3e-8 below that.  Static operands (weights) are pre-scaled by an exact power of two so they
+// sit in the full-precision range.  Measured on B200: an MMA whose A and B formats differ (fp16 x bf16)
+// raises an illegal-instruction trap, so a bf16 lo plane next to an fp16 hi plane is not an option.
 constexpr int FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2;  // UMMA instruction-descriptor operand formats
 
 __device__ __forceinline__ void split_f16(float x, int lo_fmt, uint16_t& hi, uint16_t& lo) {

@@ -8,6 +8,7 @@
 #include "gemm_api.cuh"
 #include "mom2.cuh"
 #include "solve.cuh"
+#include "clip.cuh"
 
 using namespace emcid;
 
@@ -44,7 +45,7 @@ int emcid_gemm3x_nt(int M, int N, int K, const float* A, long long lda, const fl
 // mom2 statistics pass
 // ---------------------------------------------------------------------------------------------
 size_t emcid_mom2_workspace_bytes(int d, int h, int slab_tokens) {
-  if (slab_tokens <= 0) slab_tokens = MOM2_DEFAULT_SLAB;
+  if (slab_tokens <= 0) slab_tokens = mom2_default_slab(d);
   return mom2_workspace_bytes(d, h, slab_tokens);
 }
 
@@ -94,6 +95,35 @@ int emcid_mom2_profile(emcid_mom2_t* h, int enable) {
 int emcid_mom2_get_profile(emcid_mom2_t* h, double* out8) { return mom2_get_profile(reinterpret_cast<Mom2Handle*>(h), out8); }
 
 int emcid_mom2_destroy(emcid_mom2_t* h) { return mom2_destroy(reinterpret_cast<Mom2Handle*>(h)); }
+
+// ---------------------------------------------------------------------------------------------
+// native text-encoder forward feeding the statistics pass
+// ---------------------------------------------------------------------------------------------
+int emcid_clip_create(emcid_clip_t** out, int device, int n_layers, int hidden, int heads, int intermediate, int act,
+                      int max_positions, int vocab, float ln_eps, long long max_tokens, int max_captions) {
+  return clip_create(reinterpret_cast<ClipHandle**>(out), device, n_layers, hidden, heads, intermediate, act,
+                     max_positions, vocab, ln_eps, max_tokens, max_captions);
+}
+
+int emcid_clip_set_embeddings(emcid_clip_t* h, const float* token_embedding, const float* position_embedding, void* stream) {
+  return clip_set_embeddings(reinterpret_cast<ClipHandle*>(h), token_embedding, position_embedding,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int emcid_clip_set_layer(emcid_clip_t* h, int layer, const float* const* tensors16, void* stream) {
+  return clip_set_layer(reinterpret_cast<ClipHandle*>(h), layer, tensors16, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
+                       int n_captions, int n_tokens, int n_layers, int n_stat, const int* stat_layers,
+                       emcid_mom2_t* const* accs, float* hidden_out, void* stream) {
+  return clip_forward(reinterpret_cast<ClipHandle*>(h), ids, positions, cu_seqlens, n_captions, n_tokens, n_layers, n_stat,
+                      stat_layers, reinterpret_cast<Mom2Handle* const*>(accs), hidden_out, static_cast<cudaStream_t>(stream));
+}
+
+long long emcid_clip_launches(emcid_clip_t* h) { return h ? reinterpret_cast<ClipHandle*>(h)->launches : 0; }
+
+int emcid_clip_destroy(emcid_clip_t* h) { return clip_destroy(reinterpret_cast<ClipHandle*>(h)); }
 
 // ---------------------------------------------------------------------------------------------
 // closed-form update

@@ -53,6 +53,7 @@ enum EpiMode : int {
   EPI_GENERIC = 0,  // C = alpha*acc + beta*Cin ; optional planes / transposed planes of the result
   EPI_RED = 1,      // C += acc via red.global.add (stream-K safe)
   EPI_FC1 = 2,      // planes = split(mask(act(acc + bias[row])))  (fc1 -> A^T slab)
+  EPI_LINEAR = 3,   // v = act(alpha*acc + bias_col[col]) + beta*Cin ; C / planes / transposed planes of v
 };
 
 enum ActMode : int { ACT_QUICK_GELU = 0, ACT_GELU_ERF = 1, ACT_NONE = 2 };
@@ -81,6 +82,7 @@ struct GemmParams {
   float* Pt_lo;
   long long ldpt, pt_batch;
   const float* bias;           // [M], EPI_FC1
+  const float* bias_col;       // [N], EPI_LINEAR (16-byte aligned)
   int act;
   int lo_fmt;                  // KIND_F16: format of the lo planes (FMT_BF16 default, FMT_F16)
 };
@@ -173,6 +175,26 @@ struct Sched {
   }
 };
 
+// Compile-time epilogue options (template parameter EFLAGS of gemm3x_kernel; EPI_LINEAR / EPI_FC1 only).
+// The epilogue is fully unrolled over the 128 accumulator columns a thread owns, so every option that is
+// not compiled out costs 32 copies of its code: with run-time options the kernel grew to 260 KB of SASS and
+// stalled on instruction fetch (measured: 48% of warp samples "no instruction", 12% tensor-pipe active).
+constexpr int EF_ACT_MASK = 3;   // bits 0-1: ActMode
+constexpr int EF_C = 4;          // store the fp32 result
+constexpr int EF_CIN = 8;        // add the fp32 residual
+constexpr int EF_P = 16;         // store split planes of the result
+constexpr int EF_PT = 32;        // store split planes of the transposed result
+constexpr int EF_DEFAULT = ACT_NONE;
+
+// Activation with the option fixed at compile time.  quick_gelu uses the MUFU fast paths (ex2.approx / rcp):
+// relative error ~2e-7, unbiased, an order of magnitude below the 3-term split's own rounding.
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v) {
+  if (ACT == ACT_QUICK_GELU) return __fdividef(v, 1.0f + __expf(-1.702f * v));
+  if (ACT == ACT_GELU_ERF) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_QUICK_GELU) {
     // HF QuickGELUActivation: x * sigmoid(1.702 x)   (transformers/activations.py)
@@ -225,7 +247,7 @@ __device__ __forceinline__ void store_plane1(float* hi_base, float* lo_base, lon
   }
 }
 
-template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32>
+template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32, int EFLAGS = EF_DEFAULT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -431,6 +453,39 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
               }
             }
           }
+        } else if (EPI == EPI_LINEAR) {
+          // a linear layer of the text encoder: row = token, col = output feature
+          constexpr int ACT = EFLAGS & EF_ACT_MASK;
+          const float* cin = (EFLAGS & EF_CIN) ? p.Cin + batch * p.cin_batch + static_cast<long long>(row) * p.ldcin + col0 : nullptr;
+          float* dst = (EFLAGS & EF_C) ? p.C + batch * p.c_batch + static_cast<long long>(row) * p.ldc + col0 : nullptr;
+          const long long pidx = batch * p.p_batch + static_cast<long long>(row) * p.ldp + col0;
+          const long long tidx = batch * p.pt_batch + static_cast<long long>(col0) * p.ldpt + row;
+          const float* bias = p.bias_col + col0;
+          const float alpha = p.alpha;
+#pragma unroll
+          for (int j = 0; j < COLS / 4; ++j) {
+            if (col0 + 4 * j < N) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + 4 * j);
+              float4 o;
+              o.x = act_ct<ACT>(fmaf(alpha, sum[4 * j], b.x));
+              o.y = act_ct<ACT>(fmaf(alpha, sum[4 * j + 1], b.y));
+              o.z = act_ct<ACT>(fmaf(alpha, sum[4 * j + 2], b.z));
+              o.w = act_ct<ACT>(fmaf(alpha, sum[4 * j + 3], b.w));
+              if (EFLAGS & EF_CIN) {
+                const float4 old = *reinterpret_cast<const float4*>(cin + 4 * j);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              if (EFLAGS & EF_C) *reinterpret_cast<float4*>(dst + 4 * j) = o;
+              if (EFLAGS & EF_P) store_planes4<KIND>(p.P_hi, p.P_lo, pidx + 4 * j, o, p.lo_fmt);
+              if (EFLAGS & EF_PT) {
+                const long long t = tidx + static_cast<long long>(4 * j) * p.ldpt;
+                store_plane1<KIND>(p.Pt_hi, p.Pt_lo, t, o.x, p.lo_fmt);
+                store_plane1<KIND>(p.Pt_hi, p.Pt_lo, t + p.ldpt, o.y, p.lo_fmt);
+                store_plane1<KIND>(p.Pt_hi, p.Pt_lo, t + 2 * p.ldpt, o.z, p.lo_fmt);
+                store_plane1<KIND>(p.Pt_hi, p.Pt_lo, t + 3 * p.ldpt, o.w, p.lo_fmt);
+              }
+            }
+          }
         } else if (EPI == EPI_FC1) {
           // acc[row = feature i][col = token t]; tokens >= N (dynamic valid count) are padding
           // rows of the compacted X slab and must contribute exactly zero to mom2.
@@ -441,10 +496,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             const int col = col0 + 4 * j;
             if (col < p.ldp) {
               float4 a;
-              a.x = (col + 0 < N) ? apply_act(sum[4 * j + 0] + bias, p.act) : 0.f;
-              a.y = (col + 1 < N) ? apply_act(sum[4 * j + 1] + bias, p.act) : 0.f;
-              a.z = (col + 2 < N) ? apply_act(sum[4 * j + 2] + bias, p.act) : 0.f;
-              a.w = (col + 3 < N) ? apply_act(sum[4 * j + 3] + bias, p.act) : 0.f;
+              constexpr int ACT = EFLAGS & EF_ACT_MASK;
+              a.x = (col + 0 < N) ? act_ct<ACT>(fmaf(p.alpha, sum[4 * j + 0], bias)) : 0.f;
+              a.y = (col + 1 < N) ? act_ct<ACT>(fmaf(p.alpha, sum[4 * j + 1], bias)) : 0.f;
+              a.z = (col + 2 < N) ? act_ct<ACT>(fmaf(p.alpha, sum[4 * j + 2], bias)) : 0.f;
+              a.w = (col + 3 < N) ? act_ct<ACT>(fmaf(p.alpha, sum[4 * j + 3], bias)) : 0.f;
               store_planes4<KIND>(p.P_hi, p.P_lo, pidx + 4 * j, a, p.lo_fmt);
             }
           }

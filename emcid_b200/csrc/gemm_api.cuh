@@ -17,7 +17,7 @@ inline size_t gemm3x_workspace_bytes(int M, int N, int K, bool same_ab) {
 
 // C = alpha * A B^T + beta * C  (fp32 in/out, 3-term split on tcgen05).  flags: bit0 = lower tiles only,
 // bit1 = stream-K with red.add epilogue (requires beta == 1, alpha == 1), bit2 = BLOCK_N 128,
-// bit3 = 16-bit planes (kind::f16; hi fp16 + lo bf16), bit4 = with bit3: lo planes in fp16,
+// bit3 = 3xFP16: 16-bit planes (fp16 hi + fp16 lo) on kind::f16,
 // bits 8-15 = k-blocks per TMEM chunk (0 = default).
 inline int gemm3x_nt(int M, int N, int K, const float* A, long long lda, const float* B,
                      long long ldb, float* C, long long ldc, float alpha, float beta, int flags,
@@ -33,7 +33,7 @@ inline int gemm3x_nt(int M, int N, int K, const float* A, long long lda, const f
               "gemm3x_nt: workspace too small (%zu < %zu)", ws_bytes,
               gemm3x_workspace_bytes(M, N, K, same_ab));
   const bool f16 = (flags >> 3) & 1;
-  const int lo_fmt = ((flags >> 4) & 1) ? FMT_F16 : FMT_BF16;
+  const int lo_fmt = FMT_F16;  // (a bf16 lo plane next to an fp16 hi plane traps: kind::f16 wants A and B formats equal per MMA... measured on B200)
   const int eb = f16 ? 2 : 4;
   const long long kp = round_up_ll(K, f16 ? 64 : GEMM_BLOCK_K);
   // plane pointers are kept as float* (the kernel reinterprets them for 16-bit planes); the workspace is

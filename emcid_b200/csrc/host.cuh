@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -128,11 +129,11 @@ struct GemmOperands {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32>
+template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32, int EFLAGS = EF_DEFAULT>
 inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid, cudaStream_t stream,
                          int batches = 1) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
-  auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI, KIND>;
+  auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI, KIND, EFLAGS>;
   static thread_local bool configured[16] = {false};
   int dev = 0;
   EMCID_CUDA_CHECK(cudaGetDevice(&dev));
@@ -177,6 +178,44 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long ld,
     hi[i] = h;
     lo[i] = l;
   }
+}
+
+// max |src| over a pitched matrix (bit pattern of a non-negative float orders like an unsigned int).
+__global__ void absmax_kernel(const float* __restrict__ src, long long ld, int rows, int cols, unsigned int* out) {
+  float m = 0.f;
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    m = fmaxf(m, fabsf(src[r * ld + (i - r * cols)]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && isfinite(m)) atomicMax(out, __float_as_uint(m));
+}
+
+// Exact power-of-two pre-scale for a static fp16-split operand: max |w| * scale lands in [2^10, 2^11), so every
+// element down to 2^-14 of the largest keeps a normal fp16 lo part (full 22-bit split).  Synchronises the stream.
+inline int f16_prescale(const float* src, long long ld, int rows, int cols, unsigned int* scratch_dev, float* scale,
+                        cudaStream_t stream) {
+  EMCID_CUDA_CHECK(cudaMemsetAsync(scratch_dev, 0, sizeof(unsigned int), stream));
+  absmax_kernel<<<148 * 4, 256, 0, stream>>>(src, ld, rows, cols, scratch_dev);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  unsigned int bits = 0;
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(&bits, scratch_dev, sizeof(bits), cudaMemcpyDeviceToHost, stream));
+  EMCID_CUDA_CHECK(cudaStreamSynchronize(stream));
+  float mx;
+  memcpy(&mx, &bits, sizeof(mx));
+  *scale = 1.0f;
+  if (mx > 0.f) {
+    int e = 0;
+    frexpf(mx, &e);           // mx = f * 2^e, f in [0.5, 1)  ->  floor(log2 mx) = e - 1
+    int k = 10 - (e - 1);
+    if (k > 100) k = 100;
+    if (k < -100) k = -100;
+    *scale = ldexpf(1.0f, k);
+  }
+  return EMCID_OK;
 }
 
 // 16-bit planes (KIND_F16): hi = fp16, lo = bf16 / fp16 of scale * src.

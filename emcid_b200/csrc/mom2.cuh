@@ -23,12 +23,20 @@
 namespace emcid {
 
 constexpr int MOM2_MAX_SLAB = 4096;
-constexpr int MOM2_DEFAULT_SLAB = 1536;
+constexpr int MOM2_DEFAULT_SLAB = 4096;
+// Default tokens per fc1/SYRK launch pair: the A^T planes of one slab (d x slab x 4 B) should stay L2 resident.
+inline int mom2_default_slab(int d) {
+  long long s = (48ll << 20) / (4ll * d) / 256 * 256;
+  if (s > MOM2_MAX_SLAB) s = MOM2_MAX_SLAB;
+  if (s < 1024) s = 1024;
+  return static_cast<int>(s);
+}
 constexpr int MOM2_FOLD_EVERY = 8;
-constexpr int MOM2_DEFAULT_KIND = KIND_TF32;
+constexpr int MOM2_DEFAULT_KIND = KIND_F16;   // 3xFP16: same accuracy as 3xTF32 on B200, twice the MMA rate
 
 struct Mom2Handle {
   int device, d, h, hp, act, slab;
+  float w_scale;       // exact power-of-two pre-scale of the fp16-split W1 planes (1 for tf32)
   int kind, lo_fmt;    // KIND_TF32 (3xTF32) or KIND_F16 (fp16 hi + bf16/fp16 lo planes, kind::f16 MMAs)
   void* workspace;
   int chunk_fc1, chunk_syrk;
@@ -254,7 +262,7 @@ inline int mom2_create(Mom2Handle** out, int device, int d, int h, int act, int 
   EMCID_CHECK(d > 0 && h > 0 && d % 4 == 0, EMCID_ERR_INVALID, "mom2_create: d must be a positive multiple of 4");
   EMCID_CHECK(act == ACT_QUICK_GELU || act == ACT_GELU_ERF || act == ACT_NONE, EMCID_ERR_INVALID,
               "mom2_create: unknown activation %d", act);
-  if (slab <= 0) slab = MOM2_DEFAULT_SLAB;
+  if (slab <= 0) slab = mom2_default_slab(d);
   EMCID_CHECK(slab % 256 == 0 && slab <= MOM2_MAX_SLAB, EMCID_ERR_INVALID,
               "mom2_create: slab_tokens must be a multiple of 256 and <= %d", MOM2_MAX_SLAB);
   EMCID_CHECK(ws_bytes >= mom2_workspace_bytes(d, h, slab), EMCID_ERR_WORKSPACE,
@@ -267,7 +275,7 @@ inline int mom2_create(Mom2Handle** out, int device, int d, int h, int act, int 
   int rc = get_device_info(&H->info);
   if (rc) { delete H; return rc; }
   H->device = device; H->d = d; H->h = h; H->act = act; H->slab = slab;
-  H->kind = MOM2_DEFAULT_KIND; H->lo_fmt = FMT_BF16; H->workspace = workspace;
+  H->kind = MOM2_DEFAULT_KIND; H->lo_fmt = FMT_F16; H->workspace = workspace;
   H->hp = static_cast<int>(round_up_ll(h, 64));
   H->chunk_fc1 = 1; H->chunk_syrk = GEMM_DEFAULT_CHUNK;  // fc1 rounding bias counts twice in mom2
   const size_t wbytes = static_cast<size_t>(d) * H->hp * sizeof(float);   // sized for either kind
@@ -328,9 +336,16 @@ inline int mom2_destroy(Mom2Handle* H) {
 inline int mom2_set_weights(Mom2Handle* H, const float* W1, long long ldw, const float* b1, cudaStream_t stream) {
   EMCID_CHECK(H && W1, EMCID_ERR_INVALID, "mom2_set_weights: null argument");
   EMCID_CUDA_CHECK(cudaSetDevice(H->device));
-  int rc = H->kind == KIND_F16
-               ? launch_split_planes16(W1, ldw, H->d, H->h, 1.0f, H->w_hi, H->w_lo, H->hp, H->lo_fmt, stream)
-               : launch_split_planes(W1, ldw, H->d, H->h, 1.0f, H->w_hi, H->w_lo, H->hp, stream);
+  int rc;
+  H->w_scale = 1.0f;
+  if (H->kind == KIND_F16) {
+    // H->n_valid doubles as the 4-byte reduction scratch (no slab is in flight while weights change)
+    rc = f16_prescale(W1, ldw, H->d, H->h, reinterpret_cast<unsigned int*>(H->n_valid), &H->w_scale, stream);
+    if (rc) return rc;
+    rc = launch_split_planes16(W1, ldw, H->d, H->h, H->w_scale, H->w_hi, H->w_lo, H->hp, H->lo_fmt, stream);
+  } else {
+    rc = launch_split_planes(W1, ldw, H->d, H->h, 1.0f, H->w_hi, H->w_lo, H->hp, stream);
+  }
   if (rc) return rc;
   if (b1) {
     EMCID_CUDA_CHECK(cudaMemcpyAsync(H->bias, b1, H->d * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -341,12 +356,12 @@ inline int mom2_set_weights(Mom2Handle* H, const float* W1, long long ldw, const
   return EMCID_OK;
 }
 
-// precision: 0 = 3xTF32, 1 = fp16 hi + bf16 lo, 2 = fp16 hi + fp16 lo.  Must precede set_weights.
+// precision: 0 = 3xTF32, 1 = 3xFP16 (fp16 hi + fp16 lo planes).  Must precede set_weights.
 inline int mom2_set_precision(Mom2Handle* H, int precision) {
-  EMCID_CHECK(H && precision >= 0 && precision <= 2, EMCID_ERR_INVALID, "mom2_set_precision: bad argument");
+  EMCID_CHECK(H && precision >= 0 && precision <= 1, EMCID_ERR_INVALID, "mom2_set_precision: bad argument");
   EMCID_CHECK(H->slabs_since_fold == 0, EMCID_ERR_INVALID, "mom2_set_precision: call before accumulating");
   H->kind = precision == 0 ? KIND_TF32 : KIND_F16;
-  H->lo_fmt = precision == 2 ? FMT_F16 : FMT_BF16;
+  H->lo_fmt = FMT_F16;
   H->has_weights = false;
   return mom2_configure(H);
 }
@@ -357,6 +372,36 @@ inline int mom2_fold(Mom2Handle* H, cudaStream_t stream) {
   EMCID_CUDA_CHECK(cudaGetLastError());
   H->launches += 1;
   H->slabs_since_fold = 0;
+  return EMCID_OK;
+}
+
+// acc32[lower tiles] += P P^T over token columns [col0, col0 + t) of the A^T planes `ops` describes
+// ([d x tokens], K-major over tokens); dyn_k optionally caps t by a device scalar.  Stream-K over
+// (tile, token block), red.add epilogue.  Also used by the native text-encoder forward (clip.cuh).
+inline int mom2_syrk_slab(Mom2Handle* H, const GemmOperands& ops, int kind, int col0, int t, const int* dyn_k,
+                          cudaStream_t stream) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = H->d; p.N = H->d; p.K = t;
+  p.a_col0 = col0; p.b_col0 = col0;
+  p.dyn_k = dyn_k;
+  p.lower = 1; p.streamk = 1;
+  p.chunk_kblocks = H->chunk_syrk;
+  p.C = H->acc32; p.ldc = H->d; p.lo_fmt = H->lo_fmt;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (H->profile) {
+    EMCID_CUDA_CHECK(cudaEventCreate(&e0)); EMCID_CUDA_CHECK(cudaEventCreate(&e1));
+    EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
+  }
+  const int sms = H->info.sm_count;
+  int rc = kind == KIND_F16 ? launch_gemm3x<256, 2, EPI_RED, KIND_F16>(ops, p, sms, stream)
+                            : launch_gemm3x<256, 2, EPI_RED>(ops, p, sms, stream);
+  if (rc) return rc;
+  H->launches += 1;
+  if (H->profile) {
+    EMCID_CUDA_CHECK(cudaEventRecord(e1, stream));
+    H->ev_syrk->push_back(e0); H->ev_syrk->push_back(e1); H->rows_syrk += t;
+  }
   return EMCID_OK;
 }
 
@@ -379,7 +424,7 @@ inline int mom2_accumulate(Mom2Handle* H, const float* X, long long ldx, const u
     const int t = static_cast<int>(T - r0 < per ? T - r0 : per);
     mom2_scan_kernel<<<1, 1024, 0, stream>>>(valid ? valid + r0 : nullptr, t, H->dest, H->n_valid, H->count);
     EMCID_CUDA_CHECK(cudaGetLastError());
-    H->launches += 4;  // scan, gather, fc1, syrk
+    H->launches += 3;  // scan, gather, fc1 (the SYRK counts itself)
     {
       int blocks = (t + 7) / 8;
       if (H->kind == KIND_F16)
@@ -399,43 +444,29 @@ inline int mom2_accumulate(Mom2Handle* H, const float* X, long long ldx, const u
       p.dyn_n = H->n_valid;
       p.chunk_kblocks = H->chunk_fc1;
       p.P_hi = H->at_hi; p.P_lo = H->at_lo; p.ldp = H->slab;
-      p.bias = H->bias; p.act = H->act; p.lo_fmt = H->lo_fmt;
+      p.bias = H->bias; p.act = H->act; p.lo_fmt = H->lo_fmt; p.alpha = 1.0f / H->w_scale;
       const int tiles = gemm_num_tiles(H->d, t, 256, 0);
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (H->profile) {
         EMCID_CUDA_CHECK(cudaEventCreate(&e0)); EMCID_CUDA_CHECK(cudaEventCreate(&e1));
         EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
       }
-      rc = H->kind == KIND_F16
-               ? launch_gemm3x<256, 2, EPI_FC1, KIND_F16>(H->fc1_ops, p, tiles < sms ? tiles : sms, stream)
-               : launch_gemm3x<256, 2, EPI_FC1>(H->fc1_ops, p, tiles < sms ? tiles : sms, stream);
+      const int g = tiles < sms ? tiles : sms;
+#define EMCID_FC1_CASE(A)                                                                            \
+  if (H->act == A)                                                                                   \
+    rc = H->kind == KIND_F16 ? launch_gemm3x<256, 2, EPI_FC1, KIND_F16, A>(H->fc1_ops, p, g, stream) \
+                             : launch_gemm3x<256, 2, EPI_FC1, KIND_TF32, A>(H->fc1_ops, p, g, stream);
+      rc = EMCID_ERR_INVALID;
+      EMCID_FC1_CASE(ACT_QUICK_GELU) EMCID_FC1_CASE(ACT_GELU_ERF) EMCID_FC1_CASE(ACT_NONE)
+#undef EMCID_FC1_CASE
       if (rc) return rc;
       if (H->profile) {
         EMCID_CUDA_CHECK(cudaEventRecord(e1, stream));
         H->ev_fc1->push_back(e0); H->ev_fc1->push_back(e1); H->rows_fc1 += t;
       }
     }
-    {
-      GemmParams p;
-      memset(&p, 0, sizeof(p));
-      p.M = H->d; p.N = H->d; p.K = t;
-      p.dyn_k = H->n_valid;
-      p.lower = 1; p.streamk = 1;
-      p.chunk_kblocks = H->chunk_syrk;
-      p.C = H->acc32; p.ldc = H->d; p.lo_fmt = H->lo_fmt;
-      cudaEvent_t e0 = nullptr, e1 = nullptr;
-      if (H->profile) {
-        EMCID_CUDA_CHECK(cudaEventCreate(&e0)); EMCID_CUDA_CHECK(cudaEventCreate(&e1));
-        EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
-      }
-      rc = H->kind == KIND_F16 ? launch_gemm3x<256, 2, EPI_RED, KIND_F16>(H->syrk_ops, p, sms, stream)
-                               : launch_gemm3x<256, 2, EPI_RED>(H->syrk_ops, p, sms, stream);
-      if (rc) return rc;
-      if (H->profile) {
-        EMCID_CUDA_CHECK(cudaEventRecord(e1, stream));
-        H->ev_syrk->push_back(e0); H->ev_syrk->push_back(e1); H->rows_syrk += t;
-      }
-    }
+    rc = mom2_syrk_slab(H, H->syrk_ops, H->kind, 0, t, H->n_valid, stream);
+    if (rc) return rc;
     if (++H->slabs_since_fold >= MOM2_FOLD_EVERY) {
       rc = mom2_fold(H, stream);
       if (rc) return rc;

@@ -7,10 +7,14 @@ numbers are produced:
 
   * ONE forward pass serves every requested layer (`layer_stats_text_encoder_multi`); the
     reference runs a full pass over the dataset per layer (emcid/layer_stats.py:112-134).
-  * The fc2 input is never materialised: a forward pre-hook on each edited layer's MLP hands the
-    h-wide LN2 output and the attention mask to `Mom2Accumulator`, whose sm_100a kernels do
-    fc1 -> activation -> pad masking -> lower-triangular SYRK (see csrc/mom2.cuh).  The forward is
-    abandoned at the deepest edited layer, like `Trace(stop=True)` (util/nethook.py:112-113).
+  * For a plain fp32 HF CLIP text tower the whole forward runs in the library (csrc/clip.cuh): packed
+    valid tokens, 3xFP16 tcgen05 GEMMs for every projection, act(fc1) of the edited layers handed
+    to the SYRK on the device.  The forward stops at the deepest edited layer, like `Trace(stop=True)`
+    (util/nethook.py:112-113).
+  * Any other module layout keeps the HF forward; a forward pre-hook on each edited layer's MLP then
+    hands the h-wide LN2 output and the attention mask to `Mom2Accumulator`, whose kernels do
+    fc1 -> activation -> pad masking -> lower-triangular SYRK (csrc/mom2.cuh).  Either way the
+    d-wide fc2 input of the reference's `Trace(retain_input=True)` is never gathered by PyTorch.
   * Captions are sharded `subset[rank::world]` across the GPUs of a torch.distributed job and the
     per-rank sums meet in one NCCL reduce per layer; counts are reduced as int64 (bit exact).
 
@@ -18,12 +22,13 @@ There is no CPU path: a model that is not on a CUDA (sm_100) device is an error.
 """
 from __future__ import annotations
 
+import os
 from pathlib import Path
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 
-from . import nethook
+from . import clip_forward, nethook
 from .runningstats import (CombinedStat, FixedSubsetSampler, Mean, NormMean, SecondMoment, load_cached_state,
                            save_cached_state, subset_indices)
 from .stat_dataset import TokenizedDataset, dict_to_, fixed_width_collation
@@ -65,9 +70,14 @@ class TextEncoderMom2Pass:
     """Streams padded caption blocks through the HF CLIP text model and accumulates mom2/count for
     a set of MLP layers in the same pass."""
 
-    def __init__(self, model, layer_names: Sequence[str], slab_tokens: int = 0, accumulator_factory=None):
+    def __init__(self, model, layer_names: Sequence[str], slab_tokens: int = 0, accumulator_factory=None,
+                 native: Optional[bool] = None):
         from .mom2 import Mom2Accumulator
 
+        if native is None:
+            native = os.environ.get("EMCID_NATIVE_FORWARD", "1") != "0"
+        self._use_native = bool(native) and accumulator_factory is None and clip_forward.supports(model)
+        self._native = None
         self.model = model
         self.layer_names = list(layer_names)
         mlps = {name: _mlp_of(model, name) for name in self.layer_names}  # LookupError before anything else
@@ -91,10 +101,37 @@ class TextEncoderMom2Pass:
             if W1.dtype != torch.float32:
                 raise NotImplementedError("the statistics pass runs on fp32 weights (reference precision float32)")
             acc = accumulator_factory(W1.shape[0], W1.shape[1], act)
-            acc.set_weights(W1, b1)
             self.accs[name] = acc
             self._mlps.append((name, mlp, name == deepest))
         self._mask = None
+        self._hook_weights_set = False
+        self._layer_index = {}
+        if self._use_native:
+            tm = getattr(model, "text_model", model)
+            for name, mlp, _ in self._mlps:
+                idx = [i for i, ly in enumerate(tm.encoder.layers) if ly.mlp is mlp]
+                if len(idx) != 1:
+                    self._use_native = False
+                    break
+                self._layer_index[name] = idx[0]
+        if not self._use_native:
+            self._ensure_hook_weights()
+
+    def _ensure_hook_weights(self):
+        if not self._hook_weights_set:
+            for name, mlp, _ in self._mlps:
+                self.accs[name].set_weights(mlp.fc1.weight, mlp.fc1.bias)
+            self._hook_weights_set = True
+
+    def _native_encoder(self, n_tokens: int, n_captions: int):
+        nat = self._native
+        if nat is None or nat.max_tokens < n_tokens or nat.max_captions < n_captions:
+            if nat is not None:
+                torch.cuda.synchronize(nat.device)
+                nat.close()
+            self._native = nat = clip_forward.NativeClipTextEncoder(
+                self.model, max(n_tokens, nat.max_tokens if nat else 0), max(n_captions, nat.max_captions if nat else 0))
+        return nat
 
     def _hook(self, name, stop):
         def pre_hook(_module, args):
@@ -105,7 +142,21 @@ class TextEncoderMom2Pass:
 
     @torch.no_grad()
     def run_batch(self, batch: Dict[str, torch.Tensor]) -> None:
-        """batch: input_ids / position_ids / attention_mask [B, L] on the model's device."""
+        """batch: input_ids / position_ids / attention_mask [B, L] (host or device tensors)."""
+        if self._use_native:
+            max_pos = getattr(self.model, "text_model", self.model).embeddings.position_embedding.weight.shape[0]
+            packed = clip_forward.pack_batch(batch, max_pos)
+            if packed is not None:
+                ids, pos, cu, S, T = packed
+                if T == 0:
+                    return
+                names = list(self._layer_index)
+                self._native_encoder(T, S).forward_stats(ids, pos, cu, S, T, [self._layer_index[n] for n in names],
+                                                         [self.accs[n] for n in names])
+                return
+            self._ensure_hook_weights()  # not a right-padding mask: keep the HF forward for this block
+        device = next(self.model.parameters()).device
+        batch = {k: v.to(device, non_blocking=True) for k, v in batch.items()}
         self._mask = batch["attention_mask"]
         handles = [mlp.register_forward_pre_hook(self._hook(name, stop)) for name, mlp, stop in self._mlps]
         try:
@@ -121,9 +172,17 @@ class TextEncoderMom2Pass:
         """{layer_name: (mom2 [d,d] fp32 on device, count 0-d int64 on device)}."""
         return {name: acc.finalize() for name, acc in self.accs.items()}
 
+    def launches(self) -> int:
+        """Kernels of this library launched so far by the pass (accumulators + native forward)."""
+        n = sum(int(acc.get_profile()["launches"]) for acc in self.accs.values() if hasattr(acc, "get_profile"))
+        return n + (self._native.launches() if self._native is not None else 0)
+
     def close(self):
         for acc in self.accs.values():
             acc.close()
+        if self._native is not None:
+            self._native.close()
+            self._native = None
 
 
 def _dist_info(distributed):
@@ -207,8 +266,7 @@ def layer_stats_text_encoder_multi(
         for batch in progress(loader, total=batch_count):
             if batch["input_ids"].numel() == 0:
                 continue
-            batch = {k: v.to(device, non_blocking=True) for k, v in batch.items()}
-            runner.run_batch(batch)
+            runner.run_batch(batch)  # host tensors: packed on the host, then one pinned H2D copy per field
         results = runner.finalize()
         for i, n in enumerate(todo):
             mom2, count = results[n]

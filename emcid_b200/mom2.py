@@ -28,7 +28,7 @@ def _shared_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 
 class Mom2Accumulator:
-    PRECISIONS = {"tf32x3": 0, "f16x3": 1, "f16x3_f16": 2}
+    PRECISIONS = {"tf32x3": 0, "f16x3": 1}
 
     def __init__(self, device, d: int, h: int, act: str = "quick_gelu", slab_tokens: int = 0,
                  fc1_chunk: Optional[int] = None, syrk_chunk: Optional[int] = None, precision: Optional[str] = None):

@@ -40,8 +40,8 @@ unsigned int emcid_hang_code(void);
  * A [M x K], B [N x K], C [M x N], row-major fp32 on the device.  Replaces the fp32/fp64 `@` /
  * `.mm` products on the path (util/runningstats.py:493, emcid/emcid_main.py:1046,1050).
  * flags: bit0 = compute only tiles touching the lower triangle, bit1 = stream-K (alpha = beta = 1,
- * accumulation by red.global.add), bit2 = 128-wide N tiles, bit3 = fp16+bf16 planes on kind::f16
- * instead of 3xTF32, bit4 (with bit3) = fp16 lo planes, bits 8-15 = k-blocks per TMEM chunk. */
+ * accumulation by red.global.add), bit2 = 128-wide N tiles, bit3 = 3xFP16 planes on kind::f16
+ * instead of 3xTF32, bits 8-15 = k-blocks per TMEM chunk. */
 size_t emcid_gemm3x_workspace_bytes(int M, int N, int K);
 int emcid_gemm3x_nt(int M, int N, int K, const float* A, long long lda, const float* B,
                     long long ldb, float* C, long long ldc, float alpha, float beta, int flags,
@@ -56,7 +56,7 @@ int emcid_gemm3x_nt(int M, int N, int K, const float* A, long long lda, const fl
  *
  * workspace: scratch of emcid_mom2_workspace_bytes() bytes on `device`, owned by the caller; it may
  * be shared by several handles that are only ever used on the same stream.  slab_tokens: rows
- * processed per fc1/SYRK launch pair (multiple of 256, <= 4096; 0 = default 1536).
+ * processed per fc1/SYRK launch pair (multiple of 256, <= 4096; 0 = default: as many as keep the slab L2 resident, 4096 at d = 3072).
  * act: EMCID_ACT_*.  The library allocates the handle-private accumulators (fp32 + fp64 [d x d],
  * tf32 planes of W1) with cudaMalloc; emcid_mom2_destroy frees them. */
 typedef struct emcid_mom2 emcid_mom2_t;
@@ -64,12 +64,10 @@ size_t emcid_mom2_workspace_bytes(int d, int h, int slab_tokens);
 int emcid_mom2_create(emcid_mom2_t** out, int device, int d, int h, int act, int slab_tokens,
                       void* workspace, size_t workspace_bytes);
 /* Operand precision of the two tensor-core products (fc1 and SYRK); call before emcid_mom2_set_weights.
- *   EMCID_PREC_TF32X3     3xTF32: hi/lo tf32 planes, tcgen05.mma.kind::tf32          (|err| <= 2^-22 |x| per operand)
- *   EMCID_PREC_F16X3      fp16 hi + bf16 lo planes, tcgen05.mma.kind::f16 (2x rate)  (|err| <= 2^-20 |x|)
- *   EMCID_PREC_F16X3_F16  fp16 hi + fp16 lo planes                                   (2^-23 |x| or 2^-25 absolute) */
+ *   EMCID_PREC_TF32X3  3xTF32: hi/lo tf32 planes, tcgen05.mma.kind::tf32                 (|err| <= 2^-23 |x| per operand)
+ *   EMCID_PREC_F16X3   3xFP16: fp16 hi + fp16 lo planes, tcgen05.mma.kind::f16 (2x rate)  (max(2^-23 |x|, 2^-25)) */
 #define EMCID_PREC_TF32X3 0
 #define EMCID_PREC_F16X3 1
-#define EMCID_PREC_F16X3_F16 2
 int emcid_mom2_set_precision(emcid_mom2_t* h, int precision);
 /* k-blocks (128 bytes of contraction each: 32 tf32 / 64 halves) accumulated in TMEM between round-to-nearest folds. */
 int emcid_mom2_set_chunks(emcid_mom2_t* h, int fc1_kblocks, int syrk_kblocks);
@@ -89,6 +87,34 @@ int emcid_mom2_reset(emcid_mom2_t* h, void* stream);
 int emcid_mom2_profile(emcid_mom2_t* h, int enable);
 int emcid_mom2_get_profile(emcid_mom2_t* h, double* out8);
 int emcid_mom2_destroy(emcid_mom2_t* h);
+
+/* ---- native text-encoder forward for the statistics pass --------------------------------------------
+ * Replaces the HF forward the reference runs under `Trace(...)` for every sub-batch
+ *     with Trace(model, layer_name, retain_input=True, retain_output=False, stop=True) as tr:
+ *         model(**batch)                                                emcid/layer_stats.py:210-216
+ * (transformers CLIPTextModel: embeddings + causal pre-LN transformer layers) with the same fp32-class
+ * arithmetic on the 3xFP16 tcgen05 GEMM, over PACKED valid tokens (right padding + causal attention:
+ * a valid token never attends a pad token, so dropping pad rows changes nothing), and feeds act(fc1)
+ * of the edited layers straight into their emcid_mom2 accumulators (mom2 += f^T f, count += tokens).
+ * The forward stops after fc1 of the deepest edited layer (Trace(stop=True), util/nethook.py:112-113).
+ *
+ * ids / positions: [n_tokens] int32 packed token ids and position ids; cu_seqlens: [n_captions + 1]
+ * int32 prefix sums of the caption lengths (each <= max_positions).  All device pointers.
+ * stat_layers: ascending edited layer indices (host array) with one accumulator each (same d, same
+ * device); n_stat = 0 runs `n_layers` full layers instead.  hidden_out (optional): [n_tokens x hidden]
+ * fp32 residual stream after the last executed full layer (parity testing against hidden_states).
+ * set_layer tensors16 (device fp32, contiguous): ln1.w ln1.b q.w q.b k.w k.b v.w v.b out.w out.b
+ * ln2.w ln2.b fc1.w fc1.b fc2.w fc2.b of one encoder layer; weights are copied/split at call time. */
+typedef struct emcid_clip emcid_clip_t;
+int emcid_clip_create(emcid_clip_t** out, int device, int n_layers, int hidden, int heads, int intermediate, int act,
+                      int max_positions, int vocab, float ln_eps, long long max_tokens, int max_captions);
+int emcid_clip_set_embeddings(emcid_clip_t* h, const float* token_embedding, const float* position_embedding, void* stream);
+int emcid_clip_set_layer(emcid_clip_t* h, int layer, const float* const* tensors16, void* stream);
+int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
+                       int n_captions, int n_tokens, int n_layers, int n_stat, const int* stat_layers,
+                       emcid_mom2_t* const* accs, float* hidden_out, void* stream);
+long long emcid_clip_launches(emcid_clip_t* h);
+int emcid_clip_destroy(emcid_clip_t* h);
 
 /* ---- closed-form multi-layer update ---------------------------------------------------------------
  * Replaces the solve block of execute_emcid_text_encoder, emcid/emcid_main.py:1037-1050 (byte-identical

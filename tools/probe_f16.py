@@ -23,8 +23,8 @@ for (M, N, K, scale) in [(128, 256, 64, 1.0), (200, 260, 72, 1.0), (512, 768, 76
     B = torch.randn(N, K, device=dev, generator=g)
     ref = A.double() @ B.double().T
     row = dict(M=M, N=N, K=K, scale=scale)
-    for name, kw in [("tf32x3", {}), ("f16_bf16", dict(f16=True)), ("f16_f16", dict(f16=True, lo_f16=True)),
-                     ("f16_bf16_chunk1", dict(f16=True, chunk=1))]:
+    for name, kw in [("tf32x3", {}), ("f16x3", dict(f16=True)), ("f16x3_chunk1", dict(f16=True, chunk=1)),
+                     ("f16x3_chunk4", dict(f16=True, chunk=4))]:
         try:
             C = _lib.gemm3x_nt(A, B, **kw)
             torch.cuda.synchronize()
@@ -50,7 +50,7 @@ def run(name, d, h, T, act="quick_gelu", frac_valid=1.0, calls=1, seed=0, wscale
     W = torch.randn(d, h, device=dev, generator=g) * (wscale if wscale else 0.7 / h ** 0.5)
     b = torch.randn(d, device=dev, generator=g) * 0.1
     row = dict(name=name, d=d, h=h, T=T, calls=calls, act=act)
-    for prec in ("tf32x3", "f16x3", "f16x3_f16"):
+    for prec in ("tf32x3", "f16x3"):
         gg = torch.Generator(device=dev).manual_seed(seed + 1)
         acc = Mom2Accumulator(dev, d, h, act, precision=prec, **kw)
         acc.set_weights(W, b)
