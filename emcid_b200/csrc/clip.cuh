@@ -22,6 +22,8 @@
 // of two (host.cuh::f16_prescale) and the scale is undone by `alpha` in the epilogue.
 #pragma once
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "mom2.cuh"
@@ -205,6 +207,139 @@ __global__ void __launch_bounds__(128) clip_attention_kernel(const float* __rest
   }
 }
 
+// Register-tiled variant for head dims 16/32/64/128: a warp handles TWO adjacent query rows at once, keeps both
+// q rows in registers and reads K/V as float4 from shared memory (row pitch DH + 4: conflict-free LDS.128), so
+// every K/V element fetched feeds two FMAs and the kernel is FMA- rather than LDS-bound.
+template <int DH>
+__global__ void __launch_bounds__(128) clip_attention2_kernel(const float* __restrict__ qkv, const int* __restrict__ cu,
+                                                              int h, int lmax, float scale, uint16_t* __restrict__ o_hi,
+                                                              uint16_t* __restrict__ o_lo, int ldo) {
+  extern __shared__ float attn_sm[];
+  constexpr int LDK = DH + 4;
+  constexpr int NC = (DH + 31) / 32;           // output columns per lane
+  const int lp = (lmax + 7) & ~3;              // padded row count / score pitch (>= lmax + 4, multiple of 4)
+  float* Ks = attn_sm;                         // [lp][LDK]
+  float* Vs = Ks + lp * LDK;                   // [lp][LDK]
+  float* Ps = Vs + lp * LDK;                   // [4 warps][2 rows][lp]
+  const int head = blockIdx.x, seq = blockIdx.y;
+  const int t0 = cu[seq];
+  int Ls = cu[seq + 1] - t0;
+  if (Ls > lmax) Ls = lmax;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long ld = 3ll * h;
+  const float* base = qkv + static_cast<long long>(t0) * ld + head * DH;
+  const int Lz = (Ls + 3) & ~3;                // V rows [Ls, Lz) must read as zeros (their p is 0, 0 * garbage is not)
+  for (int e = tid; e < Lz * (DH / 4); e += blockDim.x) {
+    const int j = e / (DH / 4), c = (e - j * (DH / 4)) * 4;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (j < Ls) {
+      kv = *reinterpret_cast<const float4*>(base + j * ld + h + c);
+      vv = *reinterpret_cast<const float4*>(base + j * ld + 2 * h + c);
+    }
+    *reinterpret_cast<float4*>(Ks + j * LDK + c) = kv;
+    *reinterpret_cast<float4*>(Vs + j * LDK + c) = vv;
+  }
+  __syncthreads();
+  float* p0 = Ps + (warp * 2) * lp;
+  float* p1 = p0 + lp;
+  for (int r0 = 2 * warp; r0 < Ls; r0 += 8) {
+    const int r1 = r0 + 1;
+    const bool has1 = r1 < Ls;
+    const int rl = has1 ? r1 : r0;             // last key index any of the two rows attends
+    float4 q0[DH / 4], q1[DH / 4];
+    {
+      const float4* g0 = reinterpret_cast<const float4*>(base + r0 * ld);
+      const float4* g1 = reinterpret_cast<const float4*>(base + (has1 ? r1 : r0) * ld);
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) { q0[c] = g0[c]; q1[c] = g1[c]; }
+    }
+    float s0[4], s1[4];
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      float d0 = -INFINITY, d1 = -INFINITY;
+      if (32 * m <= rl) {                       // warp-uniform: this key group is needed at all
+        if (j <= rl) {
+          float a0 = 0.f, a1 = 0.f;
+          const float4* kr = reinterpret_cast<const float4*>(Ks + j * LDK);
+#pragma unroll
+          for (int c = 0; c < DH / 4; ++c) {
+            const float4 k4 = kr[c];
+            a0 = fmaf(q0[c].x, k4.x, a0); a0 = fmaf(q0[c].y, k4.y, a0); a0 = fmaf(q0[c].z, k4.z, a0); a0 = fmaf(q0[c].w, k4.w, a0);
+            a1 = fmaf(q1[c].x, k4.x, a1); a1 = fmaf(q1[c].y, k4.y, a1); a1 = fmaf(q1[c].z, k4.z, a1); a1 = fmaf(q1[c].w, k4.w, a1);
+          }
+          if (j <= r0) d0 = a0 * scale;
+          d1 = a1 * scale;
+        }
+      }
+      s0[m] = d0; s1[m] = d1;
+      m0 = fmaxf(m0, d0); m1 = fmaxf(m1, d1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    }
+    float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      const float e0 = j <= r0 ? expf(s0[m] - m0) : 0.f;
+      const float e1 = j <= rl ? expf(s1[m] - m1) : 0.f;
+      s0[m] = e0; s1[m] = e1;
+      z0 += e0; z1 += e1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+      z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+    }
+    const float i0 = 1.0f / z0, i1 = 1.0f / z1;
+    const int jz = (rl + 4) & ~3;               // scores [0, jz) are read back below; masked ones are zeros
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = lane + 32 * m;
+      if (j < jz) { p0[j] = s0[m] * i0; p1[j] = s1[m] * i1; }
+    }
+    __syncwarp();
+    float acc0[NC], acc1[NC];
+#pragma unroll
+    for (int u = 0; u < NC; ++u) acc0[u] = acc1[u] = 0.f;
+    for (int j4 = 0; j4 <= rl; j4 += 4) {
+      const float4 pa = *reinterpret_cast<const float4*>(p0 + j4);
+      const float4 pb = *reinterpret_cast<const float4*>(p1 + j4);
+#pragma unroll
+      for (int u = 0; u < NC; ++u) {
+        const int c = lane + 32 * u;
+        if (DH >= 32 || c < DH) {
+          const float v0 = Vs[(j4 + 0) * LDK + c], v1 = Vs[(j4 + 1) * LDK + c];
+          const float v2 = Vs[(j4 + 2) * LDK + c], v3 = Vs[(j4 + 3) * LDK + c];
+          acc0[u] = fmaf(pa.x, v0, acc0[u]); acc0[u] = fmaf(pa.y, v1, acc0[u]);
+          acc0[u] = fmaf(pa.z, v2, acc0[u]); acc0[u] = fmaf(pa.w, v3, acc0[u]);
+          acc1[u] = fmaf(pb.x, v0, acc1[u]); acc1[u] = fmaf(pb.y, v1, acc1[u]);
+          acc1[u] = fmaf(pb.z, v2, acc1[u]); acc1[u] = fmaf(pb.w, v3, acc1[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NC; ++u) {
+      const int c = lane + 32 * u;
+      if (DH >= 32 || c < DH) {
+        uint16_t hh, ll;
+        const long long o0 = static_cast<long long>(t0 + r0) * ldo + head * DH + c;
+        split_f16(acc0[u], FMT_F16, hh, ll);
+        o_hi[o0] = hh; o_lo[o0] = ll;
+        if (has1) {
+          split_f16(acc1[u], FMT_F16, hh, ll);
+          o_hi[o0 + ldo] = hh; o_lo[o0 + ldo] = ll;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void clip_add_count_kernel(long long* count, long long n) { *count += n; }
 
 // ---- host ---------------------------------------------------------------------------------------
@@ -275,9 +410,20 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
     clip_destroy(H);
     return set_error(EMCID_ERR_CUDA, "clip_create: cudaMemset failed");
   }
-  H->attn_smem = (2 * max_pos * (H->dh + 1) + 4 * H->dh + 4 * max_pos) * static_cast<int>(sizeof(float));
-  if (H->attn_smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(clip_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
+  {
+    const int dh = H->dh;
+    const bool tiled = dh == 16 || dh == 32 || dh == 64 || dh == 128;
+    const int lp = (max_pos + 7) & ~3;
+    H->attn_smem = tiled ? (2 * lp * (dh + 4) + 8 * lp) * static_cast<int>(sizeof(float))
+                         : (2 * max_pos * (dh + 1) + 4 * dh + 4 * max_pos) * static_cast<int>(sizeof(float));
+    cudaError_t e = cudaSuccess;
+    if (H->attn_smem > 48 * 1024) {
+      if (dh == 16) e = cudaFuncSetAttribute(clip_attention2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
+      else if (dh == 32) e = cudaFuncSetAttribute(clip_attention2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
+      else if (dh == 64) e = cudaFuncSetAttribute(clip_attention2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
+      else if (dh == 128) e = cudaFuncSetAttribute(clip_attention2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
+      else e = cudaFuncSetAttribute(clip_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
+    }
     if (e != cudaSuccess) {
       clip_destroy(H);
       return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", H->attn_smem, cudaGetErrorString(e));
@@ -365,7 +511,8 @@ struct ClipActMaps {
 // out[T x N] = act(X[T x K] W^T / scale + bias) (+ residual), optionally as fp32 / planes / transposed planes.
 inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap& x_lo, const ClipWeight& W, int T,
                        int act, const float* Cin, float* C, long long ldc, uint16_t* P_hi, uint16_t* P_lo, long long ldp,
-                       uint16_t* Pt_hi, uint16_t* Pt_lo, long long ldpt, cudaStream_t stream) {
+                       uint16_t* Pt_hi, uint16_t* Pt_lo, long long ldpt, cudaStream_t stream,
+                       const GemmOutMaps* om = nullptr) {
   GemmOperands ops;
   ops.a_hi = x_hi; ops.a_lo = x_lo; ops.b_hi = W.m_hi; ops.b_lo = W.m_lo;
   GemmParams p;
@@ -383,8 +530,10 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   H->launches += 1;
   // the epilogue variant is a compile-time option (see EF_* in gemm3x.cuh): only the combinations the forward uses
   const int ef = act | (C ? EF_C : 0) | (Cin ? EF_CIN : 0) | (P_hi ? EF_P : 0) | (Pt_hi ? EF_PT : 0);
-#define EMCID_LIN_CASE(F) \
-  if (ef == (F)) return launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream);
+#define EMCID_LIN_CASE(F)                                                                                     \
+  if (ef == (F))                                                                                              \
+    return om ? launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (F)>(ops, p, grid, stream, 1, om)             \
+              : launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream);
   EMCID_LIN_CASE(ACT_NONE | EF_C)                       // q/k/v projection
   EMCID_LIN_CASE(ACT_NONE | EF_C | EF_CIN)              // out projection / fc2 with residual
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P)                 // fc1
@@ -449,6 +598,20 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       (rc = make_tmap_2d(&ft.a_hi, H->ft_hi, H->d, T, H->tp, 128, 2)) || (rc = make_tmap_2d(&ft.a_lo, H->ft_lo, H->d, T, H->tp, 128, 2)))
     return rc;
   ft.b_hi = ft.a_hi; ft.b_lo = ft.a_lo;
+  // store maps of the staged (TMA) epilogue; EMCID_LINEAR_TMA=0 keeps the direct-store epilogue
+  static const bool use_tma_epi = [] { const char* e = getenv("EMCID_LINEAR_TMA"); return !(e && e[0] == '0'); }();
+  GemmOutMaps om_qkv = {}, om_res = {}, om_f = {};
+  if (use_tma_epi) {
+    if ((rc = make_tmap_2d(&om_qkv.c, H->qkv, T, 3ll * H->h, 3ll * H->h, 128, 4)) ||
+        (rc = make_tmap_2d(&om_res.c, H->hres, T, H->h, H->h, 128, 4)) ||
+        (rc = make_tmap_2d(&om_f.t_hi, H->ft_hi, H->d, T, H->tp, 32, 2, 128)) ||
+        (rc = make_tmap_2d(&om_f.t_lo, H->ft_lo, H->d, T, H->tp, 32, 2, 128)))
+      return rc;
+    om_f.c = mf_hi; om_f.c2 = mf_lo;
+  }
+  const GemmOutMaps* pm_qkv = use_tma_epi ? &om_qkv : nullptr;
+  const GemmOutMaps* pm_res = use_tma_epi ? &om_res : nullptr;
+  const GemmOutMaps* pm_f = use_tma_epi ? &om_f : nullptr;
 
   {
     int blocks = (T + 7) / 8;
@@ -463,14 +626,23 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     const ClipLayer& Ly = (*H->layers)[l];
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln1_w, Ly.ln1_b, H->x_hi, H->x_lo, stream))) return rc;
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, nullptr,
-                          nullptr, 0, stream)))
+                          nullptr, 0, stream, pm_qkv)))
       return rc;
-    clip_attention_kernel<<<dim3(H->heads, S), 128, H->attn_smem, stream>>>(H->qkv, cu_seqlens, H->h, H->dh, H->max_pos,
-                                                                            scale, H->a_hi, H->a_lo, H->hp);
+    {
+      const dim3 ag(H->heads, S);
+#define EMCID_ATTN_CASE(D)                                                                                             \
+  if (H->dh == D)                                                                                                      \
+    clip_attention2_kernel<D><<<ag, 128, H->attn_smem, stream>>>(H->qkv, cu_seqlens, H->h, H->max_pos, scale, H->a_hi, \
+                                                                 H->a_lo, H->hp);
+      EMCID_ATTN_CASE(16) else EMCID_ATTN_CASE(32) else EMCID_ATTN_CASE(64) else EMCID_ATTN_CASE(128) else
+        clip_attention_kernel<<<ag, 128, H->attn_smem, stream>>>(H->qkv, cu_seqlens, H->h, H->dh, H->max_pos, scale,
+                                                                 H->a_hi, H->a_lo, H->hp);
+#undef EMCID_ATTN_CASE
+    }
     EMCID_CUDA_CHECK(cudaGetLastError());
     H->launches += 1;
     if ((rc = clip_linear(H, ma_hi, ma_lo, Ly.o, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
-                          stream)))
+                          stream, pm_res)))
       return rc;
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln2_w, Ly.ln2_b, H->x_hi, H->x_lo, stream))) return rc;
     const bool is_stat = si < n_stat && stat_layers[si] == l;
@@ -478,7 +650,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     // the deepest edited layer needs only f^T (no fc2 follows); other edited layers need both orientations
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.fc1, T, H->act, nullptr, nullptr, 0, is_last ? nullptr : H->f_hi,
                           is_last ? nullptr : H->f_lo, H->dp, is_stat ? H->ft_hi : nullptr, is_stat ? H->ft_lo : nullptr,
-                          H->tp, stream)))
+                          H->tp, stream, pm_f)))
       return rc;
     if (is_stat) {
       Mom2Handle* A = accs[si++];
@@ -497,7 +669,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     }
     if (is_last) break;
     if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
-                          stream)))
+                          stream, pm_res)))
       return rc;
   }
   if (hidden_out) {

@@ -54,7 +54,18 @@ enum EpiMode : int {
   EPI_RED = 1,      // C += acc via red.global.add (stream-K safe)
   EPI_FC1 = 2,      // planes = split(mask(act(acc + bias[row])))  (fc1 -> A^T slab)
   EPI_LINEAR = 3,   // v = act(alpha*acc + bias_col[col]) + beta*Cin ; C / planes / transposed planes of v
+  EPI_LINEAR_TMA = 4,  // same result, staged through 32 KB of shared memory and written by TMA bulk stores
+                       // (residual by TMA reduce-add): coalesced, asynchronous, ragged tiles clipped by hardware
 };
+
+// Output tensor maps of EPI_LINEAR_TMA (unused by the other epilogues).
+struct GemmOutMaps {
+  CUtensorMap c;     // fp32 result [M x N] (box 32 x 128, 128B swizzle)  or  hi plane [M x N] (box 64 x 128, 128B swizzle)
+  CUtensorMap c2;    // lo plane
+  CUtensorMap t_hi;  // transposed hi plane [N x M] (box 128 x 32, no swizzle)
+  CUtensorMap t_lo;
+};
+constexpr int GEMM_STAGING_BYTES = 32768;
 
 enum ActMode : int { ACT_QUICK_GELU = 0, ACT_GELU_ERF = 1, ACT_NONE = 2 };
 
@@ -95,6 +106,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = 2 * GEMM_A_PLANE_BYTES + 2 * kBPlaneBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two chunk accumulators (power of two)
   static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytesStaged = kSmemBytes + GEMM_STAGING_BYTES;
 };
 
 struct Unit {
@@ -251,7 +263,7 @@ template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32, int EFLAGS = E
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-              const GemmParams p) {
+              const __grid_constant__ GemmOutMaps om, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, STAGES>;
   constexpr int COLS = BLOCK_N / 2;  // accumulator columns owned by one epilogue thread
   constexpr int BLOCK_K = KindTraits<KIND>::kBlockK;  // elements per 128-byte k-block
@@ -259,7 +271,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   // 128B swizzle needs 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* stg = smem + STAGES * Cfg::kStageBytes;  // epilogue staging (EPI_LINEAR_TMA only), 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + (EPI == EPI_LINEAR_TMA ? GEMM_STAGING_BYTES : 0));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -308,6 +321,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   (void)chunk; (void)batch;
 
   if (warp < 4) {
+    // the staged epilogue keeps 128 running sums plus a packed 64-column piece live: give the two epilogue
+    // warpgroups 224 registers and shrink this one (producer / MMA issuer / allocator) to 56
+    if (EPI == EPI_LINEAR_TMA) setmaxnreg_dec<56>();
     if (warp == 0 && lane == 0) {
       EMCID_GEMM_ROLE_SETUP();
       // ---------------------------------------------------------------- TMA producer
@@ -387,6 +403,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
+    if (EPI == EPI_LINEAR_TMA) setmaxnreg_inc<224>();
     EMCID_GEMM_ROLE_SETUP();
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2; // column half of the tile
@@ -416,7 +433,101 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
       // -------- unit finished: registers -> global
       const int row = u.m0 + q * 32 + lane;
       const int col0 = u.n0 + half * COLS;
-      if (row < p.M) {
+      if (EPI == EPI_LINEAR_TMA) {
+        // Every thread of the half takes part (named barriers): rows >= M hold act(bias) of zero-filled operand
+        // rows and are clipped by the TMA store, like columns >= N.
+        constexpr int ACT = EFLAGS & EF_ACT_MASK;
+        const int r = q * 32 + lane;                               // row inside the tile == TMEM lane
+        const uint32_t sbase = smem_u32(stg) + half * (GEMM_STAGING_BYTES / 2);
+        const uint32_t srow = sbase + r * 128;
+        const int sw = r & 7;
+        const bool issuer = (q == 0) && (lane == 0);
+        const int bar_id = 1 + half;
+        const float alpha = p.alpha;
+        if (EFLAGS & EF_C) {
+#pragma unroll
+          for (int pc = 0; pc < COLS / 32; ++pc) {                 // 32 fp32 columns = one 128-byte swizzle row
+            if (issuer) bulk_wait_read0();
+            named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int cl = pc * 32 + 4 * k;
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col0 + cl < N) b = *reinterpret_cast<const float4*>(p.bias_col + col0 + cl);
+              const float o0 = act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), o1 = act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y));
+              const float o2 = act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), o3 = act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w));
+              sts_v4(srow + ((k ^ sw) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+            }
+            fence_proxy_async();
+            named_bar_sync(bar_id, 128);
+            if (issuer && col0 + pc * 32 < N) {
+              if (EFLAGS & EF_CIN) tma_reduce_add_2d(&om.c, sbase, col0 + pc * 32, u.m0);
+              else tma_store_2d(&om.c, sbase, col0 + pc * 32, u.m0);
+              bulk_commit();
+            }
+          }
+        }
+        if (EFLAGS & (EF_P | EF_PT)) {
+#pragma unroll
+          for (int pc = 0; pc < COLS / 64; ++pc) {                 // 64 plane columns = one 128-byte swizzle row
+            uint32_t hp[32], lp[32];                               // packed fp16 pairs of the piece
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int cl = pc * 64 + 4 * k;
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col0 + cl < N) b = *reinterpret_cast<const float4*>(p.bias_col + col0 + cl);
+              uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+              split_f16(act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), FMT_F16, h0, l0);
+              split_f16(act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y)), FMT_F16, h1, l1);
+              split_f16(act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), FMT_F16, h2, l2);
+              split_f16(act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w)), FMT_F16, h3, l3);
+              hp[2 * k] = h0 | (static_cast<uint32_t>(h1) << 16); hp[2 * k + 1] = h2 | (static_cast<uint32_t>(h3) << 16);
+              lp[2 * k] = l0 | (static_cast<uint32_t>(l1) << 16); lp[2 * k + 1] = l2 | (static_cast<uint32_t>(l3) << 16);
+            }
+            const bool in_n = col0 + pc * 64 < N;
+            if (EFLAGS & EF_P) {
+#pragma unroll
+              for (int pl = 0; pl < 2; ++pl) {                     // hi tile, then lo tile
+                if (issuer) bulk_wait_read0();
+                named_bar_sync(bar_id, 128);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  if (pl == 0) sts_v4(srow + ((k ^ sw) << 4), hp[4 * k], hp[4 * k + 1], hp[4 * k + 2], hp[4 * k + 3]);
+                  else sts_v4(srow + ((k ^ sw) << 4), lp[4 * k], lp[4 * k + 1], lp[4 * k + 2], lp[4 * k + 3]);
+                }
+                fence_proxy_async();
+                named_bar_sync(bar_id, 128);
+                if (issuer && in_n) {
+                  tma_store_2d(pl == 0 ? &om.c : &om.c2, sbase, col0 + pc * 64, u.m0);
+                  bulk_commit();
+                }
+              }
+            }
+            if (EFLAGS & EF_PT) {
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub) {                  // 32 features x 128 tokens per plane (8 KB each)
+                if (issuer) bulk_wait_read0();
+                named_bar_sync(bar_id, 128);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const int idx = sub * 32 + c;
+                  const uint16_t hv = static_cast<uint16_t>(hp[idx >> 1] >> (16 * (idx & 1)));
+                  const uint16_t lv = static_cast<uint16_t>(lp[idx >> 1] >> (16 * (idx & 1)));
+                  sts_u16(sbase + c * 256 + r * 2, hv);
+                  sts_u16(sbase + 8192 + c * 256 + r * 2, lv);
+                }
+                fence_proxy_async();
+                named_bar_sync(bar_id, 128);
+                if (issuer && col0 + pc * 64 + sub * 32 < N) {
+                  tma_store_2d(&om.t_hi, sbase, u.m0, col0 + pc * 64 + sub * 32);
+                  tma_store_2d(&om.t_lo, sbase + 8192, u.m0, col0 + pc * 64 + sub * 32);
+                  bulk_commit();
+                }
+              }
+            }
+          }
+        }
+      } else if (row < p.M) {
         if (EPI == EPI_RED) {
           float* dst = p.C + batch * p.c_batch + static_cast<long long>(row) * p.ldc + col0;
 #pragma unroll
@@ -510,6 +621,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   }
 
 #undef EMCID_GEMM_ROLE_SETUP
+  if (EPI == EPI_LINEAR_TMA) bulk_wait0();   // no-op for threads that issued nothing
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);

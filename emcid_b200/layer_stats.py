@@ -40,6 +40,9 @@ except Exception:  # pragma: no cover
 
 STAT_TYPES = {"mom2": SecondMoment, "mean": Mean, "norm_mean": NormMean}
 
+# what the last computed pass did (tests and bench.py read it): {"native_forward": bool, "launches": int}
+LAST_PASS_INFO: Dict[str, object] = {}
+
 
 def get_ccs_filtered_ds(tokenizer):
     """Dataset factory (reference :137-138); the patch point for synthetic data."""
@@ -268,6 +271,7 @@ def layer_stats_text_encoder_multi(
                 continue
             runner.run_batch(batch)  # host tensors: packed on the host, then one pinned H2D copy per field
         results = runner.finalize()
+        LAST_PASS_INFO.update(native_forward=runner._native is not None, launches=runner.launches())
         for i, n in enumerate(todo):
             mom2, count = results[n]
             root = i % world

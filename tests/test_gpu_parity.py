@@ -84,8 +84,11 @@ def test_mom2_accumulator_matches_oracle(dev, d, h, T, act, frac):
 
 
 # ------------------------------------------------------------------------------------------ layer_stats vs reference fixtures
+@pytest.mark.parametrize("native", ["1", "0"])
 @pytest.mark.parametrize("name", ["tiny_stats.npz", "tiny_gelu_stats.npz"])
-def test_layer_stats_matches_reference_fixture(dev, golden_dir, tmp_path, name):
+def test_layer_stats_matches_reference_fixture(dev, golden_dir, tmp_path, monkeypatch, name, native):
+    """native=1: the library's own forward (csrc/clip.cuh); native=0: HF forward with the fused kernels hooked in."""
+    monkeypatch.setenv("EMCID_NATIVE_FORWARD", native)
     g = np.load(os.path.join(golden_dir, name))
     model = model_from_golden(g).to(dev)
     caps = unpack_captions(g)
@@ -95,6 +98,7 @@ def test_layer_stats_matches_reference_fixture(dev, golden_dir, tmp_path, name):
     stat = ls.layer_stats_text_encoder(model, None, layer_name, stats_dir=tmp_path, sample_size=ss,
                                        precision="float32", batch_tokens=int(g["batch_tokens"]), progress=None,
                                        captions_per_batch=32, num_workers=0)
+    assert ls.LAST_PASS_INFO["native_forward"] == (native == "1") and ls.LAST_PASS_INFO["launches"] > 0
     assert stat.mom2.count == int(g["npz.mom2.count"])                       # bit exact
     assert stat.mom2.mom2.device.type == "cpu" and stat.mom2.mom2.dtype == torch.float32
     assert rel_fro(stat.mom2.mom2.numpy(), g["npz.mom2.mom2"]) < MOM2_TOL
@@ -110,7 +114,9 @@ def test_layer_stats_matches_reference_fixture(dev, golden_dir, tmp_path, name):
     assert again.mom2.count == stat.mom2.count and torch.equal(again.mom2.mom2, stat.mom2.mom2)
 
 
-def test_clipl_layer_stats_matches_reference_digest(dev, golden_dir, tmp_path):
+@pytest.mark.parametrize("native", ["1", "0"])
+def test_clipl_layer_stats_matches_reference_digest(dev, golden_dir, tmp_path, monkeypatch, native):
+    monkeypatch.setenv("EMCID_NATIVE_FORWARD", native)
     g = np.load(os.path.join(golden_dir, "clipl_stats_digest.npz"))
     model = rh.make_clip_text_model("clip-l", seed=0)
     if not np.allclose(weight_checksum(model), g["weight_checksum"], rtol=1e-12):
@@ -157,6 +163,71 @@ def test_stats_properties_at_clipl_size(dev, tmp_path):
         assert float((full[n][1] - s).norm() / s.norm()) < 3e-6
         assert float(torch.diagonal(full[n][1]).min()) > 0
         assert torch.equal(full[n][1], full[n][1].T)
+
+
+# ------------------------------------------------------------------------------------------ native forward
+def _padded(caps):
+    B, L = len(caps), max(len(c) for c in caps)
+    ids = torch.zeros(B, L, dtype=torch.long)
+    pos = torch.zeros(B, L, dtype=torch.long)
+    mask = torch.zeros(B, L, dtype=torch.long)
+    for i, c in enumerate(caps):
+        ids[i, :len(c)] = c
+        pos[i, :len(c)] = torch.arange(len(c))
+        mask[i, :len(c)] = 1
+    return {"input_ids": ids, "position_ids": pos, "attention_mask": mask}
+
+
+@pytest.mark.parametrize("kind,n_caps", [("tiny", 90), ("tiny-gelu", 41), ("clip-l", 40)])
+def test_native_forward_hidden_states_match_hf(dev, kind, n_caps):
+    """Residual stream of the library's forward vs the HF forward the reference runs (fp64 copy of the same
+    model as ground truth); the native fp32-class result must be as close to it as HF's own fp32 run."""
+    import copy
+    from emcid_b200 import clip_forward
+    model = rh.make_clip_text_model(kind, seed=3).to(dev)
+    caps = rh.make_captions(n_caps, model.config.vocab_size, seed=4, min_len=1)
+    batch = {k: v.to(dev) for k, v in _padded(caps).items()}
+    keep = batch["attention_mask"].bool()
+    with torch.no_grad():
+        hs64 = copy.deepcopy(model).double()(**batch, output_hidden_states=True).hidden_states
+        hs32 = model(**batch, output_hidden_states=True).hidden_states
+    ids, pos, cu, S, T = clip_forward.pack_batch(batch, model.config.max_position_embeddings)
+    assert T == sum(len(c) for c in caps) and S == n_caps
+    nat = clip_forward.NativeClipTextEncoder(model, T, S)
+    try:
+        for n in (0, 1, len(hs64) - 1):
+            h = nat.forward_hidden(ids, pos, cu, S, T, n)
+            ref = hs64[n][keep]
+            err = float((h.double() - ref).norm() / ref.norm())
+            err_hf = float((hs32[n][keep].double() - ref).norm() / ref.norm())
+            assert err < max(3e-6, 3 * err_hf), (n, err, err_hf)
+    finally:
+        nat.close()
+
+
+def test_native_forward_falls_back_on_non_right_padding(dev, tmp_path):
+    """A mask that is not a right-padding mask cannot be packed: the block goes through the HF forward with the
+    fused kernels hooked in, and the statistics still match a direct masked Gram."""
+    from emcid_b200 import clip_forward, layer_stats
+    model = rh.make_clip_text_model("tiny", seed=5).to(dev)
+    caps = rh.make_captions(24, model.config.vocab_size, seed=6, min_len=6)
+    batch = _padded(caps)
+    batch["attention_mask"][:, 2] = 0                          # a hole in the middle of every caption
+    assert clip_forward.pack_batch(batch, 77) is None
+    name = "text_model.encoder.layers.1.mlp.fc2"
+    runner = layer_stats.TextEncoderMom2Pass(model, [name])
+    runner.run_batch(batch)
+    mom2, count = runner.finalize()[name]
+    assert runner._native is None
+    runner.close()
+    feats = {}
+    hook = model.text_model.encoder.layers[1].mlp.fc2.register_forward_pre_hook(lambda m, a: feats.__setitem__("a", a[0]))
+    with torch.no_grad():
+        model(**{k: v.to(dev) for k, v in batch.items()})
+    hook.remove()
+    a = feats["a"][batch["attention_mask"].bool().to(dev)].double()
+    assert int(count) == a.shape[0]
+    assert float((mom2.double() - a.T @ a).norm() / (a.T @ a).norm()) < MOM2_TOL
 
 
 # ------------------------------------------------------------------------------------------ closed-form update

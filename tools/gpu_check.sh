@@ -12,7 +12,7 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --captions 1024 --no-e2e --no-cpu --no-solve > $OUT/ncu_launch_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm3x -s 12 -c 4 -f -o $OUT/prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm3x -s 28 -c 8 -f -o $OUT/prof \
     python bench.py --steps 2 --warmup 1 --captions 1024 --no-e2e --no-cpu --no-solve > $OUT/ncu_full_bench.log 2>&1
 fi
 tail -3 $OUT/pytest_gpu.log; cat $OUT/smoke.log | tail -2; cat $OUT/bench.json; tail -2 $OUT/bench.err; cat $OUT/bench_reference.json
