@@ -1,0 +1,208 @@
+// emcid_b200 — causal self-attention of the CLIP text encoder on tcgen05 (head dim 64, captions <= 128 tokens).
+//
+// One (caption, head) unit at a time per persistent CTA; both products run on the tensor core with the
+// same 3-term fp16 split as every other GEMM of the path:
+//   S = Q K^T          A = Q planes [128 x 64], B = K planes [LP x 64]        TMA from the q|k|v planes [T x 3h]
+//   P = softmax(S * dh^-1/2, causal)     fp32 in registers, one query row per thread (TMEM lane)
+//   O = P V            A = P planes [128 x LP] written to swizzled smem by the threads,
+//                      B = V^T planes [64 x LP], TMA from the transposed V planes [h x T]
+// Rows of the 128-row tiles beyond the caption belong to the next captions (finite, never stored) or are
+// zero-filled by TMA; columns j > i and j >= L get P = 0.  Replaces the softmax(QK^T)V of
+// transformers modeling_clip.py::CLIPAttention under the reference's `model(**batch)` (emcid/layer_stats.py:215).
+#pragma once
+
+#include "host.cuh"
+
+namespace emcid {
+
+constexpr int ATTN_DH = 64;
+constexpr int ATTN_THREADS = 128;
+// smem: Q hi/lo (2 x 16 KB) | K hi/lo (2 x 16 KB) | V^T hi/lo x 2 k-blocks (4 x 8 KB) | P hi/lo x 2 k-blocks (4 x 16 KB)
+constexpr int ATTN_TILE = 128 * 128;        // 16 KB: 128 rows of one 128-byte swizzle row
+constexpr int ATTN_VT_TILE = 64 * 128;      // 8 KB
+constexpr int ATTN_OFF_Q = 0;
+constexpr int ATTN_OFF_K = 2 * ATTN_TILE;
+constexpr int ATTN_OFF_V = 4 * ATTN_TILE;
+constexpr int ATTN_OFF_P = 4 * ATTN_TILE + 4 * ATTN_VT_TILE;
+constexpr int ATTN_OFF_BAR = ATTN_OFF_P + 4 * ATTN_TILE;
+constexpr int ATTN_SMEM_BYTES = ATTN_OFF_BAR + 128 + 1024;
+
+struct AttnMaps {
+  CUtensorMap qk_hi, qk_lo;   // q|k|v planes [T x 3h], box 64 x 128
+  CUtensorMap vt_hi, vt_lo;   // V^T planes [h x T], box 64 tokens x 64 features
+};
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restrict__ cu, int n_seqs, int heads, int h,
+                         int lp /* padded caption length: multiple of 16, <= 128 */, float scale,
+                         uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo, int ldo) {
+  extern __shared__ uint8_t attn_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + ATTN_OFF_BAR);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;   // S = Q K^T finished
+  uint64_t* bar_o = bar_qk + 3;   // O = P V finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm.qk_hi); tma_prefetch_desc(&tm.qk_lo);
+    tma_prefetch_desc(&tm.vt_hi); tma_prefetch_desc(&tm.vt_lo);
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);   // S: columns [0, 128), O: [128, 192)
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t s_q = smem_u32(smem + ATTN_OFF_Q), s_k = smem_u32(smem + ATTN_OFF_K);
+  const uint32_t s_v = smem_u32(smem + ATTN_OFF_V), s_p = smem_u32(smem + ATTN_OFF_P);
+  const int n_units = n_seqs * heads;
+  const int ksteps2 = lp / 16;                 // k-steps of the second product
+  const uint32_t idesc1 = make_idesc(FMT_F16, FMT_F16, 128, static_cast<uint32_t>(lp));
+  const uint32_t idesc2 = make_idesc(FMT_F16, FMT_F16, 128, ATTN_DH);
+
+  auto issue_loads = [&](int unit) {
+    const int head = unit % heads, seq = unit / heads;
+    const int t0 = cu[seq];
+    mbar_arrive_expect_tx(bar_qk, 4 * ATTN_TILE);
+    tma_load_2d(smem + ATTN_OFF_Q, &tm.qk_hi, bar_qk, head * ATTN_DH, t0);
+    tma_load_2d(smem + ATTN_OFF_Q + ATTN_TILE, &tm.qk_lo, bar_qk, head * ATTN_DH, t0);
+    tma_load_2d(smem + ATTN_OFF_K, &tm.qk_hi, bar_qk, h + head * ATTN_DH, t0);
+    tma_load_2d(smem + ATTN_OFF_K + ATTN_TILE, &tm.qk_lo, bar_qk, h + head * ATTN_DH, t0);
+    mbar_arrive_expect_tx(bar_v, 4 * ATTN_VT_TILE);
+    tma_load_2d(smem + ATTN_OFF_V, &tm.vt_hi, bar_v, t0, head * ATTN_DH);
+    tma_load_2d(smem + ATTN_OFF_V + ATTN_VT_TILE, &tm.vt_hi, bar_v, t0 + 64, head * ATTN_DH);
+    tma_load_2d(smem + ATTN_OFF_V + 2 * ATTN_VT_TILE, &tm.vt_lo, bar_v, t0, head * ATTN_DH);
+    tma_load_2d(smem + ATTN_OFF_V + 3 * ATTN_VT_TILE, &tm.vt_lo, bar_v, t0 + 64, head * ATTN_DH);
+  };
+
+  if (tid == 0 && static_cast<int>(blockIdx.x) < n_units) issue_loads(blockIdx.x);
+  uint32_t phase = 0;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, phase ^= 1) {
+    const int head = unit % heads, seq = unit / heads;
+    const int t0 = cu[seq];
+    int L = cu[seq + 1] - t0;
+    if (L > lp) L = lp;
+    // ---- S = Q K^T
+    if (tid == 0) {
+      mbar_wait(bar_qk, phase, 11);
+      tc_fence_after();
+      const uint64_t dq_hi = make_desc_k128(s_q), dq_lo = make_desc_k128(s_q + ATTN_TILE);
+      const uint64_t dk_hi = make_desc_k128(s_k), dk_lo = make_desc_k128(s_k + ATTN_TILE);
+#pragma unroll
+      for (int k = 0; k < ATTN_DH / 16; ++k) {
+        const uint64_t ko = static_cast<uint64_t>(k * 2);
+        tc_mma_f16(tmem_base, dq_lo + ko, dk_hi + ko, idesc1, k > 0);
+        tc_mma_f16(tmem_base, dq_hi + ko, dk_lo + ko, idesc1, 1);
+        tc_mma_f16(tmem_base, dq_hi + ko, dk_hi + ko, idesc1, 1);
+      }
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, phase, 12);
+    tc_fence_after();
+    // ---- causal softmax of row i = tid (TMEM lane): e = exp(s - max) goes to the swizzled P tiles as fp16 hi/lo
+    // planes (unnormalised, in (0, 1]); the 1/sum factor is applied to the output row instead
+    float inv = 0.f;
+    {
+      const int i = tid;
+      const bool live = i < L;
+      float mx = -INFINITY;
+      for (int c0 = 0; c0 < lp; c0 += 16) {       // pass 1: row maximum over j <= i
+        float v[16];
+        tmem_ld_32x16(tmem_base + lane_addr + c0, v);
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (live && c0 + u <= i) mx = fmaxf(mx, v[u] * scale);
+      }
+      float sum = 0.f;
+      const uint32_t prow = s_p + i * 128;
+      const int sw = i & 7;
+      for (int c0 = 0; c0 < lp; c0 += 16) {       // pass 2: exponentials, their sum, planes
+        float v[16];
+        tmem_ld_32x16(tmem_base + lane_addr + c0, v);
+        uint32_t hh[8], ll[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float pa = (live && c0 + 2 * u <= i) ? expf(v[2 * u] * scale - mx) : 0.f;
+          const float pb = (live && c0 + 2 * u + 1 <= i) ? expf(v[2 * u + 1] * scale - mx) : 0.f;
+          sum += pa + pb;
+          uint16_t ha, la, hb, lb;
+          split_f16(pa, FMT_F16, ha, la);
+          split_f16(pb, FMT_F16, hb, lb);
+          hh[u] = ha | (static_cast<uint32_t>(hb) << 16);
+          ll[u] = la | (static_cast<uint32_t>(lb) << 16);
+        }
+        // 16 columns = two 16-byte chunks of k-block c0 / 64
+        const int kb = c0 >> 6, ch = (c0 & 63) >> 3;
+        const uint32_t th = prow + kb * ATTN_TILE, tl = prow + (2 + kb) * ATTN_TILE;
+        sts_v4(th + (((ch) ^ sw) << 4), hh[0], hh[1], hh[2], hh[3]);
+        sts_v4(th + (((ch + 1) ^ sw) << 4), hh[4], hh[5], hh[6], hh[7]);
+        sts_v4(tl + (((ch) ^ sw) << 4), ll[0], ll[1], ll[2], ll[3]);
+        sts_v4(tl + (((ch + 1) ^ sw) << 4), ll[4], ll[5], ll[6], ll[7]);
+      }
+      inv = live ? 1.0f / sum : 0.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- O = P V
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, phase, 13);
+      tc_fence_after();
+      const uint32_t tmem_o = tmem_base + 128;
+      for (int k = 0; k < ksteps2; ++k) {
+        const int kb = k >> 2;
+        const uint64_t ko = static_cast<uint64_t>((k & 3) * 2);
+        const uint64_t dp_hi = make_desc_k128(s_p + kb * ATTN_TILE) + ko, dp_lo = make_desc_k128(s_p + (2 + kb) * ATTN_TILE) + ko;
+        const uint64_t dv_hi = make_desc_k128(s_v + kb * ATTN_VT_TILE) + ko, dv_lo = make_desc_k128(s_v + (2 + kb) * ATTN_VT_TILE) + ko;
+        tc_mma_f16(tmem_o, dp_lo, dv_hi, idesc2, k > 0);
+        tc_mma_f16(tmem_o, dp_hi, dv_lo, idesc2, 1);
+        tc_mma_f16(tmem_o, dp_hi, dv_hi, idesc2, 1);
+      }
+      tc_commit(bar_o);
+    }
+    mbar_wait(bar_o, phase, 14);
+    tc_fence_after();
+    // operands are free again: fetch the next unit while this one's output is written
+    if (tid == 0 && unit + static_cast<int>(gridDim.x) < n_units) issue_loads(unit + gridDim.x);
+    if (warp * 32 < L) {                           // warp-uniform: tcgen05.ld is warp-collective
+      uint16_t* oh = o_hi + static_cast<long long>(t0 + tid) * ldo + head * ATTN_DH;
+      uint16_t* ol = o_lo + static_cast<long long>(t0 + tid) * ldo + head * ATTN_DH;
+#pragma unroll
+      for (int c0 = 0; c0 < ATTN_DH; c0 += 16) {
+        float v[16];
+        tmem_ld_32x16(tmem_base + lane_addr + 128 + c0, v);
+        uint32_t hh[8], ll[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          uint16_t ha, la, hb, lb;
+          split_f16(v[2 * u] * inv, FMT_F16, ha, la);
+          split_f16(v[2 * u + 1] * inv, FMT_F16, hb, lb);
+          hh[u] = ha | (static_cast<uint32_t>(hb) << 16);
+          ll[u] = la | (static_cast<uint32_t>(lb) << 16);
+        }
+        if (tid < L) {
+          *reinterpret_cast<uint4*>(oh + c0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(oh + c0 + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+          *reinterpret_cast<uint4*>(ol + c0) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          *reinterpret_cast<uint4*>(ol + c0 + 8) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // all TMEM reads of this unit are done before the next unit's MMAs overwrite S / O
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace emcid

@@ -26,6 +26,7 @@
 
 #include <vector>
 
+#include "attn.cuh"
 #include "mom2.cuh"
 
 namespace emcid {
@@ -53,7 +54,10 @@ struct ClipHandle {
   float *tok_emb, *pos_emb;
   std::vector<ClipLayer>* layers;
   float* hres;                 // [cap x h]
-  float* qkv;                  // [cap x 3h]
+  float* qkv;                  // [cap x 3h]   fp32 q|k|v (CUDA-core attention path)
+  uint16_t *qp_hi, *qp_lo;     // [cap x 3h]   q|k|v planes (tensor-core attention path)
+  uint16_t *vt_hi, *vt_lo;     // [h x tp]     V^T planes
+  bool attn_tc;
   uint16_t *x_hi, *x_lo;       // [cap x hp]   LN output
   uint16_t *a_hi, *a_lo;       // [cap x hp]   attention output
   uint16_t *f_hi, *f_lo;       // [cap x dp]   act(fc1)
@@ -397,7 +401,9 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
       (rc = clip_alloc(H, &H->a_hi, cap * H->hp)) || (rc = clip_alloc(H, &H->a_lo, cap * H->hp)) ||
       (rc = clip_alloc(H, &H->f_hi, cap * H->dp)) || (rc = clip_alloc(H, &H->f_lo, cap * H->dp)) ||
       (rc = clip_alloc(H, &H->ft_hi, static_cast<size_t>(d) * H->tp)) ||
-      (rc = clip_alloc(H, &H->ft_lo, static_cast<size_t>(d) * H->tp)) || (rc = clip_alloc(H, &H->scratch, 64))) {
+      (rc = clip_alloc(H, &H->ft_lo, static_cast<size_t>(d) * H->tp)) || (rc = clip_alloc(H, &H->scratch, 64)) ||
+      (rc = clip_alloc(H, &H->qp_hi, cap * 3 * h)) || (rc = clip_alloc(H, &H->qp_lo, cap * 3 * h)) ||
+      (rc = clip_alloc(H, &H->vt_hi, static_cast<size_t>(h) * H->tp)) || (rc = clip_alloc(H, &H->vt_lo, static_cast<size_t>(h) * H->tp))) {
     clip_destroy(H);
     return rc;
   }
@@ -427,6 +433,18 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
     if (e != cudaSuccess) {
       clip_destroy(H);
       return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", H->attn_smem, cudaGetErrorString(e));
+    }
+  }
+  {
+    // tensor-core attention: head dim 64 (CLIP-L, OpenCLIP bigG), captions up to 128 tokens; EMCID_ATTN_TC=0 disables
+    const char* e = getenv("EMCID_ATTN_TC");
+    H->attn_tc = H->dh == ATTN_DH && max_pos <= 128 && (3 * h) % 8 == 0 && !(e && e[0] == '0');
+    if (H->attn_tc) {
+      cudaError_t ce = cudaFuncSetAttribute(clip_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_BYTES);
+      if (ce != cudaSuccess) {
+        clip_destroy(H);
+        return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", ATTN_SMEM_BYTES, cudaGetErrorString(ce));
+      }
     }
   }
   *out = H;
@@ -512,7 +530,7 @@ struct ClipActMaps {
 inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap& x_lo, const ClipWeight& W, int T,
                        int act, const float* Cin, float* C, long long ldc, uint16_t* P_hi, uint16_t* P_lo, long long ldp,
                        uint16_t* Pt_hi, uint16_t* Pt_lo, long long ldpt, cudaStream_t stream,
-                       const GemmOutMaps* om = nullptr) {
+                       const GemmOutMaps* om = nullptr, int pt_col_min = 0) {
   GemmOperands ops;
   ops.a_hi = x_hi; ops.a_lo = x_lo; ops.b_hi = W.m_hi; ops.b_lo = W.m_lo;
   GemmParams p;
@@ -525,6 +543,7 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   p.C = C; p.ldc = ldc;
   p.P_hi = reinterpret_cast<float*>(P_hi); p.P_lo = reinterpret_cast<float*>(P_lo); p.ldp = ldp;
   p.Pt_hi = reinterpret_cast<float*>(Pt_hi); p.Pt_lo = reinterpret_cast<float*>(Pt_lo); p.ldpt = ldpt;
+  p.pt_col_min = pt_col_min;
   const int tiles = gemm_num_tiles(T, W.N, 256, 0);
   const int grid = tiles < H->info.sm_count ? tiles : H->info.sm_count;
   H->launches += 1;
@@ -534,7 +553,9 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   if (ef == (F))                                                                                              \
     return om ? launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (F)>(ops, p, grid, stream, 1, om)             \
               : launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream);
-  EMCID_LIN_CASE(ACT_NONE | EF_C)                       // q/k/v projection
+  EMCID_LIN_CASE(ACT_NONE | EF_C)                       // q/k/v projection (fp32, CUDA-core attention)
+  if (om && ef == (ACT_NONE | EF_P | EF_PT))            // q/k/v projection as planes + V^T planes (tensor-core attention)
+    return launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P | EF_PT)>(ops, p, grid, stream, 1, om);
   EMCID_LIN_CASE(ACT_NONE | EF_C | EF_CIN)              // out projection / fc2 with residual
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P)                 // fc1
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P | EF_PT)         // fc1 of an edited layer
@@ -609,6 +630,18 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       return rc;
     om_f.c = mf_hi; om_f.c2 = mf_lo;
   }
+  const bool attn_tc = H->attn_tc && use_tma_epi;
+  AttnMaps am = {};
+  if (attn_tc) {
+    if ((rc = make_tmap_2d(&am.qk_hi, H->qp_hi, T, 3ll * H->h, 3ll * H->h, 128, 2)) ||
+        (rc = make_tmap_2d(&am.qk_lo, H->qp_lo, T, 3ll * H->h, 3ll * H->h, 128, 2)) ||
+        (rc = make_tmap_2d(&am.vt_hi, H->vt_hi, H->h, T, H->tp, 64, 2)) ||
+        (rc = make_tmap_2d(&am.vt_lo, H->vt_lo, H->h, T, H->tp, 64, 2)) ||
+        (rc = make_tmap_2d(&om_qkv.t_hi, H->vt_hi, H->h, T, H->tp, 32, 2, 128)) ||
+        (rc = make_tmap_2d(&om_qkv.t_lo, H->vt_lo, H->h, T, H->tp, 32, 2, 128)))
+      return rc;
+    om_qkv.c = am.qk_hi; om_qkv.c2 = am.qk_lo;
+  }
   const GemmOutMaps* pm_qkv = use_tma_epi ? &om_qkv : nullptr;
   const GemmOutMaps* pm_res = use_tma_epi ? &om_res : nullptr;
   const GemmOutMaps* pm_f = use_tma_epi ? &om_f : nullptr;
@@ -625,6 +658,15 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   for (int l = 0; l < run_layers; ++l) {
     const ClipLayer& Ly = (*H->layers)[l];
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln1_w, Ly.ln1_b, H->x_hi, H->x_lo, stream))) return rc;
+    if (attn_tc) {
+      if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, nullptr, 0, H->qp_hi, H->qp_lo, 3ll * H->h, H->vt_hi,
+                            H->vt_lo, H->tp, stream, pm_qkv, 2 * H->h)))
+        return rc;
+      const int units = S * H->heads;
+      const int lp = (H->max_pos + 15) & ~15;
+      clip_attention_tc_kernel<<<units < sms ? units : sms, ATTN_THREADS, ATTN_SMEM_BYTES, stream>>>(
+          am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
+    } else {
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, nullptr,
                           nullptr, 0, stream, pm_qkv)))
       return rc;
@@ -638,6 +680,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
         clip_attention_kernel<<<ag, 128, H->attn_smem, stream>>>(H->qkv, cu_seqlens, H->h, H->dh, H->max_pos, scale,
                                                                  H->a_hi, H->a_lo, H->hp);
 #undef EMCID_ATTN_CASE
+    }
     }
     EMCID_CUDA_CHECK(cudaGetLastError());
     H->launches += 1;

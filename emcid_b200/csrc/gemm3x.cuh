@@ -94,6 +94,8 @@ struct GemmParams {
   long long ldpt, pt_batch;
   const float* bias;           // [M], EPI_FC1
   const float* bias_col;       // [N], EPI_LINEAR (16-byte aligned)
+  int pt_col_min;              // EPI_LINEAR_TMA: transposed planes only for columns >= this (a multiple of 32);
+                               // the transposed tensor map starts at that column
   int act;
   int lo_fmt;                  // KIND_F16: format of the lo planes (FMT_BF16 default, FMT_F16)
 };
@@ -506,6 +508,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             if (EFLAGS & EF_PT) {
 #pragma unroll
               for (int sub = 0; sub < 2; ++sub) {                  // 32 features x 128 tokens per plane (8 KB each)
+                if (col0 + pc * 64 + sub * 32 < p.pt_col_min) continue;   // uniform over the 128 threads of the half
                 if (issuer) bulk_wait_read0();
                 named_bar_sync(bar_id, 128);
 #pragma unroll
@@ -519,8 +522,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                 fence_proxy_async();
                 named_bar_sync(bar_id, 128);
                 if (issuer && col0 + pc * 64 + sub * 32 < N) {
-                  tma_store_2d(&om.t_hi, sbase, u.m0, col0 + pc * 64 + sub * 32);
-                  tma_store_2d(&om.t_lo, sbase + 8192, u.m0, col0 + pc * 64 + sub * 32);
+                  tma_store_2d(&om.t_hi, sbase, u.m0, col0 + pc * 64 + sub * 32 - p.pt_col_min);
+                  tma_store_2d(&om.t_lo, sbase + 8192, u.m0, col0 + pc * 64 + sub * 32 - p.pt_col_min);
                   bulk_commit();
                 }
               }
