@@ -5,7 +5,9 @@
 //   S = Q K^T          A = Q planes [128 x 64], B = K planes [LP x 64]        TMA from the q|k|v planes [T x 3h]
 //   P = softmax(S * dh^-1/2, causal)     fp32 in registers, one query row per thread (TMEM lane)
 //   O = P V            A = P planes [128 x LP] written to swizzled smem by the threads,
-//                      B = V^T planes [64 x LP], TMA from the transposed V planes [h x T]
+//                      B = V planes [LP x 64] as an MN-major operand (the same TMA tile shape as Q and K: a TMA
+//                      load along the contiguous token axis of a transposed copy would need 16-byte aligned
+//                      caption starts, which packed captions do not have)
 // Rows of the 128-row tiles beyond the caption belong to the next captions (finite, never stored) or are
 // zero-filled by TMA; columns j > i and j >= L get P = 0.  Replaces the softmax(QK^T)V of
 // transformers modeling_clip.py::CLIPAttention under the reference's `model(**batch)` (emcid/layer_stats.py:215).
@@ -17,19 +19,17 @@ namespace emcid {
 
 constexpr int ATTN_DH = 64;
 constexpr int ATTN_THREADS = 128;
-// smem: Q hi/lo (2 x 16 KB) | K hi/lo (2 x 16 KB) | V^T hi/lo x 2 k-blocks (4 x 8 KB) | P hi/lo x 2 k-blocks (4 x 16 KB)
+// smem: Q hi/lo | K hi/lo | V hi/lo (2 x 16 KB each) | P hi/lo x 2 k-blocks (4 x 16 KB)
 constexpr int ATTN_TILE = 128 * 128;        // 16 KB: 128 rows of one 128-byte swizzle row
-constexpr int ATTN_VT_TILE = 64 * 128;      // 8 KB
 constexpr int ATTN_OFF_Q = 0;
 constexpr int ATTN_OFF_K = 2 * ATTN_TILE;
 constexpr int ATTN_OFF_V = 4 * ATTN_TILE;
-constexpr int ATTN_OFF_P = 4 * ATTN_TILE + 4 * ATTN_VT_TILE;
+constexpr int ATTN_OFF_P = 6 * ATTN_TILE;
 constexpr int ATTN_OFF_BAR = ATTN_OFF_P + 4 * ATTN_TILE;
 constexpr int ATTN_SMEM_BYTES = ATTN_OFF_BAR + 128 + 1024;
 
 struct AttnMaps {
   CUtensorMap qk_hi, qk_lo;   // q|k|v planes [T x 3h], box 64 x 128
-  CUtensorMap vt_hi, vt_lo;   // V^T planes [h x T], box 64 tokens x 64 features
 };
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
@@ -47,7 +47,6 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
 
   if (tid == 0) {
     tma_prefetch_desc(&tm.qk_hi); tma_prefetch_desc(&tm.qk_lo);
-    tma_prefetch_desc(&tm.vt_hi); tma_prefetch_desc(&tm.vt_lo);
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
   }
@@ -65,7 +64,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
   const int n_units = n_seqs * heads;
   const int ksteps2 = lp / 16;                 // k-steps of the second product
   const uint32_t idesc1 = make_idesc(FMT_F16, FMT_F16, 128, static_cast<uint32_t>(lp));
-  const uint32_t idesc2 = make_idesc(FMT_F16, FMT_F16, 128, ATTN_DH);
+  const uint32_t idesc2 = make_idesc(FMT_F16, FMT_F16, 128, ATTN_DH) | (1u << 16);   // B (= V) is MN-major
 
   auto issue_loads = [&](int unit) {
     const int head = unit % heads, seq = unit / heads;
@@ -75,11 +74,9 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     tma_load_2d(smem + ATTN_OFF_Q + ATTN_TILE, &tm.qk_lo, bar_qk, head * ATTN_DH, t0);
     tma_load_2d(smem + ATTN_OFF_K, &tm.qk_hi, bar_qk, h + head * ATTN_DH, t0);
     tma_load_2d(smem + ATTN_OFF_K + ATTN_TILE, &tm.qk_lo, bar_qk, h + head * ATTN_DH, t0);
-    mbar_arrive_expect_tx(bar_v, 4 * ATTN_VT_TILE);
-    tma_load_2d(smem + ATTN_OFF_V, &tm.vt_hi, bar_v, t0, head * ATTN_DH);
-    tma_load_2d(smem + ATTN_OFF_V + ATTN_VT_TILE, &tm.vt_hi, bar_v, t0 + 64, head * ATTN_DH);
-    tma_load_2d(smem + ATTN_OFF_V + 2 * ATTN_VT_TILE, &tm.vt_lo, bar_v, t0, head * ATTN_DH);
-    tma_load_2d(smem + ATTN_OFF_V + 3 * ATTN_VT_TILE, &tm.vt_lo, bar_v, t0 + 64, head * ATTN_DH);
+    mbar_arrive_expect_tx(bar_v, 2 * ATTN_TILE);
+    tma_load_2d(smem + ATTN_OFF_V, &tm.qk_hi, bar_v, 2 * h + head * ATTN_DH, t0);
+    tma_load_2d(smem + ATTN_OFF_V + ATTN_TILE, &tm.qk_lo, bar_v, 2 * h + head * ATTN_DH, t0);
   };
 
   if (tid == 0 && static_cast<int>(blockIdx.x) < n_units) issue_loads(blockIdx.x);
@@ -161,7 +158,9 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
         const int kb = k >> 2;
         const uint64_t ko = static_cast<uint64_t>((k & 3) * 2);
         const uint64_t dp_hi = make_desc_k128(s_p + kb * ATTN_TILE) + ko, dp_lo = make_desc_k128(s_p + (2 + kb) * ATTN_TILE) + ko;
-        const uint64_t dv_hi = make_desc_k128(s_v + kb * ATTN_VT_TILE) + ko, dv_lo = make_desc_k128(s_v + (2 + kb) * ATTN_VT_TILE) + ko;
+        // V tile rows are tokens (= K of this product): one k-step is 16 rows = 2048 bytes further down the tile;
+        // MN-major SW128 canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> SBO = 1024 B, as written by TMA
+        const uint64_t dv_hi = make_desc_k128(s_v + k * 2048), dv_lo = make_desc_k128(s_v + ATTN_TILE + k * 2048);
         tc_mma_f16(tmem_o, dp_lo, dv_hi, idesc2, k > 0);
         tc_mma_f16(tmem_o, dp_hi, dv_lo, idesc2, 1);
         tc_mma_f16(tmem_o, dp_hi, dv_hi, idesc2, 1);

@@ -56,7 +56,6 @@ struct ClipHandle {
   float* hres;                 // [cap x h]
   float* qkv;                  // [cap x 3h]   fp32 q|k|v (CUDA-core attention path)
   uint16_t *qp_hi, *qp_lo;     // [cap x 3h]   q|k|v planes (tensor-core attention path)
-  uint16_t *vt_hi, *vt_lo;     // [h x tp]     V^T planes
   bool attn_tc;
   uint16_t *x_hi, *x_lo;       // [cap x hp]   LN output
   uint16_t *a_hi, *a_lo;       // [cap x hp]   attention output
@@ -402,8 +401,7 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
       (rc = clip_alloc(H, &H->f_hi, cap * H->dp)) || (rc = clip_alloc(H, &H->f_lo, cap * H->dp)) ||
       (rc = clip_alloc(H, &H->ft_hi, static_cast<size_t>(d) * H->tp)) ||
       (rc = clip_alloc(H, &H->ft_lo, static_cast<size_t>(d) * H->tp)) || (rc = clip_alloc(H, &H->scratch, 64)) ||
-      (rc = clip_alloc(H, &H->qp_hi, cap * 3 * h)) || (rc = clip_alloc(H, &H->qp_lo, cap * 3 * h)) ||
-      (rc = clip_alloc(H, &H->vt_hi, static_cast<size_t>(h) * H->tp)) || (rc = clip_alloc(H, &H->vt_lo, static_cast<size_t>(h) * H->tp))) {
+      (rc = clip_alloc(H, &H->qp_hi, cap * 3 * h)) || (rc = clip_alloc(H, &H->qp_lo, cap * 3 * h))) {
     clip_destroy(H);
     return rc;
   }
@@ -554,8 +552,8 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
     return om ? launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (F)>(ops, p, grid, stream, 1, om)             \
               : launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream);
   EMCID_LIN_CASE(ACT_NONE | EF_C)                       // q/k/v projection (fp32, CUDA-core attention)
-  if (om && ef == (ACT_NONE | EF_P | EF_PT))            // q/k/v projection as planes + V^T planes (tensor-core attention)
-    return launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P | EF_PT)>(ops, p, grid, stream, 1, om);
+  if (om && ef == (ACT_NONE | EF_P))                    // q/k/v projection as planes (tensor-core attention)
+    return launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om);
   EMCID_LIN_CASE(ACT_NONE | EF_C | EF_CIN)              // out projection / fc2 with residual
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P)                 // fc1
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P | EF_PT)         // fc1 of an edited layer
@@ -634,11 +632,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   AttnMaps am = {};
   if (attn_tc) {
     if ((rc = make_tmap_2d(&am.qk_hi, H->qp_hi, T, 3ll * H->h, 3ll * H->h, 128, 2)) ||
-        (rc = make_tmap_2d(&am.qk_lo, H->qp_lo, T, 3ll * H->h, 3ll * H->h, 128, 2)) ||
-        (rc = make_tmap_2d(&am.vt_hi, H->vt_hi, H->h, T, H->tp, 64, 2)) ||
-        (rc = make_tmap_2d(&am.vt_lo, H->vt_lo, H->h, T, H->tp, 64, 2)) ||
-        (rc = make_tmap_2d(&om_qkv.t_hi, H->vt_hi, H->h, T, H->tp, 32, 2, 128)) ||
-        (rc = make_tmap_2d(&om_qkv.t_lo, H->vt_lo, H->h, T, H->tp, 32, 2, 128)))
+        (rc = make_tmap_2d(&am.qk_lo, H->qp_lo, T, 3ll * H->h, 3ll * H->h, 128, 2)))
       return rc;
     om_qkv.c = am.qk_hi; om_qkv.c2 = am.qk_lo;
   }
@@ -659,8 +653,8 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     const ClipLayer& Ly = (*H->layers)[l];
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln1_w, Ly.ln1_b, H->x_hi, H->x_lo, stream))) return rc;
     if (attn_tc) {
-      if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, nullptr, 0, H->qp_hi, H->qp_lo, 3ll * H->h, H->vt_hi,
-                            H->vt_lo, H->tp, stream, pm_qkv, 2 * H->h)))
+      if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, nullptr, 0, H->qp_hi, H->qp_lo, 3ll * H->h, nullptr,
+                            nullptr, 0, stream, pm_qkv)))
         return rc;
       const int units = S * H->heads;
       const int lp = (H->max_pos + 15) & ~15;
