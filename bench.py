@@ -226,9 +226,9 @@ def run_ours(args):
     def finish():
         out = runner.finalize()
         if world > 1:
-            for j, n in enumerate(names):
-                dist.reduce(out[n][0], dst=j % world, op=dist.ReduceOp.SUM)
-                dist.reduce(out[n][1], dst=j % world, op=dist.ReduceOp.SUM)
+            for n in names:
+                dist.all_reduce(out[n][0], op=dist.ReduceOp.SUM)
+                dist.all_reduce(out[n][1], op=dist.ReduceOp.SUM)
         return out
 
     def launches():
@@ -346,7 +346,8 @@ def run_ours(args):
         t0 = time.perf_counter()
         stats = layer_stats.layer_stats_text_encoder_multi(
             model, None, names, stats_dir=tmp, sample_size=total_caps, precision="float32", progress=None,
-            force_recompute=True, captions_per_batch=blk, slab_tokens=args.slab)
+            force_recompute=True, captions_per_batch=blk, slab_tokens=args.slab,
+            num_workers=0)  # the synthetic captions are pre-tokenised in memory: no tokeniser workers to feed
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:

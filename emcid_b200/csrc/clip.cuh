@@ -438,10 +438,11 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
     const char* e = getenv("EMCID_ATTN_TC");
     H->attn_tc = H->dh == ATTN_DH && max_pos <= 128 && (3 * h) % 8 == 0 && !(e && e[0] == '0');
     if (H->attn_tc) {
-      cudaError_t ce = cudaFuncSetAttribute(clip_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_BYTES);
+      const int lp = (max_pos + 15) & ~15;
+      cudaError_t ce = cudaFuncSetAttribute(clip_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(lp));
       if (ce != cudaSuccess) {
         clip_destroy(H);
-        return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", ATTN_SMEM_BYTES, cudaGetErrorString(ce));
+        return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", attn_smem_bytes(lp), cudaGetErrorString(ce));
       }
     }
   }
@@ -632,7 +633,9 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   AttnMaps am = {};
   if (attn_tc) {
     if ((rc = make_tmap_2d(&am.qk_hi, H->qp_hi, T, 3ll * H->h, 3ll * H->h, 128, 2)) ||
-        (rc = make_tmap_2d(&am.qk_lo, H->qp_lo, T, 3ll * H->h, 3ll * H->h, 128, 2)))
+        (rc = make_tmap_2d(&am.qk_lo, H->qp_lo, T, 3ll * H->h, 3ll * H->h, 128, 2)) ||
+        (rc = make_tmap_2d(&am.kv_hi, H->qp_hi, T, 3ll * H->h, 3ll * H->h, (H->max_pos + 15) & ~15, 2)) ||
+        (rc = make_tmap_2d(&am.kv_lo, H->qp_lo, T, 3ll * H->h, 3ll * H->h, (H->max_pos + 15) & ~15, 2)))
       return rc;
     om_qkv.c = am.qk_hi; om_qkv.c2 = am.qk_lo;
   }
@@ -658,8 +661,8 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
         return rc;
       const int units = S * H->heads;
       const int lp = (H->max_pos + 15) & ~15;
-      clip_attention_tc_kernel<<<units < sms ? units : sms, ATTN_THREADS, ATTN_SMEM_BYTES, stream>>>(
-          am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
+      clip_attention_tc_kernel<<<units < sms ? units : sms, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
+          am, cu_seqlens, S, H->heads, H->h, lp, attn_num_bufs(lp), scale, H->a_hi, H->a_lo, H->hp);
     } else {
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, nullptr,
                           nullptr, 0, stream, pm_qkv)))

@@ -277,10 +277,10 @@ def layer_stats_text_encoder_multi(
             root = i % world
             if dist is not None and world > 1:
                 # the one exchange step of the pass: per-rank partial sums -> one matrix per layer
-                dist.reduce(mom2, dst=root, op=dist.ReduceOp.SUM)
-                dist.reduce(count, dst=root, op=dist.ReduceOp.SUM)
-                dist.broadcast(mom2, src=root)
-                dist.broadcast(count, src=root)
+                # (every rank returns the full statistics, like the single-process reference call, so this is an
+                # all-reduce; rank `root` additionally writes that layer's npz)
+                dist.all_reduce(mom2, op=dist.ReduceOp.SUM)
+                dist.all_reduce(count, op=dist.ReduceOp.SUM)
             sm = stats[n].mom2
             sm.count = int(count.item())
             sm.mom2 = mom2 if keep_on_device else mom2.to("cpu")

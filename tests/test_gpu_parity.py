@@ -178,7 +178,7 @@ def _padded(caps):
     return {"input_ids": ids, "position_ids": pos, "attention_mask": mask}
 
 
-@pytest.mark.parametrize("kind,n_caps", [("tiny", 90), ("tiny-gelu", 41), ("clip-l", 40)])
+@pytest.mark.parametrize("kind,n_caps", [("tiny", 90), ("tiny-gelu", 41), ("clip-l", 40), ("bigg", 6)])
 def test_native_forward_hidden_states_match_hf(dev, kind, n_caps):
     """Residual stream of the library's forward vs the HF forward the reference runs (fp64 copy of the same
     model as ground truth); the native fp32-class result must be as close to it as HF's own fp32 run."""
