@@ -346,8 +346,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         stats = layer_stats.layer_stats_text_encoder_multi(
             model, None, names, stats_dir=tmp, sample_size=total_caps, precision="float32", progress=None,
-            force_recompute=True, captions_per_batch=blk, slab_tokens=args.slab,
-            num_workers=0)  # the synthetic captions are pre-tokenised in memory: no tokeniser workers to feed
+            force_recompute=True, captions_per_batch=blk, slab_tokens=args.slab)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:

@@ -31,7 +31,7 @@ import torch
 from . import clip_forward, nethook
 from .runningstats import (CombinedStat, FixedSubsetSampler, Mean, NormMean, SecondMoment, load_cached_state,
                            save_cached_state, subset_indices)
-from .stat_dataset import TokenizedDataset, dict_to_, fixed_width_collation
+from .stat_dataset import TokenizedDataset, dict_to_, fixed_width_collation, packed_collation, unpack_to_padded
 
 try:  # the reference's default progress bar
     from tqdm.auto import tqdm
@@ -145,7 +145,21 @@ class TextEncoderMom2Pass:
 
     @torch.no_grad()
     def run_batch(self, batch: Dict[str, torch.Tensor]) -> None:
-        """batch: input_ids / position_ids / attention_mask [B, L] (host or device tensors)."""
+        """batch: input_ids / position_ids / attention_mask [B, L] (host or device tensors), or an already
+        packed block (packed_ids / packed_pos / cu_seqlens, see stat_dataset.packed_collation)."""
+        if "packed_ids" in batch:
+            max_pos = getattr(self.model, "text_model", self.model).embeddings.position_embedding.weight.shape[0]
+            cu = batch["cu_seqlens"]
+            S, T = cu.numel() - 1, batch["packed_ids"].numel()
+            if T == 0:
+                return
+            if self._use_native and (cu.is_cuda or int((cu[1:] - cu[:-1]).max()) <= max_pos):
+                names = list(self._layer_index)
+                self._native_encoder(T, S).forward_stats(batch["packed_ids"], batch["packed_pos"], cu, S, T,
+                                                         [self._layer_index[n] for n in names],
+                                                         [self.accs[n] for n in names])
+                return
+            batch = unpack_to_padded(batch)
         if self._use_native:
             max_pos = getattr(self.model, "text_model", self.model).embeddings.position_embedding.weight.shape[0]
             packed = clip_forward.pack_batch(batch, max_pos)
@@ -259,7 +273,8 @@ def layer_stats_text_encoder_multi(
     my_indices = indices[rank::world]
     loader = torch.utils.data.DataLoader(
         ds, sampler=FixedSubsetSampler(my_indices), batch_size=captions_per_batch,
-        collate_fn=fixed_width_collation(), num_workers=num_workers, pin_memory=(device.type == "cuda"))
+        collate_fn=packed_collation() if (device.type == "cuda" and _accumulator_factory is None) else fixed_width_collation(),
+        num_workers=num_workers, pin_memory=(device.type == "cuda"))
     batch_count = -(-len(my_indices) // captions_per_batch)
     if progress is None:
         progress = lambda x, total=None: x
@@ -267,7 +282,8 @@ def layer_stats_text_encoder_multi(
     runner = TextEncoderMom2Pass(model, todo, slab_tokens=slab_tokens, accumulator_factory=_accumulator_factory)
     try:
         for batch in progress(loader, total=batch_count):
-            if batch["input_ids"].numel() == 0:
+            if ("packed_ids" in batch and batch["packed_ids"].numel() == 0) or \
+                    ("input_ids" in batch and batch["input_ids"].numel() == 0):
                 continue
             runner.run_batch(batch)  # host tensors: packed on the host, then one pinned H2D copy per field
         results = runner.finalize()

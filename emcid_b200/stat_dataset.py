@@ -106,3 +106,42 @@ def fixed_width_collation(width: int = 0):
         return batch
 
     return collate_fn
+
+
+def packed_collation():
+    """collate_fn of the native-forward driver: no padding at all.  Captions are concatenated into packed
+    int32 `packed_ids` / `packed_pos` with `cu_seqlens` prefix sums (what csrc/clip.cuh consumes); empty
+    captions are dropped like make_padded_batch drops them.  Items whose attention mask is not all ones
+    (never produced by TokenizedDataset, reference :99-110) make the block fall back to a padded batch."""
+
+    def collate_fn(items):
+        keep = [it for it in items if len(it["input_ids"])]
+        if not keep:
+            return make_padded_batch(items)
+        masks = torch.cat([it["attention_mask"] for it in keep])
+        if not bool((masks != 0).all()):
+            return make_padded_batch(items)
+        lens = torch.tensor([len(it["input_ids"]) for it in keep], dtype=torch.int32)
+        cu = torch.zeros(len(keep) + 1, dtype=torch.int32)
+        cu[1:] = torch.cumsum(lens, 0)
+        return {"packed_ids": torch.cat([it["input_ids"] for it in keep]).to(torch.int32),
+                "packed_pos": torch.cat([it["position_ids"] for it in keep]).to(torch.int32),
+                "cu_seqlens": cu}
+
+    return collate_fn
+
+
+def unpack_to_padded(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """packed block -> right-padded int64 input_ids / position_ids / attention_mask [B, L]."""
+    cu = batch["cu_seqlens"].to(torch.int64).cpu()
+    lens = cu[1:] - cu[:-1]
+    B, L = len(lens), int(lens.max()) if len(lens) else 0
+    cols = torch.arange(L)[None, :]
+    mask = cols < lens[:, None]
+    out = {}
+    for src, dst in (("packed_ids", "input_ids"), ("packed_pos", "position_ids")):
+        buf = torch.zeros(B, L, dtype=torch.int64)
+        buf[mask] = batch[src].cpu().to(torch.int64)
+        out[dst] = buf
+    out["attention_mask"] = mask.to(torch.int64)
+    return out

@@ -54,11 +54,15 @@ class CaptionIdDataset(torch.utils.data.Dataset):
 
     def __init__(self, captions):
         self.captions = captions
+        self._pos, self._ones = {}, {}      # per-length position ids / masks are shared (collation only reads them)
 
     def __len__(self):
         return len(self.captions)
 
     def __getitem__(self, i):
         ids = self.captions[i]
-        return dict(input_ids=ids, position_ids=torch.arange(len(ids)),
-                    attention_mask=torch.ones(len(ids), dtype=torch.long))
+        n = len(ids)
+        if n not in self._pos:
+            self._pos[n] = torch.arange(n)
+            self._ones[n] = torch.ones(n, dtype=torch.long)
+        return dict(input_ids=ids, position_ids=self._pos[n], attention_mask=self._ones[n])
