@@ -175,12 +175,19 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
+    global LAYERS, H, D
+    if args.layers:
+        LAYERS = [int(x) for x in args.layers.split(",")]
+    elif args.encoder == "sdxl-text2":
+        LAYERS = [26, 27, 28, 29, 30]
+    if args.encoder == "sdxl-text2":
+        H, D = 1280, 5120
     import torch
     import torch.distributed as dist
 
@@ -202,7 +209,8 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False
 
     K, W, C = args.steps, args.warmup, args.captions
-    model = synth.make_text_encoder("sd-text", seed=0).to(dev)
+    model = synth.make_text_encoder(args.encoder, seed=0).to(dev)
+    flops_per_token_layer = 2 * H * D + D * (D + 1)
     names = [LAYER_TMP.format(l) for l in LAYERS]
     tokens_per_step = C * WIDTH
 
@@ -300,7 +308,7 @@ def run_ours(args):
         "traffic": ncu_traffic(),
     }
     # whole-step fraction of the tensor roofline (what the BASELINE metric asks next to tokens/s)
-    step_tflops = value * len(LAYERS) * FLOPS_PER_TOKEN_LAYER / 1e12 / world
+    step_tflops = value * len(LAYERS) * flops_per_token_layer / 1e12 / world
     roofline["step_frac"] = step_tflops / tf32_peak
 
     # ---- second half of the metric: ms per 1000-concept 5-layer closed-form update (one GPU, batched)
@@ -361,7 +369,7 @@ def run_ours(args):
                "seconds": float(dt.item()), "captions": total_caps}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and args.encoder == "sd-text" and not args.layers:
         v, dt, tokens = cpu_port_tokens_per_s(args.ref_captions, os.cpu_count() or 1)
         cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{args.ref_captions} captions x 77 tokens, layers 7-11 (one full pass per layer as the "
@@ -372,7 +380,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16x3 (3-term fp16 split, fp32 accumulate; fp32-class accuracy)", "data": "synthetic",
-            "config": {"workload": workload_name(C), "layers": LAYERS, "captions_per_gpu_per_step": C,
+            "config": {"workload": workload_name(C) if args.encoder == "sd-text" and not args.layers else
+                       f"{args.encoder} (random-init) mom2+count of layers {LAYERS} mlp.fc2 inputs, {C} synthetic 77-token "
+                       f"captions per GPU per step", "layers": LAYERS, "captions_per_gpu_per_step": C,
                        "tokens_per_gpu_per_step": tokens_per_step, "block_captions": blk,
                        "l2": "per-step working set (X slabs, activations) >> 126 MB L2; no flush needed",
                        "parallelism": f"caption-sharded x{world}, one NCCL reduce per layer at the end of the pass",
@@ -382,20 +392,45 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solve": solve, "clocks": clocks,
             "gpu_launches": int(n_launch),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything libraries print to stdout (e.g. NCCL's version banner) to stderr: stdout carries exactly
+    one JSON line, written by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--captions", type=int, default=2048, help="captions per GPU per step")
+    ap.add_argument("--encoder", default="sd-text", choices=["sd-text", "sdxl-text1", "sdxl-text2"],
+                    help="sd-text = BASELINE configs[1] (the headline); sdxl-text2 = OpenCLIP bigG shapes (configs[3])")
+    ap.add_argument("--layers", default="", help="comma-separated edited layers (default 7-11; sdxl-text2: 26-30)")
     ap.add_argument("--block-captions", type=int, default=512, help="captions per forward block")
     ap.add_argument("--slab", type=int, default=0, help="tokens per fc1/SYRK launch pair (0 = library default)")
     ap.add_argument("--concepts", type=int, default=1000)

@@ -57,6 +57,7 @@ struct ClipHandle {
   float* qkv;                  // [cap x 3h]   fp32 q|k|v (CUDA-core attention path)
   uint16_t *qp_hi, *qp_lo;     // [cap x 3h]   q|k|v planes (tensor-core attention path)
   bool attn_tc;
+  int rowb;                    // bytes per smem row of the GEMM operand tiles: 128 (2 stages) or 64 (4 stages)
   uint16_t *x_hi, *x_lo;       // [cap x hp]   LN output
   uint16_t *a_hi, *a_lo;       // [cap x hp]   attention output
   uint16_t *f_hi, *f_lo;       // [cap x dp]   act(fc1)
@@ -434,6 +435,14 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
     }
   }
   {
+    // experiment switch: 64-byte operand rows / 4 pipeline stages (needs the staged TMA epilogue).  Measured on
+    // B200: within 2 % of the default 128-byte / 2-stage pipeline (only the K = 3072 fc2 gains ~10 %), i.e. the
+    // mainloop is not TMA-latency bound; kept off.
+    const char* e = getenv("EMCID_GEMM_S64");
+    const char* t = getenv("EMCID_LINEAR_TMA");
+    H->rowb = (e && e[0] == '1' && !(t && t[0] == '0')) ? 64 : 128;
+  }
+  {
     // tensor-core attention: head dim 64 (CLIP-L, OpenCLIP bigG), captions up to 128 tokens; EMCID_ATTN_TC=0 disables
     const char* e = getenv("EMCID_ATTN_TC");
     H->attn_tc = H->dh == ATTN_DH && max_pos <= 128 && (3 * h) % 8 == 0 && !(e && e[0] == '0');
@@ -488,7 +497,9 @@ inline int clip_prepare_weight(ClipHandle* H, ClipWeight* W, int parts, const fl
       EMCID_CUDA_CHECK(cudaMemsetAsync(W->bias + static_cast<size_t>(i) * rows_each, 0, rows_each * sizeof(float), stream));
     }
   }
-  if ((rc = make_tmap_2d(&W->m_hi, W->hi, N, K, Kp, 128, 2)) || (rc = make_tmap_2d(&W->m_lo, W->lo, N, K, Kp, 128, 2))) return rc;
+  if ((rc = make_tmap_2d(&W->m_hi, W->hi, N, K, Kp, 128, 2, 0, H->rowb)) ||
+      (rc = make_tmap_2d(&W->m_lo, W->lo, N, K, Kp, 128, 2, 0, H->rowb)))
+    return rc;
   return EMCID_OK;
 }
 
@@ -548,13 +559,16 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   H->launches += 1;
   // the epilogue variant is a compile-time option (see EF_* in gemm3x.cuh): only the combinations the forward uses
   const int ef = act | (C ? EF_C : 0) | (Cin ? EF_CIN : 0) | (P_hi ? EF_P : 0) | (Pt_hi ? EF_PT : 0);
+  if (om && H->rowb == 64) p.chunk_kblocks *= 2;   // k-blocks are half as deep
 #define EMCID_LIN_CASE(F)                                                                                     \
   if (ef == (F))                                                                                              \
-    return om ? launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (F)>(ops, p, grid, stream, 1, om)             \
-              : launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream);
+    return !om            ? launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream)            \
+           : H->rowb == 64 ? launch_gemm3x<256, 4, EPI_LINEAR_TMA, KIND_F16_S64, (F)>(ops, p, grid, stream, 1, om) \
+                           : launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (F)>(ops, p, grid, stream, 1, om);
   EMCID_LIN_CASE(ACT_NONE | EF_C)                       // q/k/v projection (fp32, CUDA-core attention)
   if (om && ef == (ACT_NONE | EF_P))                    // q/k/v projection as planes (tensor-core attention)
-    return launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om);
+    return H->rowb == 64 ? launch_gemm3x<256, 4, EPI_LINEAR_TMA, KIND_F16_S64, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om)
+                         : launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om);
   EMCID_LIN_CASE(ACT_NONE | EF_C | EF_CIN)              // out projection / fc2 with residual
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P)                 // fc1
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P | EF_PT)         // fc1 of an edited layer
@@ -612,10 +626,13 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   // per-call TMA maps over exactly T rows: out-of-range rows of the last tile read as zeros
   CUtensorMap mx_hi, mx_lo, ma_hi, ma_lo, mf_hi, mf_lo;
   GemmOperands ft;
-  if ((rc = make_tmap_2d(&mx_hi, H->x_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&mx_lo, H->x_lo, T, H->h, H->hp, 128, 2)) ||
-      (rc = make_tmap_2d(&ma_hi, H->a_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&ma_lo, H->a_lo, T, H->h, H->hp, 128, 2)) ||
-      (rc = make_tmap_2d(&mf_hi, H->f_hi, T, H->d, H->dp, 128, 2)) || (rc = make_tmap_2d(&mf_lo, H->f_lo, T, H->d, H->dp, 128, 2)) ||
-      (rc = make_tmap_2d(&ft.a_hi, H->ft_hi, H->d, T, H->tp, 128, 2)) || (rc = make_tmap_2d(&ft.a_lo, H->ft_lo, H->d, T, H->tp, 128, 2)))
+  const int rb = H->rowb;
+  CUtensorMap sf_hi, sf_lo;   // store maps of the f planes (always 128-byte swizzled staging tiles)
+  if ((rc = make_tmap_2d(&mx_hi, H->x_hi, T, H->h, H->hp, 128, 2, 0, rb)) || (rc = make_tmap_2d(&mx_lo, H->x_lo, T, H->h, H->hp, 128, 2, 0, rb)) ||
+      (rc = make_tmap_2d(&ma_hi, H->a_hi, T, H->h, H->hp, 128, 2, 0, rb)) || (rc = make_tmap_2d(&ma_lo, H->a_lo, T, H->h, H->hp, 128, 2, 0, rb)) ||
+      (rc = make_tmap_2d(&mf_hi, H->f_hi, T, H->d, H->dp, 128, 2, 0, rb)) || (rc = make_tmap_2d(&mf_lo, H->f_lo, T, H->d, H->dp, 128, 2, 0, rb)) ||
+      (rc = make_tmap_2d(&sf_hi, H->f_hi, T, H->d, H->dp, 128, 2)) || (rc = make_tmap_2d(&sf_lo, H->f_lo, T, H->d, H->dp, 128, 2)) ||
+      (rc = make_tmap_2d(&ft.a_hi, H->ft_hi, H->d, T, H->tp, 128, 2, 0, rb)) || (rc = make_tmap_2d(&ft.a_lo, H->ft_lo, H->d, T, H->tp, 128, 2, 0, rb)))
     return rc;
   ft.b_hi = ft.a_hi; ft.b_lo = ft.a_lo;
   // store maps of the staged (TMA) epilogue; EMCID_LINEAR_TMA=0 keeps the direct-store epilogue
@@ -627,7 +644,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
         (rc = make_tmap_2d(&om_f.t_hi, H->ft_hi, H->d, T, H->tp, 32, 2, 128)) ||
         (rc = make_tmap_2d(&om_f.t_lo, H->ft_lo, H->d, T, H->tp, 32, 2, 128)))
       return rc;
-    om_f.c = mf_hi; om_f.c2 = mf_lo;
+    om_f.c = sf_hi; om_f.c2 = sf_lo;
   }
   const bool attn_tc = H->attn_tc && use_tma_epi;
   AttnMaps am = {};
@@ -700,7 +717,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       if (per > slab) per = slab;
       for (long long c0 = 0; c0 < T; c0 += per) {
         const int t = static_cast<int>(T - c0 < per ? T - c0 : per);
-        if ((rc = mom2_syrk_slab(A, ft, KIND_F16, static_cast<int>(c0), t, nullptr, stream))) return rc;
+        if ((rc = mom2_syrk_slab(A, ft, rb == 64 ? KIND_F16_S64 : KIND_F16, static_cast<int>(c0), t, nullptr, stream))) return rc;
         if (++A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
       }
       clip_add_count_kernel<<<1, 1, 0, stream>>>(A->count, static_cast<long long>(T));

@@ -251,6 +251,17 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
   return d;
 }
 
+// Same for tiles of 64-byte rows written with TMA SWIZZLE_64B: 8-row groups are 512 B apart, layout_type = 4.
+__device__ __forceinline__ uint64_t make_desc_k64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;                      // SWIZZLE_64B
+  return d;
+}
+
 // Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, bool neg_a = false) {
   return (1u << 4)                  // c_format = F32

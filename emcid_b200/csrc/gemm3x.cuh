@@ -39,10 +39,14 @@ constexpr int GEMM_BLOCK_K = 32;  // tf32 kind: 32 fp32 = 128 bytes = one swizzl
 // tcgen05.mma.kind::tf32 (K = 8 per instruction).  KIND_F16: planes are 16-bit (hi = fp16, lo = bf16
 // or fp16, see split_f16), tcgen05.mma.kind::f16 (K = 16 per instruction): the same three MMAs per
 // 128-byte k-step retire twice the contraction depth and every plane moves half the bytes.
-enum GemmKind : int { KIND_TF32 = 0, KIND_F16 = 1 };
+// KIND_F16_S64: the same fp16 planes and MMAs as KIND_F16, staged as 64-byte rows (TMA SWIZZLE_64B, 32 elements
+// per k-block): stages are half the size, so twice as many fit in shared memory and the TMA round trip has
+// (stages - 1) x 768 instead of 1 x 1536 MMA cycles to hide behind.
+enum GemmKind : int { KIND_TF32 = 0, KIND_F16 = 1, KIND_F16_S64 = 2 };
 template <int KIND> struct KindTraits;
-template <> struct KindTraits<KIND_TF32> { static constexpr int kBlockK = 32; static constexpr int kElemBytes = 4; };
-template <> struct KindTraits<KIND_F16> { static constexpr int kBlockK = 64; static constexpr int kElemBytes = 2; };
+template <> struct KindTraits<KIND_TF32> { static constexpr int kBlockK = 32, kElemBytes = 4, kRowBytes = 128; };
+template <> struct KindTraits<KIND_F16> { static constexpr int kBlockK = 64, kElemBytes = 2, kRowBytes = 128; };
+template <> struct KindTraits<KIND_F16_S64> { static constexpr int kBlockK = 32, kElemBytes = 2, kRowBytes = 64; };
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_THREADS = 256;
 constexpr int GEMM_ROW_BYTES = 128;
@@ -100,12 +104,13 @@ struct GemmParams {
   int lo_fmt;                  // KIND_F16: format of the lo planes (FMT_BF16 default, FMT_F16)
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int ROWB = GEMM_ROW_BYTES>
 struct GemmCfg {
   static constexpr int kBlockN = BLOCK_N;
   static constexpr int kStages = STAGES;
-  static constexpr int kBPlaneBytes = BLOCK_N * GEMM_ROW_BYTES;
-  static constexpr int kStageBytes = 2 * GEMM_A_PLANE_BYTES + 2 * kBPlaneBytes;
+  static constexpr int kAPlaneBytes = GEMM_BLOCK_M * ROWB;
+  static constexpr int kBPlaneBytes = BLOCK_N * ROWB;
+  static constexpr int kStageBytes = 2 * kAPlaneBytes + 2 * kBPlaneBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // two chunk accumulators (power of two)
   static constexpr int kSmemBytes = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kSmemBytesStaged = kSmemBytes + GEMM_STAGING_BYTES;
@@ -266,9 +271,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
               const __grid_constant__ GemmOutMaps om, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, STAGES>;
+  constexpr int ROWB = KindTraits<KIND>::kRowBytes;
+  using Cfg = GemmCfg<BLOCK_N, STAGES, ROWB>;
   constexpr int COLS = BLOCK_N / 2;  // accumulator columns owned by one epilogue thread
-  constexpr int BLOCK_K = KindTraits<KIND>::kBlockK;  // elements per 128-byte k-block
+  constexpr int BLOCK_K = KindTraits<KIND>::kBlockK;  // elements per k-block (one swizzle row)
+  constexpr int A_PLANE = Cfg::kAPlaneBytes;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -340,13 +347,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int kc = kb * BLOCK_K;
           tma_load_2d(st, &tmA_hi, &full_bar[stage], p.a_col0 + kc, arow + u.m0);
-          tma_load_2d(st + GEMM_A_PLANE_BYTES, &tmA_lo, &full_bar[stage], p.a_col0 + kc, arow + u.m0);
-          uint8_t* sb = st + 2 * GEMM_A_PLANE_BYTES;
+          tma_load_2d(st + A_PLANE, &tmA_lo, &full_bar[stage], p.a_col0 + kc, arow + u.m0);
+          uint8_t* sb = st + 2 * A_PLANE;
 #pragma unroll
           for (int r = 0; r < BLOCK_N / 128; ++r) {
-            tma_load_2d(sb + r * GEMM_A_PLANE_BYTES, &tmB_hi, &full_bar[stage], p.b_col0 + kc,
+            tma_load_2d(sb + r * A_PLANE, &tmB_hi, &full_bar[stage], p.b_col0 + kc,
                         brow + u.n0 + r * 128);
-            tma_load_2d(sb + Cfg::kBPlaneBytes + r * GEMM_A_PLANE_BYTES, &tmB_lo, &full_bar[stage],
+            tma_load_2d(sb + Cfg::kBPlaneBytes + r * A_PLANE, &tmB_lo, &full_bar[stage],
                         p.b_col0 + kc, brow + u.n0 + r * 128);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -376,12 +383,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             mbar_wait(&full_bar[stage], phase, 3);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint64_t da_hi = make_desc_k128(sa);
-            const uint64_t da_lo = make_desc_k128(sa + GEMM_A_PLANE_BYTES);
-            const uint64_t db_hi = make_desc_k128(sa + 2 * GEMM_A_PLANE_BYTES);
-            const uint64_t db_lo = make_desc_k128(sa + 2 * GEMM_A_PLANE_BYTES + Cfg::kBPlaneBytes);
+            const uint64_t da_hi = ROWB == 128 ? make_desc_k128(sa) : make_desc_k64(sa);
+            const uint64_t da_lo = ROWB == 128 ? make_desc_k128(sa + A_PLANE) : make_desc_k64(sa + A_PLANE);
+            const uint64_t db_hi = ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE) : make_desc_k64(sa + 2 * A_PLANE);
+            const uint64_t db_lo = ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE + Cfg::kBPlaneBytes)
+                                               : make_desc_k64(sa + 2 * A_PLANE + Cfg::kBPlaneBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < ROWB / 32; ++k) {
               // one instruction contracts 32 bytes of K (8 tf32 / 16 halves): +2 in the (addr >> 4) field
               const uint64_t koff = static_cast<uint64_t>(k * 2);
               if (KIND == KIND_TF32) {

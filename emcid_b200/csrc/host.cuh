@@ -102,7 +102,7 @@ inline PFN_encodeTiled get_encode_fn() {
 // elem_bytes = 4 (tf32 planes) or 2 (fp16 / bf16 planes): the box is one 128-byte swizzle row wide unless
 // box_cols > 0 asks for an unswizzled box of that many elements (store maps of transposed planes).
 inline int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols,
-                        long long ld, int box_rows, int elem_bytes = 4, int box_cols = 0) {
+                        long long ld, int box_rows, int elem_bytes = 4, int box_cols = 0, int row_bytes = GEMM_ROW_BYTES) {
   PFN_encodeTiled fn = get_encode_fn();
   EMCID_CHECK(fn != nullptr, EMCID_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   EMCID_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, EMCID_ERR_INVALID,
@@ -112,13 +112,14 @@ inline int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long
   EMCID_CHECK(rows > 0 && cols > 0, EMCID_ERR_INVALID, "empty TMA tensor");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols > 0 ? box_cols : GEMM_ROW_BYTES / elem_bytes),
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols > 0 ? box_cols : row_bytes / elem_bytes),
                        static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
                   const_cast<void*>(base), gdim, gstride,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  box_cols > 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                  box_cols > 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                               : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EMCID_CHECK(r == CUDA_SUCCESS, EMCID_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d",
               static_cast<int>(r));
@@ -135,7 +136,7 @@ struct GemmOperands {
 template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32, int EFLAGS = EF_DEFAULT>
 inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid, cudaStream_t stream,
                          int batches = 1, const GemmOutMaps* out_maps = nullptr) {
-  using Cfg = GemmCfg<BLOCK_N, STAGES>;
+  using Cfg = GemmCfg<BLOCK_N, STAGES, KindTraits<KIND>::kRowBytes>;
   constexpr int kSmem = EPI == EPI_LINEAR_TMA ? Cfg::kSmemBytesStaged : Cfg::kSmemBytes;
   static const GemmOutMaps no_maps = {};
   auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI, KIND, EFLAGS>;

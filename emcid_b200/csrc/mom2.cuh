@@ -394,8 +394,10 @@ inline int mom2_syrk_slab(Mom2Handle* H, const GemmOperands& ops, int kind, int 
     EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
   }
   const int sms = H->info.sm_count;
-  int rc = kind == KIND_F16 ? launch_gemm3x<256, 2, EPI_RED, KIND_F16>(ops, p, sms, stream)
-                            : launch_gemm3x<256, 2, EPI_RED>(ops, p, sms, stream);
+  if (kind == KIND_F16_S64) p.chunk_kblocks *= 2;   // k-blocks are half as deep
+  int rc = kind == KIND_F16_S64 ? launch_gemm3x<256, 4, EPI_RED, KIND_F16_S64>(ops, p, sms, stream)
+           : kind == KIND_F16   ? launch_gemm3x<256, 2, EPI_RED, KIND_F16>(ops, p, sms, stream)
+                                : launch_gemm3x<256, 2, EPI_RED>(ops, p, sms, stream);
   if (rc) return rc;
   H->launches += 1;
   if (H->profile) {
