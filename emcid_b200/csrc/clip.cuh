@@ -560,12 +560,18 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   // the epilogue variant is a compile-time option (see EF_* in gemm3x.cuh): only the combinations the forward uses
   const int ef = act | (C ? EF_C : 0) | (Cin ? EF_CIN : 0) | (P_hi ? EF_P : 0) | (Pt_hi ? EF_PT : 0);
   if (om && H->rowb == 64) p.chunk_kblocks *= 2;   // k-blocks are half as deep
+  const bool cta2 = om && H->rowb == 128 && gemm_cta2_enabled();
+  const int pair_tiles = ((T + 255) / 256) * ((W.N + 255) / 256);
+  const int grid2 = 2 * pair_tiles < (H->info.sm_count & ~1) ? 2 * pair_tiles : (H->info.sm_count & ~1);
 #define EMCID_LIN_CASE(F)                                                                                     \
   if (ef == (F))                                                                                              \
     return !om            ? launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream)            \
+           : cta2          ? launch_gemm3x<256, 3, EPI_LINEAR_TMA, KIND_F16, (F), 1>(ops, p, grid2, stream, 1, om) \
            : H->rowb == 64 ? launch_gemm3x<256, 4, EPI_LINEAR_TMA, KIND_F16_S64, (F)>(ops, p, grid, stream, 1, om) \
                            : launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (F)>(ops, p, grid, stream, 1, om);
   EMCID_LIN_CASE(ACT_NONE | EF_C)                       // q/k/v projection (fp32, CUDA-core attention)
+  if (cta2 && ef == (ACT_NONE | EF_P))
+    return launch_gemm3x<256, 3, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P), 1>(ops, p, grid2, stream, 1, om);
   if (om && ef == (ACT_NONE | EF_P))                    // q/k/v projection as planes (tensor-core attention)
     return H->rowb == 64 ? launch_gemm3x<256, 4, EPI_LINEAR_TMA, KIND_F16_S64, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om)
                          : launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om);

@@ -123,16 +123,19 @@ struct Unit {
 
 // Deterministic work enumeration, evaluated identically by the producer, MMA and epilogue roles.
 struct Sched {
-  int m_tiles, n_tiles, kb_tile, R, lower, streamk, block_n;
+  int m_tiles, n_tiles, kb_tile, R, lower, streamk, block_n, block_m;
   long long pos, end;          // stream-K: position in the flattened (tile, kb) space
   int tile, tile_step, num_tiles;
 
-  __device__ void init(const GemmParams& p, int block_n_, int block_k, int M, int N, int K) {
+  // bid / nb: index and number of the scheduling entities (CTAs, or CTA pairs with 256-row tiles)
+  __device__ void init(const GemmParams& p, int block_n_, int block_k, int M, int N, int K, int block_m_ = GEMM_BLOCK_M,
+                       int bid = blockIdx.x, int nb = gridDim.x) {
     block_n = block_n_;
-    m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+    block_m = block_m_;
+    m_tiles = (M + block_m - 1) / block_m;
     n_tiles = (N + block_n - 1) / block_n;
     kb_tile = (K + block_k - 1) / block_k;
-    R = block_n / GEMM_BLOCK_M;
+    R = block_n / block_m;
     lower = p.lower;
     streamk = p.streamk;
     if (lower) {
@@ -147,12 +150,12 @@ struct Sched {
     if (kb_tile == 0) num_tiles = 0;
     if (streamk) {
       long long total = static_cast<long long>(num_tiles) * kb_tile;
-      long long per = (total + gridDim.x - 1) / gridDim.x;
-      pos = per * blockIdx.x;
+      long long per = (total + nb - 1) / nb;
+      pos = per * bid;
       end = pos + per < total ? pos + per : total;
     } else {
-      tile = blockIdx.x;
-      tile_step = gridDim.x;
+      tile = bid;
+      tile_step = nb;
     }
   }
 
@@ -164,10 +167,10 @@ struct Sched {
         if (t < c) break;
         t -= c;
       }
-      m0 = (j * R + t) * GEMM_BLOCK_M;
+      m0 = (j * R + t) * block_m;
       n0 = j * block_n;
     } else {
-      m0 = (t % m_tiles) * GEMM_BLOCK_M;
+      m0 = (t % m_tiles) * block_m;
       n0 = (t / m_tiles) * block_n;
     }
   }
@@ -266,7 +269,10 @@ __device__ __forceinline__ void store_plane1(float* hi_base, float* lo_base, lon
   }
 }
 
-template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32, int EFLAGS = EF_DEFAULT>
+// CTA2 = 1: the kernel is launched in clusters of two CTAs that form one cta_group::2 pair per 256 x BLOCK_N tile
+// (see common.cuh).  Rank 0 issues the MMAs for both; both produce (their own A rows and their half of B), both
+// run the epilogue on their own 128 accumulator rows.
+template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32, int EFLAGS = EF_DEFAULT, int CTA2 = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -276,11 +282,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   constexpr int COLS = BLOCK_N / 2;  // accumulator columns owned by one epilogue thread
   constexpr int BLOCK_K = KindTraits<KIND>::kBlockK;  // elements per k-block (one swizzle row)
   constexpr int A_PLANE = Cfg::kAPlaneBytes;
+  constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;           // B rows staged by this CTA
+  constexpr int B_PLANE = B_ROWS * ROWB;
+  constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* stg = smem + STAGES * Cfg::kStageBytes;  // epilogue staging (EPI_LINEAR_TMA only), 1024-byte aligned
+  uint8_t* stg = smem + STAGES * STAGE_BYTES;  // epilogue staging (EPI_LINEAR_TMA only), 1024-byte aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + (EPI == EPI_LINEAR_TMA ? GEMM_STAGING_BYTES : 0));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -303,16 +313,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], GEMM_EPI_THREADS);
+      // pair mode: one elected lane per epilogue warp of BOTH CTAs arrives on the leader's barrier
+      mbar_init(&tempty_bar[a], CTA2 ? 2 * (GEMM_EPI_THREADS / 32) : GEMM_EPI_THREADS);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CTA2) { tmem_alloc2(tmem_slot, Cfg::kTmemCols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync();   // the peer's barriers exist before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -325,7 +337,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   const int chunk = p.chunk_kblocks > 0 ? p.chunk_kblocks : GEMM_DEFAULT_CHUNK; \
   const int batch = blockIdx.y;                                              \
   Sched sched;                                                               \
-  sched.init(p, BLOCK_N, BLOCK_K, p.M, N, K);                                         \
+  sched.init(p, BLOCK_N, BLOCK_K, p.M, N, K, CTA2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M,  \
+             CTA2 ? blockIdx.x >> 1 : blockIdx.x, CTA2 ? gridDim.x >> 1 : gridDim.x);  \
   Unit u;                                                                    \
   (void)chunk; (void)batch;
 
@@ -343,9 +356,20 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
       while (sched.next(u)) {
         for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          uint8_t* st = smem + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* st = smem + stage * STAGE_BYTES;
           const int kc = kb * BLOCK_K;
+          if (CTA2) {
+            // both CTAs of the pair load into their own stage; all bytes are counted on the leader's barrier
+            const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            const int am = arow + u.m0 + static_cast<int>(rank) * GEMM_BLOCK_M;
+            const int bn = brow + u.n0 + static_cast<int>(rank) * B_ROWS;
+            tma_load_2d_2sm(st, &tmA_hi, lbar, p.a_col0 + kc, am);
+            tma_load_2d_2sm(st + A_PLANE, &tmA_lo, lbar, p.a_col0 + kc, am);
+            tma_load_2d_2sm(st + 2 * A_PLANE, &tmB_hi, lbar, p.b_col0 + kc, bn);
+            tma_load_2d_2sm(st + 2 * A_PLANE + B_PLANE, &tmB_lo, lbar, p.b_col0 + kc, bn);
+          } else {
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(st, &tmA_hi, &full_bar[stage], p.a_col0 + kc, arow + u.m0);
           tma_load_2d(st + A_PLANE, &tmA_lo, &full_bar[stage], p.a_col0 + kc, arow + u.m0);
           uint8_t* sb = st + 2 * A_PLANE;
@@ -353,21 +377,23 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
           for (int r = 0; r < BLOCK_N / 128; ++r) {
             tma_load_2d(sb + r * A_PLANE, &tmB_hi, &full_bar[stage], p.b_col0 + kc,
                         brow + u.n0 + r * 128);
-            tma_load_2d(sb + Cfg::kBPlaneBytes + r * A_PLANE, &tmB_lo, &full_bar[stage],
+            tma_load_2d(sb + B_PLANE + r * A_PLANE, &tmB_lo, &full_bar[stage],
                         p.b_col0 + kc, brow + u.n0 + r * 128);
+          }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (pair mode: the leader CTA only)
       EMCID_GEMM_ROLE_SETUP();
       // three MMAs per k-step: lo*hi, hi*lo, hi*hi (small terms first)
       const uint32_t f_hi = KIND == KIND_TF32 ? FMT_TF32 : FMT_F16;
       const uint32_t f_lo = KIND == KIND_TF32 ? FMT_TF32 : static_cast<uint32_t>(p.lo_fmt);
-      const uint32_t idesc_lh = make_idesc(f_lo, f_hi, GEMM_BLOCK_M, BLOCK_N);
-      const uint32_t idesc_hl = make_idesc(f_hi, f_lo, GEMM_BLOCK_M, BLOCK_N);
-      const uint32_t idesc_hh = make_idesc(f_hi, f_hi, GEMM_BLOCK_M, BLOCK_N);
+      constexpr uint32_t MMA_M = CTA2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M;
+      const uint32_t idesc_lh = make_idesc(f_lo, f_hi, MMA_M, BLOCK_N);
+      const uint32_t idesc_hl = make_idesc(f_hi, f_lo, MMA_M, BLOCK_N);
+      const uint32_t idesc_hh = make_idesc(f_hi, f_hi, MMA_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -375,19 +401,20 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
       while (sched.next(u)) {
         for (int kc0 = u.kb0; kc0 < u.kb1; kc0 += chunk) {
           const int kc1 = kc0 + chunk < u.kb1 ? kc0 + chunk : u.kb1;
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+          if (CTA2) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1, 2);
+          else mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
           uint32_t accumulate = 0;
           for (int kb = kc0; kb < kc1; ++kb) {
             mbar_wait(&full_bar[stage], phase, 3);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
             const uint64_t da_hi = ROWB == 128 ? make_desc_k128(sa) : make_desc_k64(sa);
             const uint64_t da_lo = ROWB == 128 ? make_desc_k128(sa + A_PLANE) : make_desc_k64(sa + A_PLANE);
             const uint64_t db_hi = ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE) : make_desc_k64(sa + 2 * A_PLANE);
-            const uint64_t db_lo = ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE + Cfg::kBPlaneBytes)
-                                               : make_desc_k64(sa + 2 * A_PLANE + Cfg::kBPlaneBytes);
+            const uint64_t db_lo = ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE + B_PLANE)
+                                               : make_desc_k64(sa + 2 * A_PLANE + B_PLANE);
 #pragma unroll
             for (int k = 0; k < ROWB / 32; ++k) {
               // one instruction contracts 32 bytes of K (8 tf32 / 16 halves): +2 in the (addr >> 4) field
@@ -396,6 +423,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                 tc_mma_tf32(tmem_d, da_lo + koff, db_hi + koff, idesc_lh, accumulate);
                 tc_mma_tf32(tmem_d, da_hi + koff, db_lo + koff, idesc_hl, 1);
                 tc_mma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc_hh, 1);
+              } else if (CTA2) {
+                tc_mma_f16_2(tmem_d, da_lo + koff, db_hi + koff, idesc_lh, accumulate);
+                tc_mma_f16_2(tmem_d, da_hi + koff, db_lo + koff, idesc_hl, 1);
+                tc_mma_f16_2(tmem_d, da_hi + koff, db_hi + koff, idesc_hh, 1);
               } else {
                 tc_mma_f16(tmem_d, da_lo + koff, db_hi + koff, idesc_lh, accumulate);
                 tc_mma_f16(tmem_d, da_hi + koff, db_lo + koff, idesc_hl, 1);
@@ -403,10 +434,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
               }
               accumulate = 1;
             }
-            tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            if (CTA2) tc_commit2(&empty_bar[stage], 3);   // frees the slot in both CTAs
+            else tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&tfull_bar[acc]);      // chunk complete -> epilogue folds it into registers
+          if (CTA2) tc_commit2(&tfull_bar[acc], 3);
+          else tc_commit(&tfull_bar[acc]);      // chunk complete -> epilogue folds it into registers
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -436,12 +469,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
           for (int i = 0; i < 16; ++i) sum[c * 16 + i] += v[i];
         }
         tc_fence_before();
-        mbar_arrive(&tempty_bar[acc]);
+        if (CTA2) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+        } else {
+          mbar_arrive(&tempty_bar[acc]);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
 
       // -------- unit finished: registers -> global
-      const int row = u.m0 + q * 32 + lane;
+      const int m_cta = u.m0 + static_cast<int>(rank) * GEMM_BLOCK_M;   // first row this CTA's accumulators hold
+      const int row = m_cta + q * 32 + lane;
       const int col0 = u.n0 + half * COLS;
       if (EPI == EPI_LINEAR_TMA) {
         // Every thread of the half takes part (named barriers): rows >= M hold act(bias) of zero-filled operand
@@ -471,8 +510,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             fence_proxy_async();
             named_bar_sync(bar_id, 128);
             if (issuer && col0 + pc * 32 < N) {
-              if (EFLAGS & EF_CIN) tma_reduce_add_2d(&om.c, sbase, col0 + pc * 32, u.m0);
-              else tma_store_2d(&om.c, sbase, col0 + pc * 32, u.m0);
+              if (EFLAGS & EF_CIN) tma_reduce_add_2d(&om.c, sbase, col0 + pc * 32, m_cta);
+              else tma_store_2d(&om.c, sbase, col0 + pc * 32, m_cta);
               bulk_commit();
             }
           }
@@ -508,7 +547,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                 fence_proxy_async();
                 named_bar_sync(bar_id, 128);
                 if (issuer && in_n) {
-                  tma_store_2d(pl == 0 ? &om.c : &om.c2, sbase, col0 + pc * 64, u.m0);
+                  tma_store_2d(pl == 0 ? &om.c : &om.c2, sbase, col0 + pc * 64, m_cta);
                   bulk_commit();
                 }
               }
@@ -530,8 +569,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                 fence_proxy_async();
                 named_bar_sync(bar_id, 128);
                 if (issuer && col0 + pc * 64 + sub * 32 < N) {
-                  tma_store_2d(&om.t_hi, sbase, u.m0, col0 + pc * 64 + sub * 32 - p.pt_col_min);
-                  tma_store_2d(&om.t_lo, sbase + 8192, u.m0, col0 + pc * 64 + sub * 32 - p.pt_col_min);
+                  tma_store_2d(&om.t_hi, sbase, m_cta, col0 + pc * 64 + sub * 32 - p.pt_col_min);
+                  tma_store_2d(&om.t_lo, sbase + 8192, m_cta, col0 + pc * 64 + sub * 32 - p.pt_col_min);
                   bulk_commit();
                 }
               }
@@ -635,7 +674,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   if (EPI == EPI_LINEAR_TMA) bulk_wait0();   // no-op for threads that issued nothing
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (CTA2) {
+    cluster_sync();   // the leader's MMAs read the peer's shared memory and signal its barriers until the very end
+    if (warp == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+  } else if (warp == 2) {
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 }  // namespace emcid

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gemm3x.cuh"
@@ -133,13 +134,16 @@ struct GemmOperands {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32, int EFLAGS = EF_DEFAULT>
+template <int BLOCK_N, int STAGES, int EPI, int KIND = KIND_TF32, int EFLAGS = EF_DEFAULT, int CTA2 = 0>
 inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid, cudaStream_t stream,
                          int batches = 1, const GemmOutMaps* out_maps = nullptr) {
   using Cfg = GemmCfg<BLOCK_N, STAGES, KindTraits<KIND>::kRowBytes>;
-  constexpr int kSmem = EPI == EPI_LINEAR_TMA ? Cfg::kSmemBytesStaged : Cfg::kSmemBytes;
+  // pair mode stages only half of B per CTA
+  constexpr int kStage = 2 * Cfg::kAPlaneBytes + (CTA2 ? Cfg::kBPlaneBytes : 2 * Cfg::kBPlaneBytes);
+  constexpr int kSmem = STAGES * kStage + 1024 + 256 + (EPI == EPI_LINEAR_TMA ? GEMM_STAGING_BYTES : 0);
+  static_assert(kSmem <= 227 * 1024, "shared memory budget exceeded");
   static const GemmOutMaps no_maps = {};
-  auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI, KIND, EFLAGS>;
+  auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI, KIND, EFLAGS, CTA2>;
   static thread_local bool configured[16] = {false};
   int dev = 0;
   EMCID_CUDA_CHECK(cudaGetDevice(&dev));
@@ -148,10 +152,33 @@ inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid,
     if (dev >= 0 && dev < 16) configured[dev] = true;
   }
   if (grid < 1) grid = 1;
+  if (CTA2) {
+    // clusters of two CTAs along x: `grid` counts CTAs and must be even
+    if (grid & 1) grid += 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, batches);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EMCID_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo,
+                                        out_maps ? *out_maps : no_maps, p));
+    return EMCID_OK;
+  }
   kern<<<dim3(grid, batches), GEMM_THREADS, kSmem, stream>>>(ops.a_hi, ops.a_lo, ops.b_hi, ops.b_lo,
                                                               out_maps ? *out_maps : no_maps, p);
   EMCID_CUDA_CHECK(cudaGetLastError());
   return EMCID_OK;
+}
+
+// CTA-pair (cta_group::2) kernels for the hot GEMMs; EMCID_CTA2=0 falls back to single-CTA tiles.
+inline bool gemm_cta2_enabled() {
+  static const bool on = [] { const char* e = getenv("EMCID_CTA2"); return e && e[0] == '1'; }();
+  return on;
 }
 
 inline int gemm_num_tiles(int M, int N, int block_n, int lower) {
