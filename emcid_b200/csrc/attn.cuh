@@ -19,41 +19,37 @@ namespace emcid {
 
 constexpr int ATTN_DH = 64;
 constexpr int ATTN_THREADS = 128;
-// smem: P hi/lo x 2 k-blocks (4 x 16 KB) | barriers (1 KB) | NBUF x { Q hi/lo (2 x 16 KB), K hi/lo, V hi/lo (2 x lp*128 B each) }
-// The operand set is double-buffered when it fits (lp <= 80, i.e. CLIP's 77 tokens): the next unit's TMA loads
-// are issued at the start of the current unit.
-constexpr int ATTN_TILE = 128 * 128;        // 16 KB: 128 rows of one 128-byte swizzle row
-constexpr int ATTN_OFF_P = 0;
-constexpr int ATTN_OFF_BAR = 4 * ATTN_TILE;
-constexpr int ATTN_OFF_BUF = ATTN_OFF_BAR + 1024;
-inline int attn_buf_bytes(int lp) { return 2 * ATTN_TILE + 4 * lp * 128; }
-inline int attn_num_bufs(int lp) { return ATTN_OFF_BUF + 2 * attn_buf_bytes(lp) + 1024 <= 227 * 1024 ? 2 : 1; }
-inline int attn_smem_bytes(int lp) { return ATTN_OFF_BUF + attn_num_bufs(lp) * attn_buf_bytes(lp) + 1024; }
+// smem: P hi/lo x 2 k-blocks | Q hi/lo | K hi/lo | V hi/lo | barriers.  Every tile holds lp rows of one 128-byte
+// swizzle row (lp * 128 B, a multiple of 2 KB).  The A operands (Q, P) are read by the MMA as 128-row tiles: rows
+// [lp, 128) alias whatever follows in shared memory — garbage in, garbage out, in accumulator rows that are never
+// stored (an output row depends on its own A row only) — so no A tile may be the last one of the allocation.
+// With CLIP's 77 tokens (lp = 80) the set is 102 KB and TWO CTAs are resident per SM: one unit's serial chain
+// (TMA -> S -> softmax -> P V -> store) hides behind the other CTA's.
+inline int attn_tile_bytes(int lp) { return lp * 128; }
+inline int attn_smem_bytes(int lp) { return 10 * attn_tile_bytes(lp) + 1024 /*barriers*/ + 1024 /*align slack*/; }
 
 struct AttnMaps {
-  CUtensorMap qk_hi, qk_lo;   // q|k|v planes [T x 3h], box 64 x 128 (Q tiles)
-  CUtensorMap kv_hi, kv_lo;   // same tensor, box 64 x lp (K and V tiles)
+  CUtensorMap qk_hi, qk_lo;   // q|k|v planes [T x 3h], box 64 x 128: the store maps of the q/k/v projection
+  CUtensorMap kv_hi, kv_lo;   // same tensor, box 64 x lp (Q, K and V tiles of one caption)
 };
 
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
+__global__ void __launch_bounds__(ATTN_THREADS, 2)
 clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restrict__ cu, int n_seqs, int heads, int h,
-                         int lp /* padded caption length: multiple of 16, <= 128 */, int nbuf, float scale,
+                         int lp /* padded caption length: multiple of 16, <= 128 */, float scale,
                          uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo, int ldo) {
   extern __shared__ uint8_t attn_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + ATTN_OFF_BAR);   // [2]
-  uint64_t* bar_v = bar_qk + 2;                                          // [2]
-  uint64_t* bar_s = bar_qk + 4;   // S = Q K^T finished
-  uint64_t* bar_o = bar_qk + 5;   // O = P V finished
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 6);
+  const int kt = lp * 128;                       // bytes of one tile
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + 10 * kt);
+  uint64_t* bar_v = bar_qk + 1;
+  uint64_t* bar_s = bar_qk + 2;   // S = Q K^T finished
+  uint64_t* bar_o = bar_qk + 3;   // O = P V finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int kt = lp * 128;                       // bytes of one K / V plane tile
-  const int buf_bytes = 2 * ATTN_TILE + 4 * kt;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tm.qk_hi); tma_prefetch_desc(&tm.qk_lo);
     tma_prefetch_desc(&tm.kv_hi); tma_prefetch_desc(&tm.kv_lo);
-    for (int b = 0; b < 2; ++b) { mbar_init(&bar_qk[b], 1); mbar_init(&bar_v[b], 1); }
+    mbar_init(bar_qk, 1); mbar_init(bar_v, 1);
     mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
   }
@@ -66,45 +62,41 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-  const uint32_t s_p = smem_u32(smem + ATTN_OFF_P);
+  const uint32_t s_p = smem_u32(smem);          // P hi kb0 | P hi kb1 | P lo kb0 | P lo kb1
+  const uint32_t s_q = s_p + 4 * kt;            // Q hi | Q lo
+  const uint32_t s_k = s_q + 2 * kt, s_v = s_k + 2 * kt;
   const int n_units = n_seqs * heads;
   const int ksteps2 = lp / 16;                 // k-steps of the second product
   const uint32_t idesc1 = make_idesc(FMT_F16, FMT_F16, 128, static_cast<uint32_t>(lp));
   const uint32_t idesc2 = make_idesc(FMT_F16, FMT_F16, 128, ATTN_DH) | (1u << 16);   // B (= V) is MN-major
 
-  auto issue_loads = [&](int unit, int b) {
+  auto issue_loads = [&](int unit) {
     const int head = unit % heads, seq = unit / heads;
     const int t0 = cu[seq];
-    uint8_t* base = smem + ATTN_OFF_BUF + b * buf_bytes;
-    mbar_arrive_expect_tx(&bar_qk[b], 2 * ATTN_TILE + 2 * kt);
-    tma_load_2d(base, &tm.qk_hi, &bar_qk[b], head * ATTN_DH, t0);
-    tma_load_2d(base + ATTN_TILE, &tm.qk_lo, &bar_qk[b], head * ATTN_DH, t0);
-    tma_load_2d(base + 2 * ATTN_TILE, &tm.kv_hi, &bar_qk[b], h + head * ATTN_DH, t0);
-    tma_load_2d(base + 2 * ATTN_TILE + kt, &tm.kv_lo, &bar_qk[b], h + head * ATTN_DH, t0);
-    mbar_arrive_expect_tx(&bar_v[b], 2 * kt);
-    tma_load_2d(base + 2 * ATTN_TILE + 2 * kt, &tm.kv_hi, &bar_v[b], 2 * h + head * ATTN_DH, t0);
-    tma_load_2d(base + 2 * ATTN_TILE + 3 * kt, &tm.kv_lo, &bar_v[b], 2 * h + head * ATTN_DH, t0);
+    uint8_t* base = smem + 4 * kt;
+    mbar_arrive_expect_tx(bar_qk, 4 * kt);
+    tma_load_2d(base, &tm.kv_hi, bar_qk, head * ATTN_DH, t0);
+    tma_load_2d(base + kt, &tm.kv_lo, bar_qk, head * ATTN_DH, t0);
+    tma_load_2d(base + 2 * kt, &tm.kv_hi, bar_qk, h + head * ATTN_DH, t0);
+    tma_load_2d(base + 3 * kt, &tm.kv_lo, bar_qk, h + head * ATTN_DH, t0);
+    mbar_arrive_expect_tx(bar_v, 2 * kt);
+    tma_load_2d(base + 4 * kt, &tm.kv_hi, bar_v, 2 * h + head * ATTN_DH, t0);
+    tma_load_2d(base + 5 * kt, &tm.kv_lo, bar_v, 2 * h + head * ATTN_DH, t0);
   };
 
-  if (tid == 0 && static_cast<int>(blockIdx.x) < n_units) issue_loads(blockIdx.x, 0);
+  if (tid == 0 && static_cast<int>(blockIdx.x) < n_units) issue_loads(blockIdx.x);
   int it = 0;
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-    const int b = nbuf == 2 ? (it & 1) : 0;
-    const uint32_t ld_phase = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
     const uint32_t phase = it & 1;
     const int head = unit % heads, seq = unit / heads;
     const int t0 = cu[seq];
     int L = cu[seq + 1] - t0;
     if (L > lp) L = lp;
-    const uint32_t s_q = smem_u32(smem + ATTN_OFF_BUF + b * buf_bytes);
-    const uint32_t s_k = s_q + 2 * ATTN_TILE, s_v = s_k + 2 * kt;
     // ---- S = Q K^T
     if (tid == 0) {
-      // double-buffered: the other buffer was released by the previous unit's bar_o wait
-      if (nbuf == 2 && unit + static_cast<int>(gridDim.x) < n_units) issue_loads(unit + gridDim.x, b ^ 1);
-      mbar_wait(&bar_qk[b], ld_phase, 11);
+      mbar_wait(bar_qk, phase, 11);
       tc_fence_after();
-      const uint64_t dq_hi = make_desc_k128(s_q), dq_lo = make_desc_k128(s_q + ATTN_TILE);
+      const uint64_t dq_hi = make_desc_k128(s_q), dq_lo = make_desc_k128(s_q + kt);
       const uint64_t dk_hi = make_desc_k128(s_k), dk_lo = make_desc_k128(s_k + kt);
 #pragma unroll
       for (int k = 0; k < ATTN_DH / 16; ++k) {
@@ -120,7 +112,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     // ---- causal softmax of row i = tid (TMEM lane): e = exp(s - max) goes to the swizzled P tiles as fp16 hi/lo
     // planes (unnormalised, in (0, 1]); the 1/sum factor is applied to the output row instead
     float inv = 0.f;
-    {
+    if (warp * 32 < lp) {                          // warp-uniform; rows >= lp have no P row in the lp-row tiles
       const int i = tid;
       const bool live = i < L;
       float v[8][16];
@@ -154,11 +146,13 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
           }
           // 16 columns = two 16-byte chunks of k-block c / 4
           const int kb = c >> 2, ch = (c & 3) * 2;
-          const uint32_t th = prow + kb * ATTN_TILE, tl = prow + (2 + kb) * ATTN_TILE;
-          sts_v4(th + (((ch) ^ sw) << 4), hh[0], hh[1], hh[2], hh[3]);
-          sts_v4(th + (((ch + 1) ^ sw) << 4), hh[4], hh[5], hh[6], hh[7]);
-          sts_v4(tl + (((ch) ^ sw) << 4), ll[0], ll[1], ll[2], ll[3]);
-          sts_v4(tl + (((ch + 1) ^ sw) << 4), ll[4], ll[5], ll[6], ll[7]);
+          const uint32_t th = prow + kb * kt, tl = prow + (2 + kb) * kt;
+          if (i < lp) {
+            sts_v4(th + (((ch) ^ sw) << 4), hh[0], hh[1], hh[2], hh[3]);
+            sts_v4(th + (((ch + 1) ^ sw) << 4), hh[4], hh[5], hh[6], hh[7]);
+            sts_v4(tl + (((ch) ^ sw) << 4), ll[0], ll[1], ll[2], ll[3]);
+            sts_v4(tl + (((ch + 1) ^ sw) << 4), ll[4], ll[5], ll[6], ll[7]);
+          }
         }
       }
       inv = live ? 1.0f / sum : 0.f;
@@ -169,13 +163,13 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     // ---- O = P V
     if (tid == 0) {
       tc_fence_after();
-      mbar_wait(&bar_v[b], ld_phase, 13);
+      mbar_wait(bar_v, phase, 13);
       tc_fence_after();
       const uint32_t tmem_o = tmem_base + 128;
       for (int k = 0; k < ksteps2; ++k) {
         const int kb = k >> 2;
         const uint64_t ko = static_cast<uint64_t>((k & 3) * 2);
-        const uint64_t dp_hi = make_desc_k128(s_p + kb * ATTN_TILE) + ko, dp_lo = make_desc_k128(s_p + (2 + kb) * ATTN_TILE) + ko;
+        const uint64_t dp_hi = make_desc_k128(s_p + kb * kt) + ko, dp_lo = make_desc_k128(s_p + (2 + kb) * kt) + ko;
         // V tile rows are tokens (= K of this product): one k-step is 16 rows = 2048 bytes further down the tile;
         // MN-major SW128 canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> SBO = 1024 B, as written by TMA
         const uint64_t dv_hi = make_desc_k128(s_v + k * 2048), dv_lo = make_desc_k128(s_v + kt + k * 2048);
@@ -187,8 +181,8 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     }
     mbar_wait(bar_o, phase, 14);
     tc_fence_after();
-    // single-buffered: the operands are free again, fetch the next unit while this one's output is written
-    if (nbuf == 1 && tid == 0 && unit + static_cast<int>(gridDim.x) < n_units) issue_loads(unit + gridDim.x, 0);
+    // the operands are free again: fetch the next unit while this one's output is written
+    if (tid == 0 && unit + static_cast<int>(gridDim.x) < n_units) issue_loads(unit + gridDim.x);
     if (warp * 32 < L) {                           // warp-uniform: tcgen05.ld is warp-collective
       uint16_t* oh = o_hi + static_cast<long long>(t0 + tid) * ldo + head * ATTN_DH;
       uint16_t* ol = o_lo + static_cast<long long>(t0 + tid) * ldo + head * ATTN_DH;

@@ -547,6 +547,11 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   memset(&p, 0, sizeof(p));
   p.M = T; p.N = W.N; p.K = W.K;
   p.chunk_kblocks = 2;
+  // token tiles outermost: the activation planes (121-484 MB per block) stream from HBM once while the weight
+  // planes (<= 19 MB) stay L2-resident.  EMCID_TILE_ORDER=m restores the M-fastest walk (measured: every N tile
+  // re-read the activations from DRAM, 1.1-1.5 GB per launch).
+  static const bool m_fast = [] { const char* e = getenv("EMCID_TILE_ORDER"); return e && e[0] == 'm'; }();
+  p.n_fastest = m_fast ? 0 : 1;
   p.alpha = 1.0f / W.scale; p.beta = Cin ? 1.0f : 0.0f;
   p.bias_col = W.bias; p.act = act; p.lo_fmt = FMT_F16;
   p.Cin = Cin; p.ldcin = ldc;
@@ -684,8 +689,10 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
         return rc;
       const int units = S * H->heads;
       const int lp = (H->max_pos + 15) & ~15;
-      clip_attention_tc_kernel<<<units < sms ? units : sms, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
-          am, cu_seqlens, S, H->heads, H->h, lp, attn_num_bufs(lp), scale, H->a_hi, H->a_lo, H->hp);
+      // two resident CTAs per SM when the operand set fits twice (lp <= 80: CLIP's 77 tokens)
+      const int per_sm = 2 * (attn_smem_bytes(lp) + 1024) <= 227 * 1024 ? 2 : 1;
+      clip_attention_tc_kernel<<<units < per_sm * sms ? units : per_sm * sms, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
+          am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
     } else {
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, nullptr,
                           nullptr, 0, stream, pm_qkv)))

@@ -81,6 +81,8 @@ struct GemmParams {
   int b_batch_rows;
   int lower;                   // 1: only tiles that intersect the lower triangle (row >= col)
   int streamk;                 // 1: split the flattened (tile, k-block) space evenly over CTAs
+  int n_fastest;               // 1: consecutive tiles walk along N (the tiles of one wave share A row blocks: the big
+                               //    operand A is then read from HBM once, not once per N tile); 0: along M
   int chunk_kblocks;           // k-blocks accumulated in TMEM between register folds
   const int* dyn_n;            // optional device scalar overriding N (fc1: number of valid tokens)
   const int* dyn_k;            // optional device scalar overriding K (SYRK: number of valid tokens)
@@ -123,7 +125,7 @@ struct Unit {
 
 // Deterministic work enumeration, evaluated identically by the producer, MMA and epilogue roles.
 struct Sched {
-  int m_tiles, n_tiles, kb_tile, R, lower, streamk, block_n, block_m;
+  int m_tiles, n_tiles, kb_tile, R, lower, streamk, block_n, block_m, n_fastest;
   long long pos, end;          // stream-K: position in the flattened (tile, kb) space
   int tile, tile_step, num_tiles;
 
@@ -138,6 +140,7 @@ struct Sched {
     R = block_n / block_m;
     lower = p.lower;
     streamk = p.streamk;
+    n_fastest = p.n_fastest;
     if (lower) {
       num_tiles = 0;
       for (int j = 0; j < n_tiles; ++j) {
@@ -169,6 +172,9 @@ struct Sched {
       }
       m0 = (j * R + t) * block_m;
       n0 = j * block_n;
+    } else if (n_fastest) {
+      m0 = (t / n_tiles) * block_m;
+      n0 = (t % n_tiles) * block_n;
     } else {
       m0 = (t % m_tiles) * block_m;
       n0 = (t / m_tiles) * block_n;

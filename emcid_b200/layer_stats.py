@@ -267,6 +267,8 @@ def layer_stats_text_encoder_multi(
     if not todo:
         return stats
 
+    import time
+    t_start = time.perf_counter()
     dist, rank, world = _dist_info(distributed)
     ds = get_ccs_filtered_ds(tokenizer=tokenizer)
     indices = subset_indices(len(ds), sample_size, random_sample=1)  # tally(..., random_sample=1), reference :204
@@ -280,12 +282,14 @@ def layer_stats_text_encoder_multi(
         progress = lambda x, total=None: x
 
     runner = TextEncoderMom2Pass(model, todo, slab_tokens=slab_tokens, accumulator_factory=_accumulator_factory)
+    t_loop = time.perf_counter()
     try:
         for batch in progress(loader, total=batch_count):
             if ("packed_ids" in batch and batch["packed_ids"].numel() == 0) or \
                     ("input_ids" in batch and batch["input_ids"].numel() == 0):
                 continue
             runner.run_batch(batch)  # host tensors: packed on the host, then one pinned H2D copy per field
+        t_fin = time.perf_counter()
         results = runner.finalize()
         LAST_PASS_INFO.update(native_forward=runner._native is not None, launches=runner.launches())
         for i, n in enumerate(todo):
@@ -304,6 +308,9 @@ def layer_stats_text_encoder_multi(
                 save_cached_state(files[n], stats[n], args)
         if dist is not None and world > 1:
             dist.barrier()
+        # host-side timeline of the pass (no extra synchronisation: the loop time includes whatever the host waited for)
+        t_end = time.perf_counter()
+        LAST_PASS_INFO["timing"] = {"setup_s": t_loop - t_start, "loop_s": t_fin - t_loop, "finalize_s": t_end - t_fin}
     finally:
         runner.close()
     return stats

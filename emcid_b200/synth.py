@@ -66,3 +66,29 @@ class CaptionIdDataset(torch.utils.data.Dataset):
             self._pos[n] = torch.arange(n)
             self._ones[n] = torch.ones(n, dtype=torch.long)
         return dict(input_ids=ids, position_ids=self._pos[n], attention_mask=self._ones[n])
+
+
+class CaptionMatrixDataset(torch.utils.data.Dataset):
+    """Full-width captions held as one [n, width] int64 matrix (the throughput set of SURVEY.md §8d): same item
+    layout as CaptionIdDataset without materialising n row tensors up front."""
+
+    def __init__(self, ids: torch.Tensor):
+        assert ids.dim() == 2 and ids.dtype == torch.int64
+        self.ids = ids
+        n = ids.shape[1]
+        self._pos, self._ones = torch.arange(n), torch.ones(n, dtype=torch.long)
+
+    def __len__(self):
+        return self.ids.shape[0]
+
+    def __getitem__(self, i):
+        return dict(input_ids=self.ids[i], position_ids=self._pos, attention_mask=self._ones)
+
+
+def make_caption_matrix(n: int, vocab: int = 49408, seed: int = 0, width: int = 77) -> torch.Tensor:
+    """[n, width] int64: BOS first, EOS last, ids ~ U{0..vocab-3} (every caption full width)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, vocab - 2, (n, width), generator=g)
+    ids[:, 0] = vocab - 2
+    ids[:, -1] = vocab - 1
+    return ids
