@@ -138,11 +138,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
             const float pa = (live && c * 16 + 2 * u <= i) ? __expf(fmaf(v[c][2 * u], scale, -mx)) : 0.f;
             const float pb = (live && c * 16 + 2 * u + 1 <= i) ? __expf(fmaf(v[c][2 * u + 1], scale, -mx)) : 0.f;
             sum += pa + pb;
-            uint16_t ha, la, hb, lb;
-            split_f16(pa, FMT_F16, ha, la);
-            split_f16(pb, FMT_F16, hb, lb);
-            hh[u] = ha | (static_cast<uint32_t>(hb) << 16);
-            ll[u] = la | (static_cast<uint32_t>(lb) << 16);
+            split_f16x2(pa, pb, hh[u], ll[u]);
           }
           // 16 columns = two 16-byte chunks of k-block c / 4
           const int kb = c >> 2, ch = (c & 3) * 2;
@@ -193,11 +189,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
         uint32_t hh[8], ll[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          uint16_t ha, la, hb, lb;
-          split_f16(v[2 * u] * inv, FMT_F16, ha, la);
-          split_f16(v[2 * u + 1] * inv, FMT_F16, hb, lb);
-          hh[u] = ha | (static_cast<uint32_t>(hb) << 16);
-          ll[u] = la | (static_cast<uint32_t>(lb) << 16);
+          split_f16x2(v[2 * u] * inv, v[2 * u + 1] * inv, hh[u], ll[u]);
         }
         if (tid < L) {
           *reinterpret_cast<uint4*>(oh + c0) = make_uint4(hh[0], hh[1], hh[2], hh[3]);

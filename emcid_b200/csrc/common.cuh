@@ -74,6 +74,17 @@ __device__ __forceinline__ void split_f16(float x, int lo_fmt, uint16_t& hi, uin
   lo = lo_fmt == FMT_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(r)) : __half_as_ushort(__float2half_rn(r));
 }
 
+// Two values at once, fp16 hi + fp16 lo, packed as {b : a} (a in the low half): one F2FP pack per plane instead of
+// two scalar conversions plus clamps and byte permutes per value (the epilogues and the softmax are conversion-bound).
+// Same result as split_f16(.., FMT_F16, ..): round-to-nearest, saturating at +-65504.
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(b), "f"(a));
+  float fa, fb;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(fa), "=f"(fb) : "r"(hi2));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(b - fb), "f"(a - fa));
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -83,6 +83,9 @@ struct GemmParams {
   int streamk;                 // 1: split the flattened (tile, k-block) space evenly over CTAs
   int n_fastest;               // 1: consecutive tiles walk along N (the tiles of one wave share A row blocks: the big
                                //    operand A is then read from HBM once, not once per N tile); 0: along M
+  int k_tri;                   // triangular operand: skip the k-blocks that are known zeros.  1: B is lower triangular
+                               // (k < n0 + BLOCK_N); 2: B is upper triangular (k >= n0); 3: A is lower triangular
+                               // (k < m0 + BLOCK_M).  Tile-level only (not with stream-K).
   int chunk_kblocks;           // k-blocks accumulated in TMEM between register folds
   const int* dyn_n;            // optional device scalar overriding N (fc1: number of valid tokens)
   const int* dyn_k;            // optional device scalar overriding K (SYRK: number of valid tokens)
@@ -125,22 +128,24 @@ struct Unit {
 
 // Deterministic work enumeration, evaluated identically by the producer, MMA and epilogue roles.
 struct Sched {
-  int m_tiles, n_tiles, kb_tile, R, lower, streamk, block_n, block_m, n_fastest;
+  int m_tiles, n_tiles, kb_tile, R, lower, streamk, block_n, block_m, n_fastest, k_tri, block_k;
   long long pos, end;          // stream-K: position in the flattened (tile, kb) space
   int tile, tile_step, num_tiles;
 
   // bid / nb: index and number of the scheduling entities (CTAs, or CTA pairs with 256-row tiles)
-  __device__ void init(const GemmParams& p, int block_n_, int block_k, int M, int N, int K, int block_m_ = GEMM_BLOCK_M,
+  __device__ void init(const GemmParams& p, int block_n_, int block_k_, int M, int N, int K, int block_m_ = GEMM_BLOCK_M,
                        int bid = blockIdx.x, int nb = gridDim.x) {
     block_n = block_n_;
     block_m = block_m_;
     m_tiles = (M + block_m - 1) / block_m;
     n_tiles = (N + block_n - 1) / block_n;
+    block_k = block_k_;
     kb_tile = (K + block_k - 1) / block_k;
     R = block_n / block_m;
     lower = p.lower;
     streamk = p.streamk;
     n_fastest = p.n_fastest;
+    k_tri = p.k_tri;
     if (lower) {
       num_tiles = 0;
       for (int j = 0; j < n_tiles; ++j) {
@@ -198,6 +203,9 @@ struct Sched {
     tile_origin(tile, u.m0, u.n0);
     u.kb0 = 0;
     u.kb1 = kb_tile;
+    if (k_tri == 1) { const int e = (u.n0 + block_n + block_k - 1) / block_k; if (e < u.kb1) u.kb1 = e; }
+    else if (k_tri == 2) { u.kb0 = u.n0 / block_k; }
+    else if (k_tri == 3) { const int e = (u.m0 + block_m + block_k - 1) / block_k; if (e < u.kb1) u.kb1 = e; }
     tile += tile_step;
     return true;
   }
@@ -531,13 +539,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
               const int cl = pc * 64 + 4 * k;
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
               if (col0 + cl < N) b = *reinterpret_cast<const float4*>(p.bias_col + col0 + cl);
-              uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-              split_f16(act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), FMT_F16, h0, l0);
-              split_f16(act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y)), FMT_F16, h1, l1);
-              split_f16(act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), FMT_F16, h2, l2);
-              split_f16(act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w)), FMT_F16, h3, l3);
-              hp[2 * k] = h0 | (static_cast<uint32_t>(h1) << 16); hp[2 * k + 1] = h2 | (static_cast<uint32_t>(h3) << 16);
-              lp[2 * k] = l0 | (static_cast<uint32_t>(l1) << 16); lp[2 * k + 1] = l2 | (static_cast<uint32_t>(l3) << 16);
+              split_f16x2(act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y)), hp[2 * k], lp[2 * k]);
+              split_f16x2(act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w)), hp[2 * k + 1],
+                          lp[2 * k + 1]);
             }
             const bool in_n = col0 + pc * 64 < N;
             if (EFLAGS & EF_P) {

@@ -8,9 +8,13 @@
 //        diag block   fp64 potrf + triangular inverse in shared memory (one CTA per layer)
 //        panel        L_ik = M_ik Linv_kk^T            tcgen05 GEMM (K = 128)
 //        trailing     M_ij -= L_ik L_jk^T  (i>=j>k)    tcgen05 GEMM, lower tiles
-//   L Y = Ks, L^T X = Y                        blocked right-looking TRSM on the transposed
-//                                              right-hand side [n x d]; every block product is a
-//                                              tcgen05 GEMM against L / L^T / Linv_kk planes
+//   Linv = L^-1                                blocked triangular inverse (block columns from the right): two
+//                                              tcgen05 GEMMs per block column, zero k-blocks skipped (k_tri)
+//   X = Linv^T (Linv Ks)                       two tcgen05 GEMMs per application on the transposed right-hand
+//                                              side [n x d] (the explicit inverse replaces ~100 dependent TRSM
+//                                              launches per application; what it loses in backward stability
+//                                              the fp64 refinement takes back).  EMCID_SOLVE_TRSM=1 keeps the
+//                                              blocked TRSM against L / L^T / Linv_kk planes.
 //   refinement (fp64 residual on DMMA):        R^T = Ks^T - X^T M64 ; X += solve(R)
 //   dW = resid adj_k^T                         fp64 DMMA GEMM, rounded once to fp32
 //
@@ -37,6 +41,8 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
                                                          float* __restrict__ LL_hi, float* __restrict__ LL_lo,
                                                          float* __restrict__ Li_hi, float* __restrict__ Li_lo,
                                                          float* __restrict__ LiT_hi, float* __restrict__ LiT_lo,
+                                                         float* __restrict__ Lv_hi, float* __restrict__ Lv_lo,
+                                                         float* __restrict__ LvT_hi, float* __restrict__ LvT_lo,
                                                          int* __restrict__ status) {
   extern __shared__ double sm[];
   constexpr int LD = SOLVE_NB + 1;
@@ -50,24 +56,45 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
     A[r * LD + c] = (c <= r) ? static_cast<double>(M32[base + static_cast<long long>(r) * d + c]) : 0.0;
   }
   __syncthreads();
-  // right-looking Cholesky
+  // right-looking Cholesky, two barriers per column.  The scaled column goes through colbuf so that the trailing
+  // update (16 x 16 thread grid, cyclic over the lower triangle) reads only colbuf and its own elements; loads are
+  // grouped ahead of the stores (shared-memory aliasing would otherwise serialise every element).  No division:
+  // rsqrt gives 1/L_jj, which the inverse sweep below reuses.
+  double* invd = colbuf + SOLVE_NB;  // [128] reciprocal diagonal of L
+  const int ty = tid >> 4, tx = tid & 15;
   for (int j = 0; j < SOLVE_NB; ++j) {
-    if (tid == 0) {
-      double ajj = A[j * LD + j];
-      if (!(ajj > 0.0)) {  // also catches NaN
-        atomicOr(status, 1);
-        ajj = 1.0;
-      }
-      A[j * LD + j] = sqrt(ajj);
-    }
-    __syncthreads();
-    const double inv = 1.0 / A[j * LD + j];
-    for (int i = j + 1 + tid; i < SOLVE_NB; i += blockDim.x) A[i * LD + j] *= inv;
-    __syncthreads();
+    double ajj = A[j * LD + j];
+    const bool bad = !(ajj > 0.0);  // also catches NaN
+    if (bad) ajj = 1.0;
+    const double inv = rsqrt(ajj);
     const int rem = SOLVE_NB - 1 - j;
-    for (int e = tid; e < rem * rem; e += blockDim.x) {
-      const int i = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= i) A[i * LD + c] -= A[i * LD + j] * A[c * LD + j];
+    if (tid < rem) colbuf[j + 1 + tid] = A[(j + 1 + tid) * LD + j] * inv;
+    __syncthreads();
+    double cv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = j + 1 + tx + 16 * u;
+      cv[u] = c < SOLVE_NB ? colbuf[c] : 0.0;
+    }
+    for (int i = j + 1 + ty; i < SOLVE_NB; i += 16) {
+      const double li = colbuf[i];
+      double av[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = j + 1 + tx + 16 * u;
+        av[u] = c <= i ? A[i * LD + c] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = j + 1 + tx + 16 * u;
+        if (c <= i) A[i * LD + c] = av[u] - li * cv[u];
+      }
+    }
+    if (tid < rem) A[(j + 1 + tid) * LD + j] = colbuf[j + 1 + tid];
+    if (tid == 0) {
+      A[j * LD + j] = ajj * inv;
+      invd[j] = inv;
+      if (bad) atomicOr(status, 1);
     }
     __syncthreads();
   }
@@ -81,25 +108,31 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
     LL_lo[base + static_cast<long long>(r) * d + c] = lo;
   }
   __syncthreads();
-  // in-place inverse of the lower-triangular A (column sweep from the right)
+  // in-place inverse of the lower-triangular A (column sweep from the right): columns > j already hold Linv,
+  //   Linv[i][j] = -(sum_{k=j+1..i} Linv[i][k] L[k][j]) / L[j][j];  the two threads of a row split the sum
+  const int rp = tid >> 1, par = tid & 1;
   for (int j = SOLVE_NB - 1; j >= 0; --j) {
-    for (int i = j + 1 + tid; i < SOLVE_NB; i += blockDim.x) colbuf[i] = A[i * LD + j];
+    const int i = j + 1 + rp;
+    if (i < SOLVE_NB && par == 0) colbuf[i] = A[i * LD + j];
     __syncthreads();
-    const double ajj = 1.0 / A[j * LD + j];
-    for (int i = j + 1 + tid; i < SOLVE_NB; i += blockDim.x) {
-      double s0 = 0.0, s1 = 0.0;
-      int kk = j + 1;
-      for (; kk + 1 <= i; kk += 2) {
+    const double ajj = invd[j];
+    double s0 = 0.0, s1 = 0.0;
+    if (i < SOLVE_NB) {
+      int kk = j + 1 + par;
+#pragma unroll 2
+      for (; kk + 2 <= i; kk += 4) {
         s0 += A[i * LD + kk] * colbuf[kk];
-        s1 += A[i * LD + kk + 1] * colbuf[kk + 1];
+        s1 += A[i * LD + kk + 2] * colbuf[kk + 2];
       }
       if (kk <= i) s0 += A[i * LD + kk] * colbuf[kk];
-      A[i * LD + j] = -(s0 + s1) * ajj;
     }
-    __syncthreads();
+    s0 += s1;
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    if (i < SOLVE_NB && par == 0) A[i * LD + j] = -s0 * ajj;
+    __syncthreads();   // colbuf is free
     if (tid == 0) A[j * LD + j] = ajj;
-    __syncthreads();
   }
+  __syncthreads();
   const long long ibase = (static_cast<long long>(b) * d + static_cast<long long>(k) * SOLVE_NB) * SOLVE_NB;
   for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
     const int r = e / SOLVE_NB, c = e % SOLVE_NB;
@@ -107,9 +140,17 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
     split_tf32(static_cast<float>((c <= r) ? A[r * LD + c] : 0.0), hi, lo);
     Li_hi[ibase + r * SOLVE_NB + c] = hi;
     Li_lo[ibase + r * SOLVE_NB + c] = lo;
+    if (Lv_hi) {   // diagonal block of the explicit inverse
+      Lv_hi[base + static_cast<long long>(r) * d + c] = hi;
+      Lv_lo[base + static_cast<long long>(r) * d + c] = lo;
+    }
     split_tf32(static_cast<float>((r <= c) ? A[c * LD + r] : 0.0), hi, lo);
     LiT_hi[ibase + r * SOLVE_NB + c] = hi;
     LiT_lo[ibase + r * SOLVE_NB + c] = lo;
+    if (Lv_hi) {
+      LvT_hi[base + static_cast<long long>(r) * d + c] = hi;
+      LvT_lo[base + static_cast<long long>(r) * d + c] = lo;
+    }
   }
 }
 
@@ -239,6 +280,9 @@ __global__ void resid_kernel(const float* __restrict__ St, long long lds, long l
 struct SolveWs {
   // fp32
   float *M32, *Mp_hi, *Mp_lo, *LL_hi, *LL_lo, *Li_hi, *Li_lo, *LiT_hi, *LiT_lo, *W, *Wp_hi, *Wp_lo, *Kd_hi, *Kd_lo;
+  float *Lv_hi, *Lv_lo, *LvT_hi, *LvT_lo;   // explicit inverse L^-1 and its transpose (planes)
+  float *Tp_hi, *Tp_lo;                     // [B][d x 128] scratch of the inverse's block-column step
+  float *W2p_hi, *W2p_lo;                   // [B][n_pad x d] intermediate of an application (planes of Linv-applied rhs)
   // fp64
   double *M64, *Ks64t, *X64t, *Kd64, *inv_left, *norms;
   size_t bytes;
@@ -273,6 +317,14 @@ inline SolveWs solve_carve(void* base, int B, int d, int h, int n) {
   w.Wp_lo = reinterpret_cast<float*>(take(nd * 4));
   w.Kd_hi = reinterpret_cast<float*>(take(nd * 4));
   w.Kd_lo = reinterpret_cast<float*>(take(nd * 4));
+  w.Lv_hi = reinterpret_cast<float*>(take(dd * 4));
+  w.Lv_lo = reinterpret_cast<float*>(take(dd * 4));
+  w.LvT_hi = reinterpret_cast<float*>(take(dd * 4));
+  w.LvT_lo = reinterpret_cast<float*>(take(dd * 4));
+  w.Tp_hi = reinterpret_cast<float*>(take(d128 * 4));
+  w.Tp_lo = reinterpret_cast<float*>(take(d128 * 4));
+  w.W2p_hi = reinterpret_cast<float*>(take(nd * 4));
+  w.W2p_lo = reinterpret_cast<float*>(take(nd * 4));
   w.bytes = static_cast<size_t>(p - p0) + 1024;
   return w;
 }
@@ -294,6 +346,7 @@ struct SubGemm {
   const PlaneMaps* A; int a_row0, a_col0, a_batch_rows;
   const PlaneMaps* B; int b_row0, b_col0, b_batch_rows;
   int M, N, K, lower;
+  int k_tri;   // see GemmParams::k_tri
   float alpha, beta;
   const float* Cin; long long ldcin, cin_batch;
   float* C; long long ldc, c_batch;
@@ -311,6 +364,7 @@ inline int run_subgemm(const SubGemm& g, int batches, int sm_count, cudaStream_t
   p.a_row0 = g.a_row0; p.a_col0 = g.a_col0; p.a_batch_rows = g.a_batch_rows;
   p.b_row0 = g.b_row0; p.b_col0 = g.b_col0; p.b_batch_rows = g.b_batch_rows;
   p.lower = g.lower;
+  p.k_tri = g.k_tri;
   p.chunk_kblocks = 1;  // shortest TMEM chains: the factorisation wants every bit 3xTF32 can give
   p.alpha = g.alpha; p.beta = g.beta;
   p.Cin = g.Cin; p.ldcin = g.ldcin; p.cin_batch = g.cin_batch;
@@ -348,7 +402,7 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
   const long long dd = static_cast<long long>(d) * d, nd = static_cast<long long>(n_pad) * d;
 
   static thread_local bool potrf_configured[16] = {false};
-  const int potrf_smem = (SOLVE_NB * (SOLVE_NB + 1) + SOLVE_NB) * sizeof(double);
+  const int potrf_smem = (SOLVE_NB * (SOLVE_NB + 1) + 2 * SOLVE_NB) * sizeof(double);
   if (device < 0 || device >= 16 || !potrf_configured[device]) {
     EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem));
     if (device >= 0 && device < 16) potrf_configured[device] = true;
@@ -369,13 +423,27 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
                                                         w.Ks64t, w.W, w.Wp_hi, w.Wp_lo, w.Kd64, w.Kd_hi, w.Kd_lo);
     EMCID_CUDA_CHECK(cudaGetLastError());
   }
-  PlaneMaps mKd, mMp, mLL, mLi, mLiT, mW;
+  // EMCID_SOLVE_TRSM=1: blocked TRSM sweeps instead of the explicit inverse
+  static const bool use_trsm = [] { const char* e = getenv("EMCID_SOLVE_TRSM"); return e && e[0] == '1'; }();
+  if (!use_trsm) {
+    // the strictly upper (Lv) / lower (LvT) blocks are never written and never read by the k_tri-limited products;
+    // zero them anyway so that no stale NaN pattern can ever reach a TMA box
+    EMCID_CUDA_CHECK(cudaMemsetAsync(w.Lv_hi, 0, B * dd * sizeof(float), stream));
+    EMCID_CUDA_CHECK(cudaMemsetAsync(w.Lv_lo, 0, B * dd * sizeof(float), stream));
+    EMCID_CUDA_CHECK(cudaMemsetAsync(w.LvT_hi, 0, B * dd * sizeof(float), stream));
+    EMCID_CUDA_CHECK(cudaMemsetAsync(w.LvT_lo, 0, B * dd * sizeof(float), stream));
+  }
+  PlaneMaps mKd, mMp, mLL, mLi, mLiT, mW, mLv, mLvT, mTp, mW2;
   if ((rc = make_plane_maps(&mKd, w.Kd_hi, w.Kd_lo, static_cast<long long>(B) * d, n_pad, n_pad)) ||
       (rc = make_plane_maps(&mMp, w.Mp_hi, w.Mp_lo, static_cast<long long>(B) * d, d, d)) ||
       (rc = make_plane_maps(&mLL, w.LL_hi, w.LL_lo, static_cast<long long>(B) * d, d, d)) ||
       (rc = make_plane_maps(&mLi, w.Li_hi, w.Li_lo, static_cast<long long>(B) * d, SOLVE_NB, SOLVE_NB)) ||
       (rc = make_plane_maps(&mLiT, w.LiT_hi, w.LiT_lo, static_cast<long long>(B) * d, SOLVE_NB, SOLVE_NB)) ||
-      (rc = make_plane_maps(&mW, w.Wp_hi, w.Wp_lo, static_cast<long long>(B) * n_pad, d, d)))
+      (rc = make_plane_maps(&mW, w.Wp_hi, w.Wp_lo, static_cast<long long>(B) * n_pad, d, d)) ||
+      (rc = make_plane_maps(&mLv, w.Lv_hi, w.Lv_lo, static_cast<long long>(B) * d, d, d)) ||
+      (rc = make_plane_maps(&mLvT, w.LvT_hi, w.LvT_lo, static_cast<long long>(B) * d, d, d)) ||
+      (rc = make_plane_maps(&mTp, w.Tp_hi, w.Tp_lo, static_cast<long long>(B) * d, SOLVE_NB, SOLVE_NB)) ||
+      (rc = make_plane_maps(&mW2, w.W2p_hi, w.W2p_lo, static_cast<long long>(B) * n_pad, d, d)))
     return rc;
 
   // 2. M32 = lambda*C32 + Ks Ks^T (lower tiles; fp32 + planes)   and   M64 (fp64, full)
@@ -389,6 +457,8 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
     g.C = w.M32; g.ldc = d; g.c_batch = dd;
     g.P_hi = w.Mp_hi; g.P_lo = w.Mp_lo; g.ldp = d; g.p_batch = dd;
     if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+    // (forming M64 on a side stream next to the factorisation was considered and dropped: its 2880 long-running
+    // CTAs would sit in front of every short, dependent launch of the Cholesky chain)
     DgemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = d; p.N = d; p.K = n;
@@ -406,7 +476,8 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
   // 3. blocked right-looking Cholesky of M32
   for (int k = 0; k < nblk; ++k) {
     potrf_diag_kernel<<<B, 256, potrf_smem, stream>>>(w.M32, d, k, w.LL_hi, w.LL_lo, w.Li_hi, w.Li_lo, w.LiT_hi,
-                                                      w.LiT_lo, status_dev);
+                                                      w.LiT_lo, use_trsm ? nullptr : w.Lv_hi, w.Lv_lo, w.LvT_hi, w.LvT_lo,
+                                                      status_dev);
     EMCID_CUDA_CHECK(cudaGetLastError());
     const int rem = d - (k + 1) * SOLVE_NB;
     if (rem <= 0) break;
@@ -433,7 +504,52 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
     if ((rc = run_subgemm(g, B, sms, stream))) return rc;
   }
 
+  // 3b. explicit inverse, block columns from the right (the diagonal blocks came from potrf_diag_kernel):
+  //        T          = Linv[k+1:, k+1:] L[k+1:, k]        (A lower triangular: k_tri = 3)
+  //        Linv[k+1:, k] = -T Linv_kk                      (planes into Lv, transposed planes into LvT)
+  if (!use_trsm) {
+    for (int k = nblk - 2; k >= 0; --k) {
+      const int r0 = (k + 1) * SOLVE_NB, rem = d - r0;
+      SubGemm g;
+      memset(&g, 0, sizeof(g));
+      g.A = &mLv; g.a_row0 = r0; g.a_col0 = r0; g.a_batch_rows = d;
+      g.B = &mLL; g.b_row0 = k * SOLVE_NB; g.b_col0 = r0; g.b_batch_rows = d;   // upper blocks of LL hold L^T
+      g.M = rem; g.N = SOLVE_NB; g.K = rem; g.k_tri = 3;
+      g.alpha = 1.0f;
+      g.P_hi = w.Tp_hi + static_cast<long long>(r0) * SOLVE_NB; g.P_lo = w.Tp_lo + static_cast<long long>(r0) * SOLVE_NB;
+      g.ldp = SOLVE_NB; g.p_batch = static_cast<long long>(d) * SOLVE_NB;
+      if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+      memset(&g, 0, sizeof(g));
+      g.A = &mTp; g.a_row0 = r0; g.a_col0 = 0; g.a_batch_rows = d;
+      g.B = &mLiT; g.b_row0 = k * SOLVE_NB; g.b_col0 = 0; g.b_batch_rows = d;
+      g.M = rem; g.N = SOLVE_NB; g.K = SOLVE_NB;
+      g.alpha = -1.0f;
+      const long long off = static_cast<long long>(r0) * d + static_cast<long long>(k) * SOLVE_NB;
+      const long long off_t = static_cast<long long>(k) * SOLVE_NB * d + r0;
+      g.P_hi = w.Lv_hi + off; g.P_lo = w.Lv_lo + off; g.ldp = d; g.p_batch = dd;
+      g.Pt_hi = w.LvT_hi + off_t; g.Pt_lo = w.LvT_lo + off_t; g.ldpt = d; g.pt_batch = dd;
+      if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+    }
+  }
+
   // 4./5. solve + refinement; W holds the current right-hand side (transposed), then the solution
+  //   Y^T = W Linv^T  (B = Linv, lower triangular: k_tri = 1)  ->  planes only
+  //   X^T = Y^T Linv  (B = Linv^T, upper triangular: k_tri = 2) ->  fp32 into W
+  auto apply_inverse = [&]() -> int {
+    SubGemm g;
+    memset(&g, 0, sizeof(g));
+    g.A = &mW; g.a_batch_rows = n_pad;
+    g.B = &mLv; g.b_batch_rows = d;
+    g.M = n_pad; g.N = d; g.K = d; g.k_tri = 1; g.alpha = 1.0f;
+    g.P_hi = w.W2p_hi; g.P_lo = w.W2p_lo; g.ldp = d; g.p_batch = nd;
+    if (int r = run_subgemm(g, B, sms, stream)) return r;
+    memset(&g, 0, sizeof(g));
+    g.A = &mW2; g.a_batch_rows = n_pad;
+    g.B = &mLvT; g.b_batch_rows = d;
+    g.M = n_pad; g.N = d; g.K = d; g.k_tri = 2; g.alpha = 1.0f;
+    g.C = w.W; g.ldc = d; g.c_batch = nd;
+    return run_subgemm(g, B, sms, stream);
+  };
   auto trsm_both = [&]() -> int {
     SubGemm g;
     for (int i = 0; i < nblk; ++i) {  // forward: Y^T L^T = W
@@ -497,7 +613,7 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
       if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
       if ((rc = launch_split_planes(w.W, d, B * n_pad, d, 1.0f, w.Wp_hi, w.Wp_lo, d, stream))) return rc;
     }
-    if ((rc = trsm_both())) return rc;
+    if ((rc = use_trsm ? trsm_both() : apply_inverse())) return rc;
     solve_axpy_kernel<<<sms * 8, 256, 0, stream>>>(w.W, w.X64t, tot, it > 0 ? 1 : 0);
     EMCID_CUDA_CHECK(cudaGetLastError());
     if (adaptive && it > 0) {
