@@ -56,47 +56,79 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
     A[r * LD + c] = (c <= r) ? static_cast<double>(M32[base + static_cast<long long>(r) * d + c]) : 0.0;
   }
   __syncthreads();
-  // right-looking Cholesky, two barriers per column.  The scaled column goes through colbuf so that the trailing
-  // update (16 x 16 thread grid, cyclic over the lower triangle) reads only colbuf and its own elements; loads are
-  // grouped ahead of the stores (shared-memory aliasing would otherwise serialise every element).  No division:
-  // rsqrt gives 1/L_jj, which the inverse sweep below reuses.
-  double* invd = colbuf + SOLVE_NB;  // [128] reciprocal diagonal of L
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int j = 0; j < SOLVE_NB; ++j) {
-    double ajj = A[j * LD + j];
-    const bool bad = !(ajj > 0.0);  // also catches NaN
-    if (bad) ajj = 1.0;
-    const double inv = rsqrt(ajj);
-    const int rem = SOLVE_NB - 1 - j;
-    if (tid < rem) colbuf[j + 1 + tid] = A[(j + 1 + tid) * LD + j] * inv;
-    __syncthreads();
-    double cv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = j + 1 + tx + 16 * u;
-      cv[u] = c < SOLVE_NB ? colbuf[c] : 0.0;
-    }
-    for (int i = j + 1 + ty; i < SOLVE_NB; i += 16) {
-      const double li = colbuf[i];
-      double av[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c = j + 1 + tx + 16 * u;
-        av[u] = c <= i ? A[i * LD + c] : 0.0;
+  // Right-looking Cholesky in 32-column panels.  Inside a panel every column costs two barriers and a rank-1 update
+  // restricted to the panel's own columns (lane = column, warp = row phase); the rest of the block is updated once
+  // per panel with a 32-deep product (4 independent rows in flight per thread).  Loads are grouped ahead of the
+  // stores: with shared-memory aliasing the compiler would otherwise serialise every element.  No division: rsqrt
+  // gives 1/L_jj, which the inverse below reuses.
+  double* invd = colbuf + SOLVE_NB;        // [128] reciprocal diagonal of L
+  double* T = invd + SOLVE_NB;             // [96][33] scratch of the blocked inverse
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int p0 = 0; p0 < SOLVE_NB; p0 += 32) {
+    const int p1 = p0 + 32;
+    for (int j = p0; j < p1; ++j) {
+      double ajj = A[j * LD + j];
+      const bool bad = !(ajj > 0.0);  // also catches NaN
+      if (bad) ajj = 1.0;
+      const double inv = rsqrt(ajj);
+      const int rem = SOLVE_NB - 1 - j;
+      if (tid < rem) colbuf[j + 1 + tid] = A[(j + 1 + tid) * LD + j] * inv;
+      __syncthreads();
+      const int c = j + 1 + lane;
+      if (c < p1) {
+        const double lc = colbuf[c];
+        int i = c + wid;
+        for (; i + 24 < SOLVE_NB; i += 32) {
+          const double l0 = colbuf[i], l1 = colbuf[i + 8], l2 = colbuf[i + 16], l3 = colbuf[i + 24];
+          const double a0 = A[i * LD + c], a1 = A[(i + 8) * LD + c], a2 = A[(i + 16) * LD + c], a3 = A[(i + 24) * LD + c];
+          A[i * LD + c] = a0 - l0 * lc;
+          A[(i + 8) * LD + c] = a1 - l1 * lc;
+          A[(i + 16) * LD + c] = a2 - l2 * lc;
+          A[(i + 24) * LD + c] = a3 - l3 * lc;
+        }
+        for (; i < SOLVE_NB; i += 8) A[i * LD + c] -= colbuf[i] * lc;
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c = j + 1 + tx + 16 * u;
-        if (c <= i) A[i * LD + c] = av[u] - li * cv[u];
+      if (tid < rem) A[(j + 1 + tid) * LD + j] = colbuf[j + 1 + tid];
+      if (tid == 0) {
+        A[j * LD + j] = ajj * inv;
+        invd[j] = inv;
+        if (bad) atomicOr(status, 1);
       }
+      __syncthreads();
     }
-    if (tid < rem) A[(j + 1 + tid) * LD + j] = colbuf[j + 1 + tid];
-    if (tid == 0) {
-      A[j * LD + j] = ajj * inv;
-      invd[j] = inv;
-      if (bad) atomicOr(status, 1);
+    if (p1 < SOLVE_NB) {
+      // A[i][c] -= sum_{t in panel} L[i][t] L[c][t]   for p1 <= c <= i
+      for (int c = p1 + lane; c < SOLVE_NB; c += 32) {
+        double lc[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) lc[t] = A[c * LD + p0 + t];
+        int i = c + wid;
+        for (; i + 24 < SOLVE_NB; i += 32) {
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            s0 += A[i * LD + p0 + t] * lc[t];
+            s1 += A[(i + 8) * LD + p0 + t] * lc[t];
+            s2 += A[(i + 16) * LD + p0 + t] * lc[t];
+            s3 += A[(i + 24) * LD + p0 + t] * lc[t];
+          }
+          A[i * LD + c] -= s0;
+          A[(i + 8) * LD + c] -= s1;
+          A[(i + 16) * LD + c] -= s2;
+          A[(i + 24) * LD + c] -= s3;
+        }
+        for (; i < SOLVE_NB; i += 8) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int t = 0; t < 32; t += 2) {
+            s0 += A[i * LD + p0 + t] * lc[t];
+            s1 += A[i * LD + p0 + t + 1] * lc[t + 1];
+          }
+          A[i * LD + c] -= s0 + s1;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   // L_kk -> LL planes (lower = L, upper = L^T)
   for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
@@ -108,31 +140,66 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
     LL_lo[base + static_cast<long long>(r) * d + c] = lo;
   }
   __syncthreads();
-  // in-place inverse of the lower-triangular A (column sweep from the right): columns > j already hold Linv,
-  //   Linv[i][j] = -(sum_{k=j+1..i} Linv[i][k] L[k][j]) / L[j][j];  the two threads of a row split the sum
-  const int rp = tid >> 1, par = tid & 1;
-  for (int j = SOLVE_NB - 1; j >= 0; --j) {
-    const int i = j + 1 + rp;
-    if (i < SOLVE_NB && par == 0) colbuf[i] = A[i * LD + j];
-    __syncthreads();
-    const double ajj = invd[j];
-    double s0 = 0.0, s1 = 0.0;
-    if (i < SOLVE_NB) {
-      int kk = j + 1 + par;
-#pragma unroll 2
-      for (; kk + 2 <= i; kk += 4) {
-        s0 += A[i * LD + kk] * colbuf[kk];
-        s1 += A[i * LD + kk + 2] * colbuf[kk + 2];
+  // In-place inverse X = L^-1 in 32 x 32 blocks.
+  // (1) the four diagonal blocks, one warp each (column sweep from the right, warp-synchronous):
+  //       X[l][j] = -(sum_{k=j+1..l} X[l][k] L[k][j]) / L[j][j]
+  if (wid < 4) {
+    const int r0 = 32 * wid;
+    double* cbw = colbuf + r0;
+    const double* row = A + (r0 + lane) * LD + r0;
+    for (int j = 31; j >= 0; --j) {
+      if (lane > j) cbw[lane] = row[j];
+      __syncwarp();
+      double s0 = 0.0, s1 = 0.0;
+      if (lane > j) {
+        int kk = j + 1;
+        for (; kk + 1 <= lane; kk += 2) {
+          s0 += row[kk] * cbw[kk];
+          s1 += row[kk + 1] * cbw[kk + 1];
+        }
+        if (kk <= lane) s0 += row[kk] * cbw[kk];
       }
-      if (kk <= i) s0 += A[i * LD + kk] * colbuf[kk];
+      const double dj = invd[r0 + j];
+      __syncwarp();
+      if (lane > j) A[(r0 + lane) * LD + r0 + j] = -(s0 + s1) * dj;
+      if (lane == j) A[(r0 + j) * LD + r0 + j] = dj;
+      __syncwarp();
     }
-    s0 += s1;
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-    if (i < SOLVE_NB && par == 0) A[i * LD + j] = -s0 * ajj;
-    __syncthreads();   // colbuf is free
-    if (tid == 0) A[j * LD + j] = ajj;
   }
   __syncthreads();
+  // (2) block columns from the right (from X L = I):  X_ij = -(sum_{k=j+1..i} X_ik L_kj) X_jj   for i > j.
+  //     Phase a gathers the sums of a whole block column into T (L_kj of that column is still intact and the X_ik
+  //     to its right are final); phase b multiplies by the diagonal block and overwrites L_ij.
+  for (int jb = 2; jb >= 0; --jb) {
+    const int c0 = 32 * jb, nbk = 3 - jb;
+    for (int e = tid; e < nbk * 1024; e += 256) {
+      const int bi = e >> 10, r = (e >> 5) & 31, c = e & 31;
+      const int rowi = 32 * (jb + 1 + bi) + r;
+      const double* xr = A + rowi * LD;
+      double s0 = 0.0, s1 = 0.0;
+      int kc = c0 + 32;
+      for (; kc + 1 <= rowi; kc += 2) {
+        s0 += xr[kc] * A[kc * LD + c0 + c];
+        s1 += xr[kc + 1] * A[(kc + 1) * LD + c0 + c];
+      }
+      if (kc <= rowi) s0 += xr[kc] * A[kc * LD + c0 + c];
+      T[(bi * 32 + r) * 33 + c] = s0 + s1;
+    }
+    __syncthreads();
+    for (int e = tid; e < nbk * 1024; e += 256) {
+      const int bi = e >> 10, r = (e >> 5) & 31, c = e & 31;
+      const double* tr = T + (bi * 32 + r) * 33;
+      double s0 = 0.0, s1 = 0.0;
+      int t = c;
+      for (; t + 1 < 32; t += 2) {
+        s0 += tr[t] * A[(c0 + t) * LD + c0 + c];
+        s1 += tr[t + 1] * A[(c0 + t + 1) * LD + c0 + c];
+      }
+      if (t < 32) s0 += tr[t] * A[(c0 + t) * LD + c0 + c];
+      A[(32 * (jb + 1 + bi) + r) * LD + c0 + c] = -(s0 + s1);
+    }
+    __syncthreads();
+  }
   const long long ibase = (static_cast<long long>(b) * d + static_cast<long long>(k) * SOLVE_NB) * SOLVE_NB;
   for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
     const int r = e / SOLVE_NB, c = e % SOLVE_NB;
@@ -402,7 +469,7 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
   const long long dd = static_cast<long long>(d) * d, nd = static_cast<long long>(n_pad) * d;
 
   static thread_local bool potrf_configured[16] = {false};
-  const int potrf_smem = (SOLVE_NB * (SOLVE_NB + 1) + 2 * SOLVE_NB) * sizeof(double);
+  const int potrf_smem = (SOLVE_NB * (SOLVE_NB + 1) + 2 * SOLVE_NB + 96 * 33) * sizeof(double);
   if (device < 0 || device >= 16 || !potrf_configured[device]) {
     EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem));
     if (device >= 0 && device < 16) potrf_configured[device] = true;

@@ -1,6 +1,6 @@
 #!/bin/bash
-# r01l: restructured diagonal-block factorisation
-OUT=gpurun_out/r01l
+# r01m: panel-blocked diagonal-block factorisation
+OUT=gpurun_out/r01m
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "exit=$?" >> $OUT/pytest_gpu.log
 for cfg in "5 1000" "1 1000" "1 100" "5 100"; do
