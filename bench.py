@@ -342,6 +342,43 @@ def run_ours(args):
         M0 = 4000.0 * C32[0].double() + Kt[0].double().T @ Kt[0].double()
         solve["rel_residual_fp64"] = float((M0 @ adj[0] - Kt[0].double().T).norm() / Kt[0].double().norm())
         del M0, adj, resid, dW
+    # ---- the same update through the public edit API (BASELINE configs[2]): execute_emcid_text_encoder on 1000
+    # ICEB-style requests with cached v* and device-resident C: key extraction (library forward), 5 sequential
+    # solves (layer i+1 sees dW_i), deltas returned on the host as the reference returns them.
+    edit = None
+    if not args.no_solve and not args.no_edit and args.encoder == "sd-text" and not args.layers:
+        from types import SimpleNamespace
+
+        from emcid_b200 import compute_ks, emcid_main
+
+        reqs = synth.make_edit_requests(args.concepts)
+        tok = synth.WordHashTokenizer(49408)
+        tmp_e = tempfile.mkdtemp(prefix="emcid_bench_edit_")
+        cache = os.path.join(tmp_e, "vstar", "c_")
+        synth.write_vstar_cache(cache, reqs, H, seed=2)
+        hp = synth.make_edit_hparams(LAYERS, mom2_n_samples=K * C)
+        pipe = SimpleNamespace(text_encoder=model, tokenizer=tok, device=dev)
+        emcid_main.COV_CACHE.clear()
+        for nm in names:   # C = mom2 / count of this run's statistics, device resident (what get_cov_text_encoder caches)
+            emcid_main.COV_CACHE[(model.config._name_or_path.replace("/", "_"), nm)] = (out[nm][0] / max(count0, 1)).float()
+        times = []
+        for rep in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            deltas = emcid_main.execute_emcid_text_encoder(pipe, reqs, hp, cache_name=cache, stat_dir=tmp_e, verbose=False)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        emcid_main.TIMING = True   # one more repetition with a device synchronise between the stages
+        emcid_main.execute_emcid_text_encoder(pipe, reqs, hp, cache_name=cache, stat_dir=tmp_e, verbose=False)
+        emcid_main.TIMING = False
+        stages = {k: round(v, 2) for k, v in emcid_main.LAST_EDIT_TIMING.items()}
+        edit = {"ms": 1e3 * min(times[1:]), "first_call_ms": 1e3 * times[0], "stages_ms": stages,
+                "concepts": args.concepts, "prompts": 3 * args.concepts,
+                "layers": len(LAYERS), "native_keys": bool(compute_ks.LAST_PATH["native"]),
+                "what": "execute_emcid_text_encoder(pipe, requests, hparams, cache_name): v* npz reads, tokenisation, key/"
+                        "output extraction per layer, 5 sequential solves with in-place weight writes, deltas to host (fp64)"}
+        del deltas
+        emcid_main.COV_CACHE.clear()
     runner.close()
 
     # ---- e2e: the public API (reference signature) from HOST captions to HOST mom2, copies inside the timed region.
@@ -404,7 +441,7 @@ def run_ours(args):
                        "forward": "native (csrc/clip.cuh, packed tokens, 3xFP16 GEMMs)" if native else
                                   "HF torch fp32 forward with fused kernels hooked in",
                        "count_check": count0},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solve": solve, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solve": solve, "edit": edit, "clocks": clocks,
             "gpu_launches": int(n_launch),
         }
         emit(line)
@@ -454,6 +491,7 @@ def main():
                     help="captions per GPU of the end-to-end call (default: BASELINE configs[1], 100k; 0 = steps x captions)")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-edit", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -56,6 +56,8 @@ SIGNATURES = {
     "emcid_clip_set_layer": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p), c_void_p]),
     "emcid_clip_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    ctypes.POINTER(c_int), ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
+    "emcid_clip_forward_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                        c_void_p, c_void_p, c_void_p]),
     "emcid_clip_launches": (c_longlong, [c_void_p]),
     "emcid_clip_destroy": (c_int, [c_void_p]),
     "emcid_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

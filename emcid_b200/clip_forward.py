@@ -11,6 +11,8 @@ spliced in by hooks (``layer_stats.TextEncoderMom2Pass``) — still no CPU path.
 from __future__ import annotations
 
 import ctypes
+import os
+import weakref
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -88,20 +90,52 @@ class NativeClipTextEncoder:
                 ctypes.byref(self._h), self.device.index, self.n_layers, self.hidden, cfg.num_attention_heads, self.inter,
                 _lib.act_code(cfg.hidden_act), self.max_positions, tm.embeddings.token_embedding.weight.shape[0], eps,
                 self.max_tokens, self.max_captions))
+        self._sig: Dict[object, tuple] = {}   # what was uploaded: (data_ptr, version) of every source tensor
+        self.sync_weights(model)
+
+    @staticmethod
+    def _layer_tensors(ly):
+        a = ly.self_attn
+        mods = [ly.layer_norm1, a.q_proj, a.k_proj, a.v_proj, a.out_proj, ly.layer_norm2, ly.mlp.fc1, ly.mlp.fc2]
+        out = []
+        for m in mods:
+            out.append(m.weight)
+            out.append(m.bias)
+        return out
+
+    @staticmethod
+    def _signature(tensors) -> tuple:
+        return tuple((0, 0) if t is None else (t.data_ptr(), t._version) for t in tensors)
+
+    def sync_weights(self, model, upto_layer: Optional[int] = None) -> int:
+        """(Re-)upload the embeddings and layers [0, upto_layer] whose source tensors changed since the last upload
+        (PyTorch bumps `Tensor._version` on every in-place write: that is how the edit loop's `w[...] = w0 + dW`,
+        reference emcid_main.py:1061, becomes visible here).  Returns the number of layers uploaded."""
+        tm = _text_model(model)
+        lib = _lib.lib()
+        n = 0
+        with torch.cuda.device(self.device):
             stream = _lib.current_stream_ptr()
-            tok = tm.embeddings.token_embedding.weight.detach().contiguous()
-            pos = tm.embeddings.position_embedding.weight.detach().contiguous()
-            _lib.check(lib.emcid_clip_set_embeddings(self._h, _lib.ptr(tok), _lib.ptr(pos), stream))
-            for i, ly in enumerate(tm.encoder.layers):
-                a = ly.self_attn
-                mods = [ly.layer_norm1, a.q_proj, a.k_proj, a.v_proj, a.out_proj, ly.layer_norm2, ly.mlp.fc1, ly.mlp.fc2]
-                tensors = []
-                for m in mods:
-                    tensors.append(m.weight.detach().contiguous())
-                    tensors.append(None if m.bias is None else m.bias.detach().contiguous())
+            emb = [tm.embeddings.token_embedding.weight, tm.embeddings.position_embedding.weight]
+            sig = self._signature(emb)
+            if self._sig.get("emb") != sig:
+                tok, pos = emb[0].detach().contiguous(), emb[1].detach().contiguous()
+                _lib.check(lib.emcid_clip_set_embeddings(self._h, _lib.ptr(tok), _lib.ptr(pos), stream))
+                self._sig["emb"] = sig
+            last = self.n_layers - 1 if upto_layer is None else min(int(upto_layer), self.n_layers - 1)
+            for i in range(last + 1):
+                src = self._layer_tensors(tm.encoder.layers[i])
+                sig = self._signature(src)
+                if self._sig.get(i) == sig:
+                    continue
+                tensors = [None if t is None else t.detach().contiguous() for t in src]
                 arr = (ctypes.c_void_p * 16)(*[_lib.ptr(t) or None for t in tensors])
                 _lib.check(lib.emcid_clip_set_layer(self._h, i, arr, stream))
-            torch.cuda.synchronize(self.device)  # the library copied / split everything: sources may change now
+                self._sig[i] = sig
+                n += 1
+            if n:
+                torch.cuda.synchronize(self.device)  # the library copied / split everything: sources may change now
+        return n
 
     def _stream(self) -> int:
         return int(torch.cuda.current_stream(self.device).cuda_stream)
@@ -132,6 +166,24 @@ class NativeClipTextEncoder:
         self._run(ids, pos, cu, S, T, n_layers, [], [], out)
         return out
 
+    def forward_keys(self, ids, pos, cu, S: int, T: int, layer: int, rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """fc2 input [R, intermediate] and fc2 output [R, hidden] of encoder layer `layer` at the packed token rows
+        `rows` (int32), see emcid_clip_forward_keys in include/emcid_b200.h."""
+        ids = ids.to(self.device, non_blocking=True)
+        pos = pos.to(self.device, non_blocking=True)
+        cu = cu.to(self.device, non_blocking=True)
+        rows = rows.to(self.device, dtype=torch.int32, non_blocking=True).contiguous()
+        R = rows.numel()
+        k = torch.empty(R, self.inter, dtype=torch.float32, device=self.device)
+        z = torch.empty(R, self.hidden, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().emcid_clip_forward_keys(self._h, _lib.ptr(ids), _lib.ptr(pos), _lib.ptr(cu), S, T, int(layer),
+                                                          _lib.ptr(rows), R, _lib.ptr(k), _lib.ptr(z), self._stream()))
+        s = torch.cuda.current_stream(self.device)
+        for t in (ids, pos, cu, rows):
+            t.record_stream(s)
+        return k, z
+
     def launches(self) -> int:
         return int(_lib.lib().emcid_clip_launches(self._h))
 
@@ -143,5 +195,57 @@ class NativeClipTextEncoder:
     def __del__(self):
         try:
             self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one cached native encoder per live model for the key extraction of the edit (emcid_b200/compute_ks.py)
+# ---------------------------------------------------------------------------------------------------------
+_KEY_ENCODERS: Dict[int, Tuple["weakref.ref", NativeClipTextEncoder]] = {}
+
+
+def release_key_encoders() -> None:
+    for _, enc in list(_KEY_ENCODERS.values()):
+        enc.close()
+    _KEY_ENCODERS.clear()
+
+
+def key_encoder(model, n_tokens: int, n_captions: int, upto_layer: int) -> Optional[NativeClipTextEncoder]:
+    """The cached encoder of `model`, grown to the requested capacity, with the weights of layers [0, upto_layer]
+    brought up to date.  None when the model is not a plain fp32 CLIP text tower on a CUDA device or
+    EMCID_NATIVE_KEYS=0."""
+    if os.environ.get("EMCID_NATIVE_KEYS", "1") == "0" or not supports(model):
+        return None
+    key = id(model)
+    hit = _KEY_ENCODERS.get(key)
+    enc = None
+    if hit is not None:
+        ref, enc = hit
+        if ref() is not model:        # id reuse after the old model died
+            enc.close()
+            enc = None
+    if enc is not None and (enc.max_tokens < n_tokens or enc.max_captions < n_captions):
+        n_tokens, n_captions = max(n_tokens, enc.max_tokens), max(n_captions, enc.max_captions)
+        torch.cuda.synchronize(enc.device)
+        enc.close()
+        enc = None
+    if enc is None:
+        enc = NativeClipTextEncoder(model, max(int(n_tokens), 1024), max(int(n_captions), 64))
+        try:
+            ref = weakref.ref(model, lambda _r, k=key: _drop_key_encoder(k))
+        except TypeError:
+            ref = (lambda m=model: m)
+        _KEY_ENCODERS[key] = (ref, enc)
+    else:
+        enc.sync_weights(model, upto_layer)
+    return enc
+
+
+def _drop_key_encoder(key: int) -> None:
+    hit = _KEY_ENCODERS.pop(key, None)
+    if hit is not None:
+        try:
+            hit[1].close()
         except Exception:
             pass

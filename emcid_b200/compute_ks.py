@@ -2,19 +2,52 @@
 
 Behavioural mirror of emcid/compute_z.py::get_module_input_output_at_words (:2252-2384),
 tokenize_prompts (:56-74), emcid/compute_ks.py::compute_ks_text_encoder (:21-41) and
-experiments/causal_trace.py::find_token_range (:1057-1103).  The forward itself stays in PyTorch
-(HF CLIP); SURVEY.md §8(a9) keeps this producer on the caller side of the hot path.  One forward
-yields both the fc2 input and output, so callers that need both (the edit loop does, reference
-emcid_main.py:987-1014) pay for one pass instead of two.
+experiments/causal_trace.py::find_token_range (:1057-1103).  One forward yields both the fc2 input and output, so callers that need both (the edit loop does,
+reference emcid_main.py:987-1014) pay for one pass instead of two.  For a plain fp32 HF CLIP text tower on a
+CUDA device that forward runs in the library (emcid_clip_forward_keys: packed prompts, 3xFP16 tcgen05 GEMMs,
+fc2 evaluated on the looked-up rows only); the edit loop's in-place weight writes reach the library through
+`Tensor._version` (clip_forward.NativeClipTextEncoder.sync_weights).  Everything else (CLIPModel, several
+edit tokens per prompt, non-right-padded masks, EMCID_NATIVE_KEYS=0) keeps the traced HF forward.
 """
 from __future__ import annotations
 
+import re
 import unicodedata
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from . import nethook
+from . import clip_forward, nethook
+
+_FC2_NAME = re.compile(r"^(?:text_model\.)?encoder\.layers\.(\d+)\.mlp\.fc2$")
+LAST_PATH = {"native": False}   # which path served the last call (tests / bench read it)
+
+
+def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name: str):
+    """(fc2 input [P, d], fc2 output [P, h]) at lookup[p][0] of every prompt through the library, or None when
+    this model / module / mask is not covered."""
+    m = _FC2_NAME.match(module_name)
+    if m is None or not text_encoder.device.type == "cuda":
+        return None
+    layer = int(m.group(1))
+    tm = getattr(text_encoder, "text_model", text_encoder)
+    if not hasattr(tm, "encoder") or layer >= len(tm.encoder.layers):
+        return None
+    if not clip_forward.supports(text_encoder):
+        return None
+    max_pos = tm.embeddings.position_embedding.weight.shape[0]
+    packed = clip_forward.pack_batch({"input_ids": enc["input_ids"], "attention_mask": enc["attention_mask"]}, max_pos)
+    if packed is None:
+        return None
+    ids, pos, cu, S, T = packed
+    if T == 0:
+        return None
+    native = clip_forward.key_encoder(text_encoder, T, S, layer)
+    if native is None:
+        return None
+    first = torch.tensor([row[0] for row in lookup], dtype=torch.int32, device=cu.device)
+    rows = cu[:-1] + first
+    return native.forward_keys(ids, pos, cu, S, T, layer, rows)
 
 
 def tokenize_prompts(prompts, tokenizer, device, padding_length=None):
@@ -69,39 +102,61 @@ def _prompts_and_subjects(requests: List[Dict]):
     return prompts, subjects, counts
 
 
-def get_module_input_output_at_words(text_encoder, tok, requests: List[Dict], module_name: str,
-                                     num_fact_token: int = 1):
-    """(input, output) of `module_name` at the last subject token of every source prompt, averaged
-    over each request's prompts: [n, d] and [n, h]  (num_fact_token == 1) or with an extra
-    token dimension [n, num_fact_token, ·] (last subject token, EOS, then padding positions)."""
-    device = text_encoder.device
+def prepare_lookup(tok, requests: List[Dict], num_fact_token: int, device):
+    """Tokenised source prompts, the looked-up token positions of every prompt and the prompts-per-request counts
+    (compute_z.py:2284-2300).  Independent of the layer: the edit loop computes it once per edit."""
     prompts, subjects, counts = _prompts_and_subjects(requests)
     enc = tokenize_prompts(prompts, tok, device)
+    # token ids as host lists: find_token_range walks them one by one (a device tensor would cost a sync per token)
     if num_fact_token == 1:
-        lookup = [[find_token_range(tok, ids, w)[-1] - 1] for ids, w in zip(enc["input_ids"], subjects)]
+        lookup = [[find_token_range(tok, ids, w)[-1] - 1] for ids, w in zip(enc["input_ids"].tolist(), subjects)]
     else:
         extra = num_fact_token - 2
         enc = tokenize_prompts(prompts, tok, device, padding_length=len(enc["input_ids"][0]) + extra)
         lookup = []
-        for ids, w, mask in zip(enc["input_ids"], subjects, enc["attention_mask"]):
-            eos = int(mask.sum()) - 1
+        for ids, w, n_valid in zip(enc["input_ids"].tolist(), subjects, enc["attention_mask"].sum(1).tolist()):
+            eos = int(n_valid) - 1
             lookup.append([find_token_range(tok, ids, w)[-1] - 1] + list(range(eos, eos + extra + 1)))
+    return enc, lookup, counts
+
+
+def get_module_input_output_at_words(text_encoder, tok, requests: List[Dict], module_name: str,
+                                     num_fact_token: int = 1, prepared=None):
+    """(input, output) of `module_name` at the last subject token of every source prompt, averaged
+    over each request's prompts: [n, d] and [n, h]  (num_fact_token == 1) or with an extra
+    token dimension [n, num_fact_token, ·] (last subject token, EOS, then padding positions)."""
+    device = text_encoder.device
+    enc, lookup, counts = prepared if prepared is not None else prepare_lookup(tok, requests, num_fact_token, device)
     assert len(enc["input_ids"]) == len(lookup)
-    with torch.no_grad(), nethook.TraceDict(text_encoder, [module_name], retain_input=True, retain_output=True) as td:
-        if type(text_encoder).__name__ == "CLIPModel":
-            text_encoder.get_text_features(**enc)
-        else:
-            text_encoder(**enc)
-        idx = torch.tensor(lookup, device=device)                        # [P, F]
-        rows = torch.arange(len(lookup), device=device)[:, None]
-        l_in = td[module_name].input[rows, idx].detach().clone()         # [P, F, d]
-        l_out = td[module_name].output[rows, idx].detach().clone()       # [P, F, h]
-    ins, outs, at = [], [], 0
-    for c in counts:
-        ins.append(l_in[at: at + c].mean(0))
-        outs.append(l_out[at: at + c].mean(0))
-        at += c
-    ins, outs = torch.stack(ins, 0), torch.stack(outs, 0)
+    native = None
+    if num_fact_token == 1 and type(text_encoder).__name__ != "CLIPModel":
+        with torch.no_grad():
+            native = _native_keys(text_encoder, enc, lookup, module_name)
+    LAST_PATH["native"] = native is not None
+    if native is not None:
+        l_in, l_out = native[0][:, None, :], native[1][:, None, :]      # [P, 1, d], [P, 1, h]
+    else:
+        with torch.no_grad(), nethook.TraceDict(text_encoder, [module_name], retain_input=True, retain_output=True) as td:
+            if type(text_encoder).__name__ == "CLIPModel":
+                text_encoder.get_text_features(**enc)
+            else:
+                text_encoder(**enc)
+            idx = torch.tensor(lookup, device=device)                        # [P, F]
+            rows = torch.arange(len(lookup), device=device)[:, None]
+            l_in = td[module_name].input[rows, idx].detach().clone()         # [P, F, d]
+            l_out = td[module_name].output[rows, idx].detach().clone()       # [P, F, h]
+    if len(set(counts)) == 1:
+        # every request has the same number of prompts (ICEB / artist templates): one reduction instead of n
+        c = counts[0]
+        ins = l_in.reshape(len(counts), c, *l_in.shape[1:]).mean(1)
+        outs = l_out.reshape(len(counts), c, *l_out.shape[1:]).mean(1)
+    else:
+        ins, outs, at = [], [], 0
+        for c in counts:
+            ins.append(l_in[at: at + c].mean(0))
+            outs.append(l_out[at: at + c].mean(0))
+            at += c
+        ins, outs = torch.stack(ins, 0), torch.stack(outs, 0)
     if num_fact_token == 1:
         ins, outs = ins[:, 0], outs[:, 0]
     return ins, outs

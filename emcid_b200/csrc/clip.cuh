@@ -609,12 +609,35 @@ inline int clip_layernorm(ClipHandle* H, const float* x, int T, const float* w, 
   return set_error(EMCID_ERR_UNSUPPORTED, "clip_layernorm: hidden size %d too large", H->h);
 }
 
+// Key extraction: rows `rows[r]` of the act(fc1) planes -> fp32 keys (hi + lo: the 22-bit split is exact to 2^-23) and a
+// compact copy of the planes (operand of the fc2 product on those rows only).
+__global__ void clip_gather_keys_kernel(const uint16_t* __restrict__ f_hi, const uint16_t* __restrict__ f_lo, long long ldf,
+                                        const int* __restrict__ rows, int R, int T, int d, int dp, float* __restrict__ k_out,
+                                        uint16_t* __restrict__ g_hi, uint16_t* __restrict__ g_lo) {
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    int src = rows[r];
+    src = src < 0 ? 0 : (src >= T ? T - 1 : src);
+    const uint16_t* sh = f_hi + static_cast<long long>(src) * ldf;
+    const uint16_t* sl = f_lo + static_cast<long long>(src) * ldf;
+    for (int c = threadIdx.x; c < dp; c += blockDim.x) {
+      const uint16_t hh = sh[c], ll = sl[c];
+      g_hi[static_cast<long long>(r) * dp + c] = hh;
+      g_lo[static_cast<long long>(r) * dp + c] = ll;
+      if (c < d) k_out[static_cast<long long>(r) * d + c] = __half2float(__ushort_as_half(hh)) + __half2float(__ushort_as_half(ll));
+    }
+  }
+}
+
 // Runs layers [0, n_layers) (full layers) — or, when stats are requested, up to fc1 of the deepest edited
 // layer — over `T` packed tokens of `S` captions.  stat_layers / accs: edited layers (ascending) and their
 // accumulators.  hidden_out (optional, [T x h] fp32): the residual stream after the last executed FULL layer.
+// Key-extraction mode (keys_layer >= 0; replaces the traced HF forward of emcid/compute_z.py:2300-2316): full layers
+// [0, keys_layer), then layer keys_layer up to act(fc1); k_out [n_keys x d] = fc2 INPUT rows `key_rows` (packed token
+// indices, device), z_out [n_keys x h] = fc2 OUTPUT of those rows (fc2 runs on the gathered rows only).
 inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int* cu_seqlens, int S, int T,
                         int n_layers, int n_stat, const int* stat_layers, Mom2Handle* const* accs, float* hidden_out,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int keys_layer = -1, const int* key_rows = nullptr, int n_keys = 0,
+                        float* k_out = nullptr, float* z_out = nullptr) {
   EMCID_CHECK(H && ids && pos && cu_seqlens, EMCID_ERR_INVALID, "clip_forward: null argument");
   EMCID_CHECK(T >= 0 && T <= H->cap_tokens && S >= 0 && S <= H->cap_seqs, EMCID_ERR_INVALID,
               "clip_forward: %d tokens / %d captions exceed the handle capacity (%lld / %d)", T, S, H->cap_tokens, H->cap_seqs);
@@ -627,7 +650,15 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
                 "clip_forward: accumulator %d does not match the encoder (d=%d vs %d)", i, accs[i]->d, H->d);
     last_stat = stat_layers[i];
   }
-  const int run_layers = n_stat > 0 ? last_stat + 1 : n_layers;
+  if (keys_layer >= 0) {
+    EMCID_CHECK(n_stat == 0 && keys_layer < H->L && key_rows && k_out && z_out && n_keys > 0 && n_keys <= T, EMCID_ERR_INVALID,
+                "clip_forward: bad key-extraction arguments (layer %d, %d keys, %d tokens)", keys_layer, n_keys, T);
+    EMCID_CHECK(static_cast<long long>(n_keys) * H->dp <= static_cast<long long>(H->d) * H->tp, EMCID_ERR_INVALID,
+                "clip_forward: %d keys do not fit the gather buffer", n_keys);
+    EMCID_CHECK((reinterpret_cast<uintptr_t>(z_out) & 15) == 0 && (H->h % 4) == 0, EMCID_ERR_INVALID,
+                "clip_forward: z_out must be 16-byte aligned");
+  }
+  const int run_layers = keys_layer >= 0 ? keys_layer + 1 : (n_stat > 0 ? last_stat + 1 : n_layers);
   for (int l = 0; l < run_layers; ++l)
     EMCID_CHECK((*H->layers)[l].set, EMCID_ERR_INVALID, "clip_forward: weights of layer %d were never set", l);
   if (T == 0) return EMCID_OK;
@@ -738,6 +769,24 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       A->launches += 1;
     }
     if (is_last) break;
+    if (l == keys_layer) {
+      uint16_t* g_hi = H->ft_hi;   // the transposed planes are idle in this mode: compact [n_keys x dp] copy of the key rows
+      uint16_t* g_lo = H->ft_lo;
+      clip_gather_keys_kernel<<<n_keys < sms * 8 ? n_keys : sms * 8, 256, 0, stream>>>(
+          H->f_hi, H->f_lo, H->dp, key_rows, n_keys, T, H->d, H->dp, k_out, g_hi, g_lo);
+      EMCID_CUDA_CHECK(cudaGetLastError());
+      H->launches += 1;
+      CUtensorMap mg_hi, mg_lo;
+      GemmOutMaps om_z = {};
+      if ((rc = make_tmap_2d(&mg_hi, g_hi, n_keys, H->d, H->dp, 128, 2, 0, rb)) ||
+          (rc = make_tmap_2d(&mg_lo, g_lo, n_keys, H->d, H->dp, 128, 2, 0, rb)) ||
+          (use_tma_epi && (rc = make_tmap_2d(&om_z.c, z_out, n_keys, H->h, H->h, 128, 4))))
+        return rc;
+      if ((rc = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, nullptr,
+                            nullptr, 0, stream, use_tma_epi ? &om_z : nullptr)))
+        return rc;
+      break;
+    }
     if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
                           stream, pm_res)))
       return rc;

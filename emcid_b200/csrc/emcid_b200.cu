@@ -121,6 +121,13 @@ int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* posit
                       stat_layers, reinterpret_cast<Mom2Handle* const*>(accs), hidden_out, static_cast<cudaStream_t>(stream));
 }
 
+int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
+                            int n_captions, int n_tokens, int layer, const int32_t* key_rows, int n_keys, float* k_out,
+                            float* z_out, void* stream) {
+  return clip_forward(reinterpret_cast<ClipHandle*>(h), ids, positions, cu_seqlens, n_captions, n_tokens, 0, 0, nullptr,
+                      nullptr, nullptr, static_cast<cudaStream_t>(stream), layer, key_rows, n_keys, k_out, z_out);
+}
+
 long long emcid_clip_launches(emcid_clip_t* h) { return h ? reinterpret_cast<ClipHandle*>(h)->launches : 0; }
 
 int emcid_clip_destroy(emcid_clip_t* h) { return clip_destroy(reinterpret_cast<ClipHandle*>(h)); }

@@ -27,12 +27,29 @@ import numpy as np
 import torch
 
 from . import nethook
-from .compute_ks import get_module_input_output_at_words
+from .compute_ks import get_module_input_output_at_words, prepare_lookup
 from .globals import STATS_DIR, XL_STATS_DIR1, XL_STATS_DIR2
 from .layer_stats import layer_stats_text_encoder
 from .solve import DEFAULT_REFINE_STEPS, solve_layers
 
 COV_CACHE: Dict[Tuple[str, str], torch.Tensor] = {}
+
+# Set TIMING = True to have the edit loop synchronise the device between its stages and leave their wall-clock
+# milliseconds in LAST_EDIT_TIMING (bench.py does, for one extra repetition; off by default: no extra syncs).
+TIMING = False
+LAST_EDIT_TIMING: Dict[str, float] = {}
+
+
+def _tick(device, key: str, t0: float) -> float:
+    import time
+
+    if not TIMING:
+        return t0
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
+    t1 = time.perf_counter()
+    LAST_EDIT_TIMING[key] = LAST_EDIT_TIMING.get(key, 0.0) + 1e3 * (t1 - t0)
+    return t1
 
 
 def get_cov_text_encoder(model, tok, layer_name: str, mom2_dataset: str, mom2_n_samples: int, mom2_dtype: str,
@@ -80,11 +97,12 @@ def _load_vstars(requests, hparams, cache_name, device, suffix=""):
             raise NotImplementedError(
                 f"v_star cache miss for request {request['source']!r} ({path}): stage 1 (compute_z, UNet/VAE "
                 "optimisation) is outside the B200 hot path — precompute v_star with the reference")
-        zs.append(torch.from_numpy(np.load(path)["v_star"]).to(device))
+        zs.append(torch.from_numpy(np.load(path)["v_star"]))
+    # stacked on the host, one H2D copy (the reference moves every v* separately, :892-901)
     if getattr(hparams, "use_new_compute_z", False):
-        z = torch.stack(zs, dim=0)                      # [rq, num, h]
+        z = torch.stack(zs, dim=0).to(device)           # [rq, num, h]
         return z.permute(2, 0, 1).reshape(z.shape[2], -1)
-    return torch.stack(zs, dim=1)                       # [h, n]
+    return torch.stack(zs, dim=1).to(device)            # [h, n]
 
 
 def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_update_weight, stat_dir, verbose,
@@ -96,13 +114,21 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
     weights_copy = {n: w.detach().clone() for n, w in weights.items()}
     deltas = {}
     ew = hparams.edit_weight
+    # prompts, token ids and last-subject-token positions are the same for every layer: tokenise / look up once
+    import time
+
+    t = time.perf_counter()
+    prepared = prepare_lookup(tokenizer, requests, hparams.num_edit_tokens, device)
+    t = _tick(device, "tokenise_lookup_ms", t)
     try:
         with torch.no_grad():
             for i, layer in enumerate(layers):
                 module_name = hparams.rewrite_module_tmp.format(layer)
                 # one forward gives both the keys (:987-996) and the current outputs (:1004-1014)
                 layer_ks, cur_zs = get_module_input_output_at_words(
-                    text_encoder, tokenizer, requests, module_name, num_fact_token=hparams.num_edit_tokens)
+                    text_encoder, tokenizer, requests, module_name, num_fact_token=hparams.num_edit_tokens,
+                    prepared=prepared)
+                t = _tick(device, "keys_ms", t)
                 if hparams.num_edit_tokens > 1:
                     layer_ks = layer_ks.reshape(-1, layer_ks.shape[-1])
                     cur_zs = cur_zs.reshape(-1, cur_zs.shape[-1])
@@ -118,6 +144,7 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
                 adj_k, resid, dW = solve_layers(cov, layer_ks.float(), sources_t.float(), mom2_update_weight,
                                                 (ew / 0.5) ** 0.5, [len(layers) - i], refine_steps=refine_steps)
                 adj_k, resid, dW = adj_k[0], resid[0], dW[0]
+                t = _tick(device, "solve_ms", t)
                 name = names[i]
                 upd = upd_matrix_match_shape(dW, weights[name].shape)
                 if verbose:
@@ -125,6 +152,7 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
                     print("upd norm", torch.linalg.norm(upd))
                 weights[name][...] = weights_copy[name] + upd                     # :1061 — next layer sees it
                 deltas[name] = (adj_k.detach().cpu(), resid.detach().cpu())
+                t = _tick(device, "write_and_d2h_ms", t)
     finally:
         with torch.no_grad():
             for n, w in weights.items():
@@ -144,7 +172,12 @@ def execute_emcid_text_encoder(pipe, requests: List[Dict], hparams, cache_name: 
     if verbose:
         for request in requests:
             print(f"EMCID request sample: [{request['source']}] -> [{request['dest']}]")
+    import time
+
+    LAST_EDIT_TIMING.clear()
+    t = time.perf_counter()
     zs = _load_vstars(requests, hparams, cache_name, device)
+    _tick(device, "vstar_npz_read_ms", t)
     deltas = _insert_loop(pipe.text_encoder, pipe.tokenizer, requests, hparams, hparams.layers, zs,
                           hparams.mom2_update_weight, stat_dir, verbose, refine_steps)
     print(f"Deltas successfully computed for {list(deltas.keys())}")

@@ -284,11 +284,18 @@ def layer_stats_text_encoder_multi(
     runner = TextEncoderMom2Pass(model, todo, slab_tokens=slab_tokens, accumulator_factory=_accumulator_factory)
     t_loop = time.perf_counter()
     try:
+        t_wait = t_run = 0.0
+        t_prev = time.perf_counter()
         for batch in progress(loader, total=batch_count):
+            t_got = time.perf_counter()
+            t_wait += t_got - t_prev
             if ("packed_ids" in batch and batch["packed_ids"].numel() == 0) or \
                     ("input_ids" in batch and batch["input_ids"].numel() == 0):
+                t_prev = time.perf_counter()
                 continue
             runner.run_batch(batch)  # host tensors: packed on the host, then one pinned H2D copy per field
+            t_prev = time.perf_counter()
+            t_run += t_prev - t_got
         t_fin = time.perf_counter()
         results = runner.finalize()
         LAST_PASS_INFO.update(native_forward=runner._native is not None, launches=runner.launches())
@@ -310,7 +317,8 @@ def layer_stats_text_encoder_multi(
             dist.barrier()
         # host-side timeline of the pass (no extra synchronisation: the loop time includes whatever the host waited for)
         t_end = time.perf_counter()
-        LAST_PASS_INFO["timing"] = {"setup_s": t_loop - t_start, "loop_s": t_fin - t_loop, "finalize_s": t_end - t_fin}
+        LAST_PASS_INFO["timing"] = {"setup_s": t_loop - t_start, "loop_s": t_fin - t_loop, "finalize_s": t_end - t_fin,
+                                    "loader_wait_s": t_wait, "run_batch_s": t_run}
     finally:
         runner.close()
     return stats

@@ -92,3 +92,82 @@ def make_caption_matrix(n: int, vocab: int = 49408, seed: int = 0, width: int = 
     ids[:, 0] = vocab - 2
     ids[:, -1] = vocab - 1
     return ids
+
+
+# ---------------------------------------------------------------------------------------------- edit workload (config 3)
+class WordHashTokenizer:
+    """Offline stand-in for the CLIP tokenizer (no vocabulary files exist in the build/bench environment): whitespace
+    words hashed into the vocabulary, BOS first, EOS last, right padding with the EOS id like CLIP's tokenizer.  Implements
+    what tokenize_prompts / find_token_range call: __call__(prompts, return_tensors, padding, truncation[, max_length]),
+    decode(ids), model_max_length."""
+
+    model_max_length = 77
+
+    def __init__(self, vocab_size: int = 49408):
+        self.vocab_size = vocab_size
+        self.bos, self.eos = vocab_size - 2, vocab_size - 1
+        self._words = {}   # id -> word
+        self._ids = {}     # word -> id
+
+    def _id(self, word: str) -> int:
+        import zlib
+
+        i = self._ids.get(word)
+        if i is None:
+            i = zlib.crc32(word.encode()) % (self.vocab_size - 2)
+            while i in self._words:          # linear probing: ids stay unique, so decode() inverts encode()
+                i = (i + 1) % (self.vocab_size - 2)
+            self._words[i] = word
+            self._ids[word] = i
+        return i
+
+    def encode(self, text, truncation=True, max_length=None):
+        ids = [self.bos] + [self._id(w) for w in text.split()] + [self.eos]
+        limit = max_length or self.model_max_length
+        return ids if len(ids) <= limit else ids[: limit - 1] + [self.eos]
+
+    def __call__(self, prompts, return_tensors="pt", padding=True, truncation=True, max_length=None):
+        prompts = [prompts] if isinstance(prompts, str) else prompts
+        enc = [self.encode(p, max_length=max_length if truncation else None) for p in prompts]
+        width = max(len(e) for e in enc) if padding is True else (max_length or self.model_max_length)
+        ids = torch.full((len(enc), width), self.eos, dtype=torch.long)
+        mask = torch.zeros((len(enc), width), dtype=torch.long)
+        for i, e in enumerate(enc):
+            ids[i, : len(e)] = torch.tensor(e)
+            mask[i, : len(e)] = 1
+        return {"input_ids": ids, "attention_mask": mask}
+
+    def decode(self, ids):
+        if torch.is_tensor(ids):
+            ids = ids.tolist()
+        ids = [ids] if isinstance(ids, int) else ids
+        names = {self.bos: "<|startoftext|>", self.eos: "<|endoftext|>"}
+        return " ".join(names.get(int(i)) or self._words.get(int(i), f"w{int(i)}") for i in ids)
+
+
+def make_edit_requests(n: int):
+    """n requests with the three ICEB edit templates (dsets/iceb_dataset.py:325-329), two-word subjects."""
+    return [{"source": f"artist{i} name{i}", "dest": "art", "seed_train": 0,
+             "prompts": ["An image of {}", "A photo of {}", "{}"]} for i in range(n)]
+
+
+def make_edit_hparams(layers, mom2_n_samples: int, mom2_update_weight: float = 4000, edit_weight: float = 0.5):
+    """The fields of emcid/emcid_hparams.py::EMCIDHyperParams (:55-163) the stage-2 loop reads."""
+    from types import SimpleNamespace
+
+    return SimpleNamespace(layers=list(layers), mom2_update_weight=mom2_update_weight, edit_weight=edit_weight,
+                           rewrite_module_tmp="text_model.encoder.layers.{}.mlp.fc2", mom2_dataset="ccs_filtered",
+                           mom2_n_samples=mom2_n_samples, mom2_dtype="float32", num_edit_tokens=1, objective="ori",
+                           sld_supervision=False, use_new_compute_z=False)
+
+
+def write_vstar_cache(cache_name: str, requests, h: int, seed: int = 2):
+    """v* ~ N(0, 1) for every request, in the reference's cache layout (emcid_main.py:886-901)."""
+    import os
+
+    import numpy as np
+
+    g = torch.Generator().manual_seed(seed)
+    os.makedirs(os.path.dirname(cache_name) or ".", exist_ok=True)
+    for r in requests:
+        np.savez(cache_name + f"source_{r['source']}_dest_{r['dest']}.npz", v_star=torch.randn(h, generator=g).numpy())

@@ -113,6 +113,15 @@ int emcid_clip_set_layer(emcid_clip_t* h, int layer, const float* const* tensors
 int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
                        int n_captions, int n_tokens, int n_layers, int n_stat, const int* stat_layers,
                        emcid_mom2_t* const* accs, float* hidden_out, void* stream);
+/* Key extraction for the update (replaces the two traced HF forwards per edited layer of
+ *     get_module_input_output_at_words(...)                       emcid/compute_z.py:2252-2327, called at
+ *     emcid/emcid_main.py:987-996 (keys) and :1004-1014 (current outputs)):
+ * runs full layers [0, layer), then layer `layer` up to act(fc1), and returns for the packed token rows `key_rows`
+ * (device int32 [n_keys], the last-subject-token row of every prompt) the fc2 INPUT k_out [n_keys x intermediate] and the
+ * fc2 OUTPUT z_out [n_keys x hidden] (fc2.weight x + fc2.bias, computed on the gathered rows only), both fp32 device. */
+int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
+                            int n_captions, int n_tokens, int layer, const int32_t* key_rows, int n_keys, float* k_out,
+                            float* z_out, void* stream);
 long long emcid_clip_launches(emcid_clip_t* h);
 int emcid_clip_destroy(emcid_clip_t* h);
 

@@ -205,6 +205,43 @@ def test_native_forward_hidden_states_match_hf(dev, kind, n_caps):
         nat.close()
 
 
+@pytest.mark.parametrize("kind,layer,n_req", [("tiny", 1, 7), ("tiny-gelu", 0, 5), ("clip-l", 9, 40)])
+def test_native_key_extraction_matches_hf(dev, monkeypatch, kind, layer, n_req):
+    """Keys (fc2 input) and current outputs (fc2 output) at the last subject token: the library's forward
+    (emcid_clip_forward_keys) vs the traced HF forward of the reference (compute_z.py:2252-2327), before and
+    after an in-place weight edit (the insert loop writes W in place between layers, emcid_main.py:1061)."""
+    from emcid_b200 import clip_forward, compute_ks
+    model = rh.make_clip_text_model(kind, seed=8).to(dev)
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    reqs = rh.make_requests(n_req)
+    name = f"text_model.encoder.layers.{layer}.mlp.fc2"
+
+    def both():
+        monkeypatch.setenv("EMCID_NATIVE_KEYS", "0")
+        k_hf, z_hf = compute_ks.get_module_input_output_at_words(model, tok, reqs, name)
+        assert compute_ks.LAST_PATH["native"] is False
+        monkeypatch.setenv("EMCID_NATIVE_KEYS", "1")
+        k, z = compute_ks.get_module_input_output_at_words(model, tok, reqs, name)
+        assert compute_ks.LAST_PATH["native"] is True
+        return k, z, k_hf, z_hf
+
+    try:
+        k, z, k_hf, z_hf = both()
+        assert k.shape == k_hf.shape == (n_req, model.config.intermediate_size)
+        assert z.shape == z_hf.shape == (n_req, model.config.hidden_size)
+        assert rel_fro(k.cpu().numpy(), k_hf.cpu().numpy()) < 5e-6
+        assert rel_fro(z.cpu().numpy(), z_hf.cpu().numpy()) < 5e-6
+        with torch.no_grad():   # edit an earlier layer and the traced one in place
+            model.text_model.encoder.layers[0].mlp.fc2.weight[...] *= 1.25
+            model.text_model.encoder.layers[layer].mlp.fc2.weight[...] += 0.01
+        k2, z2, k2_hf, z2_hf = both()
+        assert rel_fro(z2_hf.cpu().numpy(), z_hf.cpu().numpy()) > 1e-3          # the edit is visible at all
+        assert rel_fro(k2.cpu().numpy(), k2_hf.cpu().numpy()) < 5e-6
+        assert rel_fro(z2.cpu().numpy(), z2_hf.cpu().numpy()) < 5e-6
+    finally:
+        clip_forward.release_key_encoders()
+
+
 def test_native_forward_falls_back_on_non_right_padding(dev, tmp_path):
     """A mask that is not a right-padding mask cannot be packed: the block goes through the HF forward with the
     fused kernels hooked in, and the statistics still match a direct masked Gram."""
