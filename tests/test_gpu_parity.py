@@ -393,6 +393,70 @@ def test_sequential_editing_matches_oracle(dev, tmp_path):
         assert rel_fro(got, want) < DW_TOL
 
 
+def test_sdxl_two_encoder_edit_matches_oracle(dev, tmp_path):
+    """apply_emcid_to_sdxl_text_encoders (emcid_main.py:38-106, :1085-1425): the stage-2 loop runs once per
+    encoder with its own layers / lambda / statistics directory and `_2` v* files (BASELINE configs[3] shape:
+    quick_gelu encoder 1, erf-gelu encoder 2)."""
+    from emcid_b200 import emcid_main
+    from types import SimpleNamespace
+    ss = 48
+    caps = rh.make_captions(64, 1000, seed=31)
+    ls = _patch_ds(caps)
+    tok = rh.FakeTokenizer(1000)
+    enc = []
+    for kind, seed, layers, lam, sub in (("tiny", 11, [0, 1], 4000.0, "text1"), ("tiny-gelu", 12, [1], 6000.0, "text2")):
+        m_gpu = rh.make_clip_text_model(kind, seed=seed).to(dev)
+        m_cpu = rh.make_clip_text_model(kind, seed=seed)
+        names = [f"text_model.encoder.layers.{l}.mlp.fc2" for l in layers]
+        sdir = tmp_path / sub
+        stats = ls.layer_stats_text_encoder_multi(m_gpu, None, names, stats_dir=sdir, sample_size=ss, precision="float32",
+                                                  progress=None, num_workers=0)
+        covs = {l: orc.cov_from_state(stats[n].mom2.mom2.numpy(), stats[n].mom2.count) for l, n in zip(layers, names)}
+        enc.append(SimpleNamespace(gpu=m_gpu, cpu=m_cpu, layers=layers, lam=lam, sdir=sdir, covs=covs))
+    reqs = rh.make_requests(6)
+    cache = str(tmp_path / "v" / "c_")
+    z1 = rh.write_vstar_cache(cache, reqs, 64, seed=5)
+    g2 = torch.Generator().manual_seed(6)
+    z2 = []
+    for r in reqs:   # encoder 2 reads the same names with a `_2` suffix (emcid_main.py:1157-1166)
+        v = torch.randn(64, generator=g2)
+        np.savez(cache + f"source_{r['source']}_dest_{r['dest']}_2.npz", v_star=v.numpy())
+        z2.append(v)
+    z2 = torch.stack(z2, dim=1)
+    hp = rh.make_hparams(enc[0].layers, ss, mom2_update_weight=enc[0].lam)
+    hp.layers_2, hp.mom2_update_weight_2 = enc[1].layers, enc[1].lam
+    pipe = SimpleNamespace(text_encoder=enc[0].gpu, tokenizer=tok, text_encoder_2=enc[1].gpu, tokenizer_2=tok, device=dev)
+    emcid_main.COV_CACHE.clear()
+    out = emcid_main.apply_emcid_to_sdxl_text_encoders(pipe, reqs, hp, device=dev, cache_name=cache, stat_dir=enc[0].sdir,
+                                                       stat_dir_2=enc[1].sdir, verbose=False, return_orig_text_encoder=True)
+    assert out[0] is pipe and out[1] is not None and out[2] is not None
+    for e, zs, orig in ((enc[0], z1, out[1]), (enc[1], z2, out[2])):
+        deltas = orc.execute_oracle(e.cpu, tok, reqs, e.layers, zs.numpy(), e.covs, e.lam, 0.5)
+        for l in e.layers:
+            w0 = e.cpu.text_model.encoder.layers[l].mlp.fc2.weight.numpy().astype(np.float64)
+            assert np.array_equal(orig.text_model.encoder.layers[l].mlp.fc2.weight.detach().cpu().numpy().astype(np.float64), w0)
+            want = orc.apply_delta(w0.astype(np.float32), *deltas[l]).astype(np.float64) - w0
+            got = e.gpu.text_model.encoder.layers[l].mlp.fc2.weight.detach().cpu().numpy().astype(np.float64) - w0
+            assert rel_fro(got, want) < DW_TOL
+
+
+def test_multi_token_edit_keeps_reference_semantics(dev, tmp_path):
+    """num_edit_tokens > 1 (emcid_main.py:993-996): n * num_edit_tokens key columns, looked up at the last subject
+    token, EOS and padding positions — served by the traced HF forward (padding rows do not exist in the packed
+    library forward), solved by the library."""
+    from emcid_b200 import compute_ks, emcid_main
+    from types import SimpleNamespace
+    model = rh.make_clip_text_model("tiny", seed=13).to(dev)
+    tok = rh.FakeTokenizer(1000)
+    reqs = rh.make_requests(4)
+    name = "text_model.encoder.layers.1.mlp.fc2"
+    k, z = compute_ks.get_module_input_output_at_words(model, tok, reqs, name, num_fact_token=3)
+    assert compute_ks.LAST_PATH["native"] is False
+    assert tuple(k.shape) == (4, 3, 256) and tuple(z.shape) == (4, 3, 64)
+    k1, z1 = compute_ks.get_module_input_output_at_words(model, tok, reqs, name, num_fact_token=1)
+    assert rel_fro(k[:, 0].cpu().numpy(), k1.cpu().numpy()) < 5e-6      # column 0 = the last subject token
+
+
 def test_smoke_entry(dev):
     import __graft_entry__
     __graft_entry__.smoke()
