@@ -755,6 +755,16 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       return rc;
     if (is_stat) {
       Mom2Handle* A = accs[si++];
+      // One launch over the whole block (hybrid schedule, gemm3x.cuh: whole tiles march through the tokens together, so
+      // each k-block of the planes is pulled from HBM once and shared through L2, and a tile is red.add'ed once per
+      // block instead of once per 4096-token slab; the 4 leftover pair tiles are stream-K'd).  EMCID_SYRK_HYBRID=0
+      // restores the slab launches (measured: 10 x 102 us per block and layer, 40 MB of red.add traffic each).
+      static const bool hybrid = [] { const char* e = getenv("EMCID_SYRK_HYBRID"); return !(e && e[0] == '0'); }();
+      if (hybrid && rb == 128) {
+        if ((rc = mom2_syrk_slab(A, ft, KIND_F16, 0, T, nullptr, stream, 2))) return rc;
+        A->slabs_since_fold += 4;
+        if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
+      } else {
       const int slab = A->slab;
       const long long nslabs = (T + slab - 1) / slab;
       long long per = round_up_ll((T + nslabs - 1) / nslabs, 64);
@@ -763,6 +773,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
         const int t = static_cast<int>(T - c0 < per ? T - c0 : per);
         if ((rc = mom2_syrk_slab(A, ft, rb == 64 ? KIND_F16_S64 : KIND_F16, static_cast<int>(c0), t, nullptr, stream))) return rc;
         if (++A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
+      }
       }
       clip_add_count_kernel<<<1, 1, 0, stream>>>(A->count, static_cast<long long>(T));
       EMCID_CUDA_CHECK(cudaGetLastError());

@@ -81,6 +81,9 @@ struct GemmParams {
   int b_batch_rows;
   int lower;                   // 1: only tiles that intersect the lower triangle (row >= col)
   int streamk;                 // 1: split the flattened (tile, k-block) space evenly over CTAs
+                               // 2: hybrid — as many whole tiles as divide evenly among the CTAs (each over the full K,
+                               //    all CTAs marching through K together: operand reuse in L2, ONE red.add per tile), then
+                               //    the leftover tiles stream-K'd; needs the red.add epilogue like 1
   int n_fastest;               // 1: consecutive tiles walk along N (the tiles of one wave share A row blocks: the big
                                //    operand A is then read from HBM once, not once per N tile); 0: along M
   int k_tri;                   // triangular operand: skip the k-blocks that are known zeros.  1: B is lower triangular
@@ -131,6 +134,7 @@ struct Sched {
   int m_tiles, n_tiles, kb_tile, R, lower, streamk, block_n, block_m, n_fastest, k_tri, block_k;
   long long pos, end;          // stream-K: position in the flattened (tile, kb) space
   int tile, tile_step, num_tiles;
+  int whole_end;               // hybrid: tiles [0, whole_end) are processed whole, [whole_end, num_tiles) are stream-K'd
 
   // bid / nb: index and number of the scheduling entities (CTAs, or CTA pairs with 256-row tiles)
   __device__ void init(const GemmParams& p, int block_n_, int block_k_, int M, int N, int K, int block_m_ = GEMM_BLOCK_M,
@@ -156,14 +160,16 @@ struct Sched {
       num_tiles = m_tiles * n_tiles;
     }
     if (kb_tile == 0) num_tiles = 0;
+    whole_end = streamk == 2 ? (num_tiles / nb) * nb : (streamk ? 0 : num_tiles);
+    tile = bid;
+    tile_step = nb;
     if (streamk) {
-      long long total = static_cast<long long>(num_tiles) * kb_tile;
+      long long total = static_cast<long long>(num_tiles - whole_end) * kb_tile;
       long long per = (total + nb - 1) / nb;
       pos = per * bid;
       end = pos + per < total ? pos + per : total;
     } else {
-      tile = bid;
-      tile_step = nb;
+      pos = end = 0;
     }
   }
 
@@ -187,19 +193,18 @@ struct Sched {
   }
 
   __device__ bool next(Unit& u) {
-    if (streamk) {
+    if (tile >= whole_end) {
       if (pos >= end) return false;
       int t = static_cast<int>(pos / kb_tile);
       int kb = static_cast<int>(pos - static_cast<long long>(t) * kb_tile);
       long long len = end - pos;
       if (len > kb_tile - kb) len = kb_tile - kb;
-      tile_origin(t, u.m0, u.n0);
+      tile_origin(whole_end + t, u.m0, u.n0);
       u.kb0 = kb;
       u.kb1 = kb + static_cast<int>(len);
       pos += len;
       return true;
     }
-    if (tile >= num_tiles) return false;
     tile_origin(tile, u.m0, u.n0);
     u.kb0 = 0;
     u.kb1 = kb_tile;

@@ -379,13 +379,13 @@ inline int mom2_fold(Mom2Handle* H, cudaStream_t stream) {
 // ([d x tokens], K-major over tokens); dyn_k optionally caps t by a device scalar.  Stream-K over
 // (tile, token block), red.add epilogue.  Also used by the native text-encoder forward (clip.cuh).
 inline int mom2_syrk_slab(Mom2Handle* H, const GemmOperands& ops, int kind, int col0, int t, const int* dyn_k,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int streamk_mode = 1) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = H->d; p.N = H->d; p.K = t;
   p.a_col0 = col0; p.b_col0 = col0;
   p.dyn_k = dyn_k;
-  p.lower = 1; p.streamk = 1;
+  p.lower = 1; p.streamk = streamk_mode;
   p.chunk_kblocks = H->chunk_syrk;
   p.C = H->acc32; p.ldc = H->d; p.lo_fmt = H->lo_fmt;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
