@@ -276,9 +276,24 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (stream-K lower SYRK on tcgen05), timed per launch with CUDA events
     for acc in runner.accs.values():
         acc.reset(); acc.profile(True)
+    if runner._native is not None:
+        runner._native.profile(True)
     for i in range(W, W + min(K, 2)):
         step(i)
     torch.cuda.synchronize()
+    forward_kernels = None
+    if runner._native is not None:
+        fk = runner._native.get_profile()
+        runner._native.profile(False)
+        forward_kernels = {}
+        for name, v in fk.items():
+            if v["launches"]:
+                e = {"launches": int(v["launches"]), "avg_launch_ms": v["ms"] / v["launches"],
+                     "share_of_step": v["ms"] / (min(K, 2) * ms_total / K)}
+                if v["flops"]:
+                    e["achieved_tflops"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
+                    e["issued_tflops"] = 3.0 * e["achieved_tflops"]
+                forward_kernels[name] = e
     prof = {"fc1_ms": 0.0, "fc1_rows": 0.0, "fc1_launches": 0.0, "syrk_ms": 0.0, "syrk_rows": 0.0, "syrk_launches": 0.0}
     for acc in runner.accs.values():
         p = acc.get_profile()
@@ -312,6 +327,9 @@ def run_ours(args):
                 "part of the native forward (EPI_LINEAR GEMM), not timed separately"),
         "kernel_share_of_step": (prof["syrk_ms"] + prof["fc1_ms"]) / (min(K, 2) * ms_total / K),
         "traffic": ncu_traffic(),
+        # the other kernels of the step, timed the same way (CUDA events on the launch stream, emcid_clip_profile);
+        # achieved = algorithmic 2MNK flops, issued = x3 for the 3-term split
+        "forward_kernels": forward_kernels,
     }
     # whole-step fraction of the tensor roofline (what the BASELINE metric asks next to tokens/s)
     step_tflops = value * len(LAYERS) * flops_per_token_layer / 1e12 / world

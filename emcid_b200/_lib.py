@@ -58,7 +58,10 @@ SIGNATURES = {
                                    ctypes.POINTER(c_int), ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "emcid_clip_forward_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                         c_void_p, c_void_p, c_void_p]),
+    "emcid_clip_profile": (c_int, [c_void_p, c_int]),
+    "emcid_clip_get_profile": (c_int, [c_void_p, ctypes.POINTER(c_double)]),
     "emcid_clip_launches": (c_longlong, [c_void_p]),
+    "emcid_release_cached_memory": (c_int, []),
     "emcid_clip_destroy": (c_int, [c_void_p]),
     "emcid_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "emcid_solve_layers": (

@@ -184,6 +184,19 @@ class NativeClipTextEncoder:
             t.record_stream(s)
         return k, z
 
+    PROFILE_TAGS = ("qkv", "out_proj", "fc1", "fc1_edited", "fc2", "attention", "layernorm")
+
+    def profile(self, enable: bool = True) -> None:
+        _lib.check(_lib.lib().emcid_clip_profile(self._h, 1 if enable else 0))
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        """{kernel class: {launches, ms, flops}} since the last call (see emcid_clip_get_profile)."""
+        out = (ctypes.c_double * (3 * len(self.PROFILE_TAGS)))()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().emcid_clip_get_profile(self._h, out))
+        return {t: {"launches": out[3 * i], "ms": out[3 * i + 1], "flops": out[3 * i + 2]}
+                for i, t in enumerate(self.PROFILE_TAGS)}
+
     def launches(self) -> int:
         return int(_lib.lib().emcid_clip_launches(self._h))
 

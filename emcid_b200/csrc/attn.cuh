@@ -19,28 +19,36 @@ namespace emcid {
 
 constexpr int ATTN_DH = 64;
 constexpr int ATTN_THREADS = 128;
-// smem: P hi/lo x 2 k-blocks | Q hi/lo | K hi/lo | V hi/lo | barriers.  Every tile holds lp rows of one 128-byte
-// swizzle row (lp * 128 B, a multiple of 2 KB).  The A operands (Q, P) are read by the MMA as 128-row tiles: rows
-// [lp, 128) alias whatever follows in shared memory — garbage in, garbage out, in accumulator rows that are never
-// stored (an output row depends on its own A row only) — so no A tile may be the last one of the allocation.
-// With CLIP's 77 tokens (lp = 80) the set is 102 KB and TWO CTAs are resident per SM: one unit's serial chain
-// (TMA -> S -> softmax -> P V -> store) hides behind the other CTA's.
+// smem: Q hi/lo | K hi/lo | V hi/lo | barriers; the P planes (hi/lo x 2 k-blocks) are written over Q and K, which
+// are dead once S = Q K^T has retired.  Every tile holds lp rows of one 128-byte swizzle row (lp * 128 B, a multiple of
+// 2 KB).  The A operands (Q, P) are read by the MMA as 128-row tiles: rows [lp, 128) alias whatever follows in shared
+// memory — garbage in, garbage out, in accumulator rows that are never stored (an output row depends on its own A row
+// only) — so the V tiles must stay behind them.  TMEM: 128 columns; O = P V accumulates over the columns S occupied
+// (S lives in registers by then).  With CLIP's 77 tokens (lp = 80) the set is 62 KB and THREE CTAs are resident per
+// SM: one unit's serial chain (TMA -> S -> softmax -> P V -> store) hides behind the other two.
 inline int attn_tile_bytes(int lp) { return lp * 128; }
-inline int attn_smem_bytes(int lp) { return 10 * attn_tile_bytes(lp) + 1024 /*barriers*/ + 1024 /*align slack*/; }
+inline int attn_smem_bytes(int lp) { return 6 * attn_tile_bytes(lp) + 1024 /*barriers*/ + 1024 /*align slack*/; }
+inline int attn_ctas_per_sm(int lp) {
+  const int by_smem = (227 * 1024) / (attn_smem_bytes(lp) + 1024);
+  const int cap = lp <= 80 ? 3 : 2;   // register file: 3 x 128 threads x 168 registers (the NC = 5 instantiation)
+  return by_smem < 1 ? 1 : (by_smem < cap ? by_smem : cap);
+}
 
 struct AttnMaps {
   CUtensorMap qk_hi, qk_lo;   // q|k|v planes [T x 3h], box 64 x 128: the store maps of the q/k/v projection
   CUtensorMap kv_hi, kv_lo;   // same tensor, box 64 x lp (Q, K and V tiles of one caption)
 };
 
-__global__ void __launch_bounds__(ATTN_THREADS, 2)
+// NC: 16-column chunks of S a thread keeps in registers (lp <= 16 * NC)
+template <int NC>
+__global__ void __launch_bounds__(ATTN_THREADS, NC <= 5 ? 3 : 2)
 clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restrict__ cu, int n_seqs, int heads, int h,
                          int lp /* padded caption length: multiple of 16, <= 128 */, float scale,
                          uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo, int ldo) {
   extern __shared__ uint8_t attn_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int kt = lp * 128;                       // bytes of one tile
-  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + 10 * kt);
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + 6 * kt);
   uint64_t* bar_v = bar_qk + 1;
   uint64_t* bar_s = bar_qk + 2;   // S = Q K^T finished
   uint64_t* bar_o = bar_qk + 3;   // O = P V finished
@@ -54,7 +62,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);   // S: columns [0, 128), O: [128, 192)
+    tmem_alloc(tmem_slot, 128);   // S: columns [0, lp); O: columns [0, 64) once S has been read
     tmem_relinquish();
   }
   tc_fence_before();
@@ -62,9 +70,9 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-  const uint32_t s_p = smem_u32(smem);          // P hi kb0 | P hi kb1 | P lo kb0 | P lo kb1
-  const uint32_t s_q = s_p + 4 * kt;            // Q hi | Q lo
+  const uint32_t s_q = smem_u32(smem);          // Q hi | Q lo
   const uint32_t s_k = s_q + 2 * kt, s_v = s_k + 2 * kt;
+  const uint32_t s_p = s_q;                     // P hi kb0 | P hi kb1 | P lo kb0 | P lo kb1 over Q and K
   const int n_units = n_seqs * heads;
   const int ksteps2 = lp / 16;                 // k-steps of the second product
   const uint32_t idesc1 = make_idesc(FMT_F16, FMT_F16, 128, static_cast<uint32_t>(lp));
@@ -73,7 +81,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
   auto issue_loads = [&](int unit) {
     const int head = unit % heads, seq = unit / heads;
     const int t0 = cu[seq];
-    uint8_t* base = smem + 4 * kt;
+    uint8_t* base = smem;
     mbar_arrive_expect_tx(bar_qk, 4 * kt);
     tma_load_2d(base, &tm.kv_hi, bar_qk, head * ATTN_DH, t0);
     tma_load_2d(base + kt, &tm.kv_lo, bar_qk, head * ATTN_DH, t0);
@@ -115,13 +123,13 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     if (warp * 32 < lp) {                          // warp-uniform; rows >= lp have no P row in the lp-row tiles
       const int i = tid;
       const bool live = i < L;
-      float v[8][16];
+      float v[NC][16];
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
+      for (int c = 0; c < NC; ++c)
         if (c * 16 < lp) tmem_ld_32x16(tmem_base + lane_addr + c * 16, v[c]);   // uniform predicate
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int u = 0; u < 16; ++u)
           if (c * 16 < lp && live && c * 16 + u <= i) mx = fmaxf(mx, v[c][u]);
@@ -130,7 +138,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
       const uint32_t prow = s_p + i * 128;
       const int sw = i & 7;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (c * 16 < lp) {
           uint32_t hh[8], ll[8];
 #pragma unroll
@@ -161,7 +169,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
       tc_fence_after();
       mbar_wait(bar_v, phase, 13);
       tc_fence_after();
-      const uint32_t tmem_o = tmem_base + 128;
+      const uint32_t tmem_o = tmem_base;
       for (int k = 0; k < ksteps2; ++k) {
         const int kb = k >> 2;
         const uint64_t ko = static_cast<uint64_t>((k & 3) * 2);
@@ -185,7 +193,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
 #pragma unroll
       for (int c0 = 0; c0 < ATTN_DH; c0 += 16) {
         float v[16];
-        tmem_ld_32x16(tmem_base + lane_addr + 128 + c0, v);
+        tmem_ld_32x16(tmem_base + lane_addr + c0, v);
         uint32_t hh[8], ll[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -205,7 +213,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 }  // namespace emcid

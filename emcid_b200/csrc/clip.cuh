@@ -67,6 +67,30 @@ struct ClipHandle {
   DeviceInfo info;
   long long launches;
   int attn_smem;
+  // measurement aid (emcid_clip_profile): CUDA events around every launch of the forward, tagged by kernel class
+  bool profile;
+  std::vector<cudaEvent_t>* ev;      // pairs (start, stop)
+  std::vector<int>* ev_tag;          // CLIP_TAG_* of each pair
+  std::vector<double>* ev_flops;     // algorithmic flops of each pair (2 M N K; 0 for memory-bound kernels)
+};
+
+// kernel classes of the profile: linear layers by role, attention, layer norm
+enum ClipTag : int { CLIP_TAG_QKV = 0, CLIP_TAG_OUT = 1, CLIP_TAG_FC1 = 2, CLIP_TAG_FC1_STAT = 3, CLIP_TAG_FC2 = 4,
+                     CLIP_TAG_ATTN = 5, CLIP_TAG_LN = 6, CLIP_TAG_COUNT = 7 };
+
+struct ClipProfScope {
+  ClipHandle* H; cudaStream_t stream; cudaEvent_t e0;
+  ClipProfScope(ClipHandle* H_, cudaStream_t s, int tag, double flops) : H(H_), stream(s), e0(nullptr) {
+    if (!H->profile) return;
+    cudaEvent_t e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e0 = nullptr; return; }
+    cudaEventRecord(e0, stream);
+    H->ev->push_back(e0); H->ev->push_back(e1);
+    H->ev_tag->push_back(tag); H->ev_flops->push_back(flops);
+  }
+  ~ClipProfScope() {
+    if (e0) cudaEventRecord(H->ev->back(), stream);
+  }
 };
 
 // ---- kernels ------------------------------------------------------------------------------------
@@ -128,6 +152,58 @@ __global__ void clip_layernorm_kernel(const float* __restrict__ x, int T, int h,
         split_f16(y, FMT_F16, hh, ll);
         oh[c] = hh;
         ol[c] = ll;
+      }
+    }
+  }
+}
+
+// Same, four consecutive columns per lane: float4 loads, one 8-byte store per plane (h % 4 == 0, ldo % 4 == 0).
+// NV4 = ceil(h / 128) float4 per lane.
+template <int NV4>
+__global__ void clip_layernorm4_kernel(const float* __restrict__ x, int T, int h, const float* __restrict__ w,
+                                       const float* __restrict__ b, float eps, uint16_t* __restrict__ o_hi,
+                                       uint16_t* __restrict__ o_lo, int ldo) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const float inv_h = 1.0f / static_cast<float>(h);
+  const int h4 = h >> 2;
+  for (int t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
+    const float4* src = reinterpret_cast<const float4*>(x + static_cast<long long>(t) * h);
+    float4 v[NV4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < h4 ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_h;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      if (lane + 32 * i < h4) {
+        const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_h + eps);
+    uint2* oh = reinterpret_cast<uint2*>(o_hi + static_cast<long long>(t) * ldo);
+    uint2* ol = reinterpret_cast<uint2*>(o_lo + static_cast<long long>(t) * ldo);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < h4) {
+        const float4 ww = w4[c], bb = b4[c];
+        uint2 hv, lv;
+        split_f16x2((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y, hv.x, lv.x);
+        split_f16x2((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w, hv.y, lv.y);
+        oh[c] = hv;
+        ol[c] = lv;
       }
     }
   }
@@ -351,7 +427,7 @@ __global__ void clip_add_count_kernel(long long* count, long long n) { *count +=
 template <typename T>
 inline int clip_alloc(ClipHandle* H, T** p, size_t elems) {
   void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, elems * sizeof(T) + 256);
+  cudaError_t e = dev_alloc(&q, elems * sizeof(T) + 256);
   if (e != cudaSuccess)
     return set_error(EMCID_ERR_CUDA, "clip: cudaMalloc(%zu) failed: %s", elems * sizeof(T), cudaGetErrorString(e));
   H->allocs->push_back(q);
@@ -363,9 +439,11 @@ inline int clip_destroy(ClipHandle* H) {
   if (!H) return EMCID_OK;
   cudaSetDevice(H->device);
   cudaDeviceSynchronize();
-  for (void* p : *H->allocs) cudaFree(p);
+  for (void* p : *H->allocs) dev_free(p);   // parked for the next handle of this shape (host.cuh::DevPool)
   delete H->allocs;
   delete H->layers;
+  if (H->ev) for (cudaEvent_t e : *H->ev) cudaEventDestroy(e);
+  delete H->ev; delete H->ev_tag; delete H->ev_flops;
   delete H;
   return EMCID_OK;
 }
@@ -385,6 +463,9 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
   memset(H, 0, sizeof(*H));
   H->allocs = new std::vector<void*>();
   H->layers = new std::vector<ClipLayer>(L);
+  H->ev = new std::vector<cudaEvent_t>();
+  H->ev_tag = new std::vector<int>();
+  H->ev_flops = new std::vector<double>();
   int rc = get_device_info(&H->info);
   if (rc) { clip_destroy(H); return rc; }
   H->device = device; H->L = L; H->h = h; H->heads = heads; H->dh = h / heads; H->d = d; H->act = act;
@@ -448,7 +529,8 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
     H->attn_tc = H->dh == ATTN_DH && max_pos <= 128 && (3 * h) % 8 == 0 && !(e && e[0] == '0');
     if (H->attn_tc) {
       const int lp = (max_pos + 15) & ~15;
-      cudaError_t ce = cudaFuncSetAttribute(clip_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(lp));
+      cudaError_t ce = lp <= 80 ? cudaFuncSetAttribute(clip_attention_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(lp))
+                                : cudaFuncSetAttribute(clip_attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(lp));
       if (ce != cudaSuccess) {
         clip_destroy(H);
         return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", attn_smem_bytes(lp), cudaGetErrorString(ce));
@@ -540,7 +622,8 @@ struct ClipActMaps {
 inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap& x_lo, const ClipWeight& W, int T,
                        int act, const float* Cin, float* C, long long ldc, uint16_t* P_hi, uint16_t* P_lo, long long ldp,
                        uint16_t* Pt_hi, uint16_t* Pt_lo, long long ldpt, cudaStream_t stream,
-                       const GemmOutMaps* om = nullptr, int pt_col_min = 0) {
+                       const GemmOutMaps* om = nullptr, int pt_col_min = 0, int tag = CLIP_TAG_QKV) {
+  ClipProfScope prof(H, stream, tag, 2.0 * T * static_cast<double>(W.N) * W.K);
   GemmOperands ops;
   ops.a_hi = x_hi; ops.a_lo = x_lo; ops.b_hi = W.m_hi; ops.b_lo = W.m_lo;
   GemmParams p;
@@ -593,10 +676,24 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
 
 inline int clip_layernorm(ClipHandle* H, const float* x, int T, const float* w, const float* b, uint16_t* o_hi,
                           uint16_t* o_lo, cudaStream_t stream) {
+  ClipProfScope prof(H, stream, CLIP_TAG_LN, 0.0);
   const int nv = (H->h + 31) / 32;
   int blocks = (T + 7) / 8;
   if (blocks > H->info.sm_count * 16) blocks = H->info.sm_count * 16;
   H->launches += 1;
+  if (H->h % 4 == 0 && H->hp % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int nv4 = (H->h / 4 + 31) / 32;
+#define EMCID_LN4_CASE(NV4)                                                                                       \
+  if (nv4 <= NV4) {                                                                                               \
+    clip_layernorm4_kernel<NV4><<<blocks, 256, 0, stream>>>(x, T, H->h, w, b, H->eps, o_hi, o_lo, H->hp);        \
+    EMCID_CUDA_CHECK(cudaGetLastError());                                                                         \
+    return EMCID_OK;                                                                                              \
+  }
+    EMCID_LN4_CASE(1) EMCID_LN4_CASE(2) EMCID_LN4_CASE(4) EMCID_LN4_CASE(6) EMCID_LN4_CASE(8) EMCID_LN4_CASE(10)
+    EMCID_LN4_CASE(16)
+#undef EMCID_LN4_CASE
+  }
 #define EMCID_LN_CASE(NV)                                                                                         \
   if (nv <= NV) {                                                                                                 \
     clip_layernorm_kernel<NV><<<blocks, 256, 0, stream>>>(x, T, H->h, w, b, H->eps, o_hi, o_lo, H->hp);          \
@@ -626,6 +723,26 @@ __global__ void clip_gather_keys_kernel(const uint16_t* __restrict__ f_hi, const
       if (c < d) k_out[static_cast<long long>(r) * d + c] = __half2float(__ushort_as_half(hh)) + __half2float(__ushort_as_half(ll));
     }
   }
+}
+
+// out[tag * 3 + {0, 1, 2}] = {launches, total ms, total algorithmic flops} per ClipTag (CLIP_TAG_COUNT * 3 doubles);
+// waits for the recorded events, then clears them.
+inline int clip_get_profile(ClipHandle* H, double* out) {
+  EMCID_CHECK(H && out, EMCID_ERR_INVALID, "clip_get_profile: null argument");
+  EMCID_CUDA_CHECK(cudaSetDevice(H->device));
+  for (int i = 0; i < CLIP_TAG_COUNT * 3; ++i) out[i] = 0.0;
+  for (size_t i = 0; i + 1 < H->ev->size(); i += 2) {
+    EMCID_CUDA_CHECK(cudaEventSynchronize((*H->ev)[i + 1]));
+    float ms = 0.f;
+    EMCID_CUDA_CHECK(cudaEventElapsedTime(&ms, (*H->ev)[i], (*H->ev)[i + 1]));
+    const int tag = (*H->ev_tag)[i / 2];
+    out[tag * 3 + 0] += 1.0;
+    out[tag * 3 + 1] += ms;
+    out[tag * 3 + 2] += (*H->ev_flops)[i / 2];
+    cudaEventDestroy((*H->ev)[i]); cudaEventDestroy((*H->ev)[i + 1]);
+  }
+  H->ev->clear(); H->ev_tag->clear(); H->ev_flops->clear();
+  return EMCID_OK;
 }
 
 // Runs layers [0, n_layers) (full layers) — or, when stats are requested, up to fc1 of the deepest edited
@@ -716,14 +833,19 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln1_w, Ly.ln1_b, H->x_hi, H->x_lo, stream))) return rc;
     if (attn_tc) {
       if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, nullptr, 0, H->qp_hi, H->qp_lo, 3ll * H->h, nullptr,
-                            nullptr, 0, stream, pm_qkv)))
+                            nullptr, 0, stream, pm_qkv, 0, CLIP_TAG_QKV)))
         return rc;
+      ClipProfScope prof_attn(H, stream, CLIP_TAG_ATTN, 0.0);
       const int units = S * H->heads;
       const int lp = (H->max_pos + 15) & ~15;
-      // two resident CTAs per SM when the operand set fits twice (lp <= 80: CLIP's 77 tokens)
-      const int per_sm = 2 * (attn_smem_bytes(lp) + 1024) <= 227 * 1024 ? 2 : 1;
-      clip_attention_tc_kernel<<<units < per_sm * sms ? units : per_sm * sms, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
-          am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
+      const int per_sm = attn_ctas_per_sm(lp);   // three resident CTAs per SM for CLIP's 77 tokens
+      const int grid = units < per_sm * sms ? units : per_sm * sms;
+      if (lp <= 80)
+        clip_attention_tc_kernel<5><<<grid, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
+            am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
+      else
+        clip_attention_tc_kernel<8><<<grid, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
+            am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
     } else {
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, nullptr,
                           nullptr, 0, stream, pm_qkv)))
@@ -743,7 +865,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     EMCID_CUDA_CHECK(cudaGetLastError());
     H->launches += 1;
     if ((rc = clip_linear(H, ma_hi, ma_lo, Ly.o, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
-                          stream, pm_res)))
+                          stream, pm_res, 0, CLIP_TAG_OUT)))
       return rc;
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln2_w, Ly.ln2_b, H->x_hi, H->x_lo, stream))) return rc;
     const bool is_stat = si < n_stat && stat_layers[si] == l;
@@ -751,7 +873,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     // the deepest edited layer needs only f^T (no fc2 follows); other edited layers need both orientations
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.fc1, T, H->act, nullptr, nullptr, 0, is_last ? nullptr : H->f_hi,
                           is_last ? nullptr : H->f_lo, H->dp, is_stat ? H->ft_hi : nullptr, is_stat ? H->ft_lo : nullptr,
-                          H->tp, stream, pm_f)))
+                          H->tp, stream, pm_f, 0, is_stat ? CLIP_TAG_FC1_STAT : CLIP_TAG_FC1)))
       return rc;
     if (is_stat) {
       Mom2Handle* A = accs[si++];
@@ -794,12 +916,12 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
           (use_tma_epi && (rc = make_tmap_2d(&om_z.c, z_out, n_keys, H->h, H->h, 128, 4))))
         return rc;
       if ((rc = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, nullptr,
-                            nullptr, 0, stream, use_tma_epi ? &om_z : nullptr)))
+                            nullptr, 0, stream, use_tma_epi ? &om_z : nullptr, 0, CLIP_TAG_FC2)))
         return rc;
       break;
     }
     if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
-                          stream, pm_res)))
+                          stream, pm_res, 0, CLIP_TAG_FC2)))
       return rc;
   }
   if (hidden_out) {

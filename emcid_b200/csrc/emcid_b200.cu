@@ -128,9 +128,20 @@ int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* 
                       nullptr, nullptr, static_cast<cudaStream_t>(stream), layer, key_rows, n_keys, k_out, z_out);
 }
 
+int emcid_clip_profile(emcid_clip_t* h, int enable) {
+  ClipHandle* H = reinterpret_cast<ClipHandle*>(h);
+  EMCID_CHECK(H, EMCID_ERR_INVALID, "emcid_clip_profile: null handle");
+  H->profile = enable != 0;
+  return EMCID_OK;
+}
+
+int emcid_clip_get_profile(emcid_clip_t* h, double* out21) { return clip_get_profile(reinterpret_cast<ClipHandle*>(h), out21); }
+
 long long emcid_clip_launches(emcid_clip_t* h) { return h ? reinterpret_cast<ClipHandle*>(h)->launches : 0; }
 
 int emcid_clip_destroy(emcid_clip_t* h) { return clip_destroy(reinterpret_cast<ClipHandle*>(h)); }
+
+int emcid_release_cached_memory(void) { return dev_release_cached(); }
 
 // ---------------------------------------------------------------------------------------------
 // closed-form update

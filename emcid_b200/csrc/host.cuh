@@ -10,6 +10,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "gemm3x.cuh"
 
 namespace emcid {
@@ -73,6 +77,73 @@ inline int get_device_info(DeviceInfo* out) {
               info.cc_major, info.cc_minor);
   if (dev >= 0 && dev < 16) cache[dev] = info;
   *out = info;
+  return EMCID_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Device memory of the handles.  cudaFree synchronises the device and was measured at up to 2.8 s for the ~140
+// buffers of one statistics pass (text-encoder planes + five accumulators), inside the timed end-to-end call.  Freed
+// buffers are therefore parked in a per-device, exact-size free list and handed out again by the next handle of the
+// same shape; emcid_release_cached_memory() returns them to the driver.
+// ----------------------------------------------------------------------------------------------
+struct DevPool {
+  std::mutex mu;
+  std::map<void*, std::pair<int, size_t>> live;                 // ptr -> (device, bytes)
+  std::multimap<std::pair<int, size_t>, void*> parked;          // (device, bytes) -> ptr
+};
+
+inline DevPool& dev_pool() {
+  static DevPool* p = new DevPool();   // leaked on purpose: no destruction-order hazards at process exit
+  return *p;
+}
+
+inline cudaError_t dev_alloc(void** out, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  DevPool& P = dev_pool();
+  std::lock_guard<std::mutex> lock(P.mu);
+  auto it = P.parked.find(std::make_pair(dev, bytes));
+  if (it != P.parked.end()) {
+    *out = it->second;
+    P.parked.erase(it);
+  } else {
+    e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+      // make room: give everything parked on this device back and retry once
+      for (auto p = P.parked.begin(); p != P.parked.end();) {
+        if (p->first.first == dev) { cudaFree(p->second); p = P.parked.erase(p); } else { ++p; }
+      }
+      (void)cudaGetLastError();
+      e = cudaMalloc(out, bytes);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  P.live[*out] = std::make_pair(dev, bytes);
+  return cudaSuccess;
+}
+
+inline void dev_free(void* p) {
+  if (!p) return;
+  DevPool& P = dev_pool();
+  std::lock_guard<std::mutex> lock(P.mu);
+  auto it = P.live.find(p);
+  if (it == P.live.end()) { cudaFree(p); return; }
+  P.parked.insert(std::make_pair(it->second, p));
+  P.live.erase(it);
+}
+
+inline int dev_release_cached() {
+  DevPool& P = dev_pool();
+  std::lock_guard<std::mutex> lock(P.mu);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (auto& kv : P.parked) {
+    cudaSetDevice(kv.first.first);
+    cudaFree(kv.second);
+  }
+  P.parked.clear();
+  cudaSetDevice(prev);
   return EMCID_OK;
 }
 

@@ -282,7 +282,7 @@ inline int mom2_create(Mom2Handle** out, int device, int d, int h, int act, int 
   const size_t dd = static_cast<size_t>(d) * d;
 #define EMCID_TRY_ALLOC(ptr, bytes)                                                          \
   do {                                                                                       \
-    cudaError_t _e = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes));                  \
+    cudaError_t _e = dev_alloc(reinterpret_cast<void**>(&(ptr)), (bytes));                   \
     if (_e != cudaSuccess) {                                                                 \
       set_error(EMCID_ERR_CUDA, "mom2_create: cudaMalloc(%zu) failed: %s", (size_t)(bytes), \
                 cudaGetErrorString(_e));                                                     \
@@ -314,8 +314,8 @@ inline int mom2_create(Mom2Handle** out, int device, int d, int h, int act, int 
 fail:
   rc = EMCID_ERR_CUDA;
 fail_rc:
-  cudaFree(H->w_hi); cudaFree(H->w_lo); cudaFree(H->bias); cudaFree(H->acc32); cudaFree(H->acc64);
-  cudaFree(H->count);
+  dev_free(H->w_hi); dev_free(H->w_lo); dev_free(H->bias); dev_free(H->acc32); dev_free(H->acc64);
+  dev_free(H->count);
   delete H->ev_fc1; delete H->ev_syrk;
   delete H;
   return rc;
@@ -324,8 +324,8 @@ fail_rc:
 inline int mom2_destroy(Mom2Handle* H) {
   if (!H) return EMCID_OK;
   cudaSetDevice(H->device);
-  cudaFree(H->w_hi); cudaFree(H->w_lo); cudaFree(H->bias); cudaFree(H->acc32); cudaFree(H->acc64);
-  cudaFree(H->count);
+  dev_free(H->w_hi); dev_free(H->w_lo); dev_free(H->bias); dev_free(H->acc32); dev_free(H->acc64);
+  dev_free(H->count);
   for (cudaEvent_t e : *H->ev_fc1) cudaEventDestroy(e);
   for (cudaEvent_t e : *H->ev_syrk) cudaEventDestroy(e);
   delete H->ev_fc1; delete H->ev_syrk;

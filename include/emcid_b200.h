@@ -122,7 +122,17 @@ int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* posit
 int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
                             int n_captions, int n_tokens, int layer, const int32_t* key_rows, int n_keys, float* k_out,
                             float* z_out, void* stream);
+/* Measurement aid: when enabled, every launch of the forward is bracketed by CUDA events on the caller's stream.
+ * emcid_clip_get_profile waits for them and fills out21[tag * 3 + {0, 1, 2}] = {launches, total ms, total algorithmic
+ * flops (2 M N K)} for tag = 0 q/k/v projection, 1 out projection, 2 fc1, 3 fc1 of an edited layer (both plane
+ * orientations), 4 fc2, 5 attention, 6 layer norm; then clears the record. */
+int emcid_clip_profile(emcid_clip_t* h, int enable);
+int emcid_clip_get_profile(emcid_clip_t* h, double* out21);
 long long emcid_clip_launches(emcid_clip_t* h);
+/* Handles park their device buffers in a per-device free list when destroyed (cudaFree synchronises the device and
+ * costs seconds for the ~140 buffers of one pass); the next handle of the same shape reuses them.  This returns the
+ * parked buffers to the driver. */
+int emcid_release_cached_memory(void);
 int emcid_clip_destroy(emcid_clip_t* h);
 
 /* ---- closed-form multi-layer update ---------------------------------------------------------------
