@@ -504,7 +504,9 @@ def main():
     ap.add_argument("--encoder", default="sd-text", choices=["sd-text", "sdxl-text1", "sdxl-text2"],
                     help="sd-text = BASELINE configs[1] (the headline); sdxl-text2 = OpenCLIP bigG shapes (configs[3])")
     ap.add_argument("--layers", default="", help="comma-separated edited layers (default 7-11; sdxl-text2: 26-30)")
-    ap.add_argument("--block-captions", type=int, default=512, help="captions per forward block")
+    ap.add_argument("--block-captions", type=int, default=492,
+                    help="captions per forward block (492 x 77 = 37 884 tokens = 148 row tiles of 256: whole waves of "
+                         "pair tiles in every linear layer, stat_dataset.DEFAULT_BLOCK_TOKENS)")
     ap.add_argument("--slab", type=int, default=0, help="tokens per fc1/SYRK launch pair (0 = library default)")
     ap.add_argument("--concepts", type=int, default=1000)
     ap.add_argument("--ref-captions", type=int, default=48, help="captions per CPU-baseline sample")

@@ -31,7 +31,8 @@ import torch
 from . import clip_forward, nethook
 from .runningstats import (CombinedStat, FixedSubsetSampler, Mean, NormMean, SecondMoment, load_cached_state,
                            save_cached_state, subset_indices)
-from .stat_dataset import TokenizedDataset, dict_to_, fixed_width_collation, packed_collation, unpack_to_padded
+from .stat_dataset import (DEFAULT_BLOCK_TOKENS, PackedReblocker, TokenizedDataset, dict_to_, fixed_width_collation,
+                           packed_collation, unpack_to_padded)
 
 try:  # the reference's default progress bar
     from tqdm.auto import tqdm
@@ -132,8 +133,9 @@ class TextEncoderMom2Pass:
             if nat is not None:
                 torch.cuda.synchronize(nat.device)
                 nat.close()
-            self._native = nat = clip_forward.NativeClipTextEncoder(
-                self.model, max(n_tokens, nat.max_tokens if nat else 0), max(n_captions, nat.max_captions if nat else 0))
+            cap_tokens = max(n_tokens, nat.max_tokens if nat else 0)
+            # captions are at least one token long: a caption capacity of cap_tokens never has to grow (it sizes nothing)
+            self._native = nat = clip_forward.NativeClipTextEncoder(self.model, cap_tokens, max(n_captions, cap_tokens))
         return nat
 
     def _hook(self, name, stop):
@@ -229,6 +231,7 @@ def layer_stats_text_encoder_multi(
     slab_tokens: int = 0,
     distributed: Optional[bool] = None,
     keep_on_device: bool = False,
+    block_tokens: int = DEFAULT_BLOCK_TOKENS,
     _accumulator_factory: Optional[Callable] = None,
 ) -> Dict[str, CombinedStat]:
     """All `layer_names` in one pass.  Arguments up to `force_recompute` mean exactly what they mean
@@ -282,6 +285,7 @@ def layer_stats_text_encoder_multi(
         progress = lambda x, total=None: x
 
     runner = TextEncoderMom2Pass(model, todo, slab_tokens=slab_tokens, accumulator_factory=_accumulator_factory)
+    reblock = PackedReblocker(block_tokens) if (block_tokens and runner._use_native) else None
     t_loop = time.perf_counter()
     try:
         t_wait = t_run = 0.0
@@ -293,9 +297,17 @@ def layer_stats_text_encoder_multi(
                     ("input_ids" in batch and batch["input_ids"].numel() == 0):
                 t_prev = time.perf_counter()
                 continue
-            runner.run_batch(batch)  # host tensors: packed on the host, then one pinned H2D copy per field
+            if reblock is not None and "packed_ids" in batch:
+                # loader batches count captions, device blocks count tokens (stat_dataset.PackedReblocker)
+                for block in reblock.push(batch):
+                    runner.run_batch(block)
+            else:
+                runner.run_batch(batch)  # host tensors: packed on the host, then one pinned H2D copy per field
             t_prev = time.perf_counter()
             t_run += t_prev - t_got
+        if reblock is not None:
+            for block in reblock.flush():
+                runner.run_batch(block)
         t_fin = time.perf_counter()
         results = runner.finalize()
         LAST_PASS_INFO.update(native_forward=runner._native is not None, launches=runner.launches())

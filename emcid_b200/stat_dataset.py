@@ -145,3 +145,57 @@ def unpack_to_padded(batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         out[dst] = buf
     out["attention_mask"] = mask.to(torch.int64)
     return out
+
+
+# 74 CTA pairs x 256-row tiles x 2: with this many packed tokens per block every linear layer of the forward fills
+# whole waves of 256 x 256 pair tiles on a 148-SM B200 (37 888 / 256 = 148 row tiles; x 3, 9, 12 column tiles of
+# CLIP-L or x 5, 15, 20 of OpenCLIP bigG are all multiples of 74).  Measured with 512 full-length captions
+# (39 424 tokens, 154 row tiles): the N = 768 products (out projection, fc2) ran 7 waves for 6.24 waves of work.
+DEFAULT_BLOCK_TOKENS = 37888
+
+
+class PackedReblocker:
+    """Regroups packed caption batches (packed_collation) into device blocks of at most `budget` tokens, cutting
+    only between captions and keeping their order.  DataLoader batches are sized in captions; the native forward
+    wants blocks sized in TOKENS (real captions are ragged: 256 of them can be 3 000 or 19 712 tokens)."""
+
+    def __init__(self, budget: int = DEFAULT_BLOCK_TOKENS):
+        self.budget = int(budget)
+        self._ids: List[torch.Tensor] = []
+        self._pos: List[torch.Tensor] = []
+        self._lens: List[torch.Tensor] = []
+        self._tokens = 0
+
+    def _emit(self) -> Dict[str, torch.Tensor]:
+        lens = torch.cat(self._lens)
+        cu = torch.zeros(lens.numel() + 1, dtype=torch.int32)
+        cu[1:] = torch.cumsum(lens, 0)
+        out = {"packed_ids": torch.cat(self._ids), "packed_pos": torch.cat(self._pos), "cu_seqlens": cu}
+        self._ids, self._pos, self._lens, self._tokens = [], [], [], 0
+        return out
+
+    def push(self, batch: Dict[str, torch.Tensor]):
+        """Yields every block completed by `batch`."""
+        ids, pos, cu = batch["packed_ids"], batch["packed_pos"], batch["cu_seqlens"].to(torch.int64)
+        lens = (cu[1:] - cu[:-1]).to(torch.int32)
+        start, n = 0, lens.numel()
+        while start < n:
+            room = self.budget - self._tokens
+            # captions [start, stop) fit: largest stop with cu[stop] - cu[start] <= room
+            stop = int(torch.searchsorted(cu, cu[start] + room, right=True)) - 1
+            stop = min(stop, n)
+            if stop <= start:
+                if self._tokens:          # the block is full
+                    yield self._emit()
+                    continue
+                stop = start + 1          # a single caption longer than the budget travels alone
+            a, b = int(cu[start]), int(cu[stop])
+            self._ids.append(ids[a:b]); self._pos.append(pos[a:b]); self._lens.append(lens[start:stop])
+            self._tokens += b - a
+            start = stop
+            if self._tokens >= self.budget:
+                yield self._emit()
+
+    def flush(self):
+        if self._tokens:
+            yield self._emit()

@@ -171,3 +171,74 @@ def test_our_npz_loads_in_the_live_reference(tmp_path):
     a = ref.stat_dataset.length_collation(256)(items)
     b = stat_dataset.length_collation(256)(items)
     assert len(a) == len(b) and all(torch.equal(x["input_ids"], y["input_ids"]) for x, y in zip(a, b))
+
+
+def test_word_hash_tokenizer_inverts_on_a_thousand_requests():
+    """bench.py's offline tokenizer: ids are unique per word (linear probing), so find_token_range
+    (experiments/causal_trace.py:1057-1103) locates every subject of the 1000-concept workload."""
+    from emcid_b200 import compute_ks, synth
+    tok = synth.WordHashTokenizer(49408)
+    reqs = synth.make_edit_requests(1000)
+    enc, lookup, counts = compute_ks.prepare_lookup(tok, reqs, 1, "cpu")
+    assert enc["input_ids"].shape[0] == 3000 and counts == [3] * 1000
+    ids = enc["input_ids"].tolist()
+    for p in (0, 1, 2, 1499, 2999):
+        r = reqs[p // 3]
+        last = lookup[p][0]
+        assert tok.decode([ids[p][last]]) == r["source"].split()[-1]
+        assert ids[p][0] == tok.bos and int(enc["attention_mask"][p].sum()) == len(r["prompts"][p % 3].format(r["source"]).split()) + 2
+    assert len(set(tok._words)) == len(tok._ids)
+
+
+def test_prepared_lookup_is_equivalent_and_cpu_keeps_the_hf_forward():
+    from emcid_b200 import compute_ks
+    model = rh.make_clip_text_model("tiny", seed=2)
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    reqs = rh.make_requests(5)
+    name = "text_model.encoder.layers.1.mlp.fc2"
+    k0, z0 = compute_ks.get_module_input_output_at_words(model, tok, reqs, name)
+    assert compute_ks.LAST_PATH["native"] is False          # no CUDA device: the traced HF forward
+    prepared = compute_ks.prepare_lookup(tok, reqs, 1, model.device)
+    k1, z1 = compute_ks.get_module_input_output_at_words(model, tok, reqs, name, prepared=prepared)
+    assert torch.equal(k0, k1) and torch.equal(z0, z1)
+
+
+def test_caption_matrix_dataset_matches_item_layout():
+    from emcid_b200 import synth
+    from emcid_b200.stat_dataset import packed_collation
+    ids = synth.make_caption_matrix(10, seed=3)
+    a, b = synth.CaptionMatrixDataset(ids), synth.CaptionIdDataset([r.clone() for r in ids])
+    assert len(a) == len(b) == 10
+    for i in (0, 9):
+        for k in ("input_ids", "position_ids", "attention_mask"):
+            assert torch.equal(a[i][k], b[i][k])
+    pa = packed_collation()([a[i] for i in range(10)])
+    pb = packed_collation()([b[i] for i in range(10)])
+    assert all(torch.equal(pa[k], pb[k]) for k in pa)
+    assert ids[:, 0].eq(49406).all() and ids[:, -1].eq(49407).all()
+
+
+def test_packed_reblocker_cuts_between_captions_only():
+    """Device blocks are sized in tokens (stat_dataset.PackedReblocker): same captions, same order, never split,
+    every block within the budget except a single over-long caption."""
+    from emcid_b200 import synth
+    from emcid_b200.stat_dataset import PackedReblocker, packed_collation
+    caps = synth.make_caption_ids(700, seed=5, full=False, min_len=1)
+    ds, col = synth.CaptionIdDataset(caps), packed_collation()
+    for budget in (77, 500, 5000, 10 ** 6):
+        rb, blocks = PackedReblocker(budget), []
+        for b0 in range(0, 700, 100):
+            blocks += list(rb.push(col([ds[i] for i in range(b0, b0 + 100)])))
+        blocks += list(rb.flush())
+        assert torch.equal(torch.cat([b["packed_ids"] for b in blocks]), torch.cat(caps).to(torch.int32))
+        lens = torch.cat([(b["cu_seqlens"][1:] - b["cu_seqlens"][:-1]) for b in blocks])
+        assert lens.tolist() == [len(c) for c in caps]
+        for b in blocks:
+            cu = b["cu_seqlens"]
+            assert int(cu[0]) == 0 and int(cu[-1]) == b["packed_ids"].numel() == b["packed_pos"].numel() <= budget
+            assert bool((b["packed_pos"][cu[:-1].long()] == 0).all())
+        if budget >= 5000:
+            assert all(b["packed_ids"].numel() > budget - 77 for b in blocks[:-1])      # blocks are filled
+    rb = PackedReblocker(10)                                                             # over-long captions travel alone
+    blocks = list(rb.push(col([ds[i] for i in range(20)]))) + list(rb.flush())
+    assert sum(b["cu_seqlens"].numel() - 1 for b in blocks) == 20
