@@ -500,7 +500,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--captions", type=int, default=2048, help="captions per GPU per step")
+    ap.add_argument("--captions", type=int, default=0, help="captions per GPU per step (default: 4 forward blocks)")
     ap.add_argument("--encoder", default="sd-text", choices=["sd-text", "sdxl-text1", "sdxl-text2"],
                     help="sd-text = BASELINE configs[1] (the headline); sdxl-text2 = OpenCLIP bigG shapes (configs[3])")
     ap.add_argument("--layers", default="", help="comma-separated edited layers (default 7-11; sdxl-text2: 26-30)")
@@ -517,6 +517,8 @@ def main():
     ap.add_argument("--no-edit", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.captions <= 0:
+        args.captions = 4 * args.block_captions
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

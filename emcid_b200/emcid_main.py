@@ -70,6 +70,15 @@ def get_cov_text_encoder(model, tok, layer_name: str, mom2_dataset: str, mom2_n_
     return torch.inverse(cov) if inv else cov
 
 
+def _to_host_async(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if not t.is_cuda:
+        return t.cpu()
+    host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    return host
+
+
 def upd_matrix_match_shape(matrix: torch.Tensor, shape: torch.Size) -> torch.Tensor:
     if matrix.shape == shape:
         return matrix
@@ -151,8 +160,12 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
                     print("orig norm", torch.linalg.norm(weights[name]))
                     print("upd norm", torch.linalg.norm(upd))
                 weights[name][...] = weights_copy[name] + upd                     # :1061 — next layer sees it
-                deltas[name] = (adj_k.detach().cpu(), resid.detach().cpu())
+                # the reference returns CPU tensors (:1062-1065); copy asynchronously into pinned memory so the transfer
+                # of layer i (30 MB of fp64) overlaps the key extraction and the solve of layer i + 1
+                deltas[name] = (_to_host_async(adj_k), _to_host_async(resid))
                 t = _tick(device, "write_and_d2h_ms", t)
+        if torch.device(device).type == "cuda":
+            torch.cuda.current_stream(device).synchronize()      # all delta copies have landed
     finally:
         with torch.no_grad():
             for n, w in weights.items():

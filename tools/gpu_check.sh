@@ -10,14 +10,14 @@ timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo
 timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit=$?" >> $OUT/bench.err
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-NCU_CMD="python bench.py --steps 2 --warmup 1 --captions 1024 --no-e2e --no-cpu --no-solve"
+NCU_CMD="python bench.py --steps 2 --warmup 1 --captions 984 --no-e2e --no-cpu --no-solve"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv \
     $NCU_CMD > $OUT/ncu_launch_bench.log 2>&1
 python tools/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1
 # full capture: the 5 SYRK launches of one edited layer's block plus the linear layers around them
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm3x|attention" -s 60 -c 14 -f -o $OUT/prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm3x|attention" -s 163 -c 14 -f -o $OUT/prof \
     $NCU_CMD > $OUT/ncu_full_bench.log 2>&1
 ncu -i $OUT/prof.ncu-rep --page raw --csv > $OUT/prof_raw.csv 2> $OUT/prof_raw.err
-python tools/summarize_ncu_raw.py $OUT/prof_raw.csv ncu --set full --clock-control none --import-source on -k "regex:gemm3x|attention" -s 60 -c 14 $NCU_CMD > $OUT/ncu_full_summary.json 2>> $OUT/prof_raw.err
+python tools/summarize_ncu_raw.py $OUT/prof_raw.csv ncu --set full --clock-control none --import-source on -k "regex:gemm3x|attention" -s 163 -c 14 $NCU_CMD > $OUT/ncu_full_summary.json 2>> $OUT/prof_raw.err
 fi
 tail -3 $OUT/pytest_gpu.log; cat $OUT/smoke.log | tail -2; cat $OUT/bench.json; tail -2 $OUT/bench.err; cat $OUT/bench_reference.json; head -14 $OUT/launches_summary.txt
