@@ -57,7 +57,7 @@ SIGNATURES = {
     "emcid_clip_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    ctypes.POINTER(c_int), ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "emcid_clip_forward_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
-                                        c_void_p, c_void_p, c_void_p]),
+                                        c_void_p, c_void_p, c_int, c_void_p]),
     "emcid_clip_profile": (c_int, [c_void_p, c_int]),
     "emcid_clip_get_profile": (c_int, [c_void_p, ctypes.POINTER(c_double)]),
     "emcid_clip_launches": (c_longlong, [c_void_p]),

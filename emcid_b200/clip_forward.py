@@ -91,6 +91,8 @@ class NativeClipTextEncoder:
                 _lib.act_code(cfg.hidden_act), self.max_positions, tm.embeddings.token_embedding.weight.shape[0], eps,
                 self.max_tokens, self.max_captions))
         self._sig: Dict[object, tuple] = {}   # what was uploaded: (data_ptr, version) of every source tensor
+        self.last_sync: Dict[object, list] = {}
+        self.keys_token = None                # (caller token, layer) of the last forward_keys call, see compute_ks.py
         self.sync_weights(model)
 
     @staticmethod
@@ -110,15 +112,18 @@ class NativeClipTextEncoder:
     def sync_weights(self, model, upto_layer: Optional[int] = None) -> int:
         """(Re-)upload the embeddings and layers [0, upto_layer] whose source tensors changed since the last upload
         (PyTorch bumps `Tensor._version` on every in-place write: that is how the edit loop's `w[...] = w0 + dW`,
-        reference emcid_main.py:1061, becomes visible here).  Returns the number of layers uploaded."""
+        reference emcid_main.py:1061, becomes visible here).  Returns the number of layers uploaded;
+        `self.last_sync` = {layer or "emb": indices of the source tensors that had changed}."""
         tm = _text_model(model)
         lib = _lib.lib()
         n = 0
+        self.last_sync = {}
         with torch.cuda.device(self.device):
             stream = _lib.current_stream_ptr()
             emb = [tm.embeddings.token_embedding.weight, tm.embeddings.position_embedding.weight]
             sig = self._signature(emb)
             if self._sig.get("emb") != sig:
+                self.last_sync["emb"] = [0, 1]
                 tok, pos = emb[0].detach().contiguous(), emb[1].detach().contiguous()
                 _lib.check(lib.emcid_clip_set_embeddings(self._h, _lib.ptr(tok), _lib.ptr(pos), stream))
                 self._sig["emb"] = sig
@@ -128,6 +133,8 @@ class NativeClipTextEncoder:
                 sig = self._signature(src)
                 if self._sig.get(i) == sig:
                     continue
+                old = self._sig.get(i)
+                self.last_sync[i] = list(range(16)) if old is None else [j for j in range(16) if old[j] != sig[j]]
                 tensors = [None if t is None else t.detach().contiguous() for t in src]
                 arr = (ctypes.c_void_p * 16)(*[_lib.ptr(t) or None for t in tensors])
                 _lib.check(lib.emcid_clip_set_layer(self._h, i, arr, stream))
@@ -166,9 +173,11 @@ class NativeClipTextEncoder:
         self._run(ids, pos, cu, S, T, n_layers, [], [], out)
         return out
 
-    def forward_keys(self, ids, pos, cu, S: int, T: int, layer: int, rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward_keys(self, ids, pos, cu, S: int, T: int, layer: int, rows: torch.Tensor,
+                     resume_layer: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
         """fc2 input [R, intermediate] and fc2 output [R, hidden] of encoder layer `layer` at the packed token rows
-        `rows` (int32), see emcid_clip_forward_keys in include/emcid_b200.h."""
+        `rows` (int32), see emcid_clip_forward_keys in include/emcid_b200.h (resume_layer: continue from the previous
+        keys call at that layer over the same tokens)."""
         ids = ids.to(self.device, non_blocking=True)
         pos = pos.to(self.device, non_blocking=True)
         cu = cu.to(self.device, non_blocking=True)
@@ -178,7 +187,8 @@ class NativeClipTextEncoder:
         z = torch.empty(R, self.hidden, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().emcid_clip_forward_keys(self._h, _lib.ptr(ids), _lib.ptr(pos), _lib.ptr(cu), S, T, int(layer),
-                                                          _lib.ptr(rows), R, _lib.ptr(k), _lib.ptr(z), self._stream()))
+                                                          _lib.ptr(rows), R, _lib.ptr(k), _lib.ptr(z), int(resume_layer),
+                                                          self._stream()))
         s = torch.cuda.current_stream(self.device)
         for t in (ids, pos, cu, rows):
             t.record_stream(s)

@@ -11,6 +11,7 @@ edit tokens per prompt, non-right-padded masks, EMCID_NATIVE_KEYS=0) keeps the t
 """
 from __future__ import annotations
 
+import itertools
 import re
 import unicodedata
 from typing import Dict, List, Optional, Tuple
@@ -19,13 +20,16 @@ import torch
 
 from . import clip_forward, nethook
 
+_SERIAL = itertools.count(1)   # identity of a prepared prompt set (continuation token of the native key extraction)
 _FC2_NAME = re.compile(r"^(?:text_model\.)?encoder\.layers\.(\d+)\.mlp\.fc2$")
 LAST_PATH = {"native": False}   # which path served the last call (tests / bench read it)
 
 
-def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name: str):
+def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name: str, token=None):
     """(fc2 input [P, d], fc2 output [P, h]) at lookup[p][0] of every prompt through the library, or None when
-    this model / module / mask is not covered."""
+    this model / module / mask is not covered.  `token` identifies the prompt set: consecutive calls with the same
+    token at increasing layers, between which only fc2 of the previous layer changed (the edit loop), continue from
+    the previous call's state instead of re-running the layers below."""
     m = _FC2_NAME.match(module_name)
     if m is None or not text_encoder.device.type == "cuda":
         return None
@@ -47,7 +51,18 @@ def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name
         return None
     first = torch.tensor([row[0] for row in lookup], dtype=torch.int32, device=cu.device)
     rows = cu[:-1] + first
-    return native.forward_keys(ids, pos, cu, S, T, layer, rows)
+    resume = -1
+    prev = native.keys_token
+    if token is not None and prev is not None and prev[0] == token and prev[1] < layer and prev[2] == T:
+        changed = native.last_sync
+        # fc2.weight / fc2.bias are source tensors 14 and 15 of a layer (NativeClipTextEncoder._layer_tensors)
+        # the saved state depends on the embeddings, on layers below prev[1] and on everything of layer prev[1] but its fc2
+        if all(isinstance(k, int) and (k > prev[1] or (k == prev[1] and set(v) <= {14, 15})) for k, v in changed.items()):
+            resume = prev[1]
+    LAST_PATH["resumed_from"] = resume
+    out = native.forward_keys(ids, pos, cu, S, T, layer, rows, resume_layer=resume)
+    native.keys_token = (token, layer, T) if token is not None else None
+    return out
 
 
 def tokenize_prompts(prompts, tokenizer, device, padding_length=None):
@@ -117,7 +132,7 @@ def prepare_lookup(tok, requests: List[Dict], num_fact_token: int, device):
         for ids, w, n_valid in zip(enc["input_ids"].tolist(), subjects, enc["attention_mask"].sum(1).tolist()):
             eos = int(n_valid) - 1
             lookup.append([find_token_range(tok, ids, w)[-1] - 1] + list(range(eos, eos + extra + 1)))
-    return enc, lookup, counts
+    return enc, lookup, counts, next(_SERIAL)
 
 
 def get_module_input_output_at_words(text_encoder, tok, requests: List[Dict], module_name: str,
@@ -126,12 +141,13 @@ def get_module_input_output_at_words(text_encoder, tok, requests: List[Dict], mo
     over each request's prompts: [n, d] and [n, h]  (num_fact_token == 1) or with an extra
     token dimension [n, num_fact_token, ·] (last subject token, EOS, then padding positions)."""
     device = text_encoder.device
-    enc, lookup, counts = prepared if prepared is not None else prepare_lookup(tok, requests, num_fact_token, device)
+    enc, lookup, counts, serial = prepared if prepared is not None else prepare_lookup(tok, requests, num_fact_token, device)
     assert len(enc["input_ids"]) == len(lookup)
     native = None
     if num_fact_token == 1 and type(text_encoder).__name__ != "CLIPModel":
         with torch.no_grad():
-            native = _native_keys(text_encoder, enc, lookup, module_name)
+            native = _native_keys(text_encoder, enc, lookup, module_name,
+                                  token=serial if prepared is not None else None)
     LAST_PATH["native"] = native is not None
     if native is not None:
         l_in, l_out = native[0][:, None, :], native[1][:, None, :]      # [P, 1, d], [P, 1, h]

@@ -67,6 +67,10 @@ struct ClipHandle {
   DeviceInfo info;
   long long launches;
   int attn_smem;
+  // key-extraction continuation: the last keys call left act(fc1) of layer keys_state_layer in the f planes and the
+  // residual stream after that layer's attention block in hres, for keys_state_tokens packed tokens (-1: nothing)
+  int keys_state_layer;
+  int keys_state_tokens;
   // measurement aid (emcid_clip_profile): CUDA events around every launch of the forward, tagged by kernel class
   bool profile;
   std::vector<cudaEvent_t>* ev;      // pairs (start, stop)
@@ -473,6 +477,7 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
   H->hp = static_cast<int>(round_up_ll(h, 64));
   H->dp = static_cast<int>(round_up_ll(d, 64));
   H->cap_tokens = cap_tokens; H->cap_seqs = cap_seqs;
+  H->keys_state_layer = -1; H->keys_state_tokens = 0;
   H->tp = round_up_ll(cap_tokens, 256);
   const size_t cap = static_cast<size_t>(cap_tokens);
   if ((rc = clip_alloc(H, &H->tok_emb, static_cast<size_t>(vocab) * h)) ||
@@ -754,7 +759,7 @@ inline int clip_get_profile(ClipHandle* H, double* out) {
 inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int* cu_seqlens, int S, int T,
                         int n_layers, int n_stat, const int* stat_layers, Mom2Handle* const* accs, float* hidden_out,
                         cudaStream_t stream, int keys_layer = -1, const int* key_rows = nullptr, int n_keys = 0,
-                        float* k_out = nullptr, float* z_out = nullptr) {
+                        float* k_out = nullptr, float* z_out = nullptr, int resume_layer = -1) {
   EMCID_CHECK(H && ids && pos && cu_seqlens, EMCID_ERR_INVALID, "clip_forward: null argument");
   EMCID_CHECK(T >= 0 && T <= H->cap_tokens && S >= 0 && S <= H->cap_seqs, EMCID_ERR_INVALID,
               "clip_forward: %d tokens / %d captions exceed the handle capacity (%lld / %d)", T, S, H->cap_tokens, H->cap_seqs);
@@ -775,6 +780,15 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     EMCID_CHECK((reinterpret_cast<uintptr_t>(z_out) & 15) == 0 && (H->h % 4) == 0, EMCID_ERR_INVALID,
                 "clip_forward: z_out must be 16-byte aligned");
   }
+  // resume_layer = r >= 0: the previous call on this handle was a keys call at layer r over the SAME packed tokens and only
+  // fc2 of layer r has changed since (the edit loop, emcid_main.py:1061): start from that call's state — finish layer r
+  // with its new fc2, then run layers (r, keys_layer] — instead of from the embeddings
+  if (resume_layer >= 0) {
+    EMCID_CHECK(keys_layer > resume_layer && H->keys_state_layer == resume_layer && H->keys_state_tokens == T, EMCID_ERR_INVALID,
+                "clip_forward: cannot resume from layer %d (state: layer %d, %d tokens; this call: layer %d, %d tokens)",
+                resume_layer, H->keys_state_layer, H->keys_state_tokens, keys_layer, T);
+  }
+  H->keys_state_layer = -1;
   const int run_layers = keys_layer >= 0 ? keys_layer + 1 : (n_stat > 0 ? last_stat + 1 : n_layers);
   for (int l = 0; l < run_layers; ++l)
     EMCID_CHECK((*H->layers)[l].set, EMCID_ERR_INVALID, "clip_forward: weights of layer %d were never set", l);
@@ -819,7 +833,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   const GemmOutMaps* pm_res = use_tma_epi ? &om_res : nullptr;
   const GemmOutMaps* pm_f = use_tma_epi ? &om_f : nullptr;
 
-  {
+  if (resume_layer < 0) {
     int blocks = (T + 7) / 8;
     if (blocks > sms * 16) blocks = sms * 16;
     clip_embed_kernel<<<blocks, 256, 0, stream>>>(ids, pos, T, H->h, H->vocab, H->max_pos, H->tok_emb, H->pos_emb, H->hres);
@@ -828,8 +842,15 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(H->dh));
   int si = 0;
-  for (int l = 0; l < run_layers; ++l) {
+  for (int l = resume_layer < 0 ? 0 : resume_layer; l < run_layers; ++l) {
     const ClipLayer& Ly = (*H->layers)[l];
+    if (l == resume_layer) {
+      // hres = h + attn(h) of this layer and f = act(fc1(LN2 hres)) are where the previous call left them
+      if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr,
+                            0, stream, pm_res, 0, CLIP_TAG_FC2)))
+        return rc;
+      continue;
+    }
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln1_w, Ly.ln1_b, H->x_hi, H->x_lo, stream))) return rc;
     if (attn_tc) {
       if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, nullptr, 0, H->qp_hi, H->qp_lo, 3ll * H->h, nullptr,
@@ -918,6 +939,8 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       if ((rc = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, nullptr,
                             nullptr, 0, stream, use_tma_epi ? &om_z : nullptr, 0, CLIP_TAG_FC2)))
         return rc;
+      H->keys_state_layer = l;
+      H->keys_state_tokens = T;
       break;
     }
     if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,

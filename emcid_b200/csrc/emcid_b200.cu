@@ -123,9 +123,9 @@ int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* posit
 
 int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
                             int n_captions, int n_tokens, int layer, const int32_t* key_rows, int n_keys, float* k_out,
-                            float* z_out, void* stream) {
+                            float* z_out, int resume_layer, void* stream) {
   return clip_forward(reinterpret_cast<ClipHandle*>(h), ids, positions, cu_seqlens, n_captions, n_tokens, 0, 0, nullptr,
-                      nullptr, nullptr, static_cast<cudaStream_t>(stream), layer, key_rows, n_keys, k_out, z_out);
+                      nullptr, nullptr, static_cast<cudaStream_t>(stream), layer, key_rows, n_keys, k_out, z_out, resume_layer);
 }
 
 int emcid_clip_profile(emcid_clip_t* h, int enable) {

@@ -118,10 +118,15 @@ int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* posit
  *     emcid/emcid_main.py:987-996 (keys) and :1004-1014 (current outputs)):
  * runs full layers [0, layer), then layer `layer` up to act(fc1), and returns for the packed token rows `key_rows`
  * (device int32 [n_keys], the last-subject-token row of every prompt) the fc2 INPUT k_out [n_keys x intermediate] and the
- * fc2 OUTPUT z_out [n_keys x hidden] (fc2.weight x + fc2.bias, computed on the gathered rows only), both fp32 device. */
+ * fc2 OUTPUT z_out [n_keys x hidden] (fc2.weight x + fc2.bias, computed on the gathered rows only), both fp32 device.
+ * resume_layer = -1 starts from the embeddings.  resume_layer = r (< layer) continues from the state the previous call on
+ * this handle left behind — a keys call at layer r over the SAME packed tokens, after which only fc2 of layer r was
+ * re-uploaded (what the edit loop does between layers, emcid/emcid_main.py:1061): layer r is finished with its new fc2
+ * and layers (r, layer] follow, so an L-layer edit costs the layers below the first edited one once plus about one
+ * layer per edited layer instead of first + ... + last.  Anything else is EMCID_ERR_INVALID. */
 int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
                             int n_captions, int n_tokens, int layer, const int32_t* key_rows, int n_keys, float* k_out,
-                            float* z_out, void* stream);
+                            float* z_out, int resume_layer, void* stream);
 /* Measurement aid: when enabled, every launch of the forward is bracketed by CUDA events on the caller's stream.
  * emcid_clip_get_profile waits for them and fills out21[tag * 3 + {0, 1, 2}] = {launches, total ms, total algorithmic
  * flops (2 M N K)} for tag = 0 q/k/v projection, 1 out projection, 2 fc1, 3 fc1 of an edited layer (both plane

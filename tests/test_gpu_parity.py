@@ -242,6 +242,52 @@ def test_native_key_extraction_matches_hf(dev, monkeypatch, kind, layer, n_req):
         clip_forward.release_key_encoders()
 
 
+@pytest.mark.parametrize("kind,la,lb", [("tiny", 0, 1), ("clip-l", 7, 9)])
+def test_native_key_extraction_resumes_after_fc2_edit(dev, monkeypatch, kind, la, lb):
+    """The edit loop asks for keys at increasing layers over the same prompts and writes only fc2 of the layer it just
+    solved in between (emcid_main.py:1061): the library continues from the previous call's state (finish layer la with
+    the new fc2, run (la, lb]) and must agree with a from-scratch traced HF forward; any other weight change in between
+    forces a fresh start."""
+    from emcid_b200 import clip_forward, compute_ks
+    model = rh.make_clip_text_model(kind, seed=9).to(dev)
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    reqs = rh.make_requests(12)
+    name = "text_model.encoder.layers.{}.mlp.fc2"
+
+    def check(k, z, layer):
+        """against an fp64 copy of the model; the library must be as close to it as HF's own fp32 run"""
+        import copy
+        monkeypatch.setenv("EMCID_NATIVE_KEYS", "0")
+        k64, z64 = compute_ks.get_module_input_output_at_words(copy.deepcopy(model).double(), tok, reqs, name.format(layer))
+        k32, z32 = compute_ks.get_module_input_output_at_words(model, tok, reqs, name.format(layer))
+        monkeypatch.setenv("EMCID_NATIVE_KEYS", "1")
+        for got, hf32, ref in ((k, k32, k64), (z, z32, z64)):
+            ref = ref.cpu().numpy()
+            assert rel_fro(got.cpu().numpy(), ref) < max(3e-6, 3 * rel_fro(hf32.cpu().numpy(), ref))
+
+    try:
+        prepared = compute_ks.prepare_lookup(tok, reqs, 1, dev)
+        compute_ks.get_module_input_output_at_words(model, tok, reqs, name.format(la), prepared=prepared)
+        assert compute_ks.LAST_PATH["native"] and compute_ks.LAST_PATH["resumed_from"] == -1
+        with torch.no_grad():
+            model.text_model.encoder.layers[la].mlp.fc2.weight[...] += 0.02
+        k, z = compute_ks.get_module_input_output_at_words(model, tok, reqs, name.format(lb), prepared=prepared)
+        assert compute_ks.LAST_PATH["resumed_from"] == la
+        check(k, z, lb)
+        # a second prompt set, and a change outside fc2 of the previous layer: no continuation
+        prepared2 = compute_ks.prepare_lookup(tok, reqs, 1, dev)
+        compute_ks.get_module_input_output_at_words(model, tok, reqs, name.format(la), prepared=prepared2)
+        assert compute_ks.LAST_PATH["resumed_from"] == -1
+        with torch.no_grad():
+            model.text_model.encoder.layers[la].mlp.fc2.weight[...] -= 0.01
+            model.text_model.encoder.layers[0].mlp.fc1.bias[...] += 0.05
+        k, z = compute_ks.get_module_input_output_at_words(model, tok, reqs, name.format(lb), prepared=prepared2)
+        assert compute_ks.LAST_PATH["resumed_from"] == -1
+        check(k, z, lb)
+    finally:
+        clip_forward.release_key_encoders()
+
+
 def test_native_forward_falls_back_on_non_right_padding(dev, tmp_path):
     """A mask that is not a right-padding mask cannot be packed: the block goes through the HF forward with the
     fused kernels hooked in, and the statistics still match a direct masked Gram."""

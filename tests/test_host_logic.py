@@ -179,7 +179,7 @@ def test_word_hash_tokenizer_inverts_on_a_thousand_requests():
     from emcid_b200 import compute_ks, synth
     tok = synth.WordHashTokenizer(49408)
     reqs = synth.make_edit_requests(1000)
-    enc, lookup, counts = compute_ks.prepare_lookup(tok, reqs, 1, "cpu")
+    enc, lookup, counts, _serial = compute_ks.prepare_lookup(tok, reqs, 1, "cpu")
     assert enc["input_ids"].shape[0] == 3000 and counts == [3] * 1000
     ids = enc["input_ids"].tolist()
     for p in (0, 1, 2, 1499, 2999):

@@ -20,10 +20,14 @@ St = torch.randn(B, n, h, device="cuda", generator=g)
 left = list(range(B, 0, -1))
 S.solve_layers(C32, Kt, St, 4000.0, 1.0, left)   # warm-up (workspace, attributes)
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
+import time
+per = []
 for _ in range(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
     adj, resid, dW = S.solve_layers(C32, Kt, St, 4000.0, 1.0, left, check=False)
-e1.record()
-torch.cuda.synchronize()
-print(json.dumps({"B": B, "n": n, "ms": e0.elapsed_time(e1) / reps}))
+    e1.record()
+    torch.cuda.synchronize()
+    per.append((round(e0.elapsed_time(e1), 2), round(1e3 * (time.perf_counter() - t0), 2)))
+print(json.dumps({"B": B, "n": n, "ms": sum(p[0] for p in per) / reps, "per_rep_device_host_ms": per}))
