@@ -891,9 +891,14 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln2_w, Ly.ln2_b, H->x_hi, H->x_lo, stream))) return rc;
     const bool is_stat = si < n_stat && stat_layers[si] == l;
     const bool is_last = n_stat > 0 && l == last_stat;
-    // the deepest edited layer needs only f^T (no fc2 follows); other edited layers need both orientations
-    if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.fc1, T, H->act, nullptr, nullptr, 0, is_last ? nullptr : H->f_hi,
-                          is_last ? nullptr : H->f_lo, H->dp, is_stat ? H->ft_hi : nullptr, is_stat ? H->ft_lo : nullptr,
+    // EMCID_SYRK_MN (default): the SYRK reads act(fc1) as MN-major operand tiles straight from the [tokens x features]
+    // planes fc2 reads as well, so an edited layer's fc1 is an ordinary fc1.  EMCID_SYRK_MN=0: the SYRK reads K-major
+    // tiles of a transposed copy f^T, which fc1 of an edited layer then has to write as well (+100 us per launch).
+    static const bool syrk_mn = [] { const char* e = getenv("EMCID_SYRK_MN"); return !(e && e[0] == '0'); }();
+    const bool mn = syrk_mn && rb == 128 && use_tma_epi;
+    const bool want_p = mn || !is_last, want_pt = is_stat && !mn;
+    if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.fc1, T, H->act, nullptr, nullptr, 0, want_p ? H->f_hi : nullptr,
+                          want_p ? H->f_lo : nullptr, H->dp, want_pt ? H->ft_hi : nullptr, want_pt ? H->ft_lo : nullptr,
                           H->tp, stream, pm_f, 0, is_stat ? CLIP_TAG_FC1_STAT : CLIP_TAG_FC1)))
       return rc;
     if (is_stat) {
@@ -903,7 +908,15 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       // block instead of once per 4096-token slab; the 4 leftover pair tiles are stream-K'd).  EMCID_SYRK_HYBRID=0
       // restores the slab launches (measured: 10 x 102 us per block and layer, 40 MB of red.add traffic each).
       static const bool hybrid = [] { const char* e = getenv("EMCID_SYRK_HYBRID"); return !(e && e[0] == '0'); }();
-      if (hybrid && rb == 128) {
+      if (mn) {
+        GemmOperands fm;   // act(fc1) planes [T x d]: boxes of 64 tokens x 64 features
+        if ((rc = make_tmap_2d(&fm.a_hi, H->f_hi, T, H->d, H->dp, 64, 2)) || (rc = make_tmap_2d(&fm.a_lo, H->f_lo, T, H->d, H->dp, 64, 2)))
+          return rc;
+        fm.b_hi = fm.a_hi; fm.b_lo = fm.a_lo;
+        if ((rc = mom2_syrk_slab(A, fm, KIND_F16_MN, 0, T, nullptr, stream, hybrid ? 2 : 1))) return rc;
+        A->slabs_since_fold += 4;
+        if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
+      } else if (hybrid && rb == 128) {
         if ((rc = mom2_syrk_slab(A, ft, KIND_F16, 0, T, nullptr, stream, 2))) return rc;
         A->slabs_since_fold += 4;
         if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;

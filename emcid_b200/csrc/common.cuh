@@ -347,6 +347,19 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile (rows of the tile = K, 64 MN elements = one 128-byte swizzle row per K row), as TMA writes a box
+// of [K rows x 64 MN elements] with SWIZZLE_128B: 8-K-row groups 1024 B apart (SBO); successive 64-element MN atoms are
+// separate boxes `atom_bytes` apart (LBO).  The instruction descriptor must flag the operand as MN-major.
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t smem_addr, uint32_t atom_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(atom_bytes >> 4) << 16;         // LBO: next MN atom
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO: next group of 8 K rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+  return d;
+}
+
 // Same for tiles of 64-byte rows written with TMA SWIZZLE_64B: 8-row groups are 512 B apart, layout_type = 4.
 __device__ __forceinline__ uint64_t make_desc_k64(uint32_t smem_addr) {
   uint64_t d = 0;

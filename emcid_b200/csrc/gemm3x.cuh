@@ -42,11 +42,14 @@ constexpr int GEMM_BLOCK_K = 32;  // tf32 kind: 32 fp32 = 128 bytes = one swizzl
 // KIND_F16_S64: the same fp16 planes and MMAs as KIND_F16, staged as 64-byte rows (TMA SWIZZLE_64B, 32 elements
 // per k-block): stages are half the size, so twice as many fit in shared memory and the TMA round trip has
 // (stages - 1) x 768 instead of 1 x 1536 MMA cycles to hide behind.
-enum GemmKind : int { KIND_TF32 = 0, KIND_F16 = 1, KIND_F16_S64 = 2 };
+// KIND_F16_MN: fp16 planes stored [K x MN] row-major (MN contiguous) — the SYRK reads act(fc1) planes [tokens x
+// features] directly: both operands are MN-major tiles of 64 tokens (K) x 64-feature atoms, no transposed copy needed.
+enum GemmKind : int { KIND_TF32 = 0, KIND_F16 = 1, KIND_F16_S64 = 2, KIND_F16_MN = 3 };
 template <int KIND> struct KindTraits;
 template <> struct KindTraits<KIND_TF32> { static constexpr int kBlockK = 32, kElemBytes = 4, kRowBytes = 128; };
 template <> struct KindTraits<KIND_F16> { static constexpr int kBlockK = 64, kElemBytes = 2, kRowBytes = 128; };
 template <> struct KindTraits<KIND_F16_S64> { static constexpr int kBlockK = 32, kElemBytes = 2, kRowBytes = 64; };
+template <> struct KindTraits<KIND_F16_MN> { static constexpr int kBlockK = 64, kElemBytes = 2, kRowBytes = 128; };
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_THREADS = 256;
 constexpr int GEMM_ROW_BYTES = 128;
@@ -377,7 +380,39 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           const int kc = kb * BLOCK_K;
-          if (CTA2) {
+          if (KIND == KIND_F16_MN) {
+            // planes are [tokens x features]: one box of 64 tokens x 64 features (8 KB) per 64-feature atom of the tile
+            constexpr int ATOM = 64 * 128;
+            const int tok = p.a_col0 + kc;
+            const int fa = arow + u.m0 + static_cast<int>(rank) * GEMM_BLOCK_M;
+            const int fb = brow + u.n0 + static_cast<int>(rank) * B_ROWS;
+            if (CTA2) {
+              const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+#pragma unroll
+              for (int j = 0; j < GEMM_BLOCK_M / 64; ++j) {
+                tma_load_2d_2sm(st + j * ATOM, &tmA_hi, lbar, fa + 64 * j, tok);
+                tma_load_2d_2sm(st + A_PLANE + j * ATOM, &tmA_lo, lbar, fa + 64 * j, tok);
+              }
+#pragma unroll
+              for (int j = 0; j < B_ROWS / 64; ++j) {
+                tma_load_2d_2sm(st + 2 * A_PLANE + j * ATOM, &tmB_hi, lbar, fb + 64 * j, tok);
+                tma_load_2d_2sm(st + 2 * A_PLANE + B_PLANE + j * ATOM, &tmB_lo, lbar, fb + 64 * j, tok);
+              }
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+#pragma unroll
+              for (int j = 0; j < GEMM_BLOCK_M / 64; ++j) {
+                tma_load_2d(st + j * ATOM, &tmA_hi, &full_bar[stage], fa + 64 * j, tok);
+                tma_load_2d(st + A_PLANE + j * ATOM, &tmA_lo, &full_bar[stage], fa + 64 * j, tok);
+              }
+#pragma unroll
+              for (int j = 0; j < B_ROWS / 64; ++j) {
+                tma_load_2d(st + 2 * A_PLANE + j * ATOM, &tmB_hi, &full_bar[stage], fb + 64 * j, tok);
+                tma_load_2d(st + 2 * A_PLANE + B_PLANE + j * ATOM, &tmB_lo, &full_bar[stage], fb + 64 * j, tok);
+              }
+            }
+          } else if (CTA2) {
             // both CTAs of the pair load into their own stage; all bytes are counted on the leader's barrier
             const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
@@ -410,9 +445,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
       const uint32_t f_hi = KIND == KIND_TF32 ? FMT_TF32 : FMT_F16;
       const uint32_t f_lo = KIND == KIND_TF32 ? FMT_TF32 : static_cast<uint32_t>(p.lo_fmt);
       constexpr uint32_t MMA_M = CTA2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M;
-      const uint32_t idesc_lh = make_idesc(f_lo, f_hi, MMA_M, BLOCK_N);
-      const uint32_t idesc_hl = make_idesc(f_hi, f_lo, MMA_M, BLOCK_N);
-      const uint32_t idesc_hh = make_idesc(f_hi, f_hi, MMA_M, BLOCK_N);
+      constexpr uint32_t MN_BITS = KIND == KIND_F16_MN ? ((1u << 15) | (1u << 16)) : 0u;   // A and B are MN-major
+      const uint32_t idesc_lh = make_idesc(f_lo, f_hi, MMA_M, BLOCK_N) | MN_BITS;
+      const uint32_t idesc_hl = make_idesc(f_hi, f_lo, MMA_M, BLOCK_N) | MN_BITS;
+      const uint32_t idesc_hh = make_idesc(f_hi, f_hi, MMA_M, BLOCK_N) | MN_BITS;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -429,15 +465,20 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             mbar_wait(&full_bar[stage], phase, 3);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t da_hi = ROWB == 128 ? make_desc_k128(sa) : make_desc_k64(sa);
-            const uint64_t da_lo = ROWB == 128 ? make_desc_k128(sa + A_PLANE) : make_desc_k64(sa + A_PLANE);
-            const uint64_t db_hi = ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE) : make_desc_k64(sa + 2 * A_PLANE);
-            const uint64_t db_lo = ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE + B_PLANE)
-                                               : make_desc_k64(sa + 2 * A_PLANE + B_PLANE);
+            constexpr bool MN = KIND == KIND_F16_MN;
+            const uint64_t da_hi = MN ? make_desc_mn128(sa, 8192) : ROWB == 128 ? make_desc_k128(sa) : make_desc_k64(sa);
+            const uint64_t da_lo = MN ? make_desc_mn128(sa + A_PLANE, 8192)
+                                      : ROWB == 128 ? make_desc_k128(sa + A_PLANE) : make_desc_k64(sa + A_PLANE);
+            const uint64_t db_hi = MN ? make_desc_mn128(sa + 2 * A_PLANE, 8192)
+                                      : ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE) : make_desc_k64(sa + 2 * A_PLANE);
+            const uint64_t db_lo = MN ? make_desc_mn128(sa + 2 * A_PLANE + B_PLANE, 8192)
+                                      : ROWB == 128 ? make_desc_k128(sa + 2 * A_PLANE + B_PLANE)
+                                                    : make_desc_k64(sa + 2 * A_PLANE + B_PLANE);
 #pragma unroll
             for (int k = 0; k < ROWB / 32; ++k) {
-              // one instruction contracts 32 bytes of K (8 tf32 / 16 halves): +2 in the (addr >> 4) field
-              const uint64_t koff = static_cast<uint64_t>(k * 2);
+              // one instruction contracts 32 bytes of K (8 tf32 / 16 halves): +2 in the (addr >> 4) field; in an MN-major
+              // tile 16 K rows are 16 x 128 B further down: +128
+              const uint64_t koff = static_cast<uint64_t>(MN ? k * 128 : k * 2);
               if (KIND == KIND_TF32) {
                 tc_mma_tf32(tmem_d, da_lo + koff, db_hi + koff, idesc_lh, accumulate);
                 tc_mma_tf32(tmem_d, da_hi + koff, db_lo + koff, idesc_hl, 1);

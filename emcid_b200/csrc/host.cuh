@@ -90,6 +90,12 @@ struct DevPool {
   std::mutex mu;
   std::map<void*, std::pair<int, size_t>> live;                 // ptr -> (device, bytes)
   std::multimap<std::pair<int, size_t>, void*> parked;          // (device, bytes) -> ptr
+  size_t parked_bytes = 0;
+  size_t limit_bytes = 24ull << 30;                             // EMCID_POOL_LIMIT_MB; beyond it buffers are freed at once
+  DevPool() {
+    const char* e = getenv("EMCID_POOL_LIMIT_MB");
+    if (e) limit_bytes = static_cast<size_t>(strtoull(e, nullptr, 10)) << 20;
+  }
 };
 
 inline DevPool& dev_pool() {
@@ -107,12 +113,13 @@ inline cudaError_t dev_alloc(void** out, size_t bytes) {
   if (it != P.parked.end()) {
     *out = it->second;
     P.parked.erase(it);
+    P.parked_bytes -= bytes;
   } else {
     e = cudaMalloc(out, bytes);
     if (e != cudaSuccess) {
       // make room: give everything parked on this device back and retry once
       for (auto p = P.parked.begin(); p != P.parked.end();) {
-        if (p->first.first == dev) { cudaFree(p->second); p = P.parked.erase(p); } else { ++p; }
+        if (p->first.first == dev) { cudaFree(p->second); P.parked_bytes -= p->first.second; p = P.parked.erase(p); } else { ++p; }
       }
       (void)cudaGetLastError();
       e = cudaMalloc(out, bytes);
@@ -129,7 +136,12 @@ inline void dev_free(void* p) {
   std::lock_guard<std::mutex> lock(P.mu);
   auto it = P.live.find(p);
   if (it == P.live.end()) { cudaFree(p); return; }
-  P.parked.insert(std::make_pair(it->second, p));
+  if (P.parked_bytes + it->second.second > P.limit_bytes) {
+    cudaFree(p);                                                  // the pool is full: do not hoard differently-shaped buffers
+  } else {
+    P.parked.insert(std::make_pair(it->second, p));
+    P.parked_bytes += it->second.second;
+  }
   P.live.erase(it);
 }
 
@@ -143,6 +155,7 @@ inline int dev_release_cached() {
     cudaFree(kv.second);
   }
   P.parked.clear();
+  P.parked_bytes = 0;
   cudaSetDevice(prev);
   return EMCID_OK;
 }
