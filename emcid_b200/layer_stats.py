@@ -110,6 +110,7 @@ class TextEncoderMom2Pass:
         self._mask = None
         self._hook_weights_set = False
         self._layer_index = {}
+        self.capacity_hint = 0     # tokens per block the caller is going to send (sizes the native encoder once)
         if self._use_native:
             tm = getattr(model, "text_model", model)
             for name, mlp, _ in self._mlps:
@@ -133,7 +134,7 @@ class TextEncoderMom2Pass:
             if nat is not None:
                 torch.cuda.synchronize(nat.device)
                 nat.close()
-            cap_tokens = max(n_tokens, nat.max_tokens if nat else 0)
+            cap_tokens = max(n_tokens, nat.max_tokens if nat else 0, int(self.capacity_hint))
             # captions are at least one token long: a caption capacity of cap_tokens never has to grow (it sizes nothing)
             self._native = nat = clip_forward.NativeClipTextEncoder(self.model, cap_tokens, max(n_captions, cap_tokens))
         return nat
@@ -286,6 +287,9 @@ def layer_stats_text_encoder_multi(
 
     runner = TextEncoderMom2Pass(model, todo, slab_tokens=slab_tokens, accumulator_factory=_accumulator_factory)
     reblock = PackedReblocker(block_tokens) if (block_tokens and runner._use_native) else None
+    if reblock is not None:
+        max_pos = getattr(model, "text_model", model).embeddings.position_embedding.weight.shape[0]
+        runner.capacity_hint = min(int(block_tokens), len(my_indices) * int(max_pos))
     t_loop = time.perf_counter()
     try:
         t_wait = t_run = 0.0

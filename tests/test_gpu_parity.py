@@ -141,6 +141,24 @@ def test_clipl_layer_stats_matches_reference_digest(dev, golden_dir, tmp_path, m
     assert rel_fro(single.mom2.mom2.numpy(), stats[names[0]].mom2.mom2.numpy()) < 2e-6
 
 
+@pytest.mark.parametrize("block_tokens", [96, 1000, 37888])
+def test_token_budget_blocks_do_not_change_the_statistics(dev, golden_dir, tmp_path, block_tokens):
+    """The native pass regroups loader batches into device blocks of at most `block_tokens` packed tokens
+    (stat_dataset.PackedReblocker): whatever the block size — down to one or two captions per block — the count is
+    bit exact and mom2 matches the reference fixture."""
+    g = np.load(os.path.join(golden_dir, "tiny_stats.npz"))
+    model = model_from_golden(g).to(dev)
+    ls = _patch_ds(unpack_captions(g))
+    ss = None if int(g["sample_size"]) < 0 else int(g["sample_size"])
+    layer_name = f"text_model.encoder.layers.{int(g['layer'])}.mlp.fc2"
+    stat = ls.layer_stats_text_encoder(model, None, layer_name, stats_dir=tmp_path, sample_size=ss, precision="float32",
+                                       batch_tokens=int(g["batch_tokens"]), progress=None, captions_per_batch=7,
+                                       num_workers=0, block_tokens=block_tokens, force_recompute=True)
+    assert ls.LAST_PASS_INFO["native_forward"]
+    assert stat.mom2.count == int(g["npz.mom2.count"])
+    assert rel_fro(stat.mom2.mom2.numpy(), g["npz.mom2.mom2"]) < MOM2_TOL
+
+
 def test_stats_properties_at_clipl_size(dev, tmp_path):
     """Linearity over caption sets, batching invariance, count = sum of lengths (CLIP-L, layers 7-11)."""
     model = rh.make_clip_text_model("clip-l", seed=0).to(dev)
