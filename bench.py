@@ -278,9 +278,13 @@ def run_ours(args):
         acc.reset(); acc.profile(True)
     if runner._native is not None:
         runner._native.profile(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
     for i in range(W, W + min(K, 2)):
         step(i)
+    p1.record()
     torch.cuda.synchronize()
+    profiled_ms = p0.elapsed_time(p1)
     forward_kernels = None
     if runner._native is not None:
         fk = runner._native.get_profile()
@@ -331,6 +335,10 @@ def run_ours(args):
         # achieved = algorithmic 2MNK flops, issued = x3 for the 3-term split
         "forward_kernels": forward_kernels,
     }
+    if forward_kernels:
+        # how much of the (event-instrumented) profiled steps was spent inside kernels: the rest is launch gaps
+        kernel_ms = prof["syrk_ms"] + prof["fc1_ms"] + sum(v["ms"] for v in fk.values())
+        roofline["profiled_steps"] = {"ms": profiled_ms, "kernel_ms": kernel_ms, "in_kernels": kernel_ms / profiled_ms}
     # whole-step fraction of the tensor roofline (what the BASELINE metric asks next to tokens/s)
     step_tflops = value * len(LAYERS) * flops_per_token_layer / 1e12 / world
     roofline["step_frac"] = step_tflops / tf32_peak

@@ -159,6 +159,34 @@ def test_token_budget_blocks_do_not_change_the_statistics(dev, golden_dir, tmp_p
     assert rel_fro(stat.mom2.mom2.numpy(), g["npz.mom2.mom2"]) < MOM2_TOL
 
 
+def test_native_stats_at_bigg_width(dev, tmp_path):
+    """OpenCLIP bigG layer shapes (h = 1280, d = 5120, 20 heads, erf-gelu; BASELINE configs[3]) through the native pass —
+    210 pair tiles on 74 CTA pairs: two whole-tile rounds plus stream-K leftovers — against an fp64 copy of the model."""
+    import copy
+    model = rh.make_clip_text_model("bigg", seed=4, num_hidden_layers=3).to(dev)
+    caps = rh.make_captions(400, model.config.vocab_size, seed=7, min_len=3)
+    ls = _patch_ds(caps)
+    names = [f"text_model.encoder.layers.{l}.mlp.fc2" for l in (1, 2)]
+    stats = ls.layer_stats_text_encoder_multi(model, None, names, stats_dir=tmp_path, sample_size=len(caps), precision="float32",
+                                              progress=None, captions_per_batch=128, num_workers=0, force_recompute=True)
+    assert ls.LAST_PASS_INFO["native_forward"]
+    m64 = copy.deepcopy(model).double()
+    batch = {k: v.to(dev) for k, v in _padded(caps).items()}
+    keep = batch["attention_mask"].bool()
+    feats = {}
+    hooks = [m64.text_model.encoder.layers[l].mlp.fc2.register_forward_pre_hook(lambda m, a, l=l: feats.__setitem__(l, a[0]))
+             for l in (1, 2)]
+    with torch.no_grad():
+        m64(**batch)
+    for h in hooks:
+        h.remove()
+    for l, n in zip((1, 2), names):
+        a = feats[l][keep]
+        ref = (a.T @ a).cpu().numpy()
+        assert stats[n].mom2.count == int(keep.sum())
+        assert rel_fro(stats[n].mom2.mom2.numpy(), ref) < MOM2_TOL
+
+
 def test_stats_properties_at_clipl_size(dev, tmp_path):
     """Linearity over caption sets, batching invariance, count = sum of lengths (CLIP-L, layers 7-11)."""
     model = rh.make_clip_text_model("clip-l", seed=0).to(dev)
