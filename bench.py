@@ -314,9 +314,10 @@ def run_ours(args):
     fc1_tflops = prof["fc1_rows"] * 2 * H * D / (prof["fc1_ms"] * 1e-3) / 1e12 if prof["fc1_ms"] else 0.0
     roofline = {
         "bound": "tensor",
-        "kernel": ("gemm3x_kernel<256,3,EPI_RED,KIND_F16,EF_DEFAULT,CTA2=1> (stream-K lower SYRK, 3xFP16 split, tcgen05 "
-                   "kind::f16 cta_group::2 pairs)" if os.environ.get("EMCID_CTA2", "1") != "0" else
-                   "gemm3x_kernel<256,2,EPI_RED,KIND_F16> (stream-K lower SYRK, 3xFP16 split on tcgen05 kind::f16)"),
+        "kernel": ("gemm3x_kernel<256,3,EPI_RED,KIND_F16_MN,EF_DEFAULT,CTA2=1> (lower SYRK of the act(fc1) planes: 3xFP16 "
+                   "split, tcgen05 kind::f16 cta_group::2 pairs, MN-major operand tiles, hybrid whole-tile + stream-K "
+                   "schedule)" if os.environ.get("EMCID_CTA2", "1") != "0" else
+                   "gemm3x_kernel<256,2,EPI_RED,KIND_F16_MN> (lower SYRK, 3xFP16 split on tcgen05 kind::f16)"),
         "achieved": syrk_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": syrk_tflops / tf32_peak,
         "peak_source": f"{peaks['source']}: bf16_tflops_sustained (cuBLAS dense 16-bit GEMM); achieved counts "
                        "ALGORITHMIC flops d(d+1) per token, the 3-term split issues 3x that",
@@ -397,7 +398,9 @@ def run_ours(args):
         for nm in names:   # C = mom2 / count of this run's statistics, device resident (what get_cov_text_encoder caches)
             emcid_main.COV_CACHE[(model.config._name_or_path.replace("/", "_"), nm)] = (out[nm][0] / max(count0, 1)).float()
         times = []
+        deltas = None
         for rep in range(3):
+            deltas = None          # a caller drops the previous edit's host tensors before the next edit
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             deltas = emcid_main.execute_emcid_text_encoder(pipe, reqs, hp, cache_name=cache, stat_dir=tmp_e, verbose=False)

@@ -634,7 +634,10 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = T; p.N = W.N; p.K = W.K;
-  p.chunk_kblocks = 2;
+  // k-blocks (64 contracted elements each) accumulated in TMEM between round-to-nearest folds: the RZ bias of the TMEM
+  // accumulation grows with it (gemm3x.cuh), the epilogue's slack behind the MMA warp too.  EMCID_LINEAR_CHUNK overrides.
+  static const int chunk_env = [] { const char* e = getenv("EMCID_LINEAR_CHUNK"); return e ? atoi(e) : 0; }();
+  p.chunk_kblocks = chunk_env > 0 ? chunk_env : 2;
   // token tiles outermost: the activation planes (121-484 MB per block) stream from HBM once while the weight
   // planes (<= 19 MB) stay L2-resident.  EMCID_TILE_ORDER=m restores the M-fastest walk (measured: every N tile
   // re-read the activations from DRAM, 1.1-1.5 GB per launch).
