@@ -406,6 +406,7 @@ def run_ours(args):
             deltas = emcid_main.execute_emcid_text_encoder(pipe, reqs, hp, cache_name=cache, stat_dir=tmp_e, verbose=False)
             torch.cuda.synchronize()
             times.append(time.perf_counter() - t0)
+        deltas = None
         emcid_main.TIMING = True   # one more repetition with a device synchronise between the stages
         emcid_main.execute_emcid_text_encoder(pipe, reqs, hp, cache_name=cache, stat_dir=tmp_e, verbose=False)
         emcid_main.TIMING = False
