@@ -254,8 +254,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Relaxed: the arrival publishes no generic-proxy data (the epilogue
+// warps only tell the MMA issuer that their tcgen05.ld of an accumulator stage has completed, ordered by
+// tcgen05.fence::before_thread_sync); with .release.cluster every arrival cost a MEMBAR.ALL.GPU + ERRBAR (6 % of all warp
+// samples of the q/k/v projection, on the path that frees the accumulator for the next MMA chunk).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait with cluster-scope acquire (arrivals come from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t dbg_code = 0) {
