@@ -636,11 +636,12 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   p.M = T; p.N = W.N; p.K = W.K;
   // k-blocks (64 contracted elements each) accumulated in TMEM between round-to-nearest folds: the RZ bias of the TMEM
   // accumulation grows with it (gemm3x.cuh), and so does the slack the epilogue's store phase has behind the MMA warp
-  // (two accumulator chunks).  Measured on one box at CLIP-L (profiles/r02d_*): chunk 2 / 3 / 4 -> 1.572 / 1.645 / 1.663 M
+  // (two accumulator chunks).  Measured at CLIP-L (profiles/r02d_*, r02g_*): chunk 2 / 3 / 4 -> 1.650 / 1.682 / 1.724 M
   // tokens/s, hidden-state error vs fp64 1.26e-6 / 1.78e-6 / 2.35e-6 (HF's own fp32 run: 1.46e-6), mom2 error 1.84e-6 /
-  // 2.4e-6 / 3.2e-6 (tolerance 1e-5).  3 keeps the forward as accurate as the fp32 reference; EMCID_LINEAR_CHUNK overrides.
+  // 2.4e-6 / 3.2e-6 (tolerance 1e-5).  2 keeps the forward MORE accurate than the fp32 reference for 2 % of the speed;
+  // EMCID_LINEAR_CHUNK overrides.
   static const int chunk_env = [] { const char* e = getenv("EMCID_LINEAR_CHUNK"); return e ? atoi(e) : 0; }();
-  p.chunk_kblocks = chunk_env > 0 ? chunk_env : 3;
+  p.chunk_kblocks = chunk_env > 0 ? chunk_env : 2;
   // token tiles outermost: the activation planes (121-484 MB per block) stream from HBM once while the weight
   // planes (<= 19 MB) stay L2-resident.  EMCID_TILE_ORDER=m restores the M-fastest walk (measured: every N tile
   // re-read the activations from DRAM, 1.1-1.5 GB per launch).
