@@ -261,7 +261,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait with cluster-scope acquire (arrivals come from the peer CTA)
+// Wait on a barrier whose arrivals come from both CTAs of the pair.  Relaxed like the arrivals: the MMA issuer reads no data
+// the epilogue warps wrote (tcgen05.fence::after_thread_sync orders the tensor-core side); with .acquire.cluster every
+// successful wait invalidated the L1 (CCTL.IVALL), once per accumulator chunk.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t dbg_code = 0) {
   const uint32_t addr = smem_u32(bar);
   uint32_t spins = 0;
@@ -270,7 +272,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
