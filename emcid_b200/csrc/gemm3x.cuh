@@ -1,4 +1,4 @@
-// emcid_b200 — generic 3xTF32 "NT" GEMM on tcgen05/TMEM fed by TMA (sm_100a).
+// emcid_b200 — generic 3-term-split "NT" GEMM on tcgen05/TMEM fed by TMA (sm_100a); 3xTF32 or 3xFP16 operand planes.
 //
 //   D[M x N] = sum_k A[m, k] * B[n, k]          A: [M x K] row-major, B: [N x K] row-major
 //
@@ -21,9 +21,12 @@
 // 384 threads x 168 registers fill the register file; the epilogue's 128 running sums fit.
 //
 // Every hot GEMM-shaped op of the EMCID path instantiates this one kernel:
-//   fc1      : A = W1 planes [d x h],  B = X planes [T x h]      -> bias/act/mask/split epilogue
-//   SYRK     : A = B = A^T planes [d x T_slab], lower tiles, stream-K over tokens -> red.add
-//   K K^T + lambda C, Cholesky panel/trailing updates, TRSM block products -> generic epilogue
+//   linear layers of the text encoder (clip.cuh): A = activation planes [T x K], B = weight planes [N x K], 3xFP16,
+//              CTA pairs (CTA2 = 1: cta_group::2, 256-row tiles), tiles walked along N, TMA-staged epilogue
+//   SYRK     : A = B = act(fc1) planes [T x d] read as MN-major tiles (KIND_F16_MN), lower pair tiles, hybrid schedule
+//              (whole tiles march through the tokens together, leftover tiles stream-K'd), red.add epilogue
+//   fc1 (hook mode): A = W1 planes [d x h], B = X planes [T x h] -> bias/act/mask/split epilogue (A^T slab)
+//   K K^T + lambda C, Cholesky panel/trailing updates, triangular inverse and its applications (k_tri) -> generic epilogue
 // It replaces the reference's `a.t().mm(a)` (util/runningstats.py:493) and the GEMM-shaped parts
 // of `torch.linalg.solve` / `@` in emcid/emcid_main.py:1045-1050.
 #pragma once
