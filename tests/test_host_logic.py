@@ -242,3 +242,34 @@ def test_packed_reblocker_cuts_between_captions_only():
     rb = PackedReblocker(10)                                                             # over-long captions travel alone
     blocks = list(rb.push(col([ds[i] for i in range(20)]))) + list(rb.flush())
     assert sum(b["cu_seqlens"].numel() - 1 for b in blocks) == 20
+
+
+def test_hparams_load_like_the_reference(tmp_path):
+    """hparams/*.json of the reference load into emcid_b200.EMCIDHyperParams (util/hparams.py:11-16): every key becomes an
+    attribute, the stage-2 fields get the reference's defaults, missing required fields raise TypeError."""
+    import json
+    import emcid_b200
+    fields = {"layers": [7, 8, 9, 10], "clamp_norm_factor": 1.5, "layer_selection": "all", "fact_token": "subject_last",
+              "v_num_grad_steps": 200, "v_lr": 0.2, "v_weight_decay": 0.0005, "mom2_adjustment": True,
+              "mom2_update_weight": 10000, "rewrite_module_tmp": "text_model.encoder.layers.{}.mlp.fc2",
+              "layer_module_tmp": "text_model.encoder.layers.{}", "mlp_module_tmp": "text_model.encoder.layers.{}.mlp",
+              "attn_module_tmp": "text_model.encoder.layers.{}.self_attn", "ln_f_module": "text_model.final_layer_norm",
+              "mom2_dataset": "ccs_filtered", "mom2_n_samples": 100000, "mom2_dtype": "float32", "objective": "ablate-dest",
+              "esd_mu": "None"}
+    f = tmp_path / "hp.json"
+    f.write_text(json.dumps(fields))
+    hp = emcid_b200.EMCIDHyperParams.from_json(f)
+    assert hp.layers == [7, 8, 9, 10] and hp.mom2_update_weight == 10000 and hp.v_lr == 0.2
+    assert hp.num_edit_tokens == 1 and hp.edit_weight == 0.5 and hp.use_new_compute_z is False
+    assert hp.rewrite_module_tmp.format(7) == "text_model.encoder.layers.7.mlp.fc2"
+    with pytest.raises(TypeError):
+        emcid_b200.EMCIDHyperParams(**{k: v for k, v in fields.items() if k != "mom2_n_samples"})
+    with pytest.raises(TypeError):
+        emcid_b200.EMCIDXLHyperParams(**fields)
+    xl = emcid_b200.EMCIDXLHyperParams(**fields, layers_2=[26, 27], mom2_update_weight_2=6000)
+    assert xl.layers_2 == [26, 27] and xl.mom2_update_weight_2 == 6000
+    if rh.reference_available():
+        import glob
+        for path in glob.glob("/root/reference/hparams/*.json"):
+            loaded = emcid_b200.EMCIDHyperParams.from_json(path)
+            assert loaded.rewrite_module_tmp.endswith("mlp.fc2") and loaded.mom2_dtype == "float32", path
