@@ -74,14 +74,24 @@ def tokenize_prompts(prompts, tokenizer, device, padding_length=None):
     return {k: v.to(device) for k, v in enc.items()}
 
 
-def find_token_range(tokenizer, token_array, substring_orig: str) -> Tuple[int, int]:
-    """[start, end) of the tokens that spell `substring_orig` inside `token_array`."""
+def find_token_range(tokenizer, token_array, substring_orig: str, piece_cache: Optional[Dict[int, str]] = None) -> Tuple[int, int]:
+    """[start, end) of the tokens that spell `substring_orig` inside `token_array`.  `piece_cache` memoises the
+    per-token decodes across the prompts of one edit (thousands of prompts share a few hundred distinct tokens)."""
     if substring_orig == "[CLS]":
         return (0, 1)
     if substring_orig in ("[EOS]", "", " "):
         return (len(token_array) - 1, len(token_array))
     needle = substring_orig.replace(" ", "").lower()
-    pieces = [tokenizer.decode([t]) for t in token_array]
+    if piece_cache is None:
+        pieces = [tokenizer.decode([t]) for t in token_array]
+    else:
+        pieces = []
+        for t in token_array:
+            t = int(t)
+            piece = piece_cache.get(t)
+            if piece is None:
+                piece = piece_cache[t] = tokenizer.decode([t])
+            pieces.append(piece)
     haystack = tokenizer.decode(token_array).replace(" ", "")
     if "’" in needle:
         haystack = haystack.replace("'", "’")
@@ -123,15 +133,16 @@ def prepare_lookup(tok, requests: List[Dict], num_fact_token: int, device):
     prompts, subjects, counts = _prompts_and_subjects(requests)
     enc = tokenize_prompts(prompts, tok, device)
     # token ids as host lists: find_token_range walks them one by one (a device tensor would cost a sync per token)
+    pieces: Dict[int, str] = {}
     if num_fact_token == 1:
-        lookup = [[find_token_range(tok, ids, w)[-1] - 1] for ids, w in zip(enc["input_ids"].tolist(), subjects)]
+        lookup = [[find_token_range(tok, ids, w, pieces)[-1] - 1] for ids, w in zip(enc["input_ids"].tolist(), subjects)]
     else:
         extra = num_fact_token - 2
         enc = tokenize_prompts(prompts, tok, device, padding_length=len(enc["input_ids"][0]) + extra)
         lookup = []
         for ids, w, n_valid in zip(enc["input_ids"].tolist(), subjects, enc["attention_mask"].sum(1).tolist()):
             eos = int(n_valid) - 1
-            lookup.append([find_token_range(tok, ids, w)[-1] - 1] + list(range(eos, eos + extra + 1)))
+            lookup.append([find_token_range(tok, ids, w, pieces)[-1] - 1] + list(range(eos, eos + extra + 1)))
     return enc, lookup, counts, next(_SERIAL)
 
 

@@ -130,19 +130,23 @@ class WordHashTokenizer:
         prompts = [prompts] if isinstance(prompts, str) else prompts
         enc = [self.encode(p, max_length=max_length if truncation else None) for p in prompts]
         width = max(len(e) for e in enc) if padding is True else (max_length or self.model_max_length)
-        ids = torch.full((len(enc), width), self.eos, dtype=torch.long)
-        mask = torch.zeros((len(enc), width), dtype=torch.long)
-        for i, e in enumerate(enc):
-            ids[i, : len(e)] = torch.tensor(e)
-            mask[i, : len(e)] = 1
+        enc = [e[:width] for e in enc]
+        ids = torch.tensor([e + [self.eos] * (width - len(e)) for e in enc], dtype=torch.long)
+        mask = torch.tensor([[1] * len(e) + [0] * (width - len(e)) for e in enc], dtype=torch.long)
         return {"input_ids": ids, "attention_mask": mask}
 
     def decode(self, ids):
         if torch.is_tensor(ids):
             ids = ids.tolist()
         ids = [ids] if isinstance(ids, int) else ids
-        names = {self.bos: "<|startoftext|>", self.eos: "<|endoftext|>"}
-        return " ".join(names.get(int(i)) or self._words.get(int(i), f"w{int(i)}") for i in ids)
+        return " ".join(self._piece(int(i)) for i in ids)
+
+    def _piece(self, i: int) -> str:
+        if i == self.bos:
+            return "<|startoftext|>"
+        if i == self.eos:
+            return "<|endoftext|>"
+        return self._words.get(i) or f"w{i}"
 
 
 def make_edit_requests(n: int):
