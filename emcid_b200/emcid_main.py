@@ -92,6 +92,46 @@ def upd_matrix_match_shape(matrix: torch.Tensor, shape: torch.Size) -> torch.Ten
                      "Check for bugs in the code?")
 
 
+def _read_npz_array(path, key: str) -> np.ndarray:
+    """`np.load(path)[key]` for the v* cache files (emcid_main.py:886-901: `np.savez(file, v_star=...)`, one small stored
+    array per file).  np.load spends ~90 us per file in zipfile / NpzFile machinery, which is most of a 1000-concept edit's
+    host time; the stored member can be located from the local file header alone.  Anything unexpected (compression, another
+    member first, object arrays, fortran order) falls back to np.load."""
+    import ast
+    import struct
+
+    try:
+        with open(path, "rb") as f:
+            raw = f.read()
+        if raw[:4] != b"PK\x03\x04":
+            raise ValueError
+        method, = struct.unpack_from("<H", raw, 8)
+        n_name, n_extra = struct.unpack_from("<HH", raw, 26)
+        name = raw[30:30 + n_name].decode()
+        if method != 0 or name != key + ".npy":
+            raise ValueError
+        off = 30 + n_name + n_extra
+        if raw[off:off + 6] != b"\x93NUMPY":
+            raise ValueError
+        major = raw[off + 6]
+        if major == 1:
+            hlen, = struct.unpack_from("<H", raw, off + 8)
+            hstart = off + 10
+        else:
+            hlen, = struct.unpack_from("<I", raw, off + 8)
+            hstart = off + 12
+        header = ast.literal_eval(raw[hstart:hstart + hlen].decode("latin1"))
+        dtype = np.dtype(header["descr"])
+        if header["fortran_order"] or dtype.hasobject:
+            raise ValueError
+        shape = tuple(header["shape"])
+        count = int(np.prod(shape)) if shape else 1
+        data = hstart + hlen
+        return np.frombuffer(raw, dtype=dtype, count=count, offset=data).reshape(shape).copy()
+    except (ValueError, KeyError, SyntaxError, struct.error, IndexError):
+        return np.load(path)[key]
+
+
 def _load_vstars(requests, hparams, cache_name, device, suffix=""):
     zs = []
     for idx, request in enumerate(requests):
@@ -106,7 +146,7 @@ def _load_vstars(requests, hparams, cache_name, device, suffix=""):
             raise NotImplementedError(
                 f"v_star cache miss for request {request['source']!r} ({path}): stage 1 (compute_z, UNet/VAE "
                 "optimisation) is outside the B200 hot path — precompute v_star with the reference")
-        zs.append(torch.from_numpy(np.load(path)["v_star"]))
+        zs.append(torch.from_numpy(_read_npz_array(path, "v_star")))
     # stacked on the host, one H2D copy (the reference moves every v* separately, :892-901)
     if getattr(hparams, "use_new_compute_z", False):
         z = torch.stack(zs, dim=0).to(device)           # [rq, num, h]

@@ -273,3 +273,23 @@ def test_hparams_load_like_the_reference(tmp_path):
         for path in glob.glob("/root/reference/hparams/*.json"):
             loaded = emcid_b200.EMCIDHyperParams.from_json(path)
             assert loaded.rewrite_module_tmp.endswith("mlp.fc2") and loaded.mom2_dtype == "float32", path
+
+
+def test_fast_npz_reader_equals_numpy_load(tmp_path):
+    """v* cache files (emcid_main.py:886-901) are read from the zip's local file header; everything the fast path does not
+    cover falls back to np.load."""
+    cases = {"plain": dict(v_star=np.random.default_rng(0).standard_normal(768).astype(np.float32)),
+             "two_d_f64": dict(v_star=np.arange(12.0).reshape(3, 4)),
+             "scalar": dict(v_star=np.float32(2.5)),
+             "second_member": dict(other=np.ones(3), v_star=np.arange(5)),
+             "fortran": dict(v_star=np.asfortranarray(np.arange(6.0).reshape(2, 3)))}
+    for name, arrays in cases.items():
+        f = tmp_path / f"{name}.npz"
+        np.savez(f, **arrays)
+        got, want = emcid_main._read_npz_array(f, "v_star"), np.load(f)["v_star"]
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want), name
+    f = tmp_path / "compressed.npz"
+    np.savez_compressed(f, v_star=np.arange(7.0))
+    assert np.array_equal(emcid_main._read_npz_array(f, "v_star"), np.arange(7.0))
+    with pytest.raises(KeyError):
+        emcid_main._read_npz_array(tmp_path / "plain.npz", "absent")
