@@ -334,6 +334,34 @@ def test_native_key_extraction_resumes_after_fc2_edit(dev, monkeypatch, kind, la
         clip_forward.release_key_encoders()
 
 
+@pytest.mark.parametrize("max_pos,heads", [(128, 2), (48, 2), (77, 1)])
+def test_native_forward_other_caption_lengths(dev, max_pos, heads):
+    """Head dim 64 with other position limits than CLIP's 77: up to 128 tokens (the 8-chunk attention instantiation, 16 KB
+    tiles, two CTAs per SM), 48 tokens (3 S chunks) and a single 77-token head; hidden states against an fp64 copy."""
+    import copy
+    from emcid_b200 import clip_forward
+    model = rh.make_clip_text_model("tiny", seed=6, hidden_size=64 * heads, num_attention_heads=heads,
+                                    max_position_embeddings=max_pos, num_hidden_layers=2).to(dev)
+    caps = rh.make_captions(70, model.config.vocab_size, seed=8, min_len=1, max_len=max_pos)
+    caps[0] = rh.make_captions(1, model.config.vocab_size, seed=9, max_len=max_pos, full=True)[0]   # one full-length caption
+    batch = {k: v.to(dev) for k, v in _padded(caps).items()}
+    keep = batch["attention_mask"].bool()
+    with torch.no_grad():
+        hs64 = copy.deepcopy(model).double()(**batch, output_hidden_states=True).hidden_states
+        hs32 = model(**batch, output_hidden_states=True).hidden_states
+    ids, pos, cu, S, T = clip_forward.pack_batch(batch, max_pos)
+    nat = clip_forward.NativeClipTextEncoder(model, T, S)
+    try:
+        for n in (1, 2):
+            h = nat.forward_hidden(ids, pos, cu, S, T, n)
+            ref = hs64[n][keep]
+            err = float((h.double() - ref).norm() / ref.norm())
+            err_hf = float((hs32[n][keep].double() - ref).norm() / ref.norm())
+            assert err < max(3e-6, 3 * err_hf), (n, err, err_hf)
+    finally:
+        nat.close()
+
+
 def test_native_forward_falls_back_on_non_right_padding(dev, tmp_path):
     """A mask that is not a right-padding mask cannot be packed: the block goes through the HF forward with the
     fused kernels hooked in, and the statistics still match a direct masked Gram."""
