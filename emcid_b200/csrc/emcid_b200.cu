@@ -156,4 +156,22 @@ int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* 
                       dW, refine_steps, workspace, workspace_bytes, status_dev, static_cast<cudaStream_t>(stream));
 }
 
+/* cached factorisation for repeated edits with the same covariance */
+int emcid_factor_create(emcid_factor_t** out, int device, int d, const float* C32, double lambda, int* status_dev,
+                        void* stream) {
+  return factor_create(reinterpret_cast<FactorHandle**>(out), device, d, C32, lambda, status_dev,
+                       static_cast<cudaStream_t>(stream));
+}
+
+size_t emcid_factor_solve_workspace_bytes(int d, int h, int n) { (void)h; return factor_solve_workspace_bytes(d, n); }
+
+int emcid_factor_solve(emcid_factor_t* f, int h, int n, const float* Kt, long long ldk, const float* St, long long lds,
+                       double scale, double inv_layers_left, double* adj_k, double* resid, float* dW, int refine_steps,
+                       void* workspace, size_t workspace_bytes, int* status_dev, void* stream) {
+  return factor_solve(reinterpret_cast<FactorHandle*>(f), h, n, Kt, ldk, St, lds, scale, inv_layers_left, adj_k, resid, dW,
+                      refine_steps, workspace, workspace_bytes, status_dev, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_factor_destroy(emcid_factor_t* f) { return factor_destroy(reinterpret_cast<FactorHandle*>(f)); }
+
 }  // extern "C"

@@ -51,11 +51,18 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
   const int b = blockIdx.x;
   const long long base = static_cast<long long>(b) * d * d + static_cast<long long>(k) * SOLVE_NB * d + k * SOLVE_NB;
   const int tid = threadIdx.x;
+#ifdef EMCID_POTRF_TIMING
+  long long tk[8]; tk[0] = clock64();
+#define EMCID_TK(i) tk[i] = clock64()
+#else
+#define EMCID_TK(i)
+#endif
   for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
     const int r = e / SOLVE_NB, c = e % SOLVE_NB;
     A[r * LD + c] = (c <= r) ? static_cast<double>(M32[base + static_cast<long long>(r) * d + c]) : 0.0;
   }
   __syncthreads();
+  EMCID_TK(1);
   // Right-looking Cholesky in 32-column panels.  Inside a panel every column costs two barriers and a rank-1 update
   // restricted to the panel's own columns (lane = column, warp = row phase); the rest of the block is updated once
   // per panel with a 32-deep product (4 independent rows in flight per thread).  Loads are grouped ahead of the
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
       __syncthreads();
     }
   }
+  EMCID_TK(2);
   // L_kk -> LL planes (lower = L, upper = L^T)
   for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
     const int r = e / SOLVE_NB, c = e % SOLVE_NB;
@@ -140,6 +148,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
     LL_lo[base + static_cast<long long>(r) * d + c] = lo;
   }
   __syncthreads();
+  EMCID_TK(3);
   // In-place inverse X = L^-1 in 32 x 32 blocks.
   // (1) the four diagonal blocks, one warp each (column sweep from the right, warp-synchronous):
   //       X[l][j] = -(sum_{k=j+1..l} X[l][k] L[k][j]) / L[j][j]
@@ -167,6 +176,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
     }
   }
   __syncthreads();
+  EMCID_TK(4);
   // (2) block columns from the right (from X L = I):  X_ij = -(sum_{k=j+1..i} X_ik L_kj) X_jj   for i > j.
   //     Phase a gathers the sums of a whole block column into T (L_kj of that column is still intact and the X_ik
   //     to its right are final); phase b multiplies by the diagonal block and overwrites L_ij.
@@ -200,6 +210,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
     }
     __syncthreads();
   }
+  EMCID_TK(5);
   const long long ibase = (static_cast<long long>(b) * d + static_cast<long long>(k) * SOLVE_NB) * SOLVE_NB;
   for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
     const int r = e / SOLVE_NB, c = e % SOLVE_NB;
@@ -219,6 +230,14 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
       LvT_lo[base + static_cast<long long>(r) * d + c] = lo;
     }
   }
+#ifdef EMCID_POTRF_TIMING
+  __syncthreads();
+  EMCID_TK(6);
+  if (tid == 0 && b == 0 && k == 3)
+    printf("potrf clk: load %lld chol %lld LLwrite %lld diaginv %lld blkinv %lld out %lld total %lld\n", tk[1] - tk[0], tk[2] - tk[1],
+           tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[6] - tk[0]);
+#endif
+#undef EMCID_TK
 }
 
 // ---- operand preparation ----------------------------------------------------------------------------
@@ -247,6 +266,7 @@ __global__ void solve_prep_kernel(const float* __restrict__ Kt, long long ldk, l
     }
   }
   __syncthreads();
+  if (!Kd64) return;   // cached-factor path: K K^T is never formed, the [d x n] copies are not needed
   for (int r = ty; r < 32; r += 8) {
     const int i = i0 + r, c = c0 + tx;
     if (i < d && c < n_pad) {
@@ -343,60 +363,91 @@ __global__ void resid_kernel(const float* __restrict__ St, long long lds, long l
   }
 }
 
-// ---- workspace --------------------------------------------------------------------------------------
-struct SolveWs {
-  // fp32
-  float *M32, *Mp_hi, *Mp_lo, *LL_hi, *LL_lo, *Li_hi, *Li_lo, *LiT_hi, *LiT_lo, *W, *Wp_hi, *Wp_lo, *Kd_hi, *Kd_lo;
-  float *Lv_hi, *Lv_lo, *LvT_hi, *LvT_lo;   // explicit inverse L^-1 and its transpose (planes)
-  float *Tp_hi, *Tp_lo;                     // [B][d x 128] scratch of the inverse's block-column step
-  float *W2p_hi, *W2p_lo;                   // [B][n_pad x d] intermediate of an application (planes of Linv-applied rhs)
-  // fp64
-  double *M64, *Ks64t, *X64t, *Kd64, *inv_left, *norms;
-  size_t bytes;
-};
-
-inline SolveWs solve_carve(void* base, int B, int d, int h, int n) {
-  (void)h;
-  const long long n_pad = round_up_ll(n, 128);
-  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* p0 = p;
-  auto take = [&](size_t bytes) { uint8_t* r = p; p += (bytes + 1023) & ~static_cast<size_t>(1023); return r; };
-  SolveWs w;
-  const size_t dd = static_cast<size_t>(B) * d * d, nd = static_cast<size_t>(B) * n_pad * d,
-               d128 = static_cast<size_t>(B) * d * SOLVE_NB;
-  w.M64 = reinterpret_cast<double*>(take(dd * 8));
-  w.Ks64t = reinterpret_cast<double*>(take(nd * 8));
-  w.X64t = reinterpret_cast<double*>(take(nd * 8));
-  w.Kd64 = reinterpret_cast<double*>(take(nd * 8));
-  w.inv_left = reinterpret_cast<double*>(take(static_cast<size_t>(B) * 8));
-  w.norms = reinterpret_cast<double*>(take(2 * 8));
-  w.M32 = reinterpret_cast<float*>(take(dd * 4));
-  w.Mp_hi = reinterpret_cast<float*>(take(dd * 4));
-  w.Mp_lo = reinterpret_cast<float*>(take(dd * 4));
-  w.LL_hi = reinterpret_cast<float*>(take(dd * 4));
-  w.LL_lo = reinterpret_cast<float*>(take(dd * 4));
-  w.Li_hi = reinterpret_cast<float*>(take(d128 * 4));
-  w.Li_lo = reinterpret_cast<float*>(take(d128 * 4));
-  w.LiT_hi = reinterpret_cast<float*>(take(d128 * 4));
-  w.LiT_lo = reinterpret_cast<float*>(take(d128 * 4));
-  w.W = reinterpret_cast<float*>(take(nd * 4));
-  w.Wp_hi = reinterpret_cast<float*>(take(nd * 4));
-  w.Wp_lo = reinterpret_cast<float*>(take(nd * 4));
-  w.Kd_hi = reinterpret_cast<float*>(take(nd * 4));
-  w.Kd_lo = reinterpret_cast<float*>(take(nd * 4));
-  w.Lv_hi = reinterpret_cast<float*>(take(dd * 4));
-  w.Lv_lo = reinterpret_cast<float*>(take(dd * 4));
-  w.LvT_hi = reinterpret_cast<float*>(take(dd * 4));
-  w.LvT_lo = reinterpret_cast<float*>(take(dd * 4));
-  w.Tp_hi = reinterpret_cast<float*>(take(d128 * 4));
-  w.Tp_lo = reinterpret_cast<float*>(take(d128 * 4));
-  w.W2p_hi = reinterpret_cast<float*>(take(nd * 4));
-  w.W2p_lo = reinterpret_cast<float*>(take(nd * 4));
-  w.bytes = static_cast<size_t>(p - p0) + 1024;
-  return w;
+// ---- kernels of the cached-factor path ----------------------------------------------------------------
+// W = float(R), planes = split(W)   (fp64 right-hand side -> operand of the fp32-class application)
+__global__ void rhs_from64_kernel(const double* __restrict__ R, long long total, float* __restrict__ W,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float f = static_cast<float>(R[i]);
+    float h, l;
+    split_tf32(f, h, l);
+    W[i] = f; hi[i] = h; lo[i] = l;
+  }
 }
 
-inline size_t solve_workspace_bytes(int B, int d, int h, int n) { return solve_carve(nullptr, B, d, h, n).bytes; }
+// A32 = float(lambda) * C32 (+ planes) and A64 = lambda * double(C32), lower 32x32 tiles mirrored to the upper ones
+// (same roundings as the direct path: fp32 product in the SYRK epilogue, fp64 product in the DMMA epilogue).
+__global__ void factor_prep_kernel(const float* __restrict__ C32, int d, double lambda, float* __restrict__ A32,
+                                   float* __restrict__ Ap_hi, float* __restrict__ Ap_lo, double* __restrict__ A64) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const float lf = static_cast<float>(lambda);
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = C32[static_cast<long long>(bi * 32 + r) * d + bj * 32 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    float c = tile[r][tx];
+    if (bi == bj && tx > r) c = tile[tx][r];
+    const long long o = static_cast<long long>(bi * 32 + r) * d + bj * 32 + tx;
+    const float a = lf * c;
+    float h, l;
+    split_tf32(a, h, l);
+    A32[o] = a; Ap_hi[o] = h; Ap_lo[o] = l;
+    A64[o] = lambda * static_cast<double>(c);
+    if (bi != bj) {
+      const float ct = tile[tx][r];
+      const long long ot = static_cast<long long>(bj * 32 + r) * d + bi * 32 + tx;
+      const float at = lf * ct;
+      split_tf32(at, h, l);
+      A32[ot] = at; Ap_hi[ot] = h; Ap_lo[ot] = l;
+      A64[ot] = lambda * static_cast<double>(ct);
+    }
+  }
+}
+
+// G (lower 32x32 tiles of the raw product Ks^T Y) -> G64 = I + that, mirrored to a full symmetric matrix in place, with
+// its fp32 copy and planes.
+__global__ void g_prepare_kernel(double* __restrict__ G64, int m, float* __restrict__ G32, float* __restrict__ Gp_hi,
+                                 float* __restrict__ Gp_lo) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = G64[static_cast<long long>(bi * 32 + r) * m + bj * 32 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    double v = tile[r][tx];
+    if (bi == bj) {
+      if (tx > r) v = tile[tx][r];
+      if (tx == r) v += 1.0;
+    }
+    const long long o = static_cast<long long>(bi * 32 + r) * m + bj * 32 + tx;
+    float f = static_cast<float>(v), h, l;
+    split_tf32(f, h, l);
+    G64[o] = v; G32[o] = f; Gp_hi[o] = h; Gp_lo[o] = l;
+    if (bi != bj) {
+      const double vt = tile[tx][r];
+      const long long ot = static_cast<long long>(bj * 32 + r) * m + bi * 32 + tx;
+      f = static_cast<float>(vt);
+      split_tf32(f, h, l);
+      G64[ot] = vt; G32[ot] = f; Gp_hi[ot] = h; Gp_lo[ot] = l;
+    }
+  }
+}
+
+// out [rows x n] = in [rows x n_pad][:, :n]
+__global__ void compact_cols_kernel(const double* __restrict__ in, long long rows, int n, int n_pad,
+                                    double* __restrict__ out) {
+  const long long total = rows * n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / n;
+    const int c = static_cast<int>(i - r * n);
+    out[i] = in[r * n_pad + c];
+  }
+}
 
 // ---- 3xTF32 GEMM helper on sub-matrices of stacked batched tensors --------------------------------------
 struct PlaneMaps {
@@ -445,7 +496,342 @@ inline int run_subgemm(const SubGemm& g, int batches, int sm_count, cudaStream_t
   return launch_gemm3x<128, 3, EPI_GENERIC>(ops, p, grid, stream, batches);
 }
 
-// ---- the solve -----------------------------------------------------------------------------------------
+inline bool solve_use_trsm() {
+  // EMCID_SOLVE_TRSM=1: blocked TRSM sweeps instead of the explicit inverse
+  static const bool v = [] { const char* e = getenv("EMCID_SOLVE_TRSM"); return e && e[0] == '1'; }();
+  return v;
+}
+
+inline int potrf_smem_bytes() { return (SOLVE_NB * (SOLVE_NB + 1) + 2 * SOLVE_NB + 96 * 33) * sizeof(double); }
+
+inline int potrf_configure(int device) {
+  static thread_local bool configured[16] = {false};
+  if (device < 0 || device >= 16 || !configured[device]) {
+    EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem_bytes()));
+    if (device >= 0 && device < 16) configured[device] = true;
+  }
+  return EMCID_OK;
+}
+
+// ---- blocked factorisation of B stacked SPD [dim x dim] matrices ------------------------------------------
+// In: M32 (lower tiles) and its planes Mp.  Out: L / L^T planes in LL (TRSM mode also Li / LiT), the explicit inverse
+// L^-1 / L^-T planes in Lv / LvT (unless `trsm`).  M32 / Mp are overwritten by the trailing updates.
+struct FactorCtx {
+  int B, dim, sms;
+  bool trsm;
+  float *M32, *Mp_hi, *Mp_lo, *LL_hi, *LL_lo, *Li_hi, *Li_lo, *LiT_hi, *LiT_lo;
+  float *Lv_hi, *Lv_lo, *LvT_hi, *LvT_lo;   // explicit inverse L^-1 and its transpose (planes)
+  float *Tp_hi, *Tp_lo;                     // [B][dim x 128] scratch of the inverse's block-column step
+  PlaneMaps mMp, mLL, mLi, mLiT, mLv, mLvT, mTp;
+};
+
+// maps of the explicit inverse only (all an application needs unless `trsm`)
+inline int factor_make_inverse_maps(FactorCtx& f) {
+  const long long rows = static_cast<long long>(f.B) * f.dim;
+  int rc;
+  if ((rc = make_plane_maps(&f.mLv, f.Lv_hi, f.Lv_lo, rows, f.dim, f.dim))) return rc;
+  return make_plane_maps(&f.mLvT, f.LvT_hi, f.LvT_lo, rows, f.dim, f.dim);
+}
+
+inline int factor_make_maps(FactorCtx& f) {
+  const long long rows = static_cast<long long>(f.B) * f.dim;
+  int rc;
+  if ((rc = make_plane_maps(&f.mMp, f.Mp_hi, f.Mp_lo, rows, f.dim, f.dim)) ||
+      (rc = make_plane_maps(&f.mLL, f.LL_hi, f.LL_lo, rows, f.dim, f.dim)) ||
+      (rc = make_plane_maps(&f.mLi, f.Li_hi, f.Li_lo, rows, SOLVE_NB, SOLVE_NB)) ||
+      (rc = make_plane_maps(&f.mLiT, f.LiT_hi, f.LiT_lo, rows, SOLVE_NB, SOLVE_NB)) ||
+      (rc = make_plane_maps(&f.mTp, f.Tp_hi, f.Tp_lo, rows, SOLVE_NB, SOLVE_NB)))
+    return rc;
+  return factor_make_inverse_maps(f);
+}
+
+// planes whose untouched halves a TMA box may still read must not hold NaN patterns
+inline int factor_clear(const FactorCtx& f, cudaStream_t stream) {
+  const size_t bytes = static_cast<size_t>(f.B) * f.dim * f.dim * sizeof(float);
+  EMCID_CUDA_CHECK(cudaMemsetAsync(f.LL_hi, 0, bytes, stream));
+  EMCID_CUDA_CHECK(cudaMemsetAsync(f.LL_lo, 0, bytes, stream));
+  if (!f.trsm) {
+    // the strictly upper (Lv) / lower (LvT) blocks are never written and never read by the k_tri-limited products;
+    // zero them anyway so that no stale NaN pattern can ever reach a TMA box
+    EMCID_CUDA_CHECK(cudaMemsetAsync(f.Lv_hi, 0, bytes, stream));
+    EMCID_CUDA_CHECK(cudaMemsetAsync(f.Lv_lo, 0, bytes, stream));
+    EMCID_CUDA_CHECK(cudaMemsetAsync(f.LvT_hi, 0, bytes, stream));
+    EMCID_CUDA_CHECK(cudaMemsetAsync(f.LvT_lo, 0, bytes, stream));
+  }
+  return EMCID_OK;
+}
+
+inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) {
+  const int B = f.B, d = f.dim, sms = f.sms;
+  const int nblk = d / SOLVE_NB;
+  const long long dd = static_cast<long long>(d) * d;
+  int rc;
+  // blocked right-looking Cholesky of M32
+  for (int k = 0; k < nblk; ++k) {
+    potrf_diag_kernel<<<B, 256, potrf_smem_bytes(), stream>>>(f.M32, d, k, f.LL_hi, f.LL_lo, f.Li_hi, f.Li_lo, f.LiT_hi,
+                                                              f.LiT_lo, f.trsm ? nullptr : f.Lv_hi, f.Lv_lo, f.LvT_hi,
+                                                              f.LvT_lo, status_dev);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    const int rem = d - (k + 1) * SOLVE_NB;
+    if (rem <= 0) break;
+    const long long off_panel = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k) * SOLVE_NB;
+    const long long off_panel_t = static_cast<long long>(k) * SOLVE_NB * d + static_cast<long long>(k + 1) * SOLVE_NB;
+    const long long off_trail = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k + 1) * SOLVE_NB;
+    SubGemm g;
+    memset(&g, 0, sizeof(g));  // panel: L_ik = M_ik Linv_kk^T
+    g.A = &f.mMp; g.a_row0 = (k + 1) * SOLVE_NB; g.a_col0 = k * SOLVE_NB; g.a_batch_rows = d;
+    g.B = &f.mLi; g.b_row0 = k * SOLVE_NB; g.b_col0 = 0; g.b_batch_rows = d;
+    g.M = rem; g.N = SOLVE_NB; g.K = SOLVE_NB;
+    g.alpha = 1.0f; g.beta = 0.0f;
+    g.P_hi = f.LL_hi + off_panel; g.P_lo = f.LL_lo + off_panel; g.ldp = d; g.p_batch = dd;
+    g.Pt_hi = f.LL_hi + off_panel_t; g.Pt_lo = f.LL_lo + off_panel_t; g.ldpt = d; g.pt_batch = dd;
+    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+    memset(&g, 0, sizeof(g));  // trailing: M_ij -= L_ik L_jk^T
+    g.A = &f.mLL; g.a_row0 = (k + 1) * SOLVE_NB; g.a_col0 = k * SOLVE_NB; g.a_batch_rows = d;
+    g.B = &f.mLL; g.b_row0 = (k + 1) * SOLVE_NB; g.b_col0 = k * SOLVE_NB; g.b_batch_rows = d;
+    g.M = rem; g.N = rem; g.K = SOLVE_NB; g.lower = 1;
+    g.alpha = -1.0f; g.beta = 1.0f;
+    g.Cin = f.M32 + off_trail; g.ldcin = d; g.cin_batch = dd;
+    g.C = f.M32 + off_trail; g.ldc = d; g.c_batch = dd;
+    g.P_hi = f.Mp_hi + off_trail; g.P_lo = f.Mp_lo + off_trail; g.ldp = d; g.p_batch = dd;
+    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+  }
+  if (f.trsm) return EMCID_OK;
+  // explicit inverse, block columns from the right (the diagonal blocks came from potrf_diag_kernel):
+  //        T          = Linv[k+1:, k+1:] L[k+1:, k]        (A lower triangular: k_tri = 3)
+  //        Linv[k+1:, k] = -T Linv_kk                      (planes into Lv, transposed planes into LvT)
+  for (int k = nblk - 2; k >= 0; --k) {
+    const int r0 = (k + 1) * SOLVE_NB, rem = d - r0;
+    SubGemm g;
+    memset(&g, 0, sizeof(g));
+    g.A = &f.mLv; g.a_row0 = r0; g.a_col0 = r0; g.a_batch_rows = d;
+    g.B = &f.mLL; g.b_row0 = k * SOLVE_NB; g.b_col0 = r0; g.b_batch_rows = d;   // upper blocks of LL hold L^T
+    g.M = rem; g.N = SOLVE_NB; g.K = rem; g.k_tri = 3;
+    g.alpha = 1.0f;
+    g.P_hi = f.Tp_hi + static_cast<long long>(r0) * SOLVE_NB; g.P_lo = f.Tp_lo + static_cast<long long>(r0) * SOLVE_NB;
+    g.ldp = SOLVE_NB; g.p_batch = static_cast<long long>(d) * SOLVE_NB;
+    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+    memset(&g, 0, sizeof(g));
+    g.A = &f.mTp; g.a_row0 = r0; g.a_col0 = 0; g.a_batch_rows = d;
+    g.B = &f.mLiT; g.b_row0 = k * SOLVE_NB; g.b_col0 = 0; g.b_batch_rows = d;
+    g.M = rem; g.N = SOLVE_NB; g.K = SOLVE_NB;
+    g.alpha = -1.0f;
+    const long long off = static_cast<long long>(r0) * d + static_cast<long long>(k) * SOLVE_NB;
+    const long long off_t = static_cast<long long>(k) * SOLVE_NB * d + r0;
+    g.P_hi = f.Lv_hi + off; g.P_lo = f.Lv_lo + off; g.ldp = d; g.p_batch = dd;
+    g.Pt_hi = f.LvT_hi + off_t; g.Pt_lo = f.LvT_lo + off_t; g.ldpt = d; g.pt_batch = dd;
+    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+  }
+  return EMCID_OK;
+}
+
+// ---- refined application of a factorisation ---------------------------------------------------------------
+// Solves  X M = R  for B stacked problems with the right-hand sides held TRANSPOSED ([rows_pad x dim], dim contiguous;
+// rows = number of right-hand sides, pad rows zero):   X^T = Linv^T (Linv R^T)  in fp32-class arithmetic, then
+// fp64-residual refinement against M64.  On entry W / Wp hold float(R) and its planes unless `rhs_from64`.
+struct ApplyCtx {
+  int rows, rows_pad;
+  const double* M64;     // [B][dim x dim] fp64, full symmetric
+  const double* R64t;    // [B][rows_pad x dim]
+  float *W, *Wp_hi, *Wp_lo, *W2p_hi, *W2p_lo;   // [B][rows_pad x dim]
+  double* X64t;          // [B][rows_pad x dim] result
+  double* norms;         // [2]
+  PlaneMaps mW, mW2;
+};
+
+inline int apply_make_maps(ApplyCtx& a, int B, int dim) {
+  int rc;
+  if ((rc = make_plane_maps(&a.mW, a.Wp_hi, a.Wp_lo, static_cast<long long>(B) * a.rows_pad, dim, dim))) return rc;
+  return make_plane_maps(&a.mW2, a.W2p_hi, a.W2p_lo, static_cast<long long>(B) * a.rows_pad, dim, dim);
+}
+
+inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64, int refine_steps, cudaStream_t stream) {
+  const int B = f.B, d = f.dim, sms = f.sms, n = a.rows, n_pad = a.rows_pad;
+  const int nblk = d / SOLVE_NB;
+  const long long dd = static_cast<long long>(d) * d, nd = static_cast<long long>(n_pad) * d;
+  const long long tot = static_cast<long long>(B) * nd;
+  int rc;
+  //   Y^T = W Linv^T  (B = Linv, lower triangular: k_tri = 1)  ->  planes only
+  //   X^T = Y^T Linv  (B = Linv^T, upper triangular: k_tri = 2) ->  fp32 into W
+  auto apply_inverse = [&]() -> int {
+    SubGemm g;
+    memset(&g, 0, sizeof(g));
+    g.A = &a.mW; g.a_batch_rows = n_pad;
+    g.B = &f.mLv; g.b_batch_rows = d;
+    g.M = n_pad; g.N = d; g.K = d; g.k_tri = 1; g.alpha = 1.0f;
+    g.P_hi = a.W2p_hi; g.P_lo = a.W2p_lo; g.ldp = d; g.p_batch = nd;
+    if (int r = run_subgemm(g, B, sms, stream)) return r;
+    memset(&g, 0, sizeof(g));
+    g.A = &a.mW2; g.a_batch_rows = n_pad;
+    g.B = &f.mLvT; g.b_batch_rows = d;
+    g.M = n_pad; g.N = d; g.K = d; g.k_tri = 2; g.alpha = 1.0f;
+    g.C = a.W; g.ldc = d; g.c_batch = nd;
+    return run_subgemm(g, B, sms, stream);
+  };
+  auto trsm_both = [&]() -> int {
+    SubGemm g;
+    for (int i = 0; i < nblk; ++i) {  // forward: Y^T L^T = W
+      memset(&g, 0, sizeof(g));
+      g.A = &a.mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
+      g.B = &f.mLi; g.b_row0 = i * SOLVE_NB; g.b_batch_rows = d;
+      g.M = n_pad; g.N = SOLVE_NB; g.K = SOLVE_NB; g.alpha = 1.0f;
+      g.C = a.W + i * SOLVE_NB; g.ldc = d; g.c_batch = nd;
+      g.P_hi = a.Wp_hi + i * SOLVE_NB; g.P_lo = a.Wp_lo + i * SOLVE_NB; g.ldp = d; g.p_batch = nd;
+      if (int r = run_subgemm(g, B, sms, stream)) return r;
+      const int rem = d - (i + 1) * SOLVE_NB;
+      if (rem <= 0) break;
+      memset(&g, 0, sizeof(g));
+      g.A = &a.mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
+      g.B = &f.mLL; g.b_row0 = (i + 1) * SOLVE_NB; g.b_col0 = i * SOLVE_NB; g.b_batch_rows = d;
+      g.M = n_pad; g.N = rem; g.K = SOLVE_NB; g.alpha = -1.0f; g.beta = 1.0f;
+      const long long off = static_cast<long long>(i + 1) * SOLVE_NB;
+      g.Cin = a.W + off; g.ldcin = d; g.cin_batch = nd;
+      g.C = a.W + off; g.ldc = d; g.c_batch = nd;
+      g.P_hi = a.Wp_hi + off; g.P_lo = a.Wp_lo + off; g.ldp = d; g.p_batch = nd;
+      if (int r = run_subgemm(g, B, sms, stream)) return r;
+    }
+    for (int i = nblk - 1; i >= 0; --i) {  // backward: X^T L = Y^T
+      memset(&g, 0, sizeof(g));
+      g.A = &a.mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
+      g.B = &f.mLiT; g.b_row0 = i * SOLVE_NB; g.b_batch_rows = d;
+      g.M = n_pad; g.N = SOLVE_NB; g.K = SOLVE_NB; g.alpha = 1.0f;
+      g.C = a.W + i * SOLVE_NB; g.ldc = d; g.c_batch = nd;
+      g.P_hi = a.Wp_hi + i * SOLVE_NB; g.P_lo = a.Wp_lo + i * SOLVE_NB; g.ldp = d; g.p_batch = nd;
+      if (int r = run_subgemm(g, B, sms, stream)) return r;
+      if (i == 0) break;
+      memset(&g, 0, sizeof(g));
+      g.A = &a.mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
+      g.B = &f.mLL; g.b_row0 = 0; g.b_col0 = i * SOLVE_NB; g.b_batch_rows = d;  // upper blocks hold L^T
+      g.M = n_pad; g.N = i * SOLVE_NB; g.K = SOLVE_NB; g.alpha = -1.0f; g.beta = 1.0f;
+      g.Cin = a.W; g.ldcin = d; g.cin_batch = nd;
+      g.C = a.W; g.ldc = d; g.c_batch = nd;
+      g.P_hi = a.Wp_hi; g.P_lo = a.Wp_lo; g.ldp = d; g.p_batch = nd;
+      if (int r = run_subgemm(g, B, sms, stream)) return r;
+    }
+    return EMCID_OK;
+  };
+
+  if (rhs_from64) {
+    rhs_from64_kernel<<<sms * 8, 256, 0, stream>>>(a.R64t, tot, a.W, a.Wp_hi, a.Wp_lo);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+  }
+  // refine_steps >= 0: exactly that many sweeps.  -1: adaptive — stop once the last correction is below
+  // SOLVE_ADAPT_TOL relative to the solution (each sweep contracts the error by ~1e-2 at cond ~1e7, so the
+  // error left after applying a correction of that size is orders of magnitude under the 1e-4 dW tolerance).
+  const bool adaptive = refine_steps < 0;
+  const int max_steps = adaptive ? SOLVE_ADAPT_MAX : refine_steps;
+  for (int it = 0; it <= max_steps; ++it) {
+    if (it > 0) {
+      // R^T = R0^T - X^T M64  (fp64), rounded to fp32 into W, then re-split
+      DgemmParams p;
+      memset(&p, 0, sizeof(p));
+      p.M = n; p.N = d; p.K = d;
+      p.A = a.X64t; p.lda = d; p.a_batch = nd;
+      p.B = a.M64; p.ldb = d; p.b_batch = dd;
+      p.alpha = -1.0; p.beta = 1.0;
+      p.Cin = a.R64t; p.ldcin = d; p.cin_batch = nd;
+      p.C32 = a.W; p.ldc32 = d; p.c32_batch = nd;
+      if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
+      if ((rc = launch_split_planes(a.W, d, B * n_pad, d, 1.0f, a.Wp_hi, a.Wp_lo, d, stream))) return rc;
+    }
+    if ((rc = f.trsm ? trsm_both() : apply_inverse())) return rc;
+    solve_axpy_kernel<<<sms * 8, 256, 0, stream>>>(a.W, a.X64t, tot, it > 0 ? 1 : 0);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    if (adaptive && it > 0) {
+      double hn[2] = {0.0, 0.0};
+      EMCID_CUDA_CHECK(cudaMemsetAsync(a.norms, 0, 2 * sizeof(double), stream));
+      solve_norms_kernel<<<sms * 4, 256, 0, stream>>>(a.W, a.X64t, tot, a.norms);
+      EMCID_CUDA_CHECK(cudaGetLastError());
+      EMCID_CUDA_CHECK(cudaMemcpyAsync(hn, a.norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      EMCID_CUDA_CHECK(cudaStreamSynchronize(stream));
+      if (!(hn[1] > 0.0) || hn[0] <= SOLVE_ADAPT_TOL * SOLVE_ADAPT_TOL * hn[1]) break;
+    }
+  }
+  return EMCID_OK;
+}
+
+// resid and dW = float(resid adj_k^T) from the finished adj_k (emcid_main.py:1048-1050)
+inline int solve_outputs(int B, int d, int h, int n, const float* St, long long lds, double scale,
+                         const double* inv_left_dev, const double* adj_k, double* resid, float* dW, cudaStream_t stream) {
+  resid_kernel<<<dim3((h + 31) / 32, (n + 31) / 32, B), dim3(32, 8), 0, stream>>>(
+      St, lds, static_cast<long long>(n) * lds, n, h, scale, inv_left_dev, resid);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  DgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = h; p.N = d; p.K = n;
+  p.A = resid; p.lda = n; p.a_batch = static_cast<long long>(h) * n;
+  p.B = adj_k; p.ldb = n; p.b_batch = static_cast<long long>(d) * n;
+  p.alpha = 1.0;
+  p.C32 = dW; p.ldc32 = d; p.c32_batch = static_cast<long long>(h) * d;
+  return launch_dgemm_nt(p, B, stream);
+}
+
+// ---- workspace of the direct solve ----------------------------------------------------------------------
+struct SolveWs {
+  FactorCtx f;
+  ApplyCtx a;
+  float *Kd_hi, *Kd_lo;
+  double *M64, *Ks64t, *Kd64, *inv_left;
+  size_t bytes;
+};
+
+struct Carver {
+  uint8_t *p, *p0;
+  explicit Carver(void* base)
+      : p(reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 1023) & ~static_cast<uintptr_t>(1023))), p0(p) {}
+  template <typename T>
+  T* take(size_t count) {
+    uint8_t* r = p;
+    p += (count * sizeof(T) + 1023) & ~static_cast<size_t>(1023);
+    return reinterpret_cast<T*>(r);
+  }
+  size_t bytes() const { return static_cast<size_t>(p - p0) + 1024; }
+};
+
+inline void carve_factor(Carver& c, FactorCtx& f, int B, int dim, bool with_inverse) {
+  const size_t dd = static_cast<size_t>(B) * dim * dim, d128 = static_cast<size_t>(B) * dim * SOLVE_NB;
+  f.M32 = c.take<float>(dd);
+  f.Mp_hi = c.take<float>(dd); f.Mp_lo = c.take<float>(dd);
+  f.LL_hi = c.take<float>(dd); f.LL_lo = c.take<float>(dd);
+  f.Li_hi = c.take<float>(d128); f.Li_lo = c.take<float>(d128);
+  f.LiT_hi = c.take<float>(d128); f.LiT_lo = c.take<float>(d128);
+  f.Tp_hi = c.take<float>(d128); f.Tp_lo = c.take<float>(d128);
+  if (with_inverse) {
+    f.Lv_hi = c.take<float>(dd); f.Lv_lo = c.take<float>(dd);
+    f.LvT_hi = c.take<float>(dd); f.LvT_lo = c.take<float>(dd);
+  }
+}
+
+inline void carve_apply(Carver& c, ApplyCtx& a, size_t elems) {
+  a.W = c.take<float>(elems);
+  a.Wp_hi = c.take<float>(elems); a.Wp_lo = c.take<float>(elems);
+  a.W2p_hi = c.take<float>(elems); a.W2p_lo = c.take<float>(elems);
+}
+
+inline SolveWs solve_carve(void* base, int B, int d, int h, int n) {
+  (void)h;
+  const long long n_pad = round_up_ll(n, 128);
+  Carver c(base);
+  SolveWs w;
+  memset(&w, 0, sizeof(w));
+  const size_t dd = static_cast<size_t>(B) * d * d, nd = static_cast<size_t>(B) * n_pad * d;
+  w.M64 = c.take<double>(dd);
+  w.Ks64t = c.take<double>(nd);
+  w.a.X64t = c.take<double>(nd);
+  w.Kd64 = c.take<double>(nd);
+  w.inv_left = c.take<double>(B);
+  w.a.norms = c.take<double>(2);
+  carve_factor(c, w.f, B, d, true);
+  carve_apply(c, w.a, nd);
+  w.Kd_hi = c.take<float>(nd);
+  w.Kd_lo = c.take<float>(nd);
+  w.bytes = c.bytes();
+  return w;
+}
+
+inline size_t solve_workspace_bytes(int B, int d, int h, int n) { return solve_carve(nullptr, B, d, h, n).bytes; }
+
+// ---- the direct solve ------------------------------------------------------------------------------------
 inline int solve_layers(int device, int B, int d, int h, int n, const float* C32, const float* Kt, long long ldk,
                         const float* St, long long lds, double lambda, double scale, const double* inv_left_host,
                         double* adj_k, double* resid, float* dW, int refine_steps, void* workspace, size_t ws_bytes,
@@ -464,53 +850,28 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
   if (rc) return rc;
   const int sms = info.sm_count;
   const int n_pad = static_cast<int>(round_up_ll(n, 128));
-  const int nblk = d / SOLVE_NB;
   SolveWs w = solve_carve(workspace, B, d, h, n);
-  const long long dd = static_cast<long long>(d) * d, nd = static_cast<long long>(n_pad) * d;
-
-  static thread_local bool potrf_configured[16] = {false};
-  const int potrf_smem = (SOLVE_NB * (SOLVE_NB + 1) + 2 * SOLVE_NB + 96 * 33) * sizeof(double);
-  if (device < 0 || device >= 16 || !potrf_configured[device]) {
-    EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem));
-    if (device >= 0 && device < 16) potrf_configured[device] = true;
-  }
+  const long long dd = static_cast<long long>(d) * d;
+  w.f.B = B; w.f.dim = d; w.f.sms = sms; w.f.trsm = solve_use_trsm();
+  w.a.rows = n; w.a.rows_pad = n_pad; w.a.M64 = w.M64; w.a.R64t = w.Ks64t;
+  if ((rc = potrf_configure(device))) return rc;
 
   EMCID_CUDA_CHECK(cudaMemsetAsync(status_dev, 0, sizeof(int), stream));
   EMCID_CUDA_CHECK(cudaMemcpyAsync(w.inv_left, inv_left_host, B * sizeof(double), cudaMemcpyHostToDevice, stream));
-  // LL planes' never-written upper/lower halves must not hold NaN patterns (TMA reads whole boxes)
-  EMCID_CUDA_CHECK(cudaMemsetAsync(w.LL_hi, 0, B * dd * sizeof(float), stream));
-  EMCID_CUDA_CHECK(cudaMemsetAsync(w.LL_lo, 0, B * dd * sizeof(float), stream));
-  EMCID_CUDA_CHECK(cudaMemsetAsync(w.Mp_hi, 0, B * dd * sizeof(float), stream));
-  EMCID_CUDA_CHECK(cudaMemsetAsync(w.Mp_lo, 0, B * dd * sizeof(float), stream));
+  if ((rc = factor_clear(w.f, stream))) return rc;
+  EMCID_CUDA_CHECK(cudaMemsetAsync(w.f.Mp_hi, 0, B * dd * sizeof(float), stream));
+  EMCID_CUDA_CHECK(cudaMemsetAsync(w.f.Mp_lo, 0, B * dd * sizeof(float), stream));
 
   // 1. operands
   {
     dim3 grid((d + 31) / 32, (n_pad + 31) / 32, B);
     solve_prep_kernel<<<grid, dim3(32, 8), 0, stream>>>(Kt, ldk, static_cast<long long>(n) * ldk, n, n_pad, d, scale,
-                                                        w.Ks64t, w.W, w.Wp_hi, w.Wp_lo, w.Kd64, w.Kd_hi, w.Kd_lo);
+                                                        w.Ks64t, w.a.W, w.a.Wp_hi, w.a.Wp_lo, w.Kd64, w.Kd_hi, w.Kd_lo);
     EMCID_CUDA_CHECK(cudaGetLastError());
   }
-  // EMCID_SOLVE_TRSM=1: blocked TRSM sweeps instead of the explicit inverse
-  static const bool use_trsm = [] { const char* e = getenv("EMCID_SOLVE_TRSM"); return e && e[0] == '1'; }();
-  if (!use_trsm) {
-    // the strictly upper (Lv) / lower (LvT) blocks are never written and never read by the k_tri-limited products;
-    // zero them anyway so that no stale NaN pattern can ever reach a TMA box
-    EMCID_CUDA_CHECK(cudaMemsetAsync(w.Lv_hi, 0, B * dd * sizeof(float), stream));
-    EMCID_CUDA_CHECK(cudaMemsetAsync(w.Lv_lo, 0, B * dd * sizeof(float), stream));
-    EMCID_CUDA_CHECK(cudaMemsetAsync(w.LvT_hi, 0, B * dd * sizeof(float), stream));
-    EMCID_CUDA_CHECK(cudaMemsetAsync(w.LvT_lo, 0, B * dd * sizeof(float), stream));
-  }
-  PlaneMaps mKd, mMp, mLL, mLi, mLiT, mW, mLv, mLvT, mTp, mW2;
+  PlaneMaps mKd;
   if ((rc = make_plane_maps(&mKd, w.Kd_hi, w.Kd_lo, static_cast<long long>(B) * d, n_pad, n_pad)) ||
-      (rc = make_plane_maps(&mMp, w.Mp_hi, w.Mp_lo, static_cast<long long>(B) * d, d, d)) ||
-      (rc = make_plane_maps(&mLL, w.LL_hi, w.LL_lo, static_cast<long long>(B) * d, d, d)) ||
-      (rc = make_plane_maps(&mLi, w.Li_hi, w.Li_lo, static_cast<long long>(B) * d, SOLVE_NB, SOLVE_NB)) ||
-      (rc = make_plane_maps(&mLiT, w.LiT_hi, w.LiT_lo, static_cast<long long>(B) * d, SOLVE_NB, SOLVE_NB)) ||
-      (rc = make_plane_maps(&mW, w.Wp_hi, w.Wp_lo, static_cast<long long>(B) * n_pad, d, d)) ||
-      (rc = make_plane_maps(&mLv, w.Lv_hi, w.Lv_lo, static_cast<long long>(B) * d, d, d)) ||
-      (rc = make_plane_maps(&mLvT, w.LvT_hi, w.LvT_lo, static_cast<long long>(B) * d, d, d)) ||
-      (rc = make_plane_maps(&mTp, w.Tp_hi, w.Tp_lo, static_cast<long long>(B) * d, SOLVE_NB, SOLVE_NB)) ||
-      (rc = make_plane_maps(&mW2, w.W2p_hi, w.W2p_lo, static_cast<long long>(B) * n_pad, d, d)))
+      (rc = factor_make_maps(w.f)) || (rc = apply_make_maps(w.a, B, d)))
     return rc;
 
   // 2. M32 = lambda*C32 + Ks Ks^T (lower tiles; fp32 + planes)   and   M64 (fp64, full)
@@ -521,8 +882,8 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
     g.M = d; g.N = d; g.K = n_pad; g.lower = 1;
     g.alpha = 1.0f; g.beta = static_cast<float>(lambda);
     g.Cin = C32; g.ldcin = d; g.cin_batch = dd;
-    g.C = w.M32; g.ldc = d; g.c_batch = dd;
-    g.P_hi = w.Mp_hi; g.P_lo = w.Mp_lo; g.ldp = d; g.p_batch = dd;
+    g.C = w.f.M32; g.ldc = d; g.c_batch = dd;
+    g.P_hi = w.f.Mp_hi; g.P_lo = w.f.Mp_lo; g.ldp = d; g.p_batch = dd;
     if ((rc = run_subgemm(g, B, sms, stream))) return rc;
     // (forming M64 on a side stream next to the factorisation was considered and dropped: its 2880 long-running
     // CTAs would sit in front of every short, dependent launch of the Cholesky chain)
@@ -540,177 +901,203 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
     EMCID_CUDA_CHECK(cudaGetLastError());
   }
 
-  // 3. blocked right-looking Cholesky of M32
-  for (int k = 0; k < nblk; ++k) {
-    potrf_diag_kernel<<<B, 256, potrf_smem, stream>>>(w.M32, d, k, w.LL_hi, w.LL_lo, w.Li_hi, w.Li_lo, w.LiT_hi,
-                                                      w.LiT_lo, use_trsm ? nullptr : w.Lv_hi, w.Lv_lo, w.LvT_hi, w.LvT_lo,
-                                                      status_dev);
-    EMCID_CUDA_CHECK(cudaGetLastError());
-    const int rem = d - (k + 1) * SOLVE_NB;
-    if (rem <= 0) break;
-    const long long off_panel = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k) * SOLVE_NB;
-    const long long off_panel_t = static_cast<long long>(k) * SOLVE_NB * d + static_cast<long long>(k + 1) * SOLVE_NB;
-    const long long off_trail = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k + 1) * SOLVE_NB;
-    SubGemm g;
-    memset(&g, 0, sizeof(g));  // panel: L_ik = M_ik Linv_kk^T
-    g.A = &mMp; g.a_row0 = (k + 1) * SOLVE_NB; g.a_col0 = k * SOLVE_NB; g.a_batch_rows = d;
-    g.B = &mLi; g.b_row0 = k * SOLVE_NB; g.b_col0 = 0; g.b_batch_rows = d;
-    g.M = rem; g.N = SOLVE_NB; g.K = SOLVE_NB;
-    g.alpha = 1.0f; g.beta = 0.0f;
-    g.P_hi = w.LL_hi + off_panel; g.P_lo = w.LL_lo + off_panel; g.ldp = d; g.p_batch = dd;
-    g.Pt_hi = w.LL_hi + off_panel_t; g.Pt_lo = w.LL_lo + off_panel_t; g.ldpt = d; g.pt_batch = dd;
-    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
-    memset(&g, 0, sizeof(g));  // trailing: M_ij -= L_ik L_jk^T
-    g.A = &mLL; g.a_row0 = (k + 1) * SOLVE_NB; g.a_col0 = k * SOLVE_NB; g.a_batch_rows = d;
-    g.B = &mLL; g.b_row0 = (k + 1) * SOLVE_NB; g.b_col0 = k * SOLVE_NB; g.b_batch_rows = d;
-    g.M = rem; g.N = rem; g.K = SOLVE_NB; g.lower = 1;
-    g.alpha = -1.0f; g.beta = 1.0f;
-    g.Cin = w.M32 + off_trail; g.ldcin = d; g.cin_batch = dd;
-    g.C = w.M32 + off_trail; g.ldc = d; g.c_batch = dd;
-    g.P_hi = w.Mp_hi + off_trail; g.P_lo = w.Mp_lo + off_trail; g.ldp = d; g.p_batch = dd;
-    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
-  }
-
-  // 3b. explicit inverse, block columns from the right (the diagonal blocks came from potrf_diag_kernel):
-  //        T          = Linv[k+1:, k+1:] L[k+1:, k]        (A lower triangular: k_tri = 3)
-  //        Linv[k+1:, k] = -T Linv_kk                      (planes into Lv, transposed planes into LvT)
-  if (!use_trsm) {
-    for (int k = nblk - 2; k >= 0; --k) {
-      const int r0 = (k + 1) * SOLVE_NB, rem = d - r0;
-      SubGemm g;
-      memset(&g, 0, sizeof(g));
-      g.A = &mLv; g.a_row0 = r0; g.a_col0 = r0; g.a_batch_rows = d;
-      g.B = &mLL; g.b_row0 = k * SOLVE_NB; g.b_col0 = r0; g.b_batch_rows = d;   // upper blocks of LL hold L^T
-      g.M = rem; g.N = SOLVE_NB; g.K = rem; g.k_tri = 3;
-      g.alpha = 1.0f;
-      g.P_hi = w.Tp_hi + static_cast<long long>(r0) * SOLVE_NB; g.P_lo = w.Tp_lo + static_cast<long long>(r0) * SOLVE_NB;
-      g.ldp = SOLVE_NB; g.p_batch = static_cast<long long>(d) * SOLVE_NB;
-      if ((rc = run_subgemm(g, B, sms, stream))) return rc;
-      memset(&g, 0, sizeof(g));
-      g.A = &mTp; g.a_row0 = r0; g.a_col0 = 0; g.a_batch_rows = d;
-      g.B = &mLiT; g.b_row0 = k * SOLVE_NB; g.b_col0 = 0; g.b_batch_rows = d;
-      g.M = rem; g.N = SOLVE_NB; g.K = SOLVE_NB;
-      g.alpha = -1.0f;
-      const long long off = static_cast<long long>(r0) * d + static_cast<long long>(k) * SOLVE_NB;
-      const long long off_t = static_cast<long long>(k) * SOLVE_NB * d + r0;
-      g.P_hi = w.Lv_hi + off; g.P_lo = w.Lv_lo + off; g.ldp = d; g.p_batch = dd;
-      g.Pt_hi = w.LvT_hi + off_t; g.Pt_lo = w.LvT_lo + off_t; g.ldpt = d; g.pt_batch = dd;
-      if ((rc = run_subgemm(g, B, sms, stream))) return rc;
-    }
-  }
+  // 3. blocked right-looking Cholesky of M32 and the explicit inverse of its factor
+  if ((rc = factor_spd(w.f, status_dev, stream))) return rc;
 
   // 4./5. solve + refinement; W holds the current right-hand side (transposed), then the solution
-  //   Y^T = W Linv^T  (B = Linv, lower triangular: k_tri = 1)  ->  planes only
-  //   X^T = Y^T Linv  (B = Linv^T, upper triangular: k_tri = 2) ->  fp32 into W
-  auto apply_inverse = [&]() -> int {
-    SubGemm g;
-    memset(&g, 0, sizeof(g));
-    g.A = &mW; g.a_batch_rows = n_pad;
-    g.B = &mLv; g.b_batch_rows = d;
-    g.M = n_pad; g.N = d; g.K = d; g.k_tri = 1; g.alpha = 1.0f;
-    g.P_hi = w.W2p_hi; g.P_lo = w.W2p_lo; g.ldp = d; g.p_batch = nd;
-    if (int r = run_subgemm(g, B, sms, stream)) return r;
-    memset(&g, 0, sizeof(g));
-    g.A = &mW2; g.a_batch_rows = n_pad;
-    g.B = &mLvT; g.b_batch_rows = d;
-    g.M = n_pad; g.N = d; g.K = d; g.k_tri = 2; g.alpha = 1.0f;
-    g.C = w.W; g.ldc = d; g.c_batch = nd;
-    return run_subgemm(g, B, sms, stream);
-  };
-  auto trsm_both = [&]() -> int {
-    SubGemm g;
-    for (int i = 0; i < nblk; ++i) {  // forward: Y^T L^T = W
-      memset(&g, 0, sizeof(g));
-      g.A = &mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
-      g.B = &mLi; g.b_row0 = i * SOLVE_NB; g.b_batch_rows = d;
-      g.M = n_pad; g.N = SOLVE_NB; g.K = SOLVE_NB; g.alpha = 1.0f;
-      g.C = w.W + i * SOLVE_NB; g.ldc = d; g.c_batch = nd;
-      g.P_hi = w.Wp_hi + i * SOLVE_NB; g.P_lo = w.Wp_lo + i * SOLVE_NB; g.ldp = d; g.p_batch = nd;
-      if (int r = run_subgemm(g, B, sms, stream)) return r;
-      const int rem = d - (i + 1) * SOLVE_NB;
-      if (rem <= 0) break;
-      memset(&g, 0, sizeof(g));
-      g.A = &mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
-      g.B = &mLL; g.b_row0 = (i + 1) * SOLVE_NB; g.b_col0 = i * SOLVE_NB; g.b_batch_rows = d;
-      g.M = n_pad; g.N = rem; g.K = SOLVE_NB; g.alpha = -1.0f; g.beta = 1.0f;
-      const long long off = static_cast<long long>(i + 1) * SOLVE_NB;
-      g.Cin = w.W + off; g.ldcin = d; g.cin_batch = nd;
-      g.C = w.W + off; g.ldc = d; g.c_batch = nd;
-      g.P_hi = w.Wp_hi + off; g.P_lo = w.Wp_lo + off; g.ldp = d; g.p_batch = nd;
-      if (int r = run_subgemm(g, B, sms, stream)) return r;
-    }
-    for (int i = nblk - 1; i >= 0; --i) {  // backward: X^T L = Y^T
-      memset(&g, 0, sizeof(g));
-      g.A = &mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
-      g.B = &mLiT; g.b_row0 = i * SOLVE_NB; g.b_batch_rows = d;
-      g.M = n_pad; g.N = SOLVE_NB; g.K = SOLVE_NB; g.alpha = 1.0f;
-      g.C = w.W + i * SOLVE_NB; g.ldc = d; g.c_batch = nd;
-      g.P_hi = w.Wp_hi + i * SOLVE_NB; g.P_lo = w.Wp_lo + i * SOLVE_NB; g.ldp = d; g.p_batch = nd;
-      if (int r = run_subgemm(g, B, sms, stream)) return r;
-      if (i == 0) break;
-      memset(&g, 0, sizeof(g));
-      g.A = &mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
-      g.B = &mLL; g.b_row0 = 0; g.b_col0 = i * SOLVE_NB; g.b_batch_rows = d;  // upper blocks hold L^T
-      g.M = n_pad; g.N = i * SOLVE_NB; g.K = SOLVE_NB; g.alpha = -1.0f; g.beta = 1.0f;
-      g.Cin = w.W; g.ldcin = d; g.cin_batch = nd;
-      g.C = w.W; g.ldc = d; g.c_batch = nd;
-      g.P_hi = w.Wp_hi; g.P_lo = w.Wp_lo; g.ldp = d; g.p_batch = nd;
-      if (int r = run_subgemm(g, B, sms, stream)) return r;
-    }
-    return EMCID_OK;
-  };
-
-  const long long tot = static_cast<long long>(B) * nd;
-  // refine_steps >= 0: exactly that many sweeps.  -1: adaptive — stop once the last correction is below
-  // SOLVE_ADAPT_TOL relative to the solution (each sweep contracts the error by ~1e-2 at cond ~1e7, so the
-  // error left after applying a correction of that size is orders of magnitude under the 1e-4 dW tolerance).
-  const bool adaptive = refine_steps < 0;
-  const int max_steps = adaptive ? SOLVE_ADAPT_MAX : refine_steps;
-  for (int it = 0; it <= max_steps; ++it) {
-    if (it > 0) {
-      // R^T = Ks^T - X^T M64  (fp64), rounded to fp32 into W, then re-split
-      DgemmParams p;
-      memset(&p, 0, sizeof(p));
-      p.M = n; p.N = d; p.K = d;
-      p.A = w.X64t; p.lda = d; p.a_batch = nd;
-      p.B = w.M64; p.ldb = d; p.b_batch = dd;
-      p.alpha = -1.0; p.beta = 1.0;
-      p.Cin = w.Ks64t; p.ldcin = d; p.cin_batch = nd;
-      p.C32 = w.W; p.ldc32 = d; p.c32_batch = nd;
-      if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
-      if ((rc = launch_split_planes(w.W, d, B * n_pad, d, 1.0f, w.Wp_hi, w.Wp_lo, d, stream))) return rc;
-    }
-    if ((rc = use_trsm ? trsm_both() : apply_inverse())) return rc;
-    solve_axpy_kernel<<<sms * 8, 256, 0, stream>>>(w.W, w.X64t, tot, it > 0 ? 1 : 0);
-    EMCID_CUDA_CHECK(cudaGetLastError());
-    if (adaptive && it > 0) {
-      double hn[2] = {0.0, 0.0};
-      EMCID_CUDA_CHECK(cudaMemsetAsync(w.norms, 0, 2 * sizeof(double), stream));
-      solve_norms_kernel<<<sms * 4, 256, 0, stream>>>(w.W, w.X64t, tot, w.norms);
-      EMCID_CUDA_CHECK(cudaGetLastError());
-      EMCID_CUDA_CHECK(cudaMemcpyAsync(hn, w.norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-      EMCID_CUDA_CHECK(cudaStreamSynchronize(stream));
-      if (!(hn[1] > 0.0) || hn[0] <= SOLVE_ADAPT_TOL * SOLVE_ADAPT_TOL * hn[1]) break;
-    }
-  }
+  if ((rc = refined_solve(w.f, w.a, false, refine_steps, stream))) return rc;
 
   // 6. outputs
-  transpose_out_kernel<<<dim3((d + 31) / 32, (n + 31) / 32, B), dim3(32, 8), 0, stream>>>(w.X64t, n, n_pad, d, adj_k);
+  transpose_out_kernel<<<dim3((d + 31) / 32, (n + 31) / 32, B), dim3(32, 8), 0, stream>>>(w.a.X64t, n, n_pad, d, adj_k);
   EMCID_CUDA_CHECK(cudaGetLastError());
-  resid_kernel<<<dim3((h + 31) / 32, (n + 31) / 32, B), dim3(32, 8), 0, stream>>>(
-      St, lds, static_cast<long long>(n) * lds, n, h, scale, w.inv_left, resid);
-  EMCID_CUDA_CHECK(cudaGetLastError());
+  return solve_outputs(B, d, h, n, St, lds, scale, w.inv_left, adj_k, resid, dW, stream);
+}
+
+// ---- cached factorisation for repeated edits with the same covariance --------------------------
+// Sequential editing (experiments/sequential_editing.py:98-171), the debias factor search
+// (emcid_main.py:1460-1472 -> cal_insert_deltas :1969-2052) and the layer ablation re-solve
+// (lambda*C + Ks Ks^T) adj_k = Ks many times with the same lambda*C =: A and a fresh, much narrower Ks.  With
+// A = L L^T factored once per (layer, lambda, edit_weight), the push-through identity
+//        (A + Ks Ks^T)^-1 Ks = A^-1 Ks (I + Ks^T A^-1 Ks)^-1
+// turns each edit into O(d^2 n) work instead of O(d^3):
+//        Y     = A^-1 Ks              explicit-inverse application + fp64 refinement against A64   [d x n]
+//        G     = I + Ks^T Y           fp64 DMMA GEMM, n_pad x n_pad, SPD, cond(G) <= 1 + |Ks^T A^-1 Ks|
+//        adj_k = Y G^-1               the same blocked factorisation + refined application, dimension n_pad, d rhs
+// Unlike the additive Woodbury form  A^-1 - A^-1 Ks G^-1 Ks^T A^-1  nothing is subtracted, so fp32-class factors with
+// fp64-residual refinement of BOTH solves reach the accuracy of the direct path (each factor only has to contract).
+struct FactorHandle {
+  int device, d;
+  double lambda;
+  double* A64;                                  // [d x d] fp64 = lambda * double(C32), full
+  float *Lv_hi, *Lv_lo, *LvT_hi, *LvT_lo;       // explicit inverse planes of chol(lambda * C32)
+};
+
+inline int factor_destroy(FactorHandle* H) {
+  if (!H) return EMCID_OK;
+  cudaSetDevice(H->device);
+  dev_free(H->A64); dev_free(H->Lv_hi); dev_free(H->Lv_lo); dev_free(H->LvT_hi); dev_free(H->LvT_lo);
+  delete H;
+  return EMCID_OK;
+}
+
+inline int factor_create(FactorHandle** out, int device, int d, const float* C32, double lambda, int* status_dev,
+                         cudaStream_t stream) {
+  EMCID_CHECK(out && C32 && status_dev, EMCID_ERR_INVALID, "factor_create: null argument");
+  EMCID_CHECK(d > 0 && d % SOLVE_NB == 0, EMCID_ERR_UNSUPPORTED, "factor_create: d must be a multiple of %d (got %d)",
+              SOLVE_NB, d);
+  EMCID_CHECK(lambda > 0.0, EMCID_ERR_INVALID, "factor_create: lambda must be positive");
+  EMCID_CUDA_CHECK(cudaSetDevice(device));
+  DeviceInfo info;
+  int rc = get_device_info(&info);
+  if (rc) return rc;
+  if ((rc = potrf_configure(device))) return rc;
+  const size_t dd = static_cast<size_t>(d) * d;
+  FactorHandle* H = new FactorHandle();
+  memset(H, 0, sizeof(*H));
+  H->device = device; H->d = d; H->lambda = lambda;
+  void* scratch = nullptr;
+  auto fail = [&](int code) { if (scratch) dev_free(scratch); factor_destroy(H); return code; };
+#define EMCID_FACTOR_ALLOC(ptr, bytes)                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = dev_alloc(reinterpret_cast<void**>(&(ptr)), (bytes));                       \
+    if (e_ != cudaSuccess) return fail(set_error(EMCID_ERR_CUDA, "factor_create: %s", cudaGetErrorString(e_))); \
+  } while (0)
+  EMCID_FACTOR_ALLOC(H->A64, dd * sizeof(double));
+  EMCID_FACTOR_ALLOC(H->Lv_hi, dd * sizeof(float));
+  EMCID_FACTOR_ALLOC(H->Lv_lo, dd * sizeof(float));
+  EMCID_FACTOR_ALLOC(H->LvT_hi, dd * sizeof(float));
+  EMCID_FACTOR_ALLOC(H->LvT_lo, dd * sizeof(float));
+  FactorCtx f;
+  memset(&f, 0, sizeof(f));
+  size_t scratch_bytes;
+  {
+    Carver c(nullptr);
+    carve_factor(c, f, 1, d, false);
+    scratch_bytes = c.bytes();
+  }
+  EMCID_FACTOR_ALLOC(scratch, scratch_bytes);
+#undef EMCID_FACTOR_ALLOC
+  {
+    Carver c(scratch);
+    carve_factor(c, f, 1, d, false);
+  }
+  f.B = 1; f.dim = d; f.sms = info.sm_count; f.trsm = false;
+  f.Lv_hi = H->Lv_hi; f.Lv_lo = H->Lv_lo; f.LvT_hi = H->LvT_hi; f.LvT_lo = H->LvT_lo;
+  if ((rc = factor_make_maps(f))) return fail(rc);
+  auto run = [&]() -> int {
+    EMCID_CUDA_CHECK(cudaMemsetAsync(status_dev, 0, sizeof(int), stream));
+    if (int r = factor_clear(f, stream)) return r;
+    factor_prep_kernel<<<dim3(d / 32, d / 32), dim3(32, 8), 0, stream>>>(C32, d, lambda, f.M32, f.Mp_hi, f.Mp_lo, H->A64);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    if (int r = factor_spd(f, status_dev, stream)) return r;
+    EMCID_CUDA_CHECK(cudaStreamSynchronize(stream));   // the scratch goes back to the pool: nothing may still use it
+    return EMCID_OK;
+  };
+  if ((rc = run())) return fail(rc);
+  dev_free(scratch);
+  *out = H;
+  return EMCID_OK;
+}
+
+struct FactorSolveWs {
+  FactorCtx g;          // factorisation of G, dimension n_pad
+  ApplyCtx a1, a2;      // stage 1: n rhs of dimension d;  stage 2: d rhs of dimension n_pad (same buffers)
+  double *Ks64t, *Yd64, *G64, *inv_left;
+  size_t bytes;
+};
+
+inline FactorSolveWs factor_solve_carve(void* base, int d, int n) {
+  const long long n_pad = round_up_ll(n, 128);
+  Carver c(base);
+  FactorSolveWs w;
+  memset(&w, 0, sizeof(w));
+  const size_t nd = static_cast<size_t>(n_pad) * d;
+  w.Ks64t = c.take<double>(nd);
+  w.a1.X64t = c.take<double>(nd);
+  w.Yd64 = c.take<double>(nd);
+  w.G64 = c.take<double>(static_cast<size_t>(n_pad) * n_pad);
+  w.inv_left = c.take<double>(1);
+  w.a1.norms = c.take<double>(2);
+  carve_factor(c, w.g, 1, static_cast<int>(n_pad), true);
+  carve_apply(c, w.a1, nd);
+  // stage 2 runs after stage 1 is finished on the same stream: its fp32 buffers and its result reuse stage 1's
+  w.a2 = w.a1;
+  w.a2.X64t = w.Ks64t;
+  w.bytes = c.bytes();
+  return w;
+}
+
+inline size_t factor_solve_workspace_bytes(int d, int n) { return factor_solve_carve(nullptr, d, n).bytes; }
+
+inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long long ldk, const float* St, long long lds,
+                        double scale, double inv_layers_left, double* adj_k, double* resid, float* dW, int refine_steps,
+                        void* workspace, size_t ws_bytes, int* status_dev, cudaStream_t stream) {
+  EMCID_CHECK(H, EMCID_ERR_INVALID, "factor_solve: null handle");
+  const int d = H->d;
+  EMCID_CHECK(h > 0 && n > 0, EMCID_ERR_INVALID, "factor_solve: empty problem");
+  EMCID_CHECK(Kt && St && adj_k && resid && dW && status_dev, EMCID_ERR_INVALID, "factor_solve: null argument");
+  EMCID_CHECK(ldk >= d && lds >= h, EMCID_ERR_INVALID, "factor_solve: bad leading dimensions");
+  EMCID_CHECK(refine_steps >= -1 && refine_steps <= 8, EMCID_ERR_INVALID, "factor_solve: refine_steps out of range");
+  EMCID_CHECK(ws_bytes >= factor_solve_workspace_bytes(d, n), EMCID_ERR_WORKSPACE,
+              "factor_solve: workspace too small (%zu < %zu)", ws_bytes, factor_solve_workspace_bytes(d, n));
+  EMCID_CUDA_CHECK(cudaSetDevice(H->device));
+  DeviceInfo info;
+  int rc = get_device_info(&info);
+  if (rc) return rc;
+  const int sms = info.sm_count;
+  const int n_pad = static_cast<int>(round_up_ll(n, 128));
+  FactorSolveWs w = factor_solve_carve(workspace, d, n);
+  if ((rc = potrf_configure(H->device))) return rc;
+
+  // the cached factor of A
+  FactorCtx fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.B = 1; fa.dim = d; fa.sms = sms; fa.trsm = false;
+  fa.Lv_hi = H->Lv_hi; fa.Lv_lo = H->Lv_lo; fa.LvT_hi = H->LvT_hi; fa.LvT_lo = H->LvT_lo;
+  if ((rc = factor_make_inverse_maps(fa))) return rc;
+  w.a1.rows = n; w.a1.rows_pad = n_pad; w.a1.M64 = H->A64; w.a1.R64t = w.Ks64t;
+  if ((rc = apply_make_maps(w.a1, 1, d))) return rc;
+
+  EMCID_CUDA_CHECK(cudaMemsetAsync(status_dev, 0, sizeof(int), stream));
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(w.inv_left, &inv_layers_left, sizeof(double), cudaMemcpyHostToDevice, stream));
+  // 1. Ks (fp64, transposed) and the planes of float(Ks)
+  {
+    dim3 grid((d + 31) / 32, (n_pad + 31) / 32, 1);
+    solve_prep_kernel<<<grid, dim3(32, 8), 0, stream>>>(Kt, ldk, static_cast<long long>(n) * ldk, n, n_pad, d, scale,
+                                                        w.Ks64t, w.a1.W, w.a1.Wp_hi, w.a1.Wp_lo, nullptr, nullptr, nullptr);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+  }
+  // 2. Y^T = Ks^T A^-1, refined against A64                                  -> a1.X64t [n_pad x d]
+  if ((rc = refined_solve(fa, w.a1, false, refine_steps, stream))) return rc;
+  // 3. G = I + Ks^T Y   (fp64; lower tiles, then mirrored with fp32 copy and planes)
   {
     DgemmParams p;
     memset(&p, 0, sizeof(p));
-    p.M = h; p.N = d; p.K = n;
-    p.A = resid; p.lda = n; p.a_batch = static_cast<long long>(h) * n;
-    p.B = adj_k; p.ldb = n; p.b_batch = static_cast<long long>(d) * n;
+    p.M = n_pad; p.N = n_pad; p.K = d;
+    p.A = w.Ks64t; p.lda = d;
+    p.B = w.a1.X64t; p.ldb = d;
     p.alpha = 1.0;
-    p.C32 = dW; p.ldc32 = d; p.c32_batch = static_cast<long long>(h) * d;
-    if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
+    p.C = w.G64; p.ldc = n_pad;
+    p.lower = 1;
+    if ((rc = launch_dgemm_nt(p, 1, stream))) return rc;
+    g_prepare_kernel<<<dim3(n_pad / 32, n_pad / 32), dim3(32, 8), 0, stream>>>(w.G64, n_pad, w.g.M32, w.g.Mp_hi, w.g.Mp_lo);
+    EMCID_CUDA_CHECK(cudaGetLastError());
   }
-  return EMCID_OK;
+  // 4. factor G
+  w.g.B = 1; w.g.dim = n_pad; w.g.sms = sms; w.g.trsm = false;
+  if ((rc = factor_make_maps(w.g)) || (rc = factor_clear(w.g, stream)) || (rc = factor_spd(w.g, status_dev, stream)))
+    return rc;
+  // 5. adj_k G = Y: the rows of Y [d x n_pad] are the right-hand sides             -> a2.X64t [d x n_pad]
+  transpose_out_kernel<<<dim3((d + 31) / 32, (n_pad + 31) / 32, 1), dim3(32, 8), 0, stream>>>(w.a1.X64t, n_pad, n_pad, d,
+                                                                                             w.Yd64);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  w.a2.rows = d; w.a2.rows_pad = d; w.a2.M64 = w.G64; w.a2.R64t = w.Yd64;
+  if ((rc = apply_make_maps(w.a2, 1, n_pad))) return rc;
+  if ((rc = refined_solve(w.g, w.a2, true, refine_steps, stream))) return rc;
+  // 6. outputs
+  compact_cols_kernel<<<sms * 4, 256, 0, stream>>>(w.a2.X64t, d, n, n_pad, adj_k);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  return solve_outputs(1, d, h, n, St, lds, scale, w.inv_left, adj_k, resid, dW, stream);
 }
 
 }  // namespace emcid

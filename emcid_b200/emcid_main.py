@@ -19,6 +19,8 @@ reference caches them (:873-969); a miss raises NotImplementedError.
 """
 from __future__ import annotations
 
+import os
+from collections import OrderedDict
 from copy import deepcopy
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple
@@ -30,9 +32,49 @@ from . import nethook
 from .compute_ks import get_module_input_output_at_words, prepare_lookup
 from .globals import STATS_DIR, XL_STATS_DIR1, XL_STATS_DIR2
 from .layer_stats import layer_stats_text_encoder
-from .solve import DEFAULT_REFINE_STEPS, solve_layers
+from .solve import DEFAULT_REFINE_STEPS, CachedFactor, solve_layers
 
 COV_CACHE: Dict[Tuple[str, str], torch.Tensor] = {}
+
+# Factorisations of mom2_update_weight * C * (1 - edit_weight) / 0.5, kept on the device next to COV_CACHE for edits that
+# come back with the same covariance and few concepts (sequential editing, experiments/sequential_editing.py:98-171, where
+# the reference re-runs torch.linalg.solve on a fresh d x d matrix per edit and layer, emcid_main.py:1045-1047).
+# Key: (model name, layer name, mom2_update_weight, edit_weight); value: (the COV_CACHE tensor it was built from, factor).
+# An entry is rebuilt when COV_CACHE holds a different tensor (force_recompute, cleared cache).  20 d^2 bytes per entry
+# (189 MB at d = 3072); least recently used entries beyond FACTOR_CACHE_MAX are dropped.  EMCID_FACTOR_CACHE=0 disables.
+FACTOR_CACHE: "OrderedDict[Tuple[str, str, float, float], Tuple[torch.Tensor, CachedFactor]]" = OrderedDict()
+FACTOR_CACHE_MAX = 16
+# the cached path wins while the n_pad x n_pad system of the push-through identity stays small next to d x d
+FACTOR_CACHE_MAX_FRACTION = 4
+
+
+def _solve_one_layer(text_encoder, module_name: str, cov_raw: torch.Tensor, layer_ks: torch.Tensor,
+                     sources_t: torch.Tensor, mom2_update_weight: float, ew: float, layers_left: int, refine_steps: int):
+    """adj_k, resid, dW of one layer (emcid_main.py:1037-1050): through the cached factor of lambda * C32 when the edit is
+    narrow (n_pad <= d / 4), else the direct batched solver."""
+    d = cov_raw.shape[0]
+    n_pad = -(-layer_ks.shape[0] // 128) * 128
+    scale = (ew / 0.5) ** 0.5
+    if os.environ.get("EMCID_FACTOR_CACHE", "1") != "0" and n_pad * FACTOR_CACHE_MAX_FRACTION <= d:
+        key = (text_encoder.config._name_or_path.replace("/", "_"), module_name, float(mom2_update_weight), float(ew))
+        entry = FACTOR_CACHE.get(key)
+        if entry is None or entry[0] is not cov_raw:
+            if entry is not None:
+                entry[1].close()
+            entry = (cov_raw, CachedFactor(cov_raw * (1 - ew) / 0.5, mom2_update_weight))      # fp32 scaling, :1037
+            FACTOR_CACHE[key] = entry
+            while len(FACTOR_CACHE) > FACTOR_CACHE_MAX:
+                FACTOR_CACHE.popitem(last=False)[1][1].close()
+        FACTOR_CACHE.move_to_end(key)
+        return entry[1].solve(layer_ks.float(), sources_t.float(), scale, layers_left, refine_steps=refine_steps)
+    adj_k, resid, dW = solve_layers(cov_raw * (1 - ew) / 0.5, layer_ks.float(), sources_t.float(), mom2_update_weight,
+                                    scale, [layers_left], refine_steps=refine_steps)
+    return adj_k[0], resid[0], dW[0]
+
+
+def clear_factor_cache() -> None:
+    while FACTOR_CACHE:
+        FACTOR_CACHE.popitem()[1][1].close()
 
 # Set TIMING = True to have the edit loop synchronise the device between its stages and leave their wall-clock
 # milliseconds in LAST_EDIT_TIMING (bench.py does, for one extra repetition; off by default: no extra syncs).
@@ -189,10 +231,9 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
                     print("z error", torch.linalg.norm(sources_t, dim=1).mean())
                 cov = get_cov_text_encoder(text_encoder, tokenizer, module_name, hparams.mom2_dataset,
                                            hparams.mom2_n_samples, hparams.mom2_dtype, stat_dir=stat_dir,
-                                           force_recompute=False, verbose=verbose) * (1 - ew) / 0.5   # fp32, :1037
-                adj_k, resid, dW = solve_layers(cov, layer_ks.float(), sources_t.float(), mom2_update_weight,
-                                                (ew / 0.5) ** 0.5, [len(layers) - i], refine_steps=refine_steps)
-                adj_k, resid, dW = adj_k[0], resid[0], dW[0]
+                                           force_recompute=False, verbose=verbose)
+                adj_k, resid, dW = _solve_one_layer(text_encoder, module_name, cov, layer_ks, sources_t,
+                                                    mom2_update_weight, ew, len(layers) - i, refine_steps)
                 t = _tick(device, "solve_ms", t)
                 name = names[i]
                 upd = upd_matrix_match_shape(dW, weights[name].shape)

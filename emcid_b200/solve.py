@@ -61,3 +61,71 @@ def solve_layers(C32: torch.Tensor, Kt: torch.Tensor, St: torch.Tensor, mom2_upd
         if st != 0:
             raise _lib.EmcidError(-4, f"Cholesky breakdown: lambda*C + K K^T is not positive definite (status {st})")
     return adj_k, resid, dW
+
+
+class CachedFactor:
+    """Factorisation of ``A = mom2_update_weight * C32`` kept on the device for repeated edits with the same
+    covariance (``emcid_factor_create`` / ``emcid_factor_solve``).
+
+    The reference re-solves a fresh ``d x d`` system per edit and layer even when only the keys changed
+    (sequential editing, experiments/sequential_editing.py:98-171; the debias factor search,
+    emcid/emcid_main.py:1460-1472; the layer ablation, experiments/ablation.py:332-338).  ``solve`` returns the
+    same ``(adj_k, resid, dW)`` as ``solve_layers`` for one layer in ``O(d^2 n)`` instead of ``O(d^3)`` work."""
+
+    def __init__(self, C32: torch.Tensor, mom2_update_weight: float):
+        assert C32.is_cuda and C32.dim() == 2 and C32.shape[0] == C32.shape[1], \
+            "emcid_b200.solve needs a square CUDA covariance (no CPU path)"
+        C32 = C32.contiguous().float()
+        self.device = C32.device
+        self.d = int(C32.shape[0])
+        self.mom2_update_weight = float(mom2_update_weight)
+        self._handle = ctypes.c_void_p()
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.emcid_factor_create(ctypes.byref(self._handle), self.device.index, self.d, _lib.ptr(C32),
+                                               self.mom2_update_weight, _lib.ptr(status), _lib.current_stream_ptr()))
+        st = int(status.item())
+        if st != 0:
+            self.close()
+            raise _lib.EmcidError(-4, f"Cholesky breakdown: lambda*C is not positive definite (status {st})")
+
+    def solve(self, Kt: torch.Tensor, St: torch.Tensor, scale: float, layers_left: int,
+              refine_steps: int = DEFAULT_REFINE_STEPS, check: bool = True
+              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Kt [n, d] fp32, St [n, h] fp32 (CUDA) -> (adj_k [d, n] fp64, resid [h, n] fp64, dW [h, d] fp32)."""
+        assert self._handle, "CachedFactor is closed"
+        assert Kt.is_cuda and St.is_cuda and Kt.device == self.device and St.device == self.device
+        Kt = Kt.contiguous().float()
+        St = St.contiguous().float()
+        n, d = Kt.shape
+        h = St.shape[1]
+        assert d == self.d and St.shape[0] == n
+        dev = self.device
+        adj_k = torch.empty(d, n, dtype=torch.float64, device=dev)
+        resid = torch.empty(h, n, dtype=torch.float64, device=dev)
+        dW = torch.empty(h, d, dtype=torch.float32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        lib = _lib.lib()
+        ws = _workspace(dev, lib.emcid_factor_solve_workspace_bytes(d, h, n))
+        with torch.cuda.device(dev):
+            _lib.check(lib.emcid_factor_solve(self._handle, h, n, _lib.ptr(Kt), d, _lib.ptr(St), h, float(scale),
+                                              1.0 / float(layers_left), _lib.ptr(adj_k), _lib.ptr(resid), _lib.ptr(dW),
+                                              int(refine_steps), _lib.ptr(ws), ws.numel(), _lib.ptr(status),
+                                              _lib.current_stream_ptr()))
+        if check:
+            st = int(status.item())
+            if st != 0:
+                raise _lib.EmcidError(-4, f"Cholesky breakdown: I + Ks^T A^-1 Ks is not positive definite (status {st})")
+        return adj_k, resid, dW
+
+    def close(self) -> None:
+        if self._handle:
+            _lib.lib().emcid_factor_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -162,6 +162,27 @@ int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* 
                        const double* inv_layers_left, double* adj_k, double* resid, float* dW,
                        int refine_steps, void* workspace, size_t workspace_bytes, int* status_dev, void* stream);
 
+/* ---- cached factorisation: repeated edits with the same covariance ------------------------------------
+ * The reference re-runs torch.linalg.solve on a fresh d x d matrix for every edit even when lambda * C has not changed:
+ * sequential editing (experiments/sequential_editing.py:98-171 -> emcid_main.py:1037-1050 once per edit and layer), the
+ * debias factor search (emcid_main.py:1460-1472 -> cal_insert_deltas :1969-2052, up to max_iter re-solves per concept)
+ * and the layer ablation (experiments/ablation.py:332-338).  emcid_factor_create factors A = lambda * C32 once
+ * (blocked Cholesky + explicit inverse of the factor, kept on the device with A in fp64: 20 d^2 bytes) and
+ * emcid_factor_solve returns the same adj_k / resid / dW as emcid_solve_layers(batch = 1) through
+ *     (A + Ks Ks^T)^-1 Ks = Y (I + Ks^T Y)^-1,   Y = A^-1 Ks
+ * with fp64-residual refinement of both solves: O(d^2 n) work per edit instead of O(d^3).
+ * C32, lambda, Kt, St, scale, inv_layers_left (= 1 / (L - i)), outputs, refine_steps, status_dev: as above.
+ * emcid_factor_create synchronises `stream` before it returns; emcid_factor_solve is asynchronous except for the
+ * adaptive refinement's per-sweep synchronisation.  Handles are not thread-safe; distinct handles are. */
+typedef struct emcid_factor emcid_factor_t;
+int emcid_factor_create(emcid_factor_t** out, int device, int d, const float* C32, double lambda, int* status_dev,
+                        void* stream);
+size_t emcid_factor_solve_workspace_bytes(int d, int h, int n);
+int emcid_factor_solve(emcid_factor_t* f, int h, int n, const float* Kt, long long ldk, const float* St, long long lds,
+                       double scale, double inv_layers_left, double* adj_k, double* resid, float* dW, int refine_steps,
+                       void* workspace, size_t workspace_bytes, int* status_dev, void* stream);
+int emcid_factor_destroy(emcid_factor_t* f);
+
 #ifdef __cplusplus
 }
 #endif

@@ -472,17 +472,51 @@ def test_solve_full_size_matches_oracle(dev, d, h, n, B):
 
 def test_solve_reports_breakdown(dev):
     from emcid_b200 import _lib
-    from emcid_b200.solve import solve_layers
+    from emcid_b200.solve import CachedFactor, solve_layers
     C = -torch.eye(256, device=dev)
     with pytest.raises(_lib.EmcidError):
         solve_layers(C, torch.zeros(4, 256, device=dev), torch.zeros(4, 64, device=dev), 4000.0, 1.0, [1])
+    with pytest.raises(_lib.EmcidError):
+        CachedFactor(C, 4000.0)
 
 
-def test_sequential_editing_matches_oracle(dev, tmp_path):
+@pytest.mark.parametrize("d,h,ns", [(3072, 768, (96, 700, 1)), (5120, 1280, (64,)), (256, 64, (12, 130))])
+def test_cached_factor_matches_oracle(dev, d, h, ns):
+    """One factorisation of lambda * C, several edits of different widths through the push-through identity:
+    same (adj_k, resid, dW) as the reference's fp64 LU of lambda * C + Ks Ks^T, and as the direct solver."""
+    from emcid_b200.solve import CachedFactor, solve_layers
+    C = orc.exact_spd_matrix(d, d + 1024, seed=5)
+    lam, ew = 4000.0, 0.6
+    s = (ew / 0.5) ** 0.5
+    C32 = torch.from_numpy(C).to(dev) * (1 - ew) / 0.5
+    fac = CachedFactor(C32, lam)
+    for j, n in enumerate(ns):
+        g = torch.Generator().manual_seed(200 + j)
+        K = (torch.randn(n, d, generator=g) * 0.3 + 0.1).numpy()
+        S = torch.randn(n, h, generator=g).numpy()
+        adj, resid, dW = fac.solve(torch.from_numpy(K).to(dev), torch.from_numpy(S).to(dev), s, 3)
+        assert tuple(adj.shape) == (d, n) and tuple(resid.shape) == (h, n) and tuple(dW.shape) == (h, d)
+        a_ref, r_ref, u_ref = orc.solve_layer(C, K.T, S.T, lam, ew, 3)
+        assert rel_fro(dW.cpu().numpy(), u_ref) < DW_TOL
+        assert rel_fro(adj.cpu().numpy(), a_ref) < DW_TOL
+        assert rel_fro(resid.cpu().numpy(), r_ref) < 1e-6
+        adj_d, _, dW_d = solve_layers(C32, torch.from_numpy(K).to(dev), torch.from_numpy(S).to(dev), lam, s, [3])
+        assert rel_fro(dW.cpu().numpy(), dW_d[0].cpu().numpy()) < 1e-5
+        assert rel_fro(adj.cpu().numpy(), adj_d[0].cpu().numpy()) < 1e-5
+    fac.close()
+
+
+@pytest.mark.parametrize("cached", [False, True])
+def test_sequential_editing_matches_oracle(dev, tmp_path, monkeypatch, cached):
     """Config-5 pattern (experiments/sequential_editing.py): successive edits on the same model reuse the
-    cached C and re-solve on the already-edited weights."""
+    cached C and re-solve on the already-edited weights — with and without the cached factorisation of lambda * C."""
     from emcid_b200 import emcid_main
     from types import SimpleNamespace
+    emcid_main.clear_factor_cache()
+    if cached:
+        monkeypatch.setattr(emcid_main, "FACTOR_CACHE_MAX_FRACTION", 1)     # tiny model: d = 256, n_pad = 128
+    else:
+        monkeypatch.setenv("EMCID_FACTOR_CACHE", "0")
     layers, ss = [0, 1], 60
     caps = rh.make_captions(80, 1000, seed=21)
     m_gpu = rh.make_clip_text_model("tiny", seed=3).to(dev)
@@ -511,6 +545,8 @@ def test_sequential_editing_matches_oracle(dev, tmp_path):
         got = m_gpu.text_model.encoder.layers[l].mlp.fc2.weight.detach().cpu().numpy().astype(np.float64) - w0
         want = m_cpu.text_model.encoder.layers[l].mlp.fc2.weight.numpy().astype(np.float64) - w0
         assert rel_fro(got, want) < DW_TOL
+    assert len(emcid_main.FACTOR_CACHE) == (len(layers) if cached else 0)    # one factor per layer, reused by every edit
+    emcid_main.clear_factor_cache()
 
 
 def test_sdxl_two_encoder_edit_matches_oracle(dev, tmp_path):
