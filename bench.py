@@ -417,6 +417,60 @@ def run_ours(args):
                 "what": "execute_emcid_text_encoder(pipe, requests, hparams, cache_name): v* npz reads, tokenisation, key/"
                         "output extraction per layer, 5 sequential solves with in-place weight writes, deltas to host (fp64)"}
         del deltas
+        # ---- BASELINE configs[4]: sequential editing — 10 successive 100-concept edits through the public
+        # apply_emcid_to_text_encoder, each reusing the cached C and re-solving on the already-edited weights
+        # (experiments/sequential_editing.py:98-171).  Timed twice on the same requests: every edit re-factoring
+        # lambda*C + K K^T (EMCID_FACTOR_CACHE=0, the reference's order of work) and with the cached factorisation of
+        # lambda*C (default).  The edited fc2 weights are put back afterwards.
+        if not args.no_sequential:
+            n_edits, per_edit = 10, 100
+            seq_reqs = [[dict(r, source=f"edit{e} {r['source']}") for r in synth.make_edit_requests(per_edit)]
+                        for e in range(n_edits)]
+            seq_cache = os.path.join(tmp_e, "vstar_seq", "c_")
+            for rq in seq_reqs:
+                synth.write_vstar_cache(seq_cache, rq, H, seed=3)
+            fc2 = [model.text_model.encoder.layers[l].mlp.fc2.weight for l in LAYERS]
+            saved = [w.detach().clone() for w in fc2]
+            sequential = {"edits": n_edits, "concepts_per_edit": per_edit, "layers": len(LAYERS),
+                          "what": "10 successive apply_emcid_to_text_encoder calls (cached v*, cached C), wall clock per "
+                                  "mode incl. key extraction, solves, host deltas and the in-place weight updates; the first "
+                                  "pass of each mode is untimed warm-up (tokeniser memo, factor build reported separately)"}
+            for mode, env in (("direct", "0"), ("cached_factor", "1")):
+                os.environ["EMCID_FACTOR_CACHE"] = env
+                emcid_main.clear_factor_cache()
+                for timed_pass in (False, True):
+                    with torch.no_grad():
+                        for w, w0 in zip(fc2, saved):
+                            w.copy_(w0)
+                    emcid_main.TIMING = timed_pass
+                    solve_ms = []
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for rq in seq_reqs:
+                        emcid_main.apply_emcid_to_text_encoder(pipe, rq, hp, device=dev, cache_name=seq_cache,
+                                                               stats_dir=tmp_e, verbose=False)
+                        solve_ms.append(emcid_main.LAST_EDIT_TIMING.get("solve_ms", 0.0))
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    emcid_main.TIMING = False
+                    if not timed_pass:
+                        sequential[mode + "_first_pass_ms"] = 1e3 * dt
+                    else:   # stage timing synchronises between stages: a slightly pessimistic wall clock
+                        sequential[mode + "_ms"] = 1e3 * dt
+                        sequential[mode + "_solve_ms_per_edit"] = round(sorted(solve_ms)[len(solve_ms) // 2], 2)
+                sequential[mode + "_dW_norm"] = float(sum((w - w0).double().norm() ** 2 for w, w0 in zip(fc2, saved)) ** 0.5)
+                if mode == "direct":
+                    direct_w = [w.detach().clone() for w in fc2]
+                else:
+                    num = sum((w - wd).double().norm() ** 2 for w, wd in zip(fc2, direct_w)) ** 0.5
+                    den = sum((wd - w0).double().norm() ** 2 for wd, w0 in zip(direct_w, saved)) ** 0.5
+                    sequential["cached_vs_direct_rel_fro"] = float(num / den)
+            os.environ.pop("EMCID_FACTOR_CACHE", None)
+            emcid_main.clear_factor_cache()
+            with torch.no_grad():
+                for w, w0 in zip(fc2, saved):
+                    w.copy_(w0)
+            edit["sequential"] = sequential
         emcid_main.COV_CACHE.clear()
     runner.close()
 
@@ -533,6 +587,7 @@ def main():
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-edit", action="store_true")
+    ap.add_argument("--no-sequential", action="store_true", help="skip the 10 x 100-concept sequential-editing timing")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.captions <= 0:

@@ -27,7 +27,18 @@ struct DgemmParams {
   double* C; long long ldc, c_batch;               // fp64 result (or null)
   float* C32; long long ldc32, c32_batch;          // fp32 copy of the result (or null)
   int lower;                                       // skip tiles strictly above the diagonal
+  // split-K (few output tiles, long K: the refinement residual of a narrow edit has 24 tiles of K = 3072 on 148 SMs):
+  // split_k > 1 -> grid.z = batches * split_k, slice z of the K range writes alpha * (partial product) to
+  // C + z * c_split (plain stores, deterministic); Cin / Cin32 / C32 / beta are ignored and the caller reduces the slices.
+  int split_k; long long c_split;
 };
+
+// slices so that about `sms` CTAs run, each with at least 256 of K
+inline int dgemm_pick_split(int tiles, int K, int sms) {
+  int s = tiles > 0 ? sms / tiles : 1;
+  if (s > K / 256) s = K / 256;
+  return s < 1 ? 1 : s;
+}
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -40,7 +51,10 @@ __global__ void __launch_bounds__(DG_THREADS) dgemm_nt_kernel(const DgemmParams 
   __shared__ double Bs[DG_BK][DG_LD];
   const int bm = blockIdx.y * DG_BM, bn = blockIdx.x * DG_BN;
   if (p.lower && bn > bm + DG_BM - 1) return;
-  const int batch = blockIdx.z;
+  const int split = p.split_k > 1 ? p.split_k : 1;
+  const int batch = blockIdx.z / split, kz = blockIdx.z - batch * split;
+  const int k_chunk = ((p.K + split - 1) / split + DG_BK - 1) / DG_BK * DG_BK;
+  const int k_begin = kz * k_chunk, k_end = min(p.K, k_begin + k_chunk);
   const double* A = p.A + batch * p.a_batch;
   const double* B = p.B + batch * p.b_batch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -54,8 +68,8 @@ __global__ void __launch_bounds__(DG_THREADS) dgemm_nt_kernel(const DgemmParams 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + lk + j;
-      ra[j] = (ar < p.M && k < p.K) ? A[static_cast<long long>(ar) * p.lda + k] : 0.0;
-      rb[j] = (br < p.N && k < p.K) ? B[static_cast<long long>(br) * p.ldb + k] : 0.0;
+      ra[j] = (ar < p.M && k < k_end) ? A[static_cast<long long>(ar) * p.lda + k] : 0.0;
+      rb[j] = (br < p.N && k < k_end) ? B[static_cast<long long>(br) * p.ldb + k] : 0.0;
     }
   };
   auto store_tiles = [&]() {
@@ -72,12 +86,12 @@ __global__ void __launch_bounds__(DG_THREADS) dgemm_nt_kernel(const DgemmParams 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int nk = (p.K + DG_BK - 1) / DG_BK;
-  load_tiles(0);
+  const int nk = k_end > k_begin ? (k_end - k_begin + DG_BK - 1) / DG_BK : 0;
+  load_tiles(k_begin);
   store_tiles();
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
-    if (kt + 1 < nk) load_tiles((kt + 1) * DG_BK);  // global loads in flight during the MMAs
+    if (kt + 1 < nk) load_tiles(k_begin + (kt + 1) * DG_BK);  // global loads in flight during the MMAs
 #pragma unroll
     for (int ks = 0; ks < DG_BK; ks += 4) {
       double af[8], bf[4];
@@ -109,6 +123,10 @@ __global__ void __launch_bounds__(DG_THREADS) dgemm_nt_kernel(const DgemmParams 
         const int c = col + e;
         if (c >= p.N) continue;
         double v = p.alpha * acc[i][j][e];
+        if (split > 1) {
+          p.C[kz * p.c_split + batch * p.c_batch + static_cast<long long>(row) * p.ldc + c] = v;
+          continue;
+        }
         if (p.Cin) v += p.beta * p.Cin[batch * p.cin_batch + static_cast<long long>(row) * p.ldcin + c];
         if (p.Cin32)
           v += p.beta * static_cast<double>(p.Cin32[batch * p.cin32_batch + static_cast<long long>(row) * p.ldcin32 + c]);
@@ -120,7 +138,7 @@ __global__ void __launch_bounds__(DG_THREADS) dgemm_nt_kernel(const DgemmParams 
 }
 
 inline int launch_dgemm_nt(const DgemmParams& p, int batches, cudaStream_t stream) {
-  dim3 grid((p.N + DG_BN - 1) / DG_BN, (p.M + DG_BM - 1) / DG_BM, batches);
+  dim3 grid((p.N + DG_BN - 1) / DG_BN, (p.M + DG_BM - 1) / DG_BM, batches * (p.split_k > 1 ? p.split_k : 1));
   dgemm_nt_kernel<<<grid, DG_THREADS, 0, stream>>>(p);
   EMCID_CUDA_CHECK(cudaGetLastError());
   return EMCID_OK;

@@ -33,6 +33,9 @@ namespace emcid {
 constexpr int SOLVE_NB = 128;
 constexpr int SOLVE_ADAPT_MAX = 8;
 constexpr double SOLVE_ADAPT_TOL = 1e-4;
+// capacity of the split-K slice buffer: dgemm_pick_split keeps slices * tiles <= #SMs (<= 160), a tile is 128 x 128, and
+// the lower-triangular G product covers at most twice its tile count in matrix elements
+constexpr long long SOLVE_SPLIT_ELEMS = 2LL * 160 * 128 * 128;
 
 // ---- diagonal block: potrf + inverse, fp64 in shared memory ---------------------------------------
 // M32: [B][d x d] fp32.  Writes L_kk (symmetric fill) into the LL planes' diagonal block and
@@ -376,6 +379,21 @@ __global__ void rhs_from64_kernel(const double* __restrict__ R, long long total,
   }
 }
 
+// W = float(R0 + sum_z P[z]), planes = split(W)   (split-K slices of -X^T M64 -> next right-hand side of the refinement)
+__global__ void residual_reduce_kernel(const double* __restrict__ R0, const double* __restrict__ P, int split,
+                                       long long stride, long long total, float* __restrict__ W, float* __restrict__ hi,
+                                       float* __restrict__ lo) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    double v = R0[i];
+    for (int z = 0; z < split; ++z) v += P[z * stride + i];
+    const float f = static_cast<float>(v);
+    float h, l;
+    split_tf32(f, h, l);
+    W[i] = f; hi[i] = h; lo[i] = l;
+  }
+}
+
 // A32 = float(lambda) * C32 (+ planes) and A64 = lambda * double(C32), lower 32x32 tiles mirrored to the upper ones
 // (same roundings as the direct path: fp32 product in the SYRK epilogue, fp64 product in the DMMA epilogue).
 __global__ void factor_prep_kernel(const float* __restrict__ C32, int d, double lambda, float* __restrict__ A32,
@@ -407,15 +425,24 @@ __global__ void factor_prep_kernel(const float* __restrict__ C32, int d, double 
   }
 }
 
-// G (lower 32x32 tiles of the raw product Ks^T Y) -> G64 = I + that, mirrored to a full symmetric matrix in place, with
-// its fp32 copy and planes.
-__global__ void g_prepare_kernel(double* __restrict__ G64, int m, float* __restrict__ G32, float* __restrict__ Gp_hi,
-                                 float* __restrict__ Gp_lo) {
+// G (lower 32x32 tiles of the raw product Ks^T Y; split > 0: the sum of `split` split-K slices P) -> G64 = I + that,
+// mirrored to a full symmetric matrix (in place when split == 0), with its fp32 copy and planes.
+__global__ void g_prepare_kernel(double* __restrict__ G64, int m, const double* __restrict__ P, int split, long long stride,
+                                 float* __restrict__ G32, float* __restrict__ Gp_hi, float* __restrict__ Gp_lo) {
   __shared__ double tile[32][33];
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj > bi) return;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  for (int r = ty; r < 32; r += 8) tile[r][tx] = G64[static_cast<long long>(bi * 32 + r) * m + bj * 32 + tx];
+  for (int r = ty; r < 32; r += 8) {
+    const long long o = static_cast<long long>(bi * 32 + r) * m + bj * 32 + tx;
+    double v = 0.0;
+    if (split > 0) {
+      for (int z = 0; z < split; ++z) v += P[z * stride + o];
+    } else {
+      v = G64[o];
+    }
+    tile[r][tx] = v;
+  }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     double v = tile[r][tx];
@@ -636,6 +663,7 @@ struct ApplyCtx {
   float *W, *Wp_hi, *Wp_lo, *W2p_hi, *W2p_lo;   // [B][rows_pad x dim]
   double* X64t;          // [B][rows_pad x dim] result
   double* norms;         // [2]
+  double* P64;           // [SOLVE_SPLIT_ELEMS] split-K slices of the residual product (or null: no split-K)
   PlaneMaps mW, mW2;
 };
 
@@ -729,10 +757,22 @@ inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64,
       p.A = a.X64t; p.lda = d; p.a_batch = nd;
       p.B = a.M64; p.ldb = d; p.b_batch = dd;
       p.alpha = -1.0; p.beta = 1.0;
-      p.Cin = a.R64t; p.ldcin = d; p.cin_batch = nd;
-      p.C32 = a.W; p.ldc32 = d; p.c32_batch = nd;
-      if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
-      if ((rc = launch_split_planes(a.W, d, B * n_pad, d, 1.0f, a.Wp_hi, a.Wp_lo, d, stream))) return rc;
+      int split = a.P64 ? dgemm_pick_split(B * (n_pad / DG_BM) * ((d + DG_BN - 1) / DG_BN), d, sms) : 1;
+      while (split > 1 && split * tot > SOLVE_SPLIT_ELEMS) --split;
+      if (split > 1) {
+        // few tiles, long K (narrow edit): K sliced over the idle SMs, slices summed with R0 by the reducer
+        p.M = n_pad;   // pad rows of X are zero: every slice element is defined
+        p.C = a.P64; p.ldc = d; p.c_batch = nd;
+        p.split_k = split; p.c_split = tot;
+        if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
+        residual_reduce_kernel<<<sms * 8, 256, 0, stream>>>(a.R64t, a.P64, split, tot, tot, a.W, a.Wp_hi, a.Wp_lo);
+        EMCID_CUDA_CHECK(cudaGetLastError());
+      } else {
+        p.Cin = a.R64t; p.ldcin = d; p.cin_batch = nd;
+        p.C32 = a.W; p.ldc32 = d; p.c32_batch = nd;
+        if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
+        if ((rc = launch_split_planes(a.W, d, B * n_pad, d, 1.0f, a.Wp_hi, a.Wp_lo, d, stream))) return rc;
+      }
     }
     if ((rc = f.trsm ? trsm_both() : apply_inverse())) return rc;
     solve_axpy_kernel<<<sms * 8, 256, 0, stream>>>(a.W, a.X64t, tot, it > 0 ? 1 : 0);
@@ -821,6 +861,7 @@ inline SolveWs solve_carve(void* base, int B, int d, int h, int n) {
   w.Kd64 = c.take<double>(nd);
   w.inv_left = c.take<double>(B);
   w.a.norms = c.take<double>(2);
+  w.a.P64 = c.take<double>(SOLVE_SPLIT_ELEMS);
   carve_factor(c, w.f, B, d, true);
   carve_apply(c, w.a, nd);
   w.Kd_hi = c.take<float>(nd);
@@ -1018,6 +1059,7 @@ inline FactorSolveWs factor_solve_carve(void* base, int d, int n) {
   w.G64 = c.take<double>(static_cast<size_t>(n_pad) * n_pad);
   w.inv_left = c.take<double>(1);
   w.a1.norms = c.take<double>(2);
+  w.a1.P64 = c.take<double>(SOLVE_SPLIT_ELEMS);
   carve_factor(c, w.g, 1, static_cast<int>(n_pad), true);
   carve_apply(c, w.a1, nd);
   // stage 2 runs after stage 1 is finished on the same stream: its fp32 buffers and its result reuse stage 1's
@@ -1079,8 +1121,16 @@ inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long lon
     p.alpha = 1.0;
     p.C = w.G64; p.ldc = n_pad;
     p.lower = 1;
+    const int t = n_pad / DG_BM;
+    const long long gg = static_cast<long long>(n_pad) * n_pad;
+    int split = dgemm_pick_split(t * (t + 1) / 2, d, sms);
+    while (split > 1 && split * gg > SOLVE_SPLIT_ELEMS) --split;
+    if (split > 1) {
+      p.C = w.a1.P64; p.split_k = split; p.c_split = gg;
+    }
     if ((rc = launch_dgemm_nt(p, 1, stream))) return rc;
-    g_prepare_kernel<<<dim3(n_pad / 32, n_pad / 32), dim3(32, 8), 0, stream>>>(w.G64, n_pad, w.g.M32, w.g.Mp_hi, w.g.Mp_lo);
+    g_prepare_kernel<<<dim3(n_pad / 32, n_pad / 32), dim3(32, 8), 0, stream>>>(w.G64, n_pad, w.a1.P64, split > 1 ? split : 0,
+                                                                                gg, w.g.M32, w.g.Mp_hi, w.g.Mp_lo);
     EMCID_CUDA_CHECK(cudaGetLastError());
   }
   // 4. factor G
