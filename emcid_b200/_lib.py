@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libemcid_b200.so")
+# EMCID_B200_LIB: another build of the same library (measurement aid, e.g. one compiled with -DEMCID_POTRF_TIMING)
+LIB_PATH = os.environ.get("EMCID_B200_LIB") or os.path.join(_HERE, "libemcid_b200.so")
 
 EMCID_OK = 0
 ACT_QUICK_GELU = 0

@@ -31,8 +31,24 @@
 namespace emcid {
 
 constexpr int SOLVE_NB = 128;
-constexpr int SOLVE_ADAPT_MAX = 8;
-constexpr double SOLVE_ADAPT_TOL = 1e-4;
+// Adaptive refinement stops on the PREDICTED error left after the sweep just applied.  With c_k = |dx_k| / |x| the size of
+// sweep k's correction (c_0 = 1: the unrefined solve) the sweeps contract geometrically, c_k ~ rho c_{k-1} (measured on
+// B200: rho = 3e-3 for 1000 concepts at d = 3072, 0.1 for 100 concepts, 0.2 / 0.45 for lambda*C alone at d = 3072 / 5120),
+// so what is left after sweep k is ~ rho c_k / (1 - rho).  rho is taken as 1.5 x the largest ratio seen so far (the ratios
+// creep up over the first sweeps) and the loop ends when that prediction is below SOLVE_ADAPT_TOL = 2e-5 relative
+// Frobenius error of adj_k, a fifth of the 1e-4 dW tolerance.  (Until r03 the rule was "last correction < 1e-4", which spent
+// a whole sweep — one fp64 product with M64, 4.3 of 22 ms for 5 layers x 1000 concepts — to confirm what the ratio already
+// said, and stopped too early when rho was large.)  EMCID_SOLVE_TOL overrides the target.
+constexpr int SOLVE_ADAPT_MAX = 16;
+constexpr double SOLVE_ADAPT_TOL = 2e-5;
+// the cached-factor path chains two refined solves whose errors add up in adj_k (and the error of Y is amplified by up to
+// cond(G) on the way): each runs to a four times smaller target
+constexpr double SOLVE_ADAPT_TOL_CHAINED = 5e-6;
+
+inline double solve_adapt_tol(double dflt) {
+  static const double env = [] { const char* e = getenv("EMCID_SOLVE_TOL"); return e ? atof(e) : 0.0; }();
+  return env > 0.0 ? env * (dflt / SOLVE_ADAPT_TOL) : dflt;
+}
 // capacity of the split-K slice buffer: dgemm_pick_split keeps slices * tiles <= #SMs (<= 160), a tile is 128 x 128, and
 // the lower-triangular G product covers at most twice its tile count in matrix elements
 constexpr long long SOLVE_SPLIT_ELEMS = 2LL * 160 * 128 * 128;
@@ -241,6 +257,323 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict
            tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[6] - tk[0]);
 #endif
 #undef EMCID_TK
+}
+
+// ---- diagonal block, register-blocked version --------------------------------------------------------------------------
+// Same contract as potrf_diag_kernel.  The column-at-a-time kernel above spends 1300 clocks per column on two block-wide
+// barriers and shared-memory round trips (170 k clocks for the factor, 97 k for the inverse of a 128 x 128 block); here the
+// block is cut into 32 x 32 sub-blocks, a lane owns one ROW of a sub-block in registers and the other operand of every
+// product is a shared-memory broadcast:
+//   factor   per 32-column panel: warp 0 factors the diagonal sub-block (no block-wide barrier inside; the rank-1 updates
+//            use the UNSCALED column and a Newton reciprocal of the pivot, so the per-column dependency chain is one
+//            broadcast + one reciprocal + one FMA, and the 32 square roots are taken at the end, off the chain), the
+//            sub-blocks below it are solved one row per lane against the transposed diagonal factor, the trailing
+//            sub-blocks get a rank-32 update; three block-wide barriers per panel instead of 64 + 1
+//   inverse  diagonal sub-blocks one warp each (right-looking row recurrence in registers), then block rows top-down:
+//            T_ij = sum_k L_ik X_kj,  X_ij = -X_ii T_ij
+// Every 32 x 32 x 32 product is cut into four 8-column items dealt round-robin to the 8 warps, which keeps the four
+// fp64 pipes of the SM evenly loaded (the kernel is DFMA-issue bound there: 2 clocks per warp instruction per quadrant).
+// The strictly upper triangles of the diagonal sub-blocks and the upper sub-blocks stay zero from the load on.
+// Even pitches: every broadcast operand is fetched as an aligned double2 (the products are bound by shared-memory
+// wavefronts, one per broadcast load: LDS.128 halves them); the price is a 2-way bank conflict on the row-per-lane loads,
+// of which there are 32 per 256 broadcasts.
+constexpr int POTRF2_LD = SOLVE_NB + 2;
+constexpr int POTRF2_TP = 34;   // pitch of the T_ij scratch
+constexpr int POTRF2_SMEM_DOUBLES = SOLVE_NB * POTRF2_LD + SOLVE_NB + 32 * 32 + 64 + 3 * 32 * POTRF2_TP;
+
+// 1 / d to ~1e-13 from the fp32 approximation and ONE Newton step: the pivot reciprocal sits on the column-to-column
+// dependency chain of the diagonal factorisation, where every dependent fp64 operation costs ~40 clocks (measured: 380
+// clocks per column with the shuffle + two-step version), and the factor is rounded to 22-bit planes afterwards anyway.
+// d outside the fp32 range takes the division.
+__device__ __forceinline__ double potrf_fast_rcp(double d) {
+  const double ad = fabs(d);
+  if (!(ad > 1e-30 && ad < 1e30)) return 1.0 / d;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__double2float_rn(d)));
+  const double y = static_cast<double>(r);
+  return fma(y, fma(-d, y, 1.0), y);
+}
+
+// s[u] += sum_t p[t] * Q[u * qs_u + t], u = 0..7: operand rows contiguous in t (Q 16-byte aligned, qs_u even)
+__device__ __forceinline__ void warp_rowdot8_tc(const double (&p)[32], const double* __restrict__ Q, int qs_u, double (&s)[8]) {
+#pragma unroll
+  for (int t = 0; t < 32; t += 2) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double2 q = *reinterpret_cast<const double2*>(Q + u * qs_u + t);
+      s[u] = fma(p[t], q.x, s[u]);
+      s[u] = fma(p[t + 1], q.y, s[u]);
+    }
+  }
+}
+
+// s[u] += sum_t p[t] * Q[t * qs_t + u], u = 0..7: operand rows contiguous in u (Q 16-byte aligned, qs_t even)
+__device__ __forceinline__ void warp_rowdot8_uc(const double (&p)[32], const double* __restrict__ Q, int qs_t, double (&s)[8]) {
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const double2 q = *reinterpret_cast<const double2*>(Q + t * qs_t + 2 * v);
+      s[2 * v] = fma(p[t], q.x, s[2 * v]);
+      s[2 * v + 1] = fma(p[t], q.y, s[2 * v + 1]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel_v2(const float* __restrict__ M32, int d, int k,
+                                                            float* __restrict__ LL_hi, float* __restrict__ LL_lo,
+                                                            float* __restrict__ Li_hi, float* __restrict__ Li_lo,
+                                                            float* __restrict__ LiT_hi, float* __restrict__ LiT_lo,
+                                                            float* __restrict__ Lv_hi, float* __restrict__ Lv_lo,
+                                                            float* __restrict__ LvT_hi, float* __restrict__ LvT_lo,
+                                                            int* __restrict__ status) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int LD = POTRF2_LD, TP = POTRF2_TP;
+  double* A = sm;                          // [128][130]
+  double* invd = sm + SOLVE_NB * LD;       // [128] reciprocal diagonal of L
+  double* LdT = invd + SOLVE_NB;           // [32][32]: LdT[j * 32 + c] = L_cj of the current diagonal sub-block
+  double* cb = LdT + 32 * 32;              // [2][32] column broadcast buffer of the diagonal factorisation
+  double* Tb = cb + 64;                    // [3][32][34] T_ij of one block row of the inverse
+  const int b = blockIdx.x;
+  const long long base = static_cast<long long>(b) * d * d + static_cast<long long>(k) * SOLVE_NB * d + k * SOLVE_NB;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#ifdef EMCID_POTRF_TIMING
+  long long tk[8]; tk[0] = clock64();
+  long long tph[3] = {0, 0, 0}, tlast;
+#define EMCID_TK(i) tk[i] = clock64()
+#define EMCID_TPH(i) do { const long long now_ = clock64(); tph[i] += now_ - tlast; tlast = now_; } while (0)
+#else
+#define EMCID_TK(i)
+#define EMCID_TPH(i)
+#endif
+  // ---- load: one row per warp instruction (float4 per lane), all 16 loads of a warp in flight together
+  {
+    float4 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      v[i] = *reinterpret_cast<const float4*>(M32 + base + static_cast<long long>(wid + 8 * i) * d + 4 * lane);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = wid + 8 * i, c = 4 * lane;
+      double* row = A + r * LD + c;
+      row[0] = (c <= r) ? static_cast<double>(v[i].x) : 0.0;
+      row[1] = (c + 1 <= r) ? static_cast<double>(v[i].y) : 0.0;
+      row[2] = (c + 2 <= r) ? static_cast<double>(v[i].z) : 0.0;
+      row[3] = (c + 3 <= r) ? static_cast<double>(v[i].w) : 0.0;
+    }
+  }
+  __syncthreads();
+  EMCID_TK(1);
+#ifdef EMCID_POTRF_TIMING
+  tlast = tk[1];
+#endif
+  // ---- factor
+  for (int p = 0; p < 4; ++p) {
+    const int p0 = 32 * p;
+    if (wid == 0) {
+      // diagonal sub-block: lane = row r, the row in registers.  Column j stays unscaled (u_rj, pivot d_j = u_jj):
+      //   a_rc -= u_rj u_cj / d_j   for c > j;      L_rj = u_rj / sqrt(d_j) once all columns are done
+      double a[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = A[(p0 + lane) * LD + p0 + c];
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        double* col = cb + (j & 1) * 32;
+        col[lane] = a[j];
+        double dj = __shfl_sync(0xffffffffu, a[j], j);   // the pivot by shuffle: shorter than the shared-memory round trip
+        __syncwarp();
+        if (!(dj > 0.0)) { bad = true; dj = 1.0; }   // also catches NaN
+        const double w = a[j] * potrf_fast_rcp(dj);
+        if (((j + 1) & 1) && j + 1 < 32) a[j + 1] = fma(-w, col[j + 1], a[j + 1]);
+#pragma unroll
+        for (int c = (j + 2) & ~1; c < 32; c += 2) {
+          const double2 q = *reinterpret_cast<const double2*>(col + c);
+          a[c] = fma(-w, q.x, a[c]);
+          a[c + 1] = fma(-w, q.y, a[c + 1]);
+        }
+      }
+      if (bad && lane == 0) atomicOr(status, 1);
+      double dg = 1.0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (lane == j) dg = a[j];
+      if (!(dg > 0.0)) dg = 1.0;
+      const double sj = rsqrt(dg);
+      invd[p0 + lane] = sj;
+      __syncwarp();
+      cb[lane] = sj;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (c <= lane) {
+          const double l = (c == lane) ? dg * sj : a[c] * cb[c];
+          A[(p0 + lane) * LD + p0 + c] = l;
+          LdT[c * 32 + lane] = l;
+        }
+      }
+    }
+    __syncthreads();
+    EMCID_TPH(0);
+    if (p == 3) break;
+    const int nb = 3 - p;
+    if (wid < nb) {
+      // sub-block below: lane = row i,  x_j = (a_j - sum_{t<j} x_t L_jt) / L_jj, right-looking
+      const int i = p0 + 32 * (1 + wid) + lane;
+      double a[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = A[i * LD + p0 + c];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const double x = a[j] * invd[p0 + j];
+        a[j] = x;
+        if (((j + 1) & 1) && j + 1 < 32) a[j + 1] = fma(-x, LdT[j * 32 + j + 1], a[j + 1]);
+#pragma unroll
+        for (int c = (j + 2) & ~1; c < 32; c += 2) {
+          const double2 q = *reinterpret_cast<const double2*>(LdT + j * 32 + c);
+          a[c] = fma(-x, q.x, a[c]);
+          a[c + 1] = fma(-x, q.y, a[c + 1]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) A[i * LD + p0 + c] = a[c];
+    }
+    __syncthreads();
+    EMCID_TPH(1);
+    {
+      // trailing sub-blocks (I, K), p < K <= I <= 3:  A_IK -= P_I P_K^T with P = the panel just finished;
+      // item q = 4 * (sub-block) + (8-column chunk)
+      const int items = 2 * nb * (nb + 1);
+      for (int q = wid; q < items; q += 8) {
+        int I = p + 1, w = q >> 2;
+        while (w > I - (p + 1)) { w -= I - p; ++I; }
+        const int K = p + 1 + w, c0 = 8 * (q & 3);
+        double pr[32], s[8];
+        const int r = 32 * I + lane;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) pr[t] = A[r * LD + p0 + t];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] = 0.0;
+        warp_rowdot8_tc(pr, A + (32 * K + c0) * LD + p0, LD, s);
+        double* dst = A + r * LD + 32 * K + c0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (I != K || c0 + u <= lane) dst[u] -= s[u];
+      }
+    }
+    __syncthreads();
+    EMCID_TPH(2);
+  }
+  EMCID_TK(2);
+  // ---- L_kk -> LL planes (lower = L, upper = L^T)
+  for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
+    const int r = e / SOLVE_NB, c = e % SOLVE_NB;
+    const double v = (c <= r) ? A[r * LD + c] : A[c * LD + r];
+    float hi, lo;
+    split_tf32(static_cast<float>(v), hi, lo);
+    LL_hi[base + static_cast<long long>(r) * d + c] = hi;
+    LL_lo[base + static_cast<long long>(r) * d + c] = lo;
+  }
+  __syncthreads();
+  EMCID_TK(3);
+  // ---- inverse X = L^-1 in place.  (1) diagonal sub-blocks, one warp each: from X L = I,
+  //        x_rk = (delta_rk - sum_{m>k} x_rm L_mk) / L_kk,  k = r .. 0;   acc[j] gathers the sums right-looking
+  if (wid < 4) {
+    const int r0 = 32 * wid;
+    double acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+#pragma unroll
+    for (int kk = 31; kk >= 0; --kk) {
+      double x = ((lane == kk) ? 1.0 : 0.0) - acc[kk];
+      x = (kk > lane) ? 0.0 : x * invd[r0 + kk];
+      acc[kk] = x;
+      const double* lrow = A + (r0 + kk) * LD + r0;
+#pragma unroll
+      for (int j = 0; j + 1 < kk; j += 2) {
+        const double2 q = *reinterpret_cast<const double2*>(lrow + j);
+        acc[j] = fma(x, q.x, acc[j]);
+        acc[j + 1] = fma(x, q.y, acc[j + 1]);
+      }
+      if (kk & 1) acc[kk - 1] = fma(x, lrow[kk - 1], acc[kk - 1]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j <= lane) A[(r0 + lane) * LD + r0 + j] = acc[j];
+  }
+  __syncthreads();
+  EMCID_TK(4);
+  // (2) block rows top-down:  T_ij = sum_{k=j..i-1} L_ik X_kj,  X_ij = -X_ii T_ij;  item q = 4 * j + (8-column chunk)
+  for (int i = 1; i < 4; ++i) {
+    for (int q = wid; q < 4 * i; q += 8) {
+      const int j = q >> 2, c0 = 8 * (q & 3);
+      const int r = 32 * i + lane;
+      double s[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] = 0.0;
+      for (int kb = j; kb < i; ++kb) {
+        double pr[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) pr[t] = A[r * LD + 32 * kb + t];
+        warp_rowdot8_uc(pr, A + (32 * kb) * LD + 32 * j + c0, LD, s);
+      }
+      double* dst = Tb + j * (32 * TP) + lane * TP + c0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dst[u] = s[u];
+    }
+    __syncthreads();
+    for (int q = wid; q < 4 * i; q += 8) {
+      const int j = q >> 2, c0 = 8 * (q & 3);
+      const int r = 32 * i + lane;
+      double pr[32], s[8];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) pr[t] = A[r * LD + 32 * i + t];      // row of X_ii (upper part zero)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] = 0.0;
+      warp_rowdot8_uc(pr, Tb + j * (32 * TP) + c0, TP, s);
+      double* dst = A + r * LD + 32 * j + c0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dst[u] = -s[u];
+    }
+    __syncthreads();
+  }
+  EMCID_TK(5);
+  // ---- Linv_kk / Linv_kk^T planes (and the diagonal block of the explicit inverse): four columns per thread, float4 stores
+  const long long ibase = (static_cast<long long>(b) * d + static_cast<long long>(k) * SOLVE_NB) * SOLVE_NB;
+  for (int e = tid; e < SOLVE_NB * SOLVE_NB / 4; e += blockDim.x) {
+    const int r = e / (SOLVE_NB / 4), c = 4 * (e % (SOLVE_NB / 4));
+    float4 h4, l4, ht4, lt4;
+    split_tf32(static_cast<float>((c <= r) ? A[r * LD + c] : 0.0), h4.x, l4.x);
+    split_tf32(static_cast<float>((c + 1 <= r) ? A[r * LD + c + 1] : 0.0), h4.y, l4.y);
+    split_tf32(static_cast<float>((c + 2 <= r) ? A[r * LD + c + 2] : 0.0), h4.z, l4.z);
+    split_tf32(static_cast<float>((c + 3 <= r) ? A[r * LD + c + 3] : 0.0), h4.w, l4.w);
+    split_tf32(static_cast<float>((r <= c) ? A[c * LD + r] : 0.0), ht4.x, lt4.x);
+    split_tf32(static_cast<float>((r <= c + 1) ? A[(c + 1) * LD + r] : 0.0), ht4.y, lt4.y);
+    split_tf32(static_cast<float>((r <= c + 2) ? A[(c + 2) * LD + r] : 0.0), ht4.z, lt4.z);
+    split_tf32(static_cast<float>((r <= c + 3) ? A[(c + 3) * LD + r] : 0.0), ht4.w, lt4.w);
+    *reinterpret_cast<float4*>(Li_hi + ibase + r * SOLVE_NB + c) = h4;
+    *reinterpret_cast<float4*>(Li_lo + ibase + r * SOLVE_NB + c) = l4;
+    *reinterpret_cast<float4*>(LiT_hi + ibase + r * SOLVE_NB + c) = ht4;
+    *reinterpret_cast<float4*>(LiT_lo + ibase + r * SOLVE_NB + c) = lt4;
+    if (Lv_hi) {   // diagonal block of the explicit inverse
+      const long long o = base + static_cast<long long>(r) * d + c;
+      *reinterpret_cast<float4*>(Lv_hi + o) = h4;
+      *reinterpret_cast<float4*>(Lv_lo + o) = l4;
+      *reinterpret_cast<float4*>(LvT_hi + o) = ht4;
+      *reinterpret_cast<float4*>(LvT_lo + o) = lt4;
+    }
+  }
+#ifdef EMCID_POTRF_TIMING
+  __syncthreads();
+  EMCID_TK(6);
+  if (tid == 0 && b == 0 && k == 3)
+    printf("potrf2 clk: load %lld chol %lld (diag %lld below %lld trailing %lld) LLwrite %lld diaginv %lld blkinv %lld out %lld "
+           "total %lld\n", tk[1] - tk[0], tk[2] - tk[1], tph[0], tph[1], tph[2], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4],
+           tk[6] - tk[5], tk[6] - tk[0]);
+#endif
+#undef EMCID_TK
+#undef EMCID_TPH
 }
 
 // ---- operand preparation ----------------------------------------------------------------------------
@@ -529,12 +862,22 @@ inline bool solve_use_trsm() {
   return v;
 }
 
-inline int potrf_smem_bytes() { return (SOLVE_NB * (SOLVE_NB + 1) + 2 * SOLVE_NB + 96 * 33) * sizeof(double); }
+inline bool potrf_use_v1() {
+  // EMCID_POTRF_V1=1: the column-at-a-time diagonal-block kernel (kept for A/B measurements)
+  static const bool v = [] { const char* e = getenv("EMCID_POTRF_V1"); return e && e[0] == '1'; }();
+  return v;
+}
+
+inline int potrf_smem_bytes() {
+  return potrf_use_v1() ? (SOLVE_NB * (SOLVE_NB + 1) + 2 * SOLVE_NB + 96 * 33) * static_cast<int>(sizeof(double))
+                        : POTRF2_SMEM_DOUBLES * static_cast<int>(sizeof(double));
+}
 
 inline int potrf_configure(int device) {
   static thread_local bool configured[16] = {false};
   if (device < 0 || device >= 16 || !configured[device]) {
-    EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem_bytes()));
+    EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_use_v1() ? potrf_diag_kernel : potrf_diag_kernel_v2,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem_bytes()));
     if (device >= 0 && device < 16) configured[device] = true;
   }
   return EMCID_OK;
@@ -595,9 +938,9 @@ inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) 
   int rc;
   // blocked right-looking Cholesky of M32
   for (int k = 0; k < nblk; ++k) {
-    potrf_diag_kernel<<<B, 256, potrf_smem_bytes(), stream>>>(f.M32, d, k, f.LL_hi, f.LL_lo, f.Li_hi, f.Li_lo, f.LiT_hi,
-                                                              f.LiT_lo, f.trsm ? nullptr : f.Lv_hi, f.Lv_lo, f.LvT_hi,
-                                                              f.LvT_lo, status_dev);
+    (potrf_use_v1() ? potrf_diag_kernel : potrf_diag_kernel_v2)<<<B, 256, potrf_smem_bytes(), stream>>>(
+        f.M32, d, k, f.LL_hi, f.LL_lo, f.Li_hi, f.Li_lo, f.LiT_hi, f.LiT_lo, f.trsm ? nullptr : f.Lv_hi, f.Lv_lo, f.LvT_hi,
+        f.LvT_lo, status_dev);
     EMCID_CUDA_CHECK(cudaGetLastError());
     const int rem = d - (k + 1) * SOLVE_NB;
     if (rem <= 0) break;
@@ -673,7 +1016,8 @@ inline int apply_make_maps(ApplyCtx& a, int B, int dim) {
   return make_plane_maps(&a.mW2, a.W2p_hi, a.W2p_lo, static_cast<long long>(B) * a.rows_pad, dim, dim);
 }
 
-inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64, int refine_steps, cudaStream_t stream) {
+inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64, int refine_steps, cudaStream_t stream,
+                         double adapt_tol = SOLVE_ADAPT_TOL) {
   const int B = f.B, d = f.dim, sms = f.sms, n = a.rows, n_pad = a.rows_pad;
   const int nblk = d / SOLVE_NB;
   const long long dd = static_cast<long long>(d) * d, nd = static_cast<long long>(n_pad) * d;
@@ -743,10 +1087,11 @@ inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64,
     rhs_from64_kernel<<<sms * 8, 256, 0, stream>>>(a.R64t, tot, a.W, a.Wp_hi, a.Wp_lo);
     EMCID_CUDA_CHECK(cudaGetLastError());
   }
-  // refine_steps >= 0: exactly that many sweeps.  -1: adaptive — stop once the last correction is below
-  // SOLVE_ADAPT_TOL relative to the solution (each sweep contracts the error by ~1e-2 at cond ~1e7, so the
-  // error left after applying a correction of that size is orders of magnitude under the 1e-4 dW tolerance).
+  // refine_steps >= 0: exactly that many sweeps.  -1: adaptive — stop once the error predicted from the contraction of
+  // the corrections is below the target (see SOLVE_ADAPT_TOL).
   const bool adaptive = refine_steps < 0;
+  const double tol = solve_adapt_tol(adapt_tol);
+  double c_prev = 1.0, rho_max = 0.0;
   const int max_steps = adaptive ? SOLVE_ADAPT_MAX : refine_steps;
   for (int it = 0; it <= max_steps; ++it) {
     if (it > 0) {
@@ -784,7 +1129,15 @@ inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64,
       EMCID_CUDA_CHECK(cudaGetLastError());
       EMCID_CUDA_CHECK(cudaMemcpyAsync(hn, a.norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
       EMCID_CUDA_CHECK(cudaStreamSynchronize(stream));
-      if (!(hn[1] > 0.0) || hn[0] <= SOLVE_ADAPT_TOL * SOLVE_ADAPT_TOL * hn[1]) break;
+      // EMCID_SOLVE_DEBUG=1: the relative size of every sweep's correction (dimension, right-hand sides, sweep, ratio)
+      static const bool debug = [] { const char* e = getenv("EMCID_SOLVE_DEBUG"); return e && e[0] == '1'; }();
+      if (debug) fprintf(stderr, "emcid refine dim=%d rhs=%d sweep=%d |dx|/|x|=%.3e\n", d, n, it, sqrt(hn[0] / hn[1]));
+      if (!(hn[1] > 0.0)) break;
+      const double c = sqrt(hn[0] / hn[1]);
+      if (c_prev > 0.0 && c / c_prev > rho_max) rho_max = c / c_prev;
+      c_prev = c;
+      const double rho = fmin(0.9, 1.5 * rho_max);
+      if (rho * c / (1.0 - rho) <= tol) break;
     }
   }
   return EMCID_OK;
@@ -1110,7 +1463,7 @@ inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long lon
     EMCID_CUDA_CHECK(cudaGetLastError());
   }
   // 2. Y^T = Ks^T A^-1, refined against A64                                  -> a1.X64t [n_pad x d]
-  if ((rc = refined_solve(fa, w.a1, false, refine_steps, stream))) return rc;
+  if ((rc = refined_solve(fa, w.a1, false, refine_steps, stream, SOLVE_ADAPT_TOL_CHAINED))) return rc;
   // 3. G = I + Ks^T Y   (fp64; lower tiles, then mirrored with fp32 copy and planes)
   {
     DgemmParams p;
@@ -1143,7 +1496,7 @@ inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long lon
   EMCID_CUDA_CHECK(cudaGetLastError());
   w.a2.rows = d; w.a2.rows_pad = d; w.a2.M64 = w.G64; w.a2.R64t = w.Yd64;
   if ((rc = apply_make_maps(w.a2, 1, n_pad))) return rc;
-  if ((rc = refined_solve(w.g, w.a2, true, refine_steps, stream))) return rc;
+  if ((rc = refined_solve(w.g, w.a2, true, refine_steps, stream, SOLVE_ADAPT_TOL_CHAINED))) return rc;
   // 6. outputs
   compact_cols_kernel<<<sms * 4, 256, 0, stream>>>(w.a2.X64t, d, n, n_pad, adj_k);
   EMCID_CUDA_CHECK(cudaGetLastError());

@@ -153,7 +153,8 @@ int emcid_clip_destroy(emcid_clip_t* h);
  *   St  [n, h] fp32 (row pitch lds)  = (zs - cur_zs)^T  (:1016)
  *   scale = sqrt(edit_weight / 0.5)  (:1041-1042);  inv_layers_left[b] = 1 / (L - i) (host array)
  * refine_steps: fp64-residual iterative-refinement sweeps after the fp32-class Cholesky solve; -1 = adaptive
- * (sweeps until the last correction is < 1e-4 of the solution, at most 8; synchronises the stream per sweep).
+ * (sweeps until the error predicted from the contraction of the corrections is < 2e-5 of the solution in Frobenius
+ * norm, a fifth of the dW tolerance; at most 16; synchronises the stream per sweep; EMCID_SOLVE_TOL overrides the target).
  * status_dev: device int, 0 on success, bit0 = a pivot was not positive (matrix not SPD).
  * d must be a multiple of 128.  Blackwell-only; asynchronous on `stream`. */
 size_t emcid_solve_workspace_bytes(int batch, int d, int h, int n);
