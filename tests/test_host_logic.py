@@ -293,3 +293,59 @@ def test_fast_npz_reader_equals_numpy_load(tmp_path):
     assert np.array_equal(emcid_main._read_npz_array(f, "v_star"), np.arange(7.0))
     with pytest.raises(KeyError):
         emcid_main._read_npz_array(tmp_path / "plain.npz", "absent")
+
+
+def test_factor_cache_policy(monkeypatch):
+    """Host logic of the cached-factorisation path of the edit loop (emcid_main._solve_one_layer): narrow edits go through
+    one factor per (encoder, layer, lambda, edit_weight), a replaced COV_CACHE tensor rebuilds it, wide edits and
+    EMCID_FACTOR_CACHE=0 take the direct solver, least recently used entries are dropped.  No GPU: the two solvers are
+    stand-ins that record their calls."""
+    from types import SimpleNamespace
+    calls = []
+
+    class FakeFactor:
+        def __init__(self, C32, lam):
+            calls.append(("create", float(lam), float(C32[0, 0])))
+            self.closed = False
+
+        def solve(self, Kt, St, scale, left, refine_steps=-1):
+            calls.append(("cached", Kt.shape[0], left))
+            return "adj", "resid", "dW"
+
+        def close(self):
+            self.closed = True
+
+    def fake_direct(C32, Kt, St, lam, scale, left, refine_steps=-1):
+        calls.append(("direct", Kt.shape[0], tuple(left)))
+        return ["adj"], ["resid"], ["dW"]
+
+    monkeypatch.setattr(emcid_main, "CachedFactor", FakeFactor)
+    monkeypatch.setattr(emcid_main, "solve_layers", fake_direct)
+    monkeypatch.setattr(emcid_main, "FACTOR_CACHE_MAX", 2)
+    monkeypatch.delenv("EMCID_FACTOR_CACHE", raising=False)
+    emcid_main.clear_factor_cache()
+    enc = SimpleNamespace(config=SimpleNamespace(_name_or_path="org/enc"))
+    d = 3072
+    cov = torch.ones(d, d)
+    k100, s100 = torch.zeros(100, d), torch.zeros(100, 8)
+    run = lambda name, c, k, lam=4000.0, ew=0.5: emcid_main._solve_one_layer(enc, name, c, k, s100[:k.shape[0]], lam, ew, 3, -1)
+    assert run("l7", cov, k100) == ("adj", "resid", "dW")
+    run("l7", cov, k100)                                        # same covariance object: the factor is reused
+    assert [c[0] for c in calls] == ["create", "cached", "cached"] and calls[0][2] == 1.0     # C32 = cov * (1 - ew) / 0.5
+    run("l7", cov, k100, ew=0.6)                                # another edit_weight scales C32 differently: new factor
+    assert calls[-2][0] == "create" and abs(calls[-2][2] - 0.8) < 1e-6
+    run("l7", cov.clone(), k100)                                # COV_CACHE holds a new tensor (force_recompute): rebuilt
+    assert calls[-2][0] == "create"
+    calls.clear()
+    run("l7", cov, torch.zeros(600, d))                         # n_pad * 6 > d: direct solver
+    assert calls == [("direct", 600, (3,))]
+    monkeypatch.setenv("EMCID_FACTOR_CACHE", "0")
+    run("l7", cov, k100)
+    assert calls[-1][0] == "direct"
+    monkeypatch.delenv("EMCID_FACTOR_CACHE")
+    first = next(iter(emcid_main.FACTOR_CACHE.values()))[1]
+    run("l8", cov, k100)
+    run("l9", cov, k100)                                        # third key with FACTOR_CACHE_MAX = 2: the oldest entry goes
+    assert len(emcid_main.FACTOR_CACHE) == 2 and first.closed
+    emcid_main.clear_factor_cache()
+    assert len(emcid_main.FACTOR_CACHE) == 0
