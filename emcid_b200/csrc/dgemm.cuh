@@ -7,15 +7,19 @@
 //   * the iterative-refinement residual  R^T = Ks^T - X^T M64   (fp64 accumulate is what makes
 //     one refinement step worth ~3 digits; SURVEY.md §7 hard part 3)
 //   * upd_matrix = resid @ adj_k.T                     emcid/emcid_main.py:1050
-// Block tile 128x128x16, 8 warps (2x4), warp tile 64x32, register-staged prefetch.
+// Block tile 64x128x16, 4 warps (1x4), warp tile 64x32, register-staged prefetch, two CTAs per SM: with one 128x128 CTA of
+// 8 warps per SM (200 registers per thread: a second one did not fit) the tensor pipe idled through every barrier and
+// global-load wait of the single CTA (ncu: 57-66 % tensor-pipe active, profiles/r03i_ncu_full_dgemm_summary.json); two
+// half-height CTAs fill each other's bubbles.
 #pragma once
 
 #include "host.cuh"
 
 namespace emcid {
 
-constexpr int DG_BM = 128, DG_BN = 128, DG_BK = 16, DG_THREADS = 256;
-constexpr int DG_LD = DG_BM + 4;  // smem pitch (doubles): k-stride == 32 B mod 128 B -> conflict-free frags
+constexpr int DG_BM = 64, DG_BN = 128, DG_BK = 16, DG_THREADS = 2 * DG_BM;
+constexpr int DG_LDA = DG_BM + 4, DG_LDB = DG_BN + 4;  // smem pitches (doubles): k-stride == 32 B mod 128 B -> conflict-free frags
+constexpr int DG_BSETS = 2 * DG_BN / DG_THREADS;       // B rows per thread and k-tile
 
 struct DgemmParams {
   int M, N, K;
@@ -33,9 +37,9 @@ struct DgemmParams {
   int split_k; long long c_split;
 };
 
-// slices so that about `sms` CTAs run, each with at least 256 of K
+// slices so that about 2 x `sms` CTAs run (two are resident per SM), each with at least 256 of K
 inline int dgemm_pick_split(int tiles, int K, int sms) {
-  int s = tiles > 0 ? sms / tiles : 1;
+  int s = tiles > 0 ? 2 * sms / tiles : 1;
   if (s > K / 256) s = K / 256;
   return s < 1 ? 1 : s;
 }
@@ -46,9 +50,9 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(DG_THREADS) dgemm_nt_kernel(const DgemmParams p) {
-  __shared__ double As[DG_BK][DG_LD];
-  __shared__ double Bs[DG_BK][DG_LD];
+__global__ void __launch_bounds__(DG_THREADS, 2) dgemm_nt_kernel(const DgemmParams p) {
+  __shared__ double As[DG_BK][DG_LDA];
+  __shared__ double Bs[DG_BK][DG_LDB];
   const int bm = blockIdx.y * DG_BM, bn = blockIdx.x * DG_BN;
   if (p.lower && bn > bm + DG_BM - 1) return;
   const int split = p.split_k > 1 ? p.split_k : 1;
@@ -60,23 +64,29 @@ __global__ void __launch_bounds__(DG_THREADS) dgemm_nt_kernel(const DgemmParams 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
 
-  // global->register staging: tile is 128 rows x 16 k; thread owns (row = tid/2 [+0], k8 = (tid&1)*8 .. +8)
+  // global->register staging: the A tile is DG_BM rows x 16 k, the B tile DG_BN rows x 16 k; thread owns
+  // (row = tid/2 [+ s * DG_THREADS/2 for B], k8 = (tid&1)*8 .. +8)
   const int lrow = tid >> 1, lk = (tid & 1) * 8;
-  double ra[8], rb[8];
+  double ra[8], rb[DG_BSETS][8];
   auto load_tiles = [&](int k0) {
-    const int ar = bm + lrow, br = bn + lrow;
+    const int ar = bm + lrow;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + lk + j;
       ra[j] = (ar < p.M && k < k_end) ? A[static_cast<long long>(ar) * p.lda + k] : 0.0;
-      rb[j] = (br < p.N && k < k_end) ? B[static_cast<long long>(br) * p.ldb + k] : 0.0;
+#pragma unroll
+      for (int sb = 0; sb < DG_BSETS; ++sb) {
+        const int br = bn + lrow + sb * (DG_THREADS / 2);
+        rb[sb][j] = (br < p.N && k < k_end) ? B[static_cast<long long>(br) * p.ldb + k] : 0.0;
+      }
     }
   };
   auto store_tiles = [&]() {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       As[lk + j][lrow] = ra[j];
-      Bs[lk + j][lrow] = rb[j];
+#pragma unroll
+      for (int sb = 0; sb < DG_BSETS; ++sb) Bs[lk + j][lrow + sb * (DG_THREADS / 2)] = rb[sb][j];
     }
   };
 

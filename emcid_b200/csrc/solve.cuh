@@ -49,8 +49,8 @@ inline double solve_adapt_tol(double dflt) {
   static const double env = [] { const char* e = getenv("EMCID_SOLVE_TOL"); return e ? atof(e) : 0.0; }();
   return env > 0.0 ? env * (dflt / SOLVE_ADAPT_TOL) : dflt;
 }
-// capacity of the split-K slice buffer: dgemm_pick_split keeps slices * tiles <= #SMs (<= 160), a tile is 128 x 128, and
-// the lower-triangular G product covers at most twice its tile count in matrix elements
+// capacity of the split-K slice buffer: dgemm_pick_split keeps slices * tiles <= 2 x #SMs (<= 320), a tile is 64 x 128, and
+// the lower-triangular G product covers at most twice its tile count in matrix elements (both uses clamp to it anyway)
 constexpr long long SOLVE_SPLIT_ELEMS = 2LL * 160 * 128 * 128;
 
 // ---- diagonal block: potrf + inverse, fp64 in shared memory ---------------------------------------
@@ -699,6 +699,9 @@ __global__ void resid_kernel(const float* __restrict__ St, long long lds, long l
   }
 }
 
+// status |= bits   (the host found something the caller should know about: see refined_solve)
+__global__ void status_or_kernel(int* __restrict__ status, int bits) { atomicOr(status, bits); }
+
 // ---- kernels of the cached-factor path ----------------------------------------------------------------
 // W = float(R), planes = split(W)   (fp64 right-hand side -> operand of the fp32-class application)
 __global__ void rhs_from64_kernel(const double* __restrict__ R, long long total, float* __restrict__ W,
@@ -931,12 +934,49 @@ inline int factor_clear(const FactorCtx& f, cudaStream_t stream) {
   return EMCID_OK;
 }
 
+// side stream + events for the look-ahead of the factorisation (one set per device and host thread, never destroyed)
+struct SolveSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+inline int solve_side(int device, SolveSide** out) {
+  static thread_local SolveSide sides[16];
+  EMCID_CHECK(device >= 0 && device < 16, EMCID_ERR_UNSUPPORTED, "solve: device index %d out of range", device);
+  SolveSide& s = sides[device];
+  if (!s.stream) {
+    EMCID_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    EMCID_CUDA_CHECK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    EMCID_CUDA_CHECK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return EMCID_OK;
+}
+
+inline bool solve_use_lookahead() {
+  // EMCID_SOLVE_LOOKAHEAD=0: the whole trailing update on the caller's stream, in front of the next diagonal block
+  static const bool v = [] { const char* e = getenv("EMCID_SOLVE_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) {
   const int B = f.B, d = f.dim, sms = f.sms;
   const int nblk = d / SOLVE_NB;
   const long long dd = static_cast<long long>(d) * d;
   int rc;
-  // blocked right-looking Cholesky of M32
+  // Blocked right-looking Cholesky of M32 with a one-step look-ahead: the diagonal-block kernel keeps B SMs busy for
+  // ~70 us and sat in front of every trailing update (24 times per d = 3072).  The trailing update of step k is cut in
+  // two: block column k+1 (all the next diagonal block and panel need) stays on the caller's stream, the rest runs on a
+  // side stream next to potrf(k+1) and panel(k+1) and is joined before block column k+2 is touched again.  The side GEMM
+  // leaves B SMs free for the diagonal-block CTAs (both kernels take a whole SM's shared memory).
+  SolveSide* side = nullptr;
+  const bool lookahead = solve_use_lookahead() && nblk > 2;
+  if (lookahead) {
+    int device = 0;
+    EMCID_CUDA_CHECK(cudaGetDevice(&device));
+    if ((rc = solve_side(device, &side))) return rc;
+  }
+  bool pending_join = false;
   for (int k = 0; k < nblk; ++k) {
     (potrf_use_v1() ? potrf_diag_kernel : potrf_diag_kernel_v2)<<<B, 256, potrf_smem_bytes(), stream>>>(
         f.M32, d, k, f.LL_hi, f.LL_lo, f.Li_hi, f.Li_lo, f.LiT_hi, f.LiT_lo, f.trsm ? nullptr : f.Lv_hi, f.Lv_lo, f.LvT_hi,
@@ -946,7 +986,6 @@ inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) 
     if (rem <= 0) break;
     const long long off_panel = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k) * SOLVE_NB;
     const long long off_panel_t = static_cast<long long>(k) * SOLVE_NB * d + static_cast<long long>(k + 1) * SOLVE_NB;
-    const long long off_trail = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k + 1) * SOLVE_NB;
     SubGemm g;
     memset(&g, 0, sizeof(g));  // panel: L_ik = M_ik Linv_kk^T
     g.A = &f.mMp; g.a_row0 = (k + 1) * SOLVE_NB; g.a_col0 = k * SOLVE_NB; g.a_batch_rows = d;
@@ -956,16 +995,37 @@ inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) 
     g.P_hi = f.LL_hi + off_panel; g.P_lo = f.LL_lo + off_panel; g.ldp = d; g.p_batch = dd;
     g.Pt_hi = f.LL_hi + off_panel_t; g.Pt_lo = f.LL_lo + off_panel_t; g.ldpt = d; g.pt_batch = dd;
     if ((rc = run_subgemm(g, B, sms, stream))) return rc;
-    memset(&g, 0, sizeof(g));  // trailing: M_ij -= L_ik L_jk^T
-    g.A = &f.mLL; g.a_row0 = (k + 1) * SOLVE_NB; g.a_col0 = k * SOLVE_NB; g.a_batch_rows = d;
-    g.B = &f.mLL; g.b_row0 = (k + 1) * SOLVE_NB; g.b_col0 = k * SOLVE_NB; g.b_batch_rows = d;
-    g.M = rem; g.N = rem; g.K = SOLVE_NB; g.lower = 1;
-    g.alpha = -1.0f; g.beta = 1.0f;
-    g.Cin = f.M32 + off_trail; g.ldcin = d; g.cin_batch = dd;
-    g.C = f.M32 + off_trail; g.ldc = d; g.c_batch = dd;
-    g.P_hi = f.Mp_hi + off_trail; g.P_lo = f.Mp_lo + off_trail; g.ldp = d; g.p_batch = dd;
-    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+    if (pending_join) {   // the rest of step k-1's trailing update wrote the tiles the next products read and write
+      EMCID_CUDA_CHECK(cudaStreamWaitEvent(stream, side->join, 0));
+      pending_join = false;
+    }
+    // trailing: M_ij -= L_ik L_jk^T  for i >= j > k;  cols = how many block columns from k+1 on, 0 = all (lower tiles)
+    auto trailing = [&](int first_blk, int cols, int sm_budget, cudaStream_t st) -> int {
+      const int r0 = first_blk * SOLVE_NB;
+      const long long off = static_cast<long long>(r0) * d + r0;
+      SubGemm t;
+      memset(&t, 0, sizeof(t));
+      t.A = &f.mLL; t.a_row0 = r0; t.a_col0 = k * SOLVE_NB; t.a_batch_rows = d;
+      t.B = &f.mLL; t.b_row0 = r0; t.b_col0 = k * SOLVE_NB; t.b_batch_rows = d;
+      t.M = d - r0; t.N = cols ? cols * SOLVE_NB : d - r0; t.K = SOLVE_NB; t.lower = cols ? 0 : 1;
+      t.alpha = -1.0f; t.beta = 1.0f;
+      t.Cin = f.M32 + off; t.ldcin = d; t.cin_batch = dd;
+      t.C = f.M32 + off; t.ldc = d; t.c_batch = dd;
+      t.P_hi = f.Mp_hi + off; t.P_lo = f.Mp_lo + off; t.ldp = d; t.p_batch = dd;
+      return run_subgemm(t, B, sm_budget, st);
+    };
+    if (!lookahead || rem <= SOLVE_NB) {
+      if ((rc = trailing(k + 1, 0, sms, stream))) return rc;
+    } else {
+      if ((rc = trailing(k + 1, 1, sms, stream))) return rc;                 // block column k+1
+      EMCID_CUDA_CHECK(cudaEventRecord(side->fork, stream));
+      EMCID_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      if ((rc = trailing(k + 2, 0, sms - B, side->stream))) return rc;       // the rest, next to potrf(k+1) / panel(k+1)
+      EMCID_CUDA_CHECK(cudaEventRecord(side->join, side->stream));
+      pending_join = true;
+    }
   }
+  if (pending_join) EMCID_CUDA_CHECK(cudaStreamWaitEvent(stream, side->join, 0));
   if (f.trsm) return EMCID_OK;
   // explicit inverse, block columns from the right (the diagonal blocks came from potrf_diag_kernel):
   //        T          = Linv[k+1:, k+1:] L[k+1:, k]        (A lower triangular: k_tri = 3)
@@ -1017,7 +1077,7 @@ inline int apply_make_maps(ApplyCtx& a, int B, int dim) {
 }
 
 inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64, int refine_steps, cudaStream_t stream,
-                         double adapt_tol = SOLVE_ADAPT_TOL) {
+                         double adapt_tol = SOLVE_ADAPT_TOL, int* status_dev = nullptr) {
   const int B = f.B, d = f.dim, sms = f.sms, n = a.rows, n_pad = a.rows_pad;
   const int nblk = d / SOLVE_NB;
   const long long dd = static_cast<long long>(d) * d, nd = static_cast<long long>(n_pad) * d;
@@ -1092,6 +1152,7 @@ inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64,
   const bool adaptive = refine_steps < 0;
   const double tol = solve_adapt_tol(adapt_tol);
   double c_prev = 1.0, rho_max = 0.0;
+  bool converged = !adaptive;
   const int max_steps = adaptive ? SOLVE_ADAPT_MAX : refine_steps;
   for (int it = 0; it <= max_steps; ++it) {
     if (it > 0) {
@@ -1132,13 +1193,19 @@ inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64,
       // EMCID_SOLVE_DEBUG=1: the relative size of every sweep's correction (dimension, right-hand sides, sweep, ratio)
       static const bool debug = [] { const char* e = getenv("EMCID_SOLVE_DEBUG"); return e && e[0] == '1'; }();
       if (debug) fprintf(stderr, "emcid refine dim=%d rhs=%d sweep=%d |dx|/|x|=%.3e\n", d, n, it, sqrt(hn[0] / hn[1]));
-      if (!(hn[1] > 0.0)) break;
+      if (!(hn[1] > 0.0)) { converged = true; break; }
       const double c = sqrt(hn[0] / hn[1]);
       if (c_prev > 0.0 && c / c_prev > rho_max) rho_max = c / c_prev;
       c_prev = c;
       const double rho = fmin(0.9, 1.5 * rho_max);
-      if (rho * c / (1.0 - rho) <= tol) break;
+      if (rho * c / (1.0 - rho) <= tol) { converged = true; break; }
     }
+  }
+  if (!converged && status_dev) {
+    // SOLVE_ADAPT_MAX sweeps did not bring the predicted error under the target (a factor that barely contracts: the
+    // matrix is too ill-conditioned for fp32-class factors): the result is the best available, flagged in bit 1
+    status_or_kernel<<<1, 1, 0, stream>>>(status_dev, 2);
+    EMCID_CUDA_CHECK(cudaGetLastError());
   }
   return EMCID_OK;
 }
@@ -1299,7 +1366,7 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
   if ((rc = factor_spd(w.f, status_dev, stream))) return rc;
 
   // 4./5. solve + refinement; W holds the current right-hand side (transposed), then the solution
-  if ((rc = refined_solve(w.f, w.a, false, refine_steps, stream))) return rc;
+  if ((rc = refined_solve(w.f, w.a, false, refine_steps, stream, SOLVE_ADAPT_TOL, status_dev))) return rc;
 
   // 6. outputs
   transpose_out_kernel<<<dim3((d + 31) / 32, (n + 31) / 32, B), dim3(32, 8), 0, stream>>>(w.a.X64t, n, n_pad, d, adj_k);
@@ -1463,7 +1530,7 @@ inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long lon
     EMCID_CUDA_CHECK(cudaGetLastError());
   }
   // 2. Y^T = Ks^T A^-1, refined against A64                                  -> a1.X64t [n_pad x d]
-  if ((rc = refined_solve(fa, w.a1, false, refine_steps, stream, SOLVE_ADAPT_TOL_CHAINED))) return rc;
+  if ((rc = refined_solve(fa, w.a1, false, refine_steps, stream, SOLVE_ADAPT_TOL_CHAINED, status_dev))) return rc;
   // 3. G = I + Ks^T Y   (fp64; lower tiles, then mirrored with fp32 copy and planes)
   {
     DgemmParams p;
@@ -1474,9 +1541,10 @@ inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long lon
     p.alpha = 1.0;
     p.C = w.G64; p.ldc = n_pad;
     p.lower = 1;
-    const int t = n_pad / DG_BM;
+    int g_tiles = 0;   // lower tiles of DG_BM x DG_BN
+    for (int bm = 0; bm < n_pad; bm += DG_BM) g_tiles += (bm + DG_BM - 1) / DG_BN + 1;
     const long long gg = static_cast<long long>(n_pad) * n_pad;
-    int split = dgemm_pick_split(t * (t + 1) / 2, d, sms);
+    int split = dgemm_pick_split(g_tiles, d, sms);
     while (split > 1 && split * gg > SOLVE_SPLIT_ELEMS) --split;
     if (split > 1) {
       p.C = w.a1.P64; p.split_k = split; p.c_split = gg;
@@ -1496,7 +1564,7 @@ inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long lon
   EMCID_CUDA_CHECK(cudaGetLastError());
   w.a2.rows = d; w.a2.rows_pad = d; w.a2.M64 = w.G64; w.a2.R64t = w.Yd64;
   if ((rc = apply_make_maps(w.a2, 1, n_pad))) return rc;
-  if ((rc = refined_solve(w.g, w.a2, true, refine_steps, stream, SOLVE_ADAPT_TOL_CHAINED))) return rc;
+  if ((rc = refined_solve(w.g, w.a2, true, refine_steps, stream, SOLVE_ADAPT_TOL_CHAINED, status_dev))) return rc;
   // 6. outputs
   compact_cols_kernel<<<sms * 4, 256, 0, stream>>>(w.a2.X64t, d, n, n_pad, adj_k);
   EMCID_CUDA_CHECK(cudaGetLastError());

@@ -57,10 +57,19 @@ def solve_layers(C32: torch.Tensor, Kt: torch.Tensor, St: torch.Tensor, mom2_upd
                                           _lib.ptr(resid), _lib.ptr(dW), int(refine_steps), _lib.ptr(ws), ws.numel(),
                                           _lib.ptr(status), _lib.current_stream_ptr()))
     if check:
-        st = int(status.item())
-        if st != 0:
-            raise _lib.EmcidError(-4, f"Cholesky breakdown: lambda*C + K K^T is not positive definite (status {st})")
+        _check_status(int(status.item()), "lambda*C + K K^T")
     return adj_k, resid, dW
+
+
+def _check_status(st: int, what: str) -> None:
+    """status bits of include/emcid_b200.h: bit 0 = breakdown (raise), bit 1 = refinement target not reached (warn)."""
+    if st & 1:
+        raise _lib.EmcidError(-4, f"Cholesky breakdown: {what} is not positive definite (status {st})")
+    if st & 2:
+        import warnings
+
+        warnings.warn(f"emcid_b200.solve: the iterative refinement of {what} did not reach its target "
+                      "(very ill-conditioned system); the update is the best available", RuntimeWarning)
 
 
 class CachedFactor:
@@ -114,9 +123,7 @@ class CachedFactor:
                                               int(refine_steps), _lib.ptr(ws), ws.numel(), _lib.ptr(status),
                                               _lib.current_stream_ptr()))
         if check:
-            st = int(status.item())
-            if st != 0:
-                raise _lib.EmcidError(-4, f"Cholesky breakdown: I + Ks^T A^-1 Ks is not positive definite (status {st})")
+            _check_status(int(status.item()), "lambda*C / I + Ks^T A^-1 Ks")
         return adj_k, resid, dW
 
     def close(self) -> None:

@@ -155,7 +155,8 @@ int emcid_clip_destroy(emcid_clip_t* h);
  * refine_steps: fp64-residual iterative-refinement sweeps after the fp32-class Cholesky solve; -1 = adaptive
  * (sweeps until the error predicted from the contraction of the corrections is < 2e-5 of the solution in Frobenius
  * norm, a fifth of the dW tolerance; at most 16; synchronises the stream per sweep; EMCID_SOLVE_TOL overrides the target).
- * status_dev: device int, 0 on success, bit0 = a pivot was not positive (matrix not SPD).
+ * status_dev: device int, 0 on success, bit0 = a pivot was not positive (matrix not SPD), bit1 = the adaptive refinement
+ * used all its sweeps without reaching the target (the outputs are the best available).
  * d must be a multiple of 128.  Blackwell-only; asynchronous on `stream`. */
 size_t emcid_solve_workspace_bytes(int batch, int d, int h, int n);
 int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* C32, const float* Kt,

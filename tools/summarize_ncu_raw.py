@@ -6,7 +6,13 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__cluster_dim_x", "sm__cycles_elapsed.avg.per_second", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_no_instructions",
         "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_sleeping",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warps_issue_stalled_long_scoreboard_per_warp_active.pct"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warps_issue_stalled_long_scoreboard_per_warp_active.pct",
+        # fp64 kernels of the solve
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.sum",
+        "smsp__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__sass_thread_inst_executed_op_dfma_pred_on.sum",
+        "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
+        "smsp__pcsamp_warps_issue_stalled_wait", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__shared_mem_per_block_dynamic", "launch__block_size"]
 rows = list(csv.reader(l for l in open(sys.argv[1]) if not l.startswith("==")))
 hdr, units = rows[0], rows[1]
 col = {n: i for i, n in enumerate(hdr)}
