@@ -20,4 +20,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gem
 ncu -i $OUT/prof.ncu-rep --page raw --csv > $OUT/prof_raw.csv 2> $OUT/prof_raw.err
 python tools/summarize_ncu_raw.py $OUT/prof_raw.csv ncu --set full --clock-control none --import-source on -k "regex:gemm3x|attention" -s 163 -c 14 $NCU_CMD > $OUT/ncu_full_summary.json 2>> $OUT/prof_raw.err
 fi
-tail -3 $OUT/pytest_gpu.log; cat $OUT/smoke.log | tail -2; cat $OUT/bench.json; tail -2 $OUT/bench.err; cat $OUT/bench_reference.json; head -14 $OUT/launches_summary.txt
+tail -3 $OUT/pytest_gpu.log; cat $OUT/smoke.log | tail -2; cat $OUT/bench.json; tail -2 $OUT/bench.err; cat $OUT/bench_reference.json
+if [ -f $OUT/launches_summary.txt ]; then head -14 $OUT/launches_summary.txt; fi
