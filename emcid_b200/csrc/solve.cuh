@@ -5,9 +5,11 @@
 //
 //   M32 = lambda*C32 + Ks Ks^T                 3xTF32 tcgen05 SYRK, lower tiles, planes kept
 //   M32 = L L^T                                blocked right-looking Cholesky, nb = 128:
-//        diag block   fp64 potrf + triangular inverse in shared memory (one CTA per layer)
+//        diag block   fp64 potrf + triangular inverse in shared memory (one CTA per layer, register-blocked:
+//                     potrf_diag_kernel_v2)
 //        panel        L_ik = M_ik Linv_kk^T            tcgen05 GEMM (K = 128)
-//        trailing     M_ij -= L_ik L_jk^T  (i>=j>k)    tcgen05 GEMM, lower tiles
+//        trailing     M_ij -= L_ik L_jk^T  (i>=j>k)    tcgen05 GEMM, lower tiles; block column k+1 first, the rest on a
+//                                                      side stream next to the following diagonal block (look-ahead)
 //   Linv = L^-1                                blocked triangular inverse (block columns from the right): two
 //                                              tcgen05 GEMMs per block column, zero k-blocks skipped (k_tri)
 //   X = Linv^T (Linv Ks)                       two tcgen05 GEMMs per application on the transposed right-hand
@@ -15,8 +17,13 @@
 //                                              launches per application; what it loses in backward stability
 //                                              the fp64 refinement takes back).  EMCID_SOLVE_TRSM=1 keeps the
 //                                              blocked TRSM against L / L^T / Linv_kk planes.
-//   refinement (fp64 residual on DMMA):        R^T = Ks^T - X^T M64 ; X += solve(R)
+//   refinement (fp64 residual on DMMA):        R^T = Ks^T - X^T M64 ; X += solve(R); sweeps until the error predicted
+//                                              from the contraction of the corrections is below SOLVE_ADAPT_TOL
 //   dW = resid adj_k^T                         fp64 DMMA GEMM, rounded once to fp32
+//
+// factor_spd / refined_solve are the two halves (factorisation of stacked SPD matrices; refined application to
+// transposed right-hand sides); solve_layers is the direct solver on M, factor_create / factor_solve the cached-factor
+// form for repeated edits with the same lambda*C (push-through identity, see below).
 //
 // Everything is batched over independent layers (grid.y / grid.z = layer): the benchmark form of
 // SURVEY.md §8d solves the 5 edited layers in one call; the faithful sequential loop calls it with
