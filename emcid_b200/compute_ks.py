@@ -95,8 +95,9 @@ def find_token_range(tokenizer, token_array, substring_orig: str, piece_cache: O
     haystack = tokenizer.decode(token_array).replace(" ", "")
     if "’" in needle:
         haystack = haystack.replace("'", "’")
-    haystack = unicodedata.normalize("NFKC", haystack)
-    needle = unicodedata.normalize("NFKC", needle)
+    if not (haystack.isascii() and needle.isascii()):     # NFKC is the identity on ASCII
+        haystack = unicodedata.normalize("NFKC", haystack)
+        needle = unicodedata.normalize("NFKC", needle)
     try:
         char_loc = haystack.index(needle)
     except ValueError:
@@ -105,12 +106,14 @@ def find_token_range(tokenizer, token_array, substring_orig: str, piece_cache: O
         print("whole string: ", haystack)
         raise ValueError
     seen, start, end = 0, None, None
+    quirk = "ń" in needle                                   # reference quirk: 2 tokens, 1 char
+    char_end = char_loc + len(needle)
     for i, piece in enumerate(pieces):
-        if not ("ń" in needle and int(token_array[i]) == 78):  # reference quirk: 2 tokens, 1 char
+        if not (quirk and int(token_array[i]) == 78):
             seen += len(piece)
         if start is None and seen > char_loc:
             start = i
-        if end is None and seen >= char_loc + len(needle):
+        if seen >= char_end:
             end = i + 1
             break
     return (start, end)

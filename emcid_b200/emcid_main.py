@@ -22,7 +22,6 @@ from __future__ import annotations
 import os
 from collections import OrderedDict
 from copy import deepcopy
-from pathlib import Path
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -136,17 +135,38 @@ def upd_matrix_match_shape(matrix: torch.Tensor, shape: torch.Size) -> torch.Ten
                      "Check for bugs in the code?")
 
 
+_NPY_HEADERS: Dict[bytes, Tuple[np.dtype, tuple, int]] = {}   # npy header bytes -> (dtype, shape, element count)
+
+
+def _parse_npy_header(text: bytes):
+    """(dtype, shape, count) of an npy header dict; every v* file of an edit carries the same header bytes, so the
+    parse (ast.literal_eval: 50 us) is memoised on them."""
+    import ast
+    import math
+
+    hit = _NPY_HEADERS.get(text)
+    if hit is None:
+        header = ast.literal_eval(text.decode("latin1"))
+        dtype = np.dtype(header["descr"])
+        if header["fortran_order"] or dtype.hasobject:
+            raise ValueError
+        shape = tuple(int(x) for x in header["shape"])
+        hit = (dtype, shape, math.prod(shape))
+        if len(_NPY_HEADERS) < 64:
+            _NPY_HEADERS[text] = hit
+    return hit
+
+
 def _read_npz_array(path, key: str) -> np.ndarray:
     """`np.load(path)[key]` for the v* cache files (emcid_main.py:886-901: `np.savez(file, v_star=...)`, one small stored
     array per file).  np.load spends ~90 us per file in zipfile / NpzFile machinery, which is most of a 1000-concept edit's
     host time; the stored member can be located from the local file header alone.  Anything unexpected (compression, another
-    member first, object arrays, fortran order) falls back to np.load."""
-    import ast
+    member first, object arrays, fortran order) falls back to np.load.  A missing file raises FileNotFoundError."""
     import struct
 
+    with open(path, "rb") as f:
+        raw = f.read()
     try:
-        with open(path, "rb") as f:
-            raw = f.read()
         if raw[:4] != b"PK\x03\x04":
             raise ValueError
         method, = struct.unpack_from("<H", raw, 8)
@@ -164,15 +184,10 @@ def _read_npz_array(path, key: str) -> np.ndarray:
         else:
             hlen, = struct.unpack_from("<I", raw, off + 8)
             hstart = off + 12
-        header = ast.literal_eval(raw[hstart:hstart + hlen].decode("latin1"))
-        dtype = np.dtype(header["descr"])
-        if header["fortran_order"] or dtype.hasobject:
-            raise ValueError
-        shape = tuple(header["shape"])
-        count = int(np.prod(shape)) if shape else 1
+        dtype, shape, count = _parse_npy_header(raw[hstart:hstart + hlen])
         data = hstart + hlen
         return np.frombuffer(raw, dtype=dtype, count=count, offset=data).reshape(shape).copy()
-    except (ValueError, KeyError, SyntaxError, struct.error, IndexError):
+    except (ValueError, KeyError, SyntaxError, TypeError, struct.error, IndexError):
         return np.load(path)[key]
 
 
@@ -185,12 +200,15 @@ def _load_vstars(requests, hparams, cache_name, device, suffix=""):
             stem = f"source_{request['source_cat']}_{idx}"
         else:
             stem = f"source_{request['source']}_dest_{request['dest']}"
-        path = Path(cache_name + stem + suffix + ".npz") if cache_name is not None else None
-        if path is None or not path.exists():
+        path = cache_name + stem + suffix + ".npz" if cache_name is not None else None
+        try:
+            if path is None:
+                raise FileNotFoundError
+            zs.append(torch.from_numpy(_read_npz_array(path, "v_star")))      # no stat() first: open() finds out
+        except FileNotFoundError:
             raise NotImplementedError(
                 f"v_star cache miss for request {request['source']!r} ({path}): stage 1 (compute_z, UNet/VAE "
-                "optimisation) is outside the B200 hot path — precompute v_star with the reference")
-        zs.append(torch.from_numpy(_read_npz_array(path, "v_star")))
+                "optimisation) is outside the B200 hot path — precompute v_star with the reference") from None
     # stacked on the host, one H2D copy (the reference moves every v* separately, :892-901)
     if getattr(hparams, "use_new_compute_z", False):
         z = torch.stack(zs, dim=0).to(device)           # [rq, num, h]
