@@ -501,8 +501,9 @@ def test_cached_factor_matches_oracle(dev, d, h, ns):
         assert rel_fro(adj.cpu().numpy(), a_ref) < DW_TOL
         assert rel_fro(resid.cpu().numpy(), r_ref) < 1e-6
         adj_d, _, dW_d = solve_layers(C32, torch.from_numpy(K).to(dev), torch.from_numpy(S).to(dev), lam, s, [3])
-        assert rel_fro(dW.cpu().numpy(), dW_d[0].cpu().numpy()) < 1e-5
-        assert rel_fro(adj.cpu().numpy(), adj_d[0].cpu().numpy()) < 1e-5
+        # consistency of the two paths: each refines to a predicted error of <= 2e-5 (SOLVE_ADAPT_TOL)
+        assert rel_fro(dW.cpu().numpy(), dW_d[0].cpu().numpy()) < 5e-5
+        assert rel_fro(adj.cpu().numpy(), adj_d[0].cpu().numpy()) < 5e-5
     fac.close()
 
 
