@@ -84,6 +84,7 @@ def find_token_range(tokenizer, token_array, substring_orig: str, piece_cache: O
     needle = substring_orig.replace(" ", "").lower()
     if piece_cache is None:
         pieces = [tokenizer.decode([t]) for t in token_array]
+        haystack = tokenizer.decode(token_array).replace(" ", "")
     else:
         pieces = []
         for t in token_array:
@@ -92,7 +93,12 @@ def find_token_range(tokenizer, token_array, substring_orig: str, piece_cache: O
             if piece is None:
                 piece = piece_cache[t] = tokenizer.decode([t])
             pieces.append(piece)
-    haystack = tokenizer.decode(token_array).replace(" ", "")
+        joined = "".join(pieces)
+        # The reference decodes the whole array (causal_trace.py:1072-1075).  When every token decodes to ASCII text the
+        # concatenated per-token decodes are the same string once the spaces are dropped (byte-level BPE only differs
+        # where a multi-byte character is split across tokens), so the second, whole-array decode per prompt — the
+        # bulk of this function's time with a Python tokenizer — is only paid for non-ASCII prompts.
+        haystack = joined.replace(" ", "") if joined.isascii() else tokenizer.decode(token_array).replace(" ", "")
     if "’" in needle:
         haystack = haystack.replace("'", "’")
     if not (haystack.isascii() and needle.isascii()):     # NFKC is the identity on ASCII

@@ -349,3 +349,32 @@ def test_factor_cache_policy(monkeypatch):
     assert len(emcid_main.FACTOR_CACHE) == 2 and first.closed
     emcid_main.clear_factor_cache()
     assert len(emcid_main.FACTOR_CACHE) == 0
+
+
+def test_token_range_fast_path_equals_whole_array_decode():
+    """find_token_range with the per-edit piece cache skips the whole-array decode for ASCII prompts; the result must be
+    the reference's (causal_trace.py:1057-1103) for ASCII prompts and for prompts whose multi-byte characters are split
+    across byte-level tokens (where per-token decodes and the whole-array decode differ)."""
+    class ByteTok:
+        # byte-level toy tokenizer: a token is a byte string, decode = utf-8 decode of the concatenation (errors -> U+FFFD)
+        vocab = [b"<s>", b"</s>", b"an ", b"image ", b"of ", b"photo ", b"van ", b"gogh ", b"mo", b"net ", b"a ", b"the ",
+                 b"pe", "ń".encode()[:1], "ń".encode()[1:], b"a ", b"caf", "é".encode(), b" ", b"art "]
+
+        def decode(self, ids):
+            if torch.is_tensor(ids):
+                ids = ids.tolist()
+            return b"".join(self.vocab[int(i)] for i in ids).decode("utf-8", errors="replace").strip()
+
+    tok = ByteTok()
+    rng = random.Random(5)
+    cases = []
+    for _ in range(200):
+        pre = [rng.choice([2, 3, 4, 5, 10, 11]) for _ in range(rng.randint(0, 4))]
+        subj, name = rng.choice([([6, 7], "van gogh"), ([8, 9], "monet"), ([12, 13, 14, 15], "peńa"), ([16, 17, 18], "café"),
+                                 ([6, 7, 16, 17, 18], "van gogh café")])
+        post = [rng.choice([2, 4, 19]) for _ in range(rng.randint(0, 3))]
+        cases.append(([0] + pre + subj + post + [1, 1, 1][: rng.randint(1, 3)], name))
+    cache = {}
+    for ids, name in cases:
+        assert compute_ks.find_token_range(tok, ids, name, cache) == compute_ks.find_token_range(tok, ids, name, None), (ids, name)
+    assert compute_ks.find_token_range(tok, cases[0][0], "[CLS]", cache) == (0, 1)
