@@ -378,3 +378,11 @@ def test_token_range_fast_path_equals_whole_array_decode():
     for ids, name in cases:
         assert compute_ks.find_token_range(tok, ids, name, cache) == compute_ks.find_token_range(tok, ids, name, None), (ids, name)
     assert compute_ks.find_token_range(tok, cases[0][0], "[CLS]", cache) == (0, 1)
+    if rh.reference_available():       # and against the unmodified reference function, where it is importable
+        import importlib
+        rh.import_reference()
+        ref_ftr = importlib.import_module("experiments.causal_trace").find_token_range
+        for ids, name in cases:
+            if "ń" in name:
+                continue               # the reference special-cases token id 78 for this character (vocabulary specific)
+            assert tuple(ref_ftr(tok, ids, name)) == compute_ks.find_token_range(tok, ids, name, cache), (ids, name)
