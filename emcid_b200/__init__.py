@@ -10,6 +10,6 @@ __version__ = "0.1.0"
 
 # the package root re-exports the edit entry points like the reference's emcid/__init__.py:1
 from .emcid_main import (apply_emcid_to_sdxl_text_encoders, apply_emcid_to_text_encoder,  # noqa: E402,F401
-                         execute_emcid_text_encoder)
+                         clear_factor_cache, execute_emcid_text_encoder)
 from .emcid_hparams import EMCIDHyperParams, EMCIDXLHyperParams  # noqa: E402,F401
 from .layer_stats import layer_stats_text_encoder, layer_stats_text_encoder_multi  # noqa: E402,F401
