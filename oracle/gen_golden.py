@@ -101,6 +101,38 @@ def tiny_solve(out, edit_weight, lam, n_req=10, layers=(0, 1), sample_size=120):
         shutil.rmtree(tmp)
 
 
+def tiny_sequential(out, n_edits=3, n_req=5, layers=(0, 1), sample_size=60, lam=4000, edit_weight=0.5):
+    """BASELINE configs[4] pattern (experiments/sequential_editing.py:98-171): successive reference
+    apply_emcid_to_text_encoder calls on the same model, each solving on the already-edited weights with the same
+    cached statistics.  Keeps the fc2 weights after every edit."""
+    model = rh.make_clip_text_model("tiny", seed=3)
+    caps = rh.make_captions(80, model.config.vocab_size, seed=21)
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    tmp = tempfile.mkdtemp()
+    try:
+        stats_dir = os.path.join(tmp, "stats")
+        d = dict(edit_weight=edit_weight, lam=lam, n_req=n_req, n_edits=n_edits, layers=np.array(layers),
+                 sample_size=sample_size)
+        for l in layers:
+            st = rh.run_reference_layer_stats(model, caps, l, stats_dir, sample_size)
+            d[f"mom2.{l}"] = st.mom2.mom2.numpy().copy()
+            d[f"count.{l}"] = st.mom2.count
+            d[f"w_before.{l}"] = model.text_model.encoder.layers[l].mlp.fc2.weight.detach().numpy().copy()
+        for e in range(n_edits):
+            reqs = [dict(r, source=f"edit{e} {r['source']}") for r in rh.make_requests(n_req)]
+            cache = os.path.join(tmp, f"v{e}", "c_")
+            d[f"zs.{e}"] = rh.write_vstar_cache(cache, reqs, model.config.hidden_size, seed=10 + e).numpy()
+            hp = rh.make_hparams(layers, sample_size, mom2_update_weight=lam, edit_weight=edit_weight)
+            rh.run_reference_apply(model, tok, reqs, hp, cache, stats_dir)
+            for l in layers:
+                d[f"w_after.{e}.{l}"] = model.text_model.encoder.layers[l].mlp.fc2.weight.detach().numpy().copy()
+        np.savez_compressed(os.path.join(GOLD, out), **d)
+        dw = d[f"w_after.{n_edits - 1}.{layers[-1]}"] - d[f"w_before.{layers[-1]}"]
+        print(out, "edits", n_edits, "|dW|/|W| last layer", np.linalg.norm(dw) / np.linalg.norm(d[f"w_before.{layers[-1]}"]))
+    finally:
+        shutil.rmtree(tmp)
+
+
 def clipl_stats_digest(out, n_caps=300, sample_size=256, layer=11, ncols=48):
     model = rh.make_clip_text_model("clip-l", seed=0)
     caps = rh.make_captions(n_caps, model.config.vocab_size, seed=5)
@@ -129,4 +161,5 @@ if __name__ == "__main__":
     tiny_stats("tiny-gelu", 0, 90, None, 512, 1, 4, "tiny_gelu_stats.npz")
     tiny_solve("tiny_solve_ew05.npz", 0.5, 4000)
     tiny_solve("tiny_solve_ew06.npz", 0.6, 10000)
+    tiny_sequential("tiny_sequential.npz")
     clipl_stats_digest("clipl_stats_digest.npz")
