@@ -617,3 +617,46 @@ def test_multi_token_edit_keeps_reference_semantics(dev, tmp_path):
 def test_smoke_entry(dev):
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+@pytest.mark.parametrize("cached", [False, True])
+def test_sequential_editing_matches_reference_fixture(dev, golden_dir, tmp_path, monkeypatch, cached):
+    """BASELINE configs[4] against the unmodified reference itself: tests/golden/tiny_sequential.npz holds the fc2 weights
+    after each of three successive reference edits (oracle/gen_golden.py::tiny_sequential); same statistics files, same
+    v*, weights compared after every edit, with and without the cached factorisation of lambda * C."""
+    from emcid_b200 import emcid_main
+    from types import SimpleNamespace
+    g = np.load(os.path.join(golden_dir, "tiny_sequential.npz"))
+    layers, ss = [int(l) for l in g["layers"]], int(g["sample_size"])
+    emcid_main.clear_factor_cache()
+    if cached:
+        monkeypatch.setattr(emcid_main, "FACTOR_CACHE_MAX_FRACTION", 1)     # tiny model: d = 256, n_pad = 128
+    else:
+        monkeypatch.setenv("EMCID_FACTOR_CACHE", "0")
+    model = rh.make_clip_text_model("tiny", seed=3)
+    for l in layers:
+        assert np.array_equal(model.text_model.encoder.layers[l].mlp.fc2.weight.numpy(), g[f"w_before.{l}"])
+    model = model.to(dev)
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    stats_dir = tmp_path / "stats"
+    for l in layers:  # the reference's own statistics files -> identical C on both sides
+        f = orc.stats_filename(str(stats_dir), "text_encoder", "ccs_filtered", f"text_model.encoder.layers.{l}.mlp.fc2",
+                               "float32", ["mom2"], 3072, ss)
+        os.makedirs(os.path.dirname(f), exist_ok=True)
+        np.savez(f, **{"mom2.constructor": "util.runningstats.SecondMoment()", "mom2.count": int(g[f"count.{l}"]),
+                       "mom2.mom2": g[f"mom2.{l}"], "sample_size": ss})
+    pipe = SimpleNamespace(text_encoder=model, tokenizer=tok, device=dev)
+    emcid_main.COV_CACHE.clear()
+    for e in range(int(g["n_edits"])):
+        reqs = [dict(r, source=f"edit{e} {r['source']}") for r in rh.make_requests(int(g["n_req"]))]
+        cache = str(tmp_path / f"v{e}" / "c_")
+        zs = rh.write_vstar_cache(cache, reqs, model.config.hidden_size, seed=10 + e)
+        assert np.array_equal(zs.numpy(), g[f"zs.{e}"])
+        hp = rh.make_hparams(layers, ss, mom2_update_weight=float(g["lam"]), edit_weight=float(g["edit_weight"]))
+        emcid_main.apply_emcid_to_text_encoder(pipe, reqs, hp, device=dev, cache_name=cache, stats_dir=stats_dir, verbose=False)
+        for l in layers:
+            w = model.text_model.encoder.layers[l].mlp.fc2.weight.detach().cpu().numpy().astype(np.float64)
+            assert rel_fro(w - g[f"w_before.{l}"], g[f"w_after.{e}.{l}"].astype(np.float64) - g[f"w_before.{l}"]) < DW_TOL, (e, l)
+    assert len(emcid_main.FACTOR_CACHE) == (len(layers) if cached else 0)
+    emcid_main.clear_factor_cache()
+    emcid_main.COV_CACHE.clear()
