@@ -51,6 +51,14 @@ SIGNATURES = {
     "emcid_mom2_profile": (c_int, [c_void_p, c_int]),
     "emcid_mom2_get_profile": (c_int, [c_void_p, ctypes.POINTER(c_double)]),
     "emcid_mom2_destroy": (c_int, [c_void_p]),
+    "emcid_nccl_available": (c_int, []),
+    "emcid_mom2_reduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "emcid_mom2_broadcast": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "emcid_mom2_state_elems": (c_size_t, [c_int]),
+    "emcid_mom2_export_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emcid_mom2_import_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emcid_symmetrize_lower": (c_int, [c_void_p, c_int, c_longlong, c_void_p]),
+    "emcid_fixed_random_subset": (c_int, [c_longlong, c_longlong, ctypes.POINTER(c_longlong), c_longlong]),
     "emcid_clip_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                   c_longlong, c_int]),
     "emcid_clip_set_embeddings": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -59,6 +67,9 @@ SIGNATURES = {
                                    ctypes.POINTER(c_int), ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "emcid_clip_forward_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                         c_void_p, c_void_p, c_int, c_void_p]),
+    "emcid_clip_set_final_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emcid_clip_forward_final": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                         c_void_p, c_void_p]),
     "emcid_clip_profile": (c_int, [c_void_p, c_int]),
     "emcid_clip_get_profile": (c_int, [c_void_p, ctypes.POINTER(c_double)]),
     "emcid_clip_launches": (c_longlong, [c_void_p]),

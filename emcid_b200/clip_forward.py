@@ -24,12 +24,19 @@ def _text_model(model):
     return getattr(model, "text_model", model)
 
 
+def text_config(model):
+    """The text tower's config: `model.config` for CLIPTextModel(WithProjection), `.text_config` for a whole CLIPModel
+    (the reference edits those through apply_emcid_to_clip, emcid/emcid_main.py:109-311)."""
+    cfg = model.config
+    return getattr(cfg, "text_config", None) or cfg
+
+
 def supports(model) -> bool:
-    """True for an fp32 HF CLIP text tower (CLIPTextModel / CLIPTextModelWithProjection layout)."""
+    """True for an fp32 HF CLIP text tower (CLIPTextModel / CLIPTextModelWithProjection / the text half of CLIPModel)."""
     try:
         tm = _text_model(model)
         emb, layers = tm.embeddings, tm.encoder.layers
-        cfg = model.config
+        cfg = text_config(model)
         if getattr(cfg, "hidden_act", None) not in ("quick_gelu", "gelu"):
             return False
         if cfg.hidden_size % cfg.num_attention_heads or cfg.hidden_size > 2048 or cfg.max_position_embeddings > 128:
@@ -76,7 +83,7 @@ class NativeClipTextEncoder:
     def __init__(self, model, max_tokens: int, max_captions: int):
         if not supports(model):
             raise NotImplementedError("not a plain fp32 HF CLIP text encoder on a CUDA device")
-        tm, cfg = _text_model(model), model.config
+        tm, cfg = _text_model(model), text_config(model)
         self.device = tm.embeddings.token_embedding.weight.device
         self.n_layers = len(tm.encoder.layers)
         self.hidden, self.inter = cfg.hidden_size, cfg.intermediate_size
@@ -91,9 +98,11 @@ class NativeClipTextEncoder:
                 _lib.act_code(cfg.hidden_act), self.max_positions, tm.embeddings.token_embedding.weight.shape[0], eps,
                 self.max_tokens, self.max_captions))
         self._sig: Dict[object, tuple] = {}   # what was uploaded: (data_ptr, version) of every source tensor
+        self._sums: Dict[object, torch.Tensor] = {}   # ... and its content checksums (verify=True catches `.data` writes)
         self.last_sync: Dict[object, list] = {}
         self.keys_token = None                # (caller token, layer) of the last forward_keys call, see compute_ks.py
-        self.sync_weights(model)
+        self.has_final_norm = False
+        self.sync_weights(model, verify=True)
 
     @staticmethod
     def _layer_tensors(ly):
@@ -109,32 +118,77 @@ class NativeClipTextEncoder:
     def _signature(tensors) -> tuple:
         return tuple((0, 0) if t is None else (t.data_ptr(), t._version) for t in tensors)
 
-    def sync_weights(self, model, upto_layer: Optional[int] = None) -> int:
-        """(Re-)upload the embeddings and layers [0, upto_layer] whose source tensors changed since the last upload
-        (PyTorch bumps `Tensor._version` on every in-place write: that is how the edit loop's `w[...] = w0 + dW`,
-        reference emcid_main.py:1061, becomes visible here).  Returns the number of layers uploaded;
-        `self.last_sync` = {layer or "emb": indices of the source tensors that had changed}."""
+    @staticmethod
+    def _checksums(tensors) -> torch.Tensor:
+        """One int64 per tensor: the wrapping sum of its 32-bit words (exact, order independent; any realistic edit of
+        a weight changes it)."""
+        return torch.stack([torch.zeros((), dtype=torch.int64, device=tensors[0].device) if t is None else
+                            t.detach().reshape(-1).view(torch.int32).sum(dtype=torch.int64) for t in tensors])
+
+    def invalidate(self) -> None:
+        """Forget what was uploaded: the next sync re-uploads everything it needs."""
+        self._sig.clear()
+        self._sums.clear()
+        self.keys_token = None
+
+    def sync_weights(self, model, upto_layer: Optional[int] = None, verify: bool = False) -> int:
+        """(Re-)upload the embeddings, the final layer norm and layers [0, upto_layer] whose source tensors changed since
+        the last upload.  Cheap test: (data_ptr, `Tensor._version`) — PyTorch bumps the version on every in-place write,
+        which is how the edit loop's `w[...] = w0 + dW` (reference emcid_main.py:1061) becomes visible here.  Writes
+        through `param.data` do NOT bump it (and a replaced Parameter can reuse a pointer): `verify=True` additionally
+        compares a content checksum of every source tensor (one small reduction per tensor, one D2H of the results; the
+        edit loop asks for it once per edit, `invalidate()` forces a full upload).  Returns the number of layers
+        uploaded; `self.last_sync` = {layer, "emb" or "final_norm": indices of the source tensors that had changed}."""
         tm = _text_model(model)
         lib = _lib.lib()
         n = 0
         self.last_sync = {}
+        last = self.n_layers - 1 if upto_layer is None else min(int(upto_layer), self.n_layers - 1)
+        groups = {"emb": [tm.embeddings.token_embedding.weight, tm.embeddings.position_embedding.weight]}
+        fln = getattr(tm, "final_layer_norm", None)
+        if isinstance(fln, torch.nn.LayerNorm) and fln.weight is not None and fln.bias is not None:
+            groups["final_norm"] = [fln.weight, fln.bias]
+        for i in range(last + 1):
+            groups[i] = self._layer_tensors(tm.encoder.layers[i])
+        stale: Dict[object, list] = {}       # group -> indices of the tensors whose content changed behind the version counter
+        if verify:
+            with torch.cuda.device(self.device):
+                sums = {k: self._checksums(v) for k, v in groups.items()}
+                flat = torch.cat([sums[k] for k in groups]).cpu()
+            at = 0
+            for k, v in groups.items():
+                cur = flat[at: at + len(v)]
+                at += len(v)
+                old = self._sums.get(k)
+                if old is not None and not torch.equal(old, cur):
+                    stale[k] = [j for j in range(len(v)) if int(old[j]) != int(cur[j])]
+                self._sums[k] = cur
         with torch.cuda.device(self.device):
             stream = _lib.current_stream_ptr()
-            emb = [tm.embeddings.token_embedding.weight, tm.embeddings.position_embedding.weight]
+            emb = groups["emb"]
             sig = self._signature(emb)
-            if self._sig.get("emb") != sig:
+            if "final_norm" in groups:
+                fsig = self._signature(groups["final_norm"])
+                if self._sig.get("final_norm") != fsig or "final_norm" in stale:
+                    self.last_sync["final_norm"] = [0, 1]
+                    w, b = (t.detach().contiguous() for t in groups["final_norm"])
+                    _lib.check(lib.emcid_clip_set_final_norm(self._h, _lib.ptr(w), _lib.ptr(b), stream))
+                    self._sig["final_norm"] = fsig
+                    self.has_final_norm = True
+                    n += 1
+            if self._sig.get("emb") != sig or "emb" in stale:
                 self.last_sync["emb"] = [0, 1]
                 tok, pos = emb[0].detach().contiguous(), emb[1].detach().contiguous()
                 _lib.check(lib.emcid_clip_set_embeddings(self._h, _lib.ptr(tok), _lib.ptr(pos), stream))
                 self._sig["emb"] = sig
-            last = self.n_layers - 1 if upto_layer is None else min(int(upto_layer), self.n_layers - 1)
             for i in range(last + 1):
-                src = self._layer_tensors(tm.encoder.layers[i])
+                src = groups[i]
                 sig = self._signature(src)
-                if self._sig.get(i) == sig:
+                if self._sig.get(i) == sig and i not in stale:
                     continue
                 old = self._sig.get(i)
-                self.last_sync[i] = list(range(16)) if old is None else [j for j in range(16) if old[j] != sig[j]]
+                self.last_sync[i] = (list(range(16)) if old is None else
+                                     sorted(set(j for j in range(16) if old[j] != sig[j]) | set(stale.get(i, ()))))
                 tensors = [None if t is None else t.detach().contiguous() for t in src]
                 arr = (ctypes.c_void_p * 16)(*[_lib.ptr(t) or None for t in tensors])
                 _lib.check(lib.emcid_clip_set_layer(self._h, i, arr, stream))
@@ -171,6 +225,35 @@ class NativeClipTextEncoder:
         n_layers = self.n_layers if n_layers is None else n_layers
         out = torch.empty(T, self.hidden, dtype=torch.float32, device=self.device)
         self._run(ids, pos, cu, S, T, n_layers, [], [], out)
+        return out
+
+    def forward_final(self, ids, pos, cu, S: int, T: int, acc=None, rows: Optional[torch.Tensor] = None,
+                      want_all: bool = False) -> Optional[torch.Tensor]:
+        """The text encoder's output last_hidden_state = final_layer_norm(all layers) over the packed tokens
+        (emcid_clip_forward_final): `acc` (a Mom2Accumulator with d == hidden) += its second moment and token count;
+        `rows` (packed token indices) or `want_all` return the fp32 rows [n, hidden]."""
+        if not getattr(self, "has_final_norm", False):
+            raise NotImplementedError("this text model has no final_layer_norm to read last_hidden_state from")
+        ids = ids.to(self.device, non_blocking=True)
+        pos = pos.to(self.device, non_blocking=True)
+        cu = cu.to(self.device, non_blocking=True)
+        out = None
+        n_rows = 0
+        if rows is not None:
+            rows = rows.to(self.device, dtype=torch.int32, non_blocking=True).contiguous()
+            n_rows = rows.numel()
+        elif want_all:
+            n_rows = T
+        if n_rows:
+            out = torch.empty(n_rows, self.hidden, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().emcid_clip_forward_final(self._h, _lib.ptr(ids), _lib.ptr(pos), _lib.ptr(cu), S, T,
+                                                           acc._h if acc is not None else None, _lib.ptr(rows), n_rows,
+                                                           _lib.ptr(out), self._stream()))
+        s = torch.cuda.current_stream(self.device)
+        for t in (ids, pos, cu) + ((rows,) if rows is not None else ()):
+            t.record_stream(s)
+        self.keys_token = None
         return out
 
     def forward_keys(self, ids, pos, cu, S: int, T: int, layer: int, rows: torch.Tensor,
@@ -234,10 +317,11 @@ def release_key_encoders() -> None:
     _KEY_ENCODERS.clear()
 
 
-def key_encoder(model, n_tokens: int, n_captions: int, upto_layer: int) -> Optional[NativeClipTextEncoder]:
+def key_encoder(model, n_tokens: int, n_captions: int, upto_layer: int, verify: bool = False
+                ) -> Optional[NativeClipTextEncoder]:
     """The cached encoder of `model`, grown to the requested capacity, with the weights of layers [0, upto_layer]
-    brought up to date.  None when the model is not a plain fp32 CLIP text tower on a CUDA device or
-    EMCID_NATIVE_KEYS=0."""
+    brought up to date (`verify`: by content checksum as well, see NativeClipTextEncoder.sync_weights).  None when the
+    model is not a plain fp32 CLIP text tower on a CUDA device or EMCID_NATIVE_KEYS=0."""
     if os.environ.get("EMCID_NATIVE_KEYS", "1") == "0" or not supports(model):
         return None
     key = id(model)
@@ -261,7 +345,7 @@ def key_encoder(model, n_tokens: int, n_captions: int, upto_layer: int) -> Optio
             ref = (lambda m=model: m)
         _KEY_ENCODERS[key] = (ref, enc)
     else:
-        enc.sync_weights(model, upto_layer)
+        enc.sync_weights(model, upto_layer, verify=verify)
     return enc
 
 

@@ -53,6 +53,8 @@ struct ClipHandle {
   int cap_seqs;
   float *tok_emb, *pos_emb;
   std::vector<ClipLayer>* layers;
+  float *fln_w, *fln_b;        // final_layer_norm (text_model.final_layer_norm): input of the UNet cross-attention K/V layers
+  bool fln_set;
   float* hres;                 // [cap x h]
   float* qkv;                  // [cap x 3h]   fp32 q|k|v (CUDA-core attention path)
   uint16_t *qp_hi, *qp_lo;     // [cap x 3h]   q|k|v planes (tensor-core attention path)
@@ -970,6 +972,73 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   if (hidden_out) {
     EMCID_CUDA_CHECK(cudaMemcpyAsync(hidden_out, H->hres, static_cast<size_t>(T) * H->h * sizeof(float),
                                      cudaMemcpyDeviceToDevice, stream));
+  }
+  return EMCID_OK;
+}
+
+inline int clip_set_final_norm(ClipHandle* H, const float* w, const float* b, cudaStream_t stream) {
+  EMCID_CHECK(H && w && b, EMCID_ERR_INVALID, "clip_set_final_norm: null argument");
+  EMCID_CUDA_CHECK(cudaSetDevice(H->device));
+  int rc;
+  if (!H->fln_w) {
+    if ((rc = clip_alloc(H, &H->fln_w, static_cast<size_t>(H->h))) || (rc = clip_alloc(H, &H->fln_b, static_cast<size_t>(H->h))))
+      return rc;
+  }
+  const size_t hb = static_cast<size_t>(H->h) * sizeof(float);
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(H->fln_w, w, hb, cudaMemcpyDeviceToDevice, stream));
+  EMCID_CUDA_CHECK(cudaMemcpyAsync(H->fln_b, b, hb, cudaMemcpyDeviceToDevice, stream));
+  H->fln_set = true;
+  return EMCID_OK;
+}
+
+// rows[r] of the hi/lo planes -> fp32 (hi + lo is the value to 2^-23); rows == nullptr: row r itself.
+__global__ void clip_planes_to_f32_kernel(const uint16_t* __restrict__ p_hi, const uint16_t* __restrict__ p_lo, long long ldp,
+                                          const int* __restrict__ rows, int R, int T, int h, float* __restrict__ out) {
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    int src = rows ? rows[r] : r;
+    src = src < 0 ? 0 : (src >= T ? T - 1 : src);
+    const uint16_t* sh = p_hi + static_cast<long long>(src) * ldp;
+    const uint16_t* sl = p_lo + static_cast<long long>(src) * ldp;
+    for (int c = threadIdx.x; c < h; c += blockDim.x)
+      out[static_cast<long long>(r) * h + c] = __half2float(__ushort_as_half(sh[c])) + __half2float(__ushort_as_half(sl[c]));
+  }
+}
+
+// The text encoder's OUTPUT, last_hidden_state = final_layer_norm(residual stream after all layers): the common input of
+// every UNet cross-attention to_k / to_v projection.  Replaces, for those modules,
+//     text_repr = pipe.text_encoder(**batch).last_hidden_state ; pipe.unet(latents, t, encoder_hidden_states=text_repr)
+//     feats = flatten_masked_batch(tr.input, mask) ; stat.add(feats)             emcid/layer_stats.py:408-426
+// (one pass per K/V layer in the reference although all 32 see the same input, :429-467) and the key extraction
+//     source_inp_repr = pipe.text_encoder(**inp)[0] ; td[module].input[i, idx]    emcid/compute_ks.py:91-124.
+// acc (optional, d == hidden): mom2 += y^T y, count += T over the packed tokens.  rows/n_rows/out (optional): fp32
+// last_hidden_state of the packed token rows `rows` (device int32; nullptr = all T tokens in order) -> out [n_rows x hidden].
+inline int clip_forward_final(ClipHandle* H, const int* ids, const int* pos, const int* cu_seqlens, int S, int T,
+                              Mom2Handle* acc, const int* rows, int n_rows, float* out, cudaStream_t stream) {
+  EMCID_CHECK(H && H->fln_set, EMCID_ERR_INVALID, "clip_forward_final: call emcid_clip_set_final_norm first");
+  EMCID_CHECK(!acc || (acc->d == H->h && acc->device == H->device), EMCID_ERR_INVALID,
+              "clip_forward_final: the accumulator must have d == hidden (%d)", H->h);
+  EMCID_CHECK(!out || n_rows > 0, EMCID_ERR_INVALID, "clip_forward_final: out needs n_rows > 0");
+  int rc = clip_forward(H, ids, pos, cu_seqlens, S, T, H->L, 0, nullptr, nullptr, nullptr, stream);
+  if (rc || T == 0) return rc;
+  if ((rc = clip_layernorm(H, H->hres, T, H->fln_w, H->fln_b, H->x_hi, H->x_lo, stream))) return rc;
+  if (acc) {
+    GemmOperands ym;   // last_hidden_state planes [T x hidden]: MN-major operand tiles of 64 tokens x 64 features
+    if ((rc = make_tmap_2d(&ym.a_hi, H->x_hi, T, H->h, H->hp, 64, 2)) || (rc = make_tmap_2d(&ym.a_lo, H->x_lo, T, H->h, H->hp, 64, 2)))
+      return rc;
+    ym.b_hi = ym.a_hi; ym.b_lo = ym.a_lo;
+    if ((rc = mom2_syrk_slab(acc, ym, KIND_F16_MN, 0, T, nullptr, stream, 2))) return rc;
+    acc->slabs_since_fold += 4;
+    if (acc->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(acc, stream))) return rc;
+    clip_add_count_kernel<<<1, 1, 0, stream>>>(acc->count, static_cast<long long>(T));
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    acc->launches += 1;
+  }
+  if (out) {
+    const int R = rows ? n_rows : (n_rows < T ? n_rows : T);
+    clip_planes_to_f32_kernel<<<R < H->info.sm_count * 8 ? R : H->info.sm_count * 8, 256, 0, stream>>>(
+        H->x_hi, H->x_lo, H->hp, rows, R, T, H->h, out);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    H->launches += 1;
   }
   return EMCID_OK;
 }

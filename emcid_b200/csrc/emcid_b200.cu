@@ -9,6 +9,7 @@
 #include "mom2.cuh"
 #include "solve.cuh"
 #include "clip.cuh"
+#include "reduce.cuh"
 
 using namespace emcid;
 
@@ -96,6 +97,34 @@ int emcid_mom2_get_profile(emcid_mom2_t* h, double* out8) { return mom2_get_prof
 
 int emcid_mom2_destroy(emcid_mom2_t* h) { return mom2_destroy(reinterpret_cast<Mom2Handle*>(h)); }
 
+int emcid_nccl_available(void) { return nccl_api() != nullptr; }
+
+int emcid_mom2_reduce(emcid_mom2_t* h, void* nccl_comm, int root, void* stream) {
+  return mom2_reduce(reinterpret_cast<Mom2Handle*>(h), nccl_comm, root, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_mom2_broadcast(float* mom2_full, long long* count_dev, int d, void* nccl_comm, int root, void* stream) {
+  return mom2_broadcast_full(mom2_full, count_dev, d, nccl_comm, root, static_cast<cudaStream_t>(stream));
+}
+
+size_t emcid_mom2_state_elems(int d) { return d > 0 ? static_cast<size_t>(packed_lower_elems(d)) : 0; }
+
+int emcid_mom2_export_state(emcid_mom2_t* h, double* lower_packed_dev, long long* count_dev, void* stream) {
+  return mom2_export_state(reinterpret_cast<Mom2Handle*>(h), lower_packed_dev, count_dev, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_mom2_import_state(emcid_mom2_t* h, const double* lower_packed_dev, const long long* count_dev, void* stream) {
+  return mom2_import_state(reinterpret_cast<Mom2Handle*>(h), lower_packed_dev, count_dev, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_symmetrize_lower(float* C, int d, long long ldc, void* stream) {
+  return symmetrize_lower(C, d, ldc, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_fixed_random_subset(long long n_items, long long seed, long long* out, long long n_out) {
+  return fixed_random_subset(n_items, seed, out, n_out);
+}
+
 // ---------------------------------------------------------------------------------------------
 // native text-encoder forward feeding the statistics pass
 // ---------------------------------------------------------------------------------------------
@@ -126,6 +155,17 @@ int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* 
                             float* z_out, int resume_layer, void* stream) {
   return clip_forward(reinterpret_cast<ClipHandle*>(h), ids, positions, cu_seqlens, n_captions, n_tokens, 0, 0, nullptr,
                       nullptr, nullptr, static_cast<cudaStream_t>(stream), layer, key_rows, n_keys, k_out, z_out, resume_layer);
+}
+
+int emcid_clip_set_final_norm(emcid_clip_t* h, const float* weight, const float* bias, void* stream) {
+  return clip_set_final_norm(reinterpret_cast<ClipHandle*>(h), weight, bias, static_cast<cudaStream_t>(stream));
+}
+
+int emcid_clip_forward_final(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
+                             int n_captions, int n_tokens, emcid_mom2_t* acc, const int32_t* rows, int n_rows, float* out,
+                             void* stream) {
+  return clip_forward_final(reinterpret_cast<ClipHandle*>(h), ids, positions, cu_seqlens, n_captions, n_tokens,
+                            reinterpret_cast<Mom2Handle*>(acc), rows, n_rows, out, static_cast<cudaStream_t>(stream));
 }
 
 int emcid_clip_profile(emcid_clip_t* h, int enable) {

@@ -58,6 +58,7 @@ struct Mom2Handle {
   std::vector<cudaEvent_t>* ev_syrk;
   double rows_fc1, rows_syrk;         // slab rows covered by the timed launches
   long long launches;                 // every kernel this handle has launched
+  float* packed;                      // lower-packed fp32 staging buffer of the exchange step (reduce.cuh), lazily allocated
 };
 
 inline size_t mom2_workspace_bytes(int d, int h, int slab) {
@@ -325,7 +326,7 @@ inline int mom2_destroy(Mom2Handle* H) {
   if (!H) return EMCID_OK;
   cudaSetDevice(H->device);
   dev_free(H->w_hi); dev_free(H->w_lo); dev_free(H->bias); dev_free(H->acc32); dev_free(H->acc64);
-  dev_free(H->count);
+  dev_free(H->count); dev_free(H->packed);
   for (cudaEvent_t e : *H->ev_fc1) cudaEventDestroy(e);
   for (cudaEvent_t e : *H->ev_syrk) cudaEventDestroy(e);
   delete H->ev_fc1; delete H->ev_syrk;

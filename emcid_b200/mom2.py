@@ -94,6 +94,35 @@ class Mom2Accumulator:
             _lib.check(_lib.lib().emcid_mom2_finalize(self._h, _lib.ptr(out), _lib.ptr(count), self._stream()))
         return out, count
 
+    def reduce(self, nccl_comm: int, root: int) -> None:
+        """The exchange step of a caption-sharded pass (emcid_mom2_reduce): sums the accumulators of all ranks of
+        `nccl_comm` (address of an ncclComm_t) onto `root`; stream-ordered on the current stream."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().emcid_mom2_reduce(self._h, ctypes.c_void_p(int(nccl_comm)), int(root), self._stream()))
+
+    def export_state(self, out: Optional[torch.Tensor] = None):
+        """(packed lower triangle of the fp64 sums [d (d + 1) / 2] float64 CUDA, count 0-d int64 CUDA): what a resumable
+        pass checkpoints (emcid_mom2_export_state; folds the fp32 accumulator first)."""
+        n = int(_lib.lib().emcid_mom2_state_elems(self.d))
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=self.device)
+        assert out.is_cuda and out.dtype == torch.float64 and out.numel() == n and out.is_contiguous()
+        count = torch.zeros((), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().emcid_mom2_export_state(self._h, _lib.ptr(out), _lib.ptr(count), self._stream()))
+        return out, count
+
+    def import_state(self, packed: torch.Tensor, count) -> None:
+        """Inverse of export_state on a fresh or reset accumulator."""
+        packed = packed.to(self.device, dtype=torch.float64).contiguous()
+        assert packed.numel() == int(_lib.lib().emcid_mom2_state_elems(self.d))
+        count = torch.as_tensor(count, dtype=torch.int64).reshape(()).to(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().emcid_mom2_import_state(self._h, _lib.ptr(packed), _lib.ptr(count), self._stream()))
+        s = torch.cuda.current_stream(self.device)
+        packed.record_stream(s)
+        count.record_stream(s)
+
     def profile(self, enable: bool = True) -> None:
         _lib.check(_lib.lib().emcid_mom2_profile(self._h, 1 if enable else 0))
 

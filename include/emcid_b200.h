@@ -88,6 +88,40 @@ int emcid_mom2_profile(emcid_mom2_t* h, int enable);
 int emcid_mom2_get_profile(emcid_mom2_t* h, double* out8);
 int emcid_mom2_destroy(emcid_mom2_t* h);
 
+/* ---- the exchange step of a caption-sharded pass ----------------------------------------------------
+ * The reference's pass is one process whose only cross-sample dependency is the running sum
+ *     self.count += a.shape[0]; self.mom2 += a.t().mm(a)                 util/runningstats.py:492-493
+ * so R ranks that each visited subset[r::R] (the subset of util/runningstats.py:1551-1556) meet in ONE reduction per
+ * layer.  emcid_mom2_reduce sums the handles of all ranks of `nccl_comm` (an ncclComm_t, passed as void*) onto `root`:
+ * the lower triangle of the per-rank sums travels as d (d + 1) / 2 fp32 values (18.9 MB at d = 3072, ncclReduce) next
+ * to the int64 counts; afterwards the root's handle holds the job-wide statistics (emcid_mom2_finalize there returns
+ * them mirrored), the other ranks' handles are unchanged.  Every rank calls it, in the same order for the same layers,
+ * on a stream that no other operation of that communicator is running on concurrently.  NCCL is resolved at run time
+ * from the process image (libnccl.so.2); emcid_nccl_available() tells whether that worked.
+ * emcid_mom2_broadcast: the finalized [d x d] fp32 matrix and the count from the root to every rank, for callers that
+ * want the statistics everywhere (the reference call returns them to its single caller). */
+int emcid_nccl_available(void);
+int emcid_mom2_reduce(emcid_mom2_t* h, void* nccl_comm, int root, void* stream);
+int emcid_mom2_broadcast(float* mom2_full, long long* count_dev, int d, void* nccl_comm, int root, void* stream);
+
+/* ---- accumulator state of a resumable pass -----------------------------------------------------------
+ * The reference saves a statistic only once its loader is exhausted (util/runningstats.py:115-119): a crash loses the
+ * pass.  export: fold, then the packed lower triangle of the fp64 sums (emcid_mom2_state_elems(d) = d (d + 1) / 2
+ * doubles, row-major: (i, j), j <= i, at i (i + 1) / 2 + j) and the count, to caller-owned DEVICE buffers;
+ * import: the inverse, on a fresh or reset handle. */
+size_t emcid_mom2_state_elems(int d);
+int emcid_mom2_export_state(emcid_mom2_t* h, double* lower_packed_dev, long long* count_dev, void* stream);
+int emcid_mom2_import_state(emcid_mom2_t* h, const double* lower_packed_dev, const long long* count_dev, void* stream);
+/* C[i][j] = C[j][i] for j > i, in place (row pitch ldc floats): the full symmetric matrix SecondMoment.state_dict() /
+ * moment() present (util/runningstats.py:499-507) after lower-triangle accumulation with emcid_gemm3x_nt(flags bit0). */
+int emcid_symmetrize_lower(float* C, int d, long long ldc, void* stream);
+
+/* ---- which captions a pass visits (host) --------------------------------------------------------------
+ * out[0 .. n_out) = random.Random(seed).shuffle(list(range(n_items)))[:n_out], the FixedRandomSubsetSampler of
+ * util/runningstats.py:1551-1556 (CPython's MT19937 + shuffle restated in C: the interpreted shuffle of an 800 k-caption
+ * index costs 0.26 s per rank).  n_items < 2^31. */
+int emcid_fixed_random_subset(long long n_items, long long seed, long long* out, long long n_out);
+
 /* ---- native text-encoder forward for the statistics pass --------------------------------------------
  * Replaces the HF forward the reference runs under `Trace(...)` for every sub-batch
  *     with Trace(model, layer_name, retain_input=True, retain_output=False, stop=True) as tr:
@@ -127,6 +161,20 @@ int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* posit
 int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
                             int n_captions, int n_tokens, int layer, const int32_t* key_rows, int n_keys, float* k_out,
                             float* z_out, int resume_layer, void* stream);
+/* The text encoder's output for the UNet cross-attention K/V modules.  last_hidden_state =
+ * final_layer_norm(residual stream after all layers) is the common input of every attn2.to_k / attn2.to_v, so ONE pass
+ * serves all of them where the reference runs one pass per module (emcid/layer_stats.py:333-427, :429-467):
+ *     text_repr = pipe.text_encoder(**batch).last_hidden_state; pipe.unet(latents, t, encoder_hidden_states=text_repr)
+ *     feats = flatten_masked_batch(tr.input, batch["attention_mask"]); stat.add(feats)
+ * and the key extraction of the cross-attention edit reads the same tensor at the last subject token
+ * (emcid/compute_ks.py:91-124).  set_final_norm: text_model.final_layer_norm weight / bias [hidden], device fp32.
+ * forward_final: acc (optional; an emcid_mom2 handle with d == hidden): mom2 += y^T y, count += n_tokens;
+ * rows / n_rows / out (optional): fp32 last_hidden_state of the packed token rows `rows` (device int32; NULL = the
+ * first n_rows tokens in order) -> out [n_rows x hidden]. */
+int emcid_clip_set_final_norm(emcid_clip_t* h, const float* weight, const float* bias, void* stream);
+int emcid_clip_forward_final(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
+                             int n_captions, int n_tokens, emcid_mom2_t* acc, const int32_t* rows, int n_rows, float* out,
+                             void* stream);
 /* Measurement aid: when enabled, every launch of the forward is bracketed by CUDA events on the caller's stream.
  * emcid_clip_get_profile waits for them and fills out21[tag * 3 + {0, 1, 2}] = {launches, total ms, total algorithmic
  * flops (2 M N K)} for tag = 0 q/k/v projection, 1 out projection, 2 fc1, 3 fc1 of an edited layer (both plane

@@ -24,5 +24,16 @@ class OracleAccumulator:
         m = self.st.mom2 if self.st.mom2 is not None else np.zeros((self.d, self.d), np.float32)
         return torch.from_numpy(m.copy()), torch.tensor(self.st.count, dtype=torch.int64)
 
+    # accumulator state of a resumable pass (Mom2Accumulator.export_state / import_state): packed lower triangle + count
+    def export_state(self):
+        m = self.st.mom2 if self.st.mom2 is not None else np.zeros((self.d, self.d), np.float32)
+        return torch.from_numpy(m[np.tril_indices(self.d)].astype(np.float64)), torch.tensor(self.st.count, dtype=torch.int64)
+
+    def import_state(self, packed, count):
+        m = np.zeros((self.d, self.d), np.float32)
+        m[np.tril_indices(self.d)] = packed.numpy().astype(np.float32)
+        self.st.mom2 = m + np.tril(m, -1).T
+        self.st.count = int(count)
+
     def close(self):
         pass

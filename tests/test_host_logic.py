@@ -60,8 +60,23 @@ def test_subset_selection_matches_oracle():
     for n, ss in [(150, 120), (10, 10), (7, None), (5, 9)]:
         assert runningstats.subset_indices(n, ss, 1) == orc.fixed_random_subset(n, ss, 1)
     assert runningstats.subset_indices(9, 4, None) == [0, 1, 2, 3]
-    s = runningstats.FixedRandomSubsetSampler(range(50), end=20, seed=1)
-    assert list(s) == orc.fixed_random_subset(50, 20, 1)
+    assert list(runningstats.FixedSubsetSampler([4, 2, 7])) == [4, 2, 7]
+
+
+def test_library_shuffle_is_cpythons():
+    """emcid_fixed_random_subset restates random.Random(seed).shuffle (MT19937, init_by_array seeding, _randbelow by
+    rejection on the top bits): identical permutations for every size class the rejection loop can see (powers of two and
+    their neighbours), seeds of one and two 32-bit words, zero and negative seeds, and the reference's own use
+    (util/runningstats.py:1551-1556: seed 1)."""
+    for n, seed in [(0, 1), (1, 1), (2, 1), (3, 5), (255, 1), (256, 1), (257, 1), (4096, 0), (65537, 1), (1000, 2 ** 40 + 3),
+                    (300, -7), (100003, 1)]:
+        rng = random.Random(seed)
+        want = list(range(n))
+        rng.shuffle(want)
+        for k in {n, n // 3}:
+            assert runningstats.fixed_random_subset(n, k, seed).tolist() == want[:k], (n, seed, k)
+    with pytest.raises(Exception):
+        runningstats.fixed_random_subset(5, 9, 1)             # more than the dataset holds
 
 
 def test_length_collation_matches_oracle():
@@ -116,6 +131,77 @@ def test_layer_stats_has_no_cpu_fallback(tmp_path):
             layer_stats.layer_stats_text_encoder(model, None, "text_model.encoder.layers.1.mlp.fc2",
                                                  stats_dir=tmp_path, sample_size=8, precision="float32",
                                                  download=True, progress=None)
+    finally:
+        layer_stats.get_ccs_filtered_ds = saved
+
+
+def test_requests_off_the_edit_path_are_delegated_or_refused(tmp_path, monkeypatch):
+    """to_collect = mean / norm_mean and float64 accumulation (emcid/layer_stats.py:26-30, :161-162) are not on the edit
+    path: they go, unchanged, to the reference's function when the reference package is importable and are
+    an explicit error otherwise.  precision=None is the reference's float64 default."""
+    import sys
+    model = rh.make_clip_text_model("tiny", seed=0)
+    name = "text_model.encoder.layers.1.mlp.fc2"
+    caps = rh.make_captions(12, 1000, seed=2)
+    for mod in ("emcid", "emcid.layer_stats"):
+        monkeypatch.setitem(sys.modules, mod, None)           # as on a machine without the reference
+    for kw in (dict(to_collect=["mean"], precision="float32"), dict(to_collect=["mom2", "norm_mean"], precision="float32"),
+               dict(to_collect=["mom2"], precision=None), dict(to_collect=["mom2"], precision="float64")):
+        with pytest.raises(NotImplementedError, match="not on the B200 path"):
+            layer_stats.layer_stats_text_encoder(model, None, name, stats_dir=tmp_path, sample_size=8, progress=None, **kw)
+    with pytest.raises(NotImplementedError, match="precision"):
+        layer_stats.layer_stats_text_encoder_multi(model, None, [name], stats_dir=tmp_path, sample_size=8, progress=None)
+    monkeypatch.undo()
+    if rh.reference_available():
+        ref = rh.import_reference()
+        ref.layer_stats.get_ccs_filtered_ds = lambda tokenizer: rh.SynthTokenDataset(caps)
+        stat = layer_stats.layer_stats_text_encoder(model, None, name, stats_dir=tmp_path, sample_size=8, precision="float32",
+                                                    to_collect=["mean"], progress=lambda x, total=None: x)
+        assert type(stat).__module__ == "util.runningstats" and tuple(stat.mean.mean().shape) == (256,)
+
+
+def test_interrupted_pass_resumes_from_its_checkpoint(tmp_path):
+    """Host logic of the resumable pass (layer_stats._Checkpointer) with the oracle accumulator standing in for the CUDA
+    one: a pass that dies after a checkpoint continues from it — same count, same matrix as an uninterrupted pass — and a
+    completed pass leaves no checkpoint behind."""
+    from cpu_accumulator import OracleAccumulator
+    model = rh.make_clip_text_model("tiny", seed=0)
+    caps = rh.make_captions(120, 1000, seed=9)
+    names = [f"text_model.encoder.layers.{l}.mlp.fc2" for l in (0, 1)]
+    saved = layer_stats.get_ccs_filtered_ds
+    layer_stats.get_ccs_filtered_ds = lambda tokenizer: rh.SynthTokenDataset(caps)
+    kw = dict(sample_size=100, precision="float32", captions_per_batch=8, num_workers=0, _accumulator_factory=OracleAccumulator,
+              checkpoint_every=3)
+
+    class Crash(Exception):
+        pass
+
+    def dying_progress(loader, total=None):
+        for i, batch in enumerate(loader):
+            if i == 8:                     # blocks 0..7 fed: checkpoints after blocks 3 and 6
+                raise Crash
+            yield batch
+
+    try:
+        whole = layer_stats.layer_stats_text_encoder_multi(model, None, names, stats_dir=tmp_path / "a", progress=None, **kw)
+        assert layer_stats.LAST_PASS_INFO["resumed_from_caption"] == 0
+        with pytest.raises(Crash):
+            layer_stats.layer_stats_text_encoder_multi(model, None, names, stats_dir=tmp_path / "b", progress=dying_progress, **kw)
+        ckpts = list((tmp_path / "b").rglob(".resume_*.npz"))
+        assert len(ckpts) == 1 and int(np.load(ckpts[0])["captions_done"]) == 48
+        assert not list((tmp_path / "b").rglob("text_model*.npz"))                     # nothing final was written
+        resumed = layer_stats.layer_stats_text_encoder_multi(model, None, names, stats_dir=tmp_path / "b", progress=None, **kw)
+        assert layer_stats.LAST_PASS_INFO["resumed_from_caption"] == 48
+        for n in names:
+            assert resumed[n].mom2.count == whole[n].mom2.count
+            assert torch.equal(resumed[n].mom2.mom2, whole[n].mom2.mom2)
+        assert not list((tmp_path / "b").rglob(".resume_*.npz")) and not list((tmp_path / "a").rglob(".resume_*.npz"))
+        # a checkpoint of another pass (different sample size) is not picked up
+        with pytest.raises(Crash):
+            layer_stats.layer_stats_text_encoder_multi(model, None, names, stats_dir=tmp_path / "c", progress=dying_progress, **kw)
+        other = dict(kw, sample_size=90)
+        layer_stats.layer_stats_text_encoder_multi(model, None, names, stats_dir=tmp_path / "c", progress=None, **other)
+        assert layer_stats.LAST_PASS_INFO["resumed_from_caption"] == 0
     finally:
         layer_stats.get_ccs_filtered_ds = saved
 

@@ -122,6 +122,32 @@ def test_sequential_editing_oracle_matches_reference_fixture(golden_dir):
             assert rel_fro(got, want) < 1e-8, (e, l)        # measured: bit-identical or <= 1.3e-10
 
 
+def test_execute_oracle_matches_reference_digest_at_clipl_size(golden_dir):
+    """The oracle at CLIP-L size against the unmodified reference (oracle/gen_golden_clipl.py): first sequential edit of
+    tests/golden/clipl_sequential_digest.npz (100 requests, layers 7-11, template-correlated keys, cond ~ 3e6)."""
+    from emcid_b200 import synth
+    from helpers import weight_checksum
+    g = np.load(os.path.join(golden_dir, "clipl_sequential_digest.npz"))
+    layers = [int(x) for x in g["layers"]]
+    model = rh.make_clip_text_model("clip-l", seed=0)
+    if not np.allclose(weight_checksum(model), g["weight_checksum"], rtol=1e-12):
+        pytest.skip("random-init CLIP-L differs from the fixture's (torch RNG stream changed)")
+    tok = synth.WordHashTokenizer(49408)
+    reqs = [dict(r, source=f"edit0 {r['source']}") for r in rh.make_requests(int(g["n_req"]))]
+    g_v = torch.Generator().manual_seed(int(g["seed_vstar0"]))          # ref_harness.write_vstar_cache without the files
+    zs = torch.stack([torch.randn(768, generator=g_v) for _ in reqs], dim=1).numpy()
+    covs = {l: orc.exact_spd_matrix(3072, 3072 + 1024, seed=l) for l in layers}
+    deltas = orc.execute_oracle(model, tok, reqs, layers, zs, covs, float(g["lam"]), float(g["edit_weight"]))
+    rng = np.random.RandomState(0)
+    P, Q = rng.randn(3072, int(g["n_probe"])), rng.randn(768, int(g["n_probe"]))
+    for l in layers:
+        w0 = model.text_model.encoder.layers[l].mlp.fc2.weight.numpy()
+        dW = orc.apply_delta(w0, *deltas[l]).astype(np.float64) - w0
+        assert rel_fro(dW @ P, g[f"cum.0.{l}.MP"]) < 1e-6, l
+        assert rel_fro(Q.T @ dW, g[f"cum.0.{l}.QtM"]) < 1e-6, l
+        assert abs(np.linalg.norm(dW) / float(g[f"cum.0.{l}.fro"]) - 1) < 1e-6, l
+
+
 def test_exact_spd_matrix_is_reproducible():
     a = orc.exact_spd_matrix(64, 128, seed=3)
     b = orc.exact_spd_matrix(64, 128, seed=3)
