@@ -144,6 +144,211 @@ def cpu_port_tokens_per_s(captions_n: int, threads: int):
     return tokens / dt, dt, tokens
 
 
+
+# ------------------------------------------------------------------------------------------ parity of the timed run
+def fp64_probe(model, ids, names, probes, dev, chunk=492):
+    """{name: A^T (A v)} in fp64, A = the fc2 inputs of `names` over the full-width captions `ids` [n, 77], from an fp64
+    copy of the HF model (the reference's forward, emcid/layer_stats.py:208-219, without its fp32 rounding); no d x d product."""
+    import copy
+
+    import torch
+
+    m64 = copy.deepcopy(model).double()
+    feats = {}
+    hooks = [m64.get_submodule(n).register_forward_pre_hook(lambda m, a, n=n: feats.__setitem__(n, a[0])) for n in names]
+    out = {n: torch.zeros(probes[n].shape, dtype=torch.float64, device=dev) for n in names}
+    try:
+        with torch.no_grad():
+            for c0 in range(0, ids.shape[0], chunk):
+                m64(input_ids=ids[c0:c0 + chunk])
+                for n in names:
+                    a = feats.pop(n).reshape(-1, probes[n].shape[0])
+                    out[n] += a.T @ (a @ probes[n])
+    finally:
+        for h in hooks:
+            h.remove()
+    del m64
+    return out
+
+
+def timed_run_parity(model, ids_timed, names, out, roots, rank, world, dev, dist, count):
+    import torch
+
+    ids = ids_timed.reshape(-1, ids_timed.shape[-1])
+    g = torch.Generator(device=dev).manual_seed(99)
+    probes = {n: torch.randn(D, 4, device=dev, dtype=torch.float64, generator=g) for n in names}   # same on every rank
+    t0 = time.perf_counter()
+    want = fp64_probe(model, ids, names, probes, dev)
+    got = {n: (out[n][0].double() @ probes[n] if out[n][0] is not None else torch.zeros(D, 4, dtype=torch.float64, device=dev))
+           for n in names}
+    if world > 1:
+        for n in names:
+            dist.all_reduce(want[n])          # sum of the per-rank fp64 partials = the job-wide reference
+            dist.all_reduce(got[n])           # only the layer's root contributes
+    errs = {n: float((got[n] - want[n]).norm() / want[n].norm()) for n in names}
+    return {"what": "|M v - G64 v| / |G64 v| per edited layer over 4 probe vectors: M = the mom2 of the TIMED run (at N > 1 "
+                    "the matrix the exchange step left on the layer's root), G64 v = sum_t a_t (a_t . v) in fp64 from an fp64 "
+                    "copy of the HF model over the same captions",
+            "captions": int(ids.shape[0]) * world, "tokens": int(ids.numel()) * world,
+            "probe_rel_err": {n.split(".")[3]: e for n, e in errs.items()}, "max_rel_err": max(errs.values()),
+            "tolerance": 1e-5, "ok": bool(max(errs.values()) < 1e-5 and count == int(ids.numel()) * world),
+            "count_bit_exact": bool(count == int(ids.numel()) * world), "seconds": time.perf_counter() - t0}
+
+
+# ------------------------------------------------------------------------------------------ update: operands and baselines
+def capture_edit_operands(model, names, out, count, n, dev):
+    """(Kt [L, n, d], St [L, n, h]): what the edit loop hands the solver for each layer of a 1000-concept edit."""
+    import torch
+    from types import SimpleNamespace
+
+    from emcid_b200 import emcid_main, synth
+
+    reqs = synth.make_edit_requests(n)
+    tmp = tempfile.mkdtemp(prefix="emcid_bench_capture_")
+    cache = os.path.join(tmp, "vstar", "c_")
+    synth.write_vstar_cache(cache, reqs, H, seed=2)
+    hp = synth.make_edit_hparams(LAYERS, mom2_n_samples=1)
+    pipe = SimpleNamespace(text_encoder=model, tokenizer=synth.WordHashTokenizer(49408), device=dev)
+    emcid_main.COV_CACHE.clear()
+    for nm in names:
+        emcid_main.COV_CACHE[(model.config._name_or_path.replace("/", "_"), nm)] = (out[nm][0] / max(count, 1)).float()
+    grabbed = []
+    inner = emcid_main._solve_one_layer
+
+    def spy(enc, module_name, cov_raw, layer_ks, sources_t, *rest):
+        grabbed.append((layer_ks.detach().float().clone(), sources_t.detach().float().clone()))
+        return inner(enc, module_name, cov_raw, layer_ks, sources_t, *rest)
+
+    emcid_main._solve_one_layer = spy
+    try:
+        emcid_main.execute_emcid_text_encoder(pipe, reqs, hp, cache_name=cache, stat_dir=tmp, verbose=False)
+    finally:
+        emcid_main._solve_one_layer = inner
+        emcid_main.COV_CACHE.clear()
+    if len(grabbed) != len(names):
+        return None
+    return torch.stack([k for k, _ in grabbed]).contiguous(), torch.stack([s_ for _, s_ in grabbed]).contiguous()
+
+
+def torch_solve_on_gpu(C32, Kt, St, lam, left):
+    """The reference's solve block as written (emcid_main.py:1037-1050: fp64 M, torch.linalg.solve, fp64 resid @ adj_k^T),
+    layer after layer, on the same GPU: what `the reference on a B200` costs for this half of the metric."""
+    import torch
+
+    def once():
+        outs = []
+        for i in range(C32.shape[0]):
+            Ks, Ss = Kt[i].double().T, St[i].double().T
+            adj = torch.linalg.solve(lam * C32[i].double() + Ks @ Ks.T, Ks)
+            resid = Ss / left[i]
+            outs.append((resid @ adj.T).float())
+        return outs
+
+    once()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        once()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return {"ms": sorted(ts)[1], "what": "torch fp64 on the same GPU: M = lam*C.double() + Ks Ks^T, torch.linalg.solve (LU), "
+                                          "resid @ adj_k^T, 5 layers in sequence (cuSOLVER / cuBLAS)"}
+
+
+def cpu_solve_baseline(C32, Kt, St, lam, left):
+    """The reference's solve block on the host cores (oracle.solve_layer = numpy/LAPACK gesv, the routine torch.linalg.solve
+    calls on CPU), same operands, all layers."""
+    import torch
+
+    from oracle import emcid_oracle as orc
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    C, K, S = C32.cpu().numpy(), Kt.cpu().numpy(), St.cpu().numpy()
+    t0 = time.perf_counter()
+    for i in range(C.shape[0]):
+        orc.solve_layer(C[i], K[i].T, S[i].T, lam, 0.5, left[i])
+    dt = time.perf_counter() - t0
+    return {"value": 1e3 * dt, "unit": "ms per 1000-concept 5-layer solve", "cores": threads, "kind": "port",
+            "sample": f"the same {C.shape[0]} (C, K, S) problems, d = {C.shape[1]}, n = {K.shape[1]}, fp64 LU (LAPACK gesv)"}
+
+
+def cpu_edit_baseline(out, names, count, n_req):
+    """The reference's stage-2 loop (oracle.execute_oracle: two traced HF forwards + fp64 LU per layer,
+    emcid/emcid_main.py:980-1078) on the host cores at a reduced request count."""
+    import torch
+
+    from emcid_b200 import synth
+    from oracle import emcid_oracle as orc
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = _CPU_MODEL if _CPU_MODEL is not None else synth.make_text_encoder("sd-text", seed=0)
+    covs = {l: (out[nm][0] / max(count, 1)).float().cpu().numpy() for l, nm in zip(LAYERS, names)}
+    reqs = synth.make_edit_requests(n_req)
+    zs = torch.randn(H, n_req, generator=torch.Generator().manual_seed(2)).numpy()
+    t0 = time.perf_counter()
+    orc.execute_oracle(model, synth.WordHashTokenizer(49408), reqs, LAYERS, zs, covs, 4000.0, 0.5)
+    dt = time.perf_counter() - t0
+    return {"value": 1e3 * dt, "unit": "ms per edit call", "cores": threads, "kind": "port",
+            "sample": f"{n_req} concepts ({3 * n_req} prompts) x {len(LAYERS)} layers instead of 1000: keys by two HF fp32 "
+                      "forwards per layer, fp64 LU per layer (its d^3 term does not shrink with the request count)"}
+
+
+def gpu_torch_stats_reference(model, ids_block, names, dev, passes_per_layer=True):
+    """The reference's statistics algorithm in torch on the same GPU (TF32 off, as torch defaults): per edited layer one
+    HF fp32 forward stopped at the traced fc2 (util/nethook.py Trace(stop=True)), masked flatten, `mom2 += a.t().mm(a)`
+    (util/runningstats.py:493) over length-collated sub-batches of <= 3072 tokens (dsets/stat_dataset.py:122-150) — one
+    full pass PER LAYER (emcid/layer_stats.py:112-134).  Returns tokens/s over `ids_block` [n, 77]."""
+    import torch
+
+    class Stop(Exception):
+        pass
+
+    n_caps = ids_block.shape[0]
+    per = 3072 // WIDTH                          # 39 full-length captions per sub-batch
+    moms = {}
+
+    def one_pass(name):
+        mod = model.get_submodule(name)
+        box = {}
+
+        def hook(m, a):
+            box["a"] = a[0]
+            raise Stop
+
+        h = mod.register_forward_pre_hook(hook)
+        mom2 = torch.zeros(D, D, device=dev)
+        try:
+            with torch.no_grad():
+                for c0 in range(0, n_caps, per):
+                    try:
+                        model(input_ids=ids_block[c0:c0 + per])
+                    except Stop:
+                        pass
+                    a = box.pop("a").reshape(-1, D)
+                    mom2 += a.t().mm(a)
+        finally:
+            h.remove()
+        moms[name] = mom2
+
+    one_pass(names[0])                            # warm-up (cuBLAS handles, autotune)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for nm in names:
+        one_pass(nm)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": n_caps * WIDTH / (ms * 1e-3), "unit": UNIT, "ms": ms, "captions": int(n_caps),
+            "what": "the reference's algorithm in torch on this GPU (HF CLIPTextModel fp32 forward, allow_tf32 = False, "
+                    "Trace(stop=True)-style hook, a.t().mm(a) in fp32): one pass per edited layer over the same captions, "
+                    "39-caption sub-batches (batch_tokens = 3072); tokens/s counts each caption once, like `value`"}
+
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path (oracle port: the
@@ -168,7 +373,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.captions), "sample": f"{sample} captions x 77 tokens per step",
-                   "layers": LAYERS},
+                   "layers": LAYERS, "same_as_headline": False,
+                   "note": "same model, layers, caption shape and algorithm as the headline workload on a bounded sample: "
+                           "the oracle port of the reference (pure Python/torch, nothing to compile) on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} captions x 77 tokens, one full forward+Gram pass per layer (5 passes) "
                                    f"per step, {args.steps} steps"},
@@ -232,12 +439,11 @@ def run_ours(args):
                               "attention_mask": mask_dev[c0:c0 + blk]})
 
     def finish():
-        out = runner.finalize()
-        if world > 1:
-            for n in names:
-                dist.all_reduce(out[n][0], op=dist.ReduceOp.SUM)
-                dist.all_reduce(out[n][1], op=dist.ReduceOp.SUM)
-        return out
+        """The exchange step of the pass (emcid_mom2_reduce: lower triangles + counts to the rank that owns the layer,
+        layer i -> rank i mod world) and the mirrored matrices on their roots: {name: (mom2 or None, count)}."""
+        res, roots = layer_stats._reduce_results(runner, names, dist if world > 1 else None, rank, world, dev,
+                                                 broadcast=False, keep_on_device=True)
+        return res, roots
 
     def launches():
         return runner.launches()
@@ -259,7 +465,7 @@ def run_ours(args):
     e0.record()
     for i in range(W, W + K):
         step(i)
-    out = finish()
+    out, roots = finish()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -270,8 +476,24 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     n_launch = launches() - l0
-    count0 = int(out[names[0]][1].item())
+    count0 = int(out[names[0]][1])
     value = world * K * tokens_per_step / (ms_total * 1e-3)
+    exchange = layer_stats.LAST_PASS_INFO.get("exchange") if world > 1 else "none (one rank)"
+
+    # ---- parity of THIS timed run: probe vectors through the reduced matrices against an fp64 copy of the HF model over
+    # the same captions (every rank probes its own shard, the partial products meet in one small all-reduce): checks the
+    # accumulation chain at the timed length and, at N > 1, the exchange step on the NCCL path
+    parity = None
+    if not args.no_parity and args.encoder == "sd-text" and not args.layers:
+        parity = timed_run_parity(model, ids_dev[W:W + K], names, out, roots, rank, world, dev, dist, count0)
+    # untimed: every rank gets every matrix (the update timings below want C on each GPU)
+    if world > 1:
+        for nm in names:
+            m = out[nm][0]
+            if m is None:
+                m = torch.empty(D, D, dtype=torch.float32, device=dev)
+            dist.broadcast(m, src=roots[nm])
+            out[nm] = (m, out[nm][1])
 
     # ---- roofline of the dominant kernel (stream-K lower SYRK on tcgen05), timed per launch with CUDA events
     for acc in runner.accs.values():
@@ -350,11 +572,21 @@ def run_ours(args):
         n = args.concepts
         gg = torch.Generator(device=dev).manual_seed(2)
         C32 = torch.stack([out[nm][0] / max(count0, 1) for nm in names]).contiguous()
-        if world > 1:  # layers were reduced to different roots; any rank's partial sum is a valid SPD C for timing
-            C32 = C32 / 1.0
-        Kt = torch.randn(len(LAYERS), n, D, device=dev, generator=gg) * 0.5 + 0.2
-        St = torch.randn(len(LAYERS), n, H, device=dev, generator=gg)
         left = [len(LAYERS) - i for i in range(len(LAYERS))]
+        captured = None
+        if not args.no_edit and args.encoder == "sd-text" and not args.layers:
+            # the per-layer (C32, K, S) of a real edit — keys at the last subject token of 3 x n templated
+            # prompts, each layer's keys taken on the model with the previous layers' updates applied — captured from one
+            # run of the edit loop
+            captured = capture_edit_operands(model, names, out, count0, n, dev)
+        if captured is not None:
+            Kt, St = captured
+            solve_inputs = ("captured from execute_emcid_text_encoder on this model: real keys of 3 x n ICEB-templated prompts "
+                            "per layer (template-correlated), S = v* - current outputs, C = this run's statistics")
+        else:
+            Kt = torch.randn(len(LAYERS), n, D, device=dev, generator=gg) * 0.5 + 0.2
+            St = torch.randn(len(LAYERS), n, H, device=dev, generator=gg)
+            solve_inputs = "synthetic: K = 0.5 randn + 0.2, S = randn (no edit loop in this run)"
         for _ in range(2):
             solve_layers(C32, Kt, St, 4000.0, 1.0, left)
         torch.cuda.synchronize()
@@ -370,14 +602,28 @@ def run_ours(args):
             s1.record()
             torch.cuda.synchronize()
             per.append(s0.elapsed_time(s1))
-        solve = {"ms": sorted(per)[reps // 2], "ms_per_rep": [round(x, 2) for x in per], "concepts": n, "layers": len(LAYERS),
-                 "d": D, "h": H, "lambda": 4000.0, "edit_weight": 0.5, "refine": "adaptive",
+        ms_solve = sorted(per)[reps // 2]
+        # algorithmic work of the Cholesky route, SURVEY.md §8d: d(d+1)n + d^3/3 + 2 d^2 n + 2 h n d per layer
+        gflop = len(LAYERS) * (D * (D + 1) * n + D ** 3 / 3 + 2 * D * D * n + 2 * H * n * D) / 1e9
+        solve = {"ms": ms_solve, "ms_per_rep": [round(x, 2) for x in per], "concepts": n, "layers": len(LAYERS),
+                 "d": D, "h": H, "lambda": 4000.0, "edit_weight": 0.5, "refine": "adaptive", "inputs": solve_inputs,
+                 "roofline": {"bound": "latency (24 dependent panel steps per factorisation) + fp64 DMMA",
+                              "algorithmic_gflop": gflop, "achieved_tflops": gflop / ms_solve,
+                              "frac_of_16bit_tensor_peak": gflop / ms_solve / measured_peaks()["bf16_sustained"],
+                              "note": "algorithmic flops of SURVEY.md 8d (Cholesky route, one application; no credit for "
+                                      "the 3-term split or the fp64 refinement sweeps: 2 x 2 d^2 n fp64 flops each on "
+                                      "mma.sync.m8n8k4.f64, whose peak on this part is ~40 TFLOP/s); the reference executes "
+                                      "61.9 GFLOP of fp64 LU per layer"},
                  "what": "K,S,C on device -> adj_k, resid (fp64), dW (fp32) on device, 5 layers batched on one GPU; "
                          "median of 5 event-timed repetitions"}
         # residual check in fp64 on layer 0 (cheap; full parity lives in tests/)
         M0 = 4000.0 * C32[0].double() + Kt[0].double().T @ Kt[0].double()
         solve["rel_residual_fp64"] = float((M0 @ adj[0] - Kt[0].double().T).norm() / Kt[0].double().norm())
         del M0, adj, resid, dW
+        if rank == 0 and not args.no_cpu:
+            solve["gpu_torch_reference"] = torch_solve_on_gpu(C32, Kt, St, 4000.0, left)
+            if world == 1:
+                solve["cpu_baseline"] = cpu_solve_baseline(C32, Kt, St, 4000.0, left)
         # N > 1: the 5 (C, K, S) problems are independent, so the benchmark form places them round-robin on the GPUs
         # (north star: "independent edited layers are placed one per GPU"; no collective on the data path — only the
         # max-over-ranks of the times).  Every rank times the batched solve of ITS layers; the job's time is the slowest rank's.
@@ -448,6 +694,9 @@ def run_ours(args):
                 "what": "execute_emcid_text_encoder(pipe, requests, hparams, cache_name): v* npz reads, tokenisation, key/"
                         "output extraction per layer, 5 sequential solves with in-place weight writes, deltas to host (fp64)"}
         del deltas
+        edit["solve_paths"] = list(emcid_main.LAST_SOLVE_PATHS)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            edit["cpu_baseline"] = cpu_edit_baseline(out, names, count0, args.ref_concepts)
         # ---- BASELINE configs[4]: sequential editing — 10 successive 100-concept edits through the public
         # apply_emcid_to_text_encoder, each reusing the cached C and re-solving on the already-edited weights
         # (experiments/sequential_editing.py:98-171).  Timed twice on the same requests: every edit re-factoring
@@ -503,6 +752,7 @@ def run_ours(args):
                     w.copy_(w0)
             edit["sequential"] = sequential
         emcid_main.COV_CACHE.clear()
+    runner_fallback_blocks = runner.fallback_blocks
     runner.close()
 
     # ---- e2e: the public API (reference signature) from HOST captions to HOST mom2, copies inside the timed region.
@@ -533,16 +783,45 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         assert stats[names[0]].mom2.count == total_caps * WIDTH
-        assert stats[names[0]].mom2.mom2.device.type == "cpu"
+        if rank == 0:      # layer 0 is reduced onto rank 0, which hands it to its caller on the host
+            assert stats[names[0]].mom2.mom2.device.type == "cpu"
         steps_equiv = per_gpu / C
         e2e = {"value": total_caps * WIDTH / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": 2 * C * WIDTH * 4 + (C + 1) * 4,
-               "d2h_bytes_per_step": int(len(LAYERS) * (D * D * 4 + 8) / steps_equiv),
+               "d2h_bytes_per_step": int(-(-len(LAYERS) // world) * (D * D * 4 + 8) / steps_equiv),
                "api": "emcid_b200.layer_stats.layer_stats_text_encoder_multi(model, None, layer_names, ...) "
-                      "host caption ids -> DataLoader -> pinned H2D -> pass -> NCCL reduce -> mom2 on host",
+                      "host caption ids -> DataLoader -> pinned H2D -> pass -> emcid_mom2_reduce (NCCL, to the layer's "
+                      "root) -> mom2 on the root's host",
                "seconds": float(dt.item()), "captions": total_caps, "captions_per_gpu": per_gpu,
                "host_timeline_s": dict(layer_stats.LAST_PASS_INFO.get("timing", {}))}
         del stats
+        # BASELINE configs[1] as written: 100k captions in TOTAL, sharded over the N GPUs (strong scaling)
+        if world > 1 and args.e2e_captions > 0:
+            strong_caps = args.e2e_captions
+            strong = synth.CaptionMatrixDataset(ids_host[:strong_caps])
+            layer_stats.get_ccs_filtered_ds = lambda tokenizer: strong
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            stats = layer_stats.layer_stats_text_encoder_multi(
+                model, None, names, stats_dir=tmp, sample_size=strong_caps, precision="float32", progress=None,
+                force_recompute=True, captions_per_batch=blk, slab_tokens=args.slab)
+            torch.cuda.synchronize()
+            dts = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(dts, op=dist.ReduceOp.MAX)
+            assert stats[names[0]].mom2.count == strong_caps * WIDTH
+            e2e["strong"] = {"value": strong_caps * WIDTH / float(dts.item()), "unit": UNIT, "seconds": float(dts.item()),
+                             "captions_total": strong_caps, "scaling": "strong",
+                             "what": "BASELINE configs[1] literally: 100k captions in total, sharded over the GPUs",
+                             "host_timeline_s": dict(layer_stats.LAST_PASS_INFO.get("timing", {}))}
+            del stats
+        elif world == 1:
+            e2e["strong"] = {"value": e2e["value"], "unit": UNIT, "seconds": e2e["seconds"], "captions_total": total_caps,
+                             "scaling": "strong", "what": "at one GPU the 100k-caption call above IS configs[1]"}
+
+    gpu_ref = None
+    if rank == 0 and not args.no_cpu and args.encoder == "sd-text" and not args.layers:
+        gpu_ref = gpu_torch_stats_reference(model, ids_dev[W, : 2 * blk], names, dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and args.encoder == "sd-text" and not args.layers:
@@ -564,8 +843,10 @@ def run_ours(args):
                        "parallelism": f"caption-sharded x{world}, one NCCL reduce per layer at the end of the pass",
                        "forward": "native (csrc/clip.cuh, packed tokens, 3xFP16 GEMMs)" if native else
                                   "HF torch fp32 forward with fused kernels hooked in",
-                       "count_check": count0},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "solve": solve, "edit": edit, "clocks": clocks,
+                       "count_check": count0, "exchange": exchange,
+                       "hf_fallback_blocks": int(runner_fallback_blocks)},
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_torch_reference": gpu_ref, "parity": parity, "e2e": e2e,
+            "solve": solve, "edit": edit, "clocks": clocks,
             "gpu_launches": int(n_launch),
         }
         emit(line)
@@ -619,7 +900,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-edit", action="store_true")
     ap.add_argument("--no-sequential", action="store_true", help="skip the 10 x 100-concept sequential-editing timing")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines and the torch-on-this-GPU reference legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the fp64 probe check of the timed run")
+    ap.add_argument("--ref-concepts", type=int, default=100, help="requests of the CPU baseline of the edit call")
     args = ap.parse_args()
     if args.captions <= 0:
         args.captions = 4 * args.block_captions

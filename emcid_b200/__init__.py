@@ -9,7 +9,9 @@ The arithmetic lives in hand-written CUDA (``csrc/``) behind the C ABI in ``incl
 __version__ = "0.1.0"
 
 # the package root re-exports the edit entry points like the reference's emcid/__init__.py:1
-from .emcid_main import (apply_emcid_to_sdxl_text_encoders, apply_emcid_to_text_encoder,  # noqa: E402,F401
-                         clear_factor_cache, execute_emcid_text_encoder)
+from .emcid_main import (apply_emcid_to_clip, apply_emcid_to_cross_attn, apply_emcid_to_sdxl_text_encoders,  # noqa: E402,F401
+                         apply_emcid_to_text_encoder, clear_factor_cache, execute_emcid_clip, execute_emcid_cross_attn,
+                         execute_emcid_text_encoder)
 from .emcid_hparams import EMCIDHyperParams, EMCIDXLHyperParams  # noqa: E402,F401
-from .layer_stats import layer_stats_text_encoder, layer_stats_text_encoder_multi  # noqa: E402,F401
+from .layer_stats import (layer_stats_cross_attn_kv, layer_stats_text_encoder,  # noqa: E402,F401
+                          layer_stats_text_encoder_multi)

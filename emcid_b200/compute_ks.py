@@ -46,10 +46,17 @@ def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name
     ids, pos, cu, S, T = packed
     if T == 0:
         return None
-    native = clip_forward.key_encoder(text_encoder, T, S, layer)
+    prev_token = getattr(_native_keys, "_last_token", None)
+    # once per edit (a new prompt set): compare content checksums too — writes through `.data` do not bump `_version`
+    native = clip_forward.key_encoder(text_encoder, T, S, layer, verify=token is None or token != prev_token)
+    _native_keys._last_token = token
     if native is None:
         return None
     first = torch.tensor([row[0] for row in lookup], dtype=torch.int32, device=cu.device)
+    if not bool((first < cu[1:] - cu[:-1]).all()):
+        # a looked-up position beyond a prompt's valid tokens (subjects "", " ", "[EOS]" with ragged prompts: the LAST
+        # COLUMN of the padded batch, causal_trace.py:1063-1064): that pad row does not exist in the packed forward
+        return None
     rows = cu[:-1] + first
     resume = -1
     prev = native.keys_token
@@ -63,6 +70,34 @@ def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name
     out = native.forward_keys(ids, pos, cu, S, T, layer, rows, resume_layer=resume)
     native.keys_token = (token, layer, T) if token is not None else None
     return out
+
+
+def last_hidden_at_words(text_encoder, tok, requests: List[Dict]) -> torch.Tensor:
+    """[n, hidden]: the text encoder's last_hidden_state at the last subject token of every source prompt, averaged over
+    each request's prompts — the input every UNet cross-attention to_k / to_v sees at that token
+    (emcid/compute_ks.py:52-139, where it is read back through a traced UNet forward).  Library forward for a plain fp32
+    CLIP text tower on a CUDA device, HF forward otherwise."""
+    device = text_encoder.device
+    enc, lookup, counts, _serial = prepare_lookup(tok, requests, 1, device)
+    assert len(set(counts)) == 1, "All the requests should have the same number of prompts."       # reference :66-67, :78-79
+    rows_out = None
+    if device.type == "cuda" and clip_forward.supports(text_encoder):
+        tm = getattr(text_encoder, "text_model", text_encoder)
+        packed = clip_forward.pack_batch({"input_ids": enc["input_ids"], "attention_mask": enc["attention_mask"]},
+                                         tm.embeddings.position_embedding.weight.shape[0])
+        if packed is not None and packed[4] > 0:
+            ids, pos, cu, S, T = packed
+            first = torch.tensor([row[0] for row in lookup], dtype=torch.int32, device=cu.device)
+            native = clip_forward.key_encoder(text_encoder, T, S, 10 ** 6, verify=True)
+            if native is not None and native.has_final_norm and bool((first < cu[1:] - cu[:-1]).all()):
+                rows_out = native.forward_final(ids, pos, cu, S, T, rows=cu[:-1] + first)
+    LAST_PATH["native"] = rows_out is not None
+    if rows_out is None:
+        with torch.no_grad():
+            hidden = text_encoder(**enc)[0]
+        rows_out = hidden[torch.arange(len(lookup), device=device), torch.tensor([r[0] for r in lookup], device=device)]
+    c = counts[0]
+    return rows_out.reshape(len(counts), c, -1).mean(1)
 
 
 def tokenize_prompts(prompts, tokenizer, device, padding_length=None):

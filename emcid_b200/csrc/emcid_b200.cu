@@ -196,6 +196,18 @@ int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* 
                       dW, refine_steps, workspace, workspace_bytes, status_dev, static_cast<cudaStream_t>(stream));
 }
 
+int emcid_delta_update(int h, int d, int n, const double* resid, const double* adj_k, float* dW, void* stream) {
+  EMCID_CHECK(h > 0 && d > 0 && n > 0 && resid && adj_k && dW, EMCID_ERR_INVALID, "emcid_delta_update: bad argument");
+  DgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = h; p.N = d; p.K = n;
+  p.A = resid; p.lda = n;
+  p.B = adj_k; p.ldb = n;
+  p.alpha = 1.0;
+  p.C32 = dW; p.ldc32 = d;
+  return launch_dgemm_nt(p, 1, static_cast<cudaStream_t>(stream));
+}
+
 /* cached factorisation for repeated edits with the same covariance */
 int emcid_factor_create(emcid_factor_t** out, int device, int d, const float* C32, double lambda, int* status_dev,
                         void* stream) {

@@ -379,8 +379,18 @@ inline int mom2_fold(Mom2Handle* H, cudaStream_t stream) {
 // acc32[lower tiles] += P P^T over token columns [col0, col0 + t) of the A^T planes `ops` describes
 // ([d x tokens], K-major over tokens); dyn_k optionally caps t by a device scalar.  Stream-K over
 // (tile, token block), red.add epilogue.  Also used by the native text-encoder forward (clip.cuh).
+// EMCID_DETERMINISTIC=1: every output tile is accumulated by ONE CTA (pair) over the whole token range, in a fixed
+// order, so a pass is reproducible to the bit (the default schedules split the token range of some tiles over several
+// CTAs whose red.add's land in arrival order: results differ in the last bits from run to run).  Costs SYRK balance:
+// 78 pair tiles on 74 CTA pairs take two rounds instead of 1.05.
+inline bool mom2_deterministic() {
+  const char* e = getenv("EMCID_DETERMINISTIC");
+  return e && e[0] == '1';
+}
+
 inline int mom2_syrk_slab(Mom2Handle* H, const GemmOperands& ops, int kind, int col0, int t, const int* dyn_k,
                           cudaStream_t stream, int streamk_mode = 1) {
+  if (mom2_deterministic()) streamk_mode = 0;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = H->d; p.N = H->d; p.K = t;

@@ -6,6 +6,9 @@ emcid/emcid_main.py in SilentView/EMCID —
     apply_emcid_to_text_encoder          :769-815
     execute_emcid_sd_xl_text_encoders    :1085-1425
     apply_emcid_to_sdxl_text_encoders    :38-106
+    execute_emcid_clip / apply_emcid_to_clip                 :109-311   (the text tower of a whole CLIPModel)
+    execute_emcid_cross_attn / apply_emcid_to_cross_attn     :314-547   (UNet cross-attention to_k / to_v)
+    get_cov_cross_attn                   :2203-2236
     upd_matrix_match_shape               :2279-2298
 
 Same signatures, same return values (adj_k / resid as fp64 CPU tensors, weights restored on return
@@ -30,7 +33,9 @@ import torch
 from . import nethook
 from .compute_ks import get_module_input_output_at_words, prepare_lookup
 from .globals import STATS_DIR, XL_STATS_DIR1, XL_STATS_DIR2
-from .layer_stats import layer_stats_text_encoder
+from . import _lib
+from .layer_stats import (get_all_cross_attn_kv_layer_names, layer_stats_cross_attn_kv, layer_stats_text_encoder,
+                          layer_stats_text_encoder_multi)
 from .solve import DEFAULT_REFINE_STEPS, CachedFactor, solve_layers
 
 COV_CACHE: Dict[Tuple[str, str], torch.Tensor] = {}
@@ -49,28 +54,72 @@ FACTOR_CACHE_MAX = 16
 FACTOR_CACHE_MAX_FRACTION = 6
 
 
+# which solver produced each layer's update in the last edit ("cached_factor", "direct", "fp64_lu"); tests / bench read it
+LAST_SOLVE_PATHS: List[str] = []
+
+
+def _fp64_lu_on_device(cov_raw, layer_ks, sources_t, mom2_update_weight, ew, layers_left):
+    """The reference's own arithmetic (emcid_main.py:1037-1050: fp64 M, torch.linalg.solve = LU with partial pivoting)
+    on the device — the last resort for systems the fp32-class Cholesky cannot factor or does not contract on."""
+    scale = (ew / 0.5) ** 0.5
+    Ks = layer_ks.double().T * scale                                   # [d, n]
+    Ss = sources_t.double().T * scale                                  # [h, n]
+    M = mom2_update_weight * (cov_raw * (1 - ew) / 0.5).double() + Ks @ Ks.T
+    adj_k = torch.linalg.solve(M, Ks)
+    resid = Ss / layers_left
+    return adj_k, resid, (resid @ adj_k.T).float()
+
+
 def _solve_one_layer(text_encoder, module_name: str, cov_raw: torch.Tensor, layer_ks: torch.Tensor,
                      sources_t: torch.Tensor, mom2_update_weight: float, ew: float, layers_left: int, refine_steps: int):
     """adj_k, resid, dW of one layer (emcid_main.py:1037-1050): through the cached factor of lambda * C32 when the edit is
-    narrow (n_pad <= d / FACTOR_CACHE_MAX_FRACTION), else the direct batched solver."""
+    narrow (n_pad <= d / FACTOR_CACHE_MAX_FRACTION), else the direct batched solver.
+
+    The reference solves with fp64 LU, which does not care about conditioning; a Cholesky factorisation in fp32-class
+    arithmetic breaks down, or stops contracting under refinement, once the DIAGONALLY SCALED condition number of the
+    matrix approaches 1 / eps_fp32 (diagonal equilibration would change nothing: with power-of-two scales the scaled
+    factorisation is bit for bit the scaled factor).  A breakdown or a refinement that misses its target therefore falls
+    through: cached factor of lambda*C  ->  direct factorisation of lambda*C + K K^T (better conditioned)  ->  the
+    reference's fp64 LU on the device (torch.linalg.solve), with a RuntimeWarning naming the layer."""
     d = cov_raw.shape[0]
     n_pad = -(-layer_ks.shape[0] // 128) * 128
     scale = (ew / 0.5) ** 0.5
     if os.environ.get("EMCID_FACTOR_CACHE", "1") != "0" and n_pad * FACTOR_CACHE_MAX_FRACTION <= d:
         key = (text_encoder.config._name_or_path.replace("/", "_"), module_name, float(mom2_update_weight), float(ew))
-        entry = FACTOR_CACHE.get(key)
-        if entry is None or entry[0] is not cov_raw:
-            if entry is not None:
-                entry[1].close()
-            entry = (cov_raw, CachedFactor(cov_raw * (1 - ew) / 0.5, mom2_update_weight))      # fp32 scaling, :1037
-            FACTOR_CACHE[key] = entry
-            while len(FACTOR_CACHE) > FACTOR_CACHE_MAX:
-                FACTOR_CACHE.popitem(last=False)[1][1].close()
-        FACTOR_CACHE.move_to_end(key)
-        return entry[1].solve(layer_ks.float(), sources_t.float(), scale, layers_left, refine_steps=refine_steps)
-    adj_k, resid, dW = solve_layers(cov_raw * (1 - ew) / 0.5, layer_ks.float(), sources_t.float(), mom2_update_weight,
-                                    scale, [layers_left], refine_steps=refine_steps)
-    return adj_k[0], resid[0], dW[0]
+        try:
+            entry = FACTOR_CACHE.get(key)
+            if entry is None or entry[0] is not cov_raw:
+                if entry is not None:
+                    FACTOR_CACHE.pop(key)[1].close()
+                entry = (cov_raw, CachedFactor(cov_raw * (1 - ew) / 0.5, mom2_update_weight))      # fp32 scaling, :1037
+                FACTOR_CACHE[key] = entry
+                while len(FACTOR_CACHE) > FACTOR_CACHE_MAX:
+                    FACTOR_CACHE.popitem(last=False)[1][1].close()
+            FACTOR_CACHE.move_to_end(key)
+            out = entry[1].solve(layer_ks.float(), sources_t.float(), scale, layers_left, refine_steps=refine_steps,
+                                 strict=True)
+            LAST_SOLVE_PATHS.append("cached_factor")
+            return out
+        except _lib.EmcidError as e:
+            if e.code != -4:
+                raise
+            hit = FACTOR_CACHE.pop(key, None)
+            if hit is not None:
+                hit[1].close()
+    try:
+        adj_k, resid, dW = solve_layers(cov_raw * (1 - ew) / 0.5, layer_ks.float(), sources_t.float(), mom2_update_weight,
+                                        scale, [layers_left], refine_steps=refine_steps, strict=True)
+        LAST_SOLVE_PATHS.append("direct")
+        return adj_k[0], resid[0], dW[0]
+    except _lib.EmcidError as e:
+        if e.code != -4:
+            raise
+        import warnings
+
+        warnings.warn(f"emcid_b200: {module_name}: {e}; solving this layer with fp64 LU on the device "
+                      "(the reference's arithmetic) instead", RuntimeWarning)
+    LAST_SOLVE_PATHS.append("fp64_lu")
+    return _fp64_lu_on_device(cov_raw, layer_ks, sources_t, mom2_update_weight, ew, layers_left)
 
 
 def clear_factor_cache() -> None:
@@ -191,16 +240,26 @@ def _read_npz_array(path, key: str) -> np.ndarray:
         return np.load(path)[key]
 
 
-def _load_vstars(requests, hparams, cache_name, device, suffix=""):
+def _vstar_stem(request, idx, hparams, naming: str) -> str:
+    """File stem of a request's cached v* (emcid_main.py:873-890; the SDXL loop only ever uses the source/dest form,
+    :1157-1166)."""
+    if naming == "sd":
+        if "esd" in getattr(hparams, "objective", ""):
+            return f"source_{request['source']}"
+        if getattr(hparams, "sld_supervision", False):
+            return f"source_{request['source_cat']}_{idx}"
+    return f"source_{request['source']}_dest_{request['dest']}"
+
+
+def _load_vstars(requests, hparams, cache_name, device, suffix="", naming="sd"):
+    """zs [h, n] on `device` from the per-request cache files.  A missing file and an unreadable one are both cache
+    misses (the reference logs the read error and recomputes, :892-907); recomputing v* is stage 1, outside this path, so
+    either is a NotImplementedError that names the file."""
+    import zipfile
+
     zs = []
     for idx, request in enumerate(requests):
-        if "esd" in getattr(hparams, "objective", ""):
-            stem = f"source_{request['source']}"
-        elif getattr(hparams, "sld_supervision", False):
-            stem = f"source_{request['source_cat']}_{idx}"
-        else:
-            stem = f"source_{request['source']}_dest_{request['dest']}"
-        path = cache_name + stem + suffix + ".npz" if cache_name is not None else None
+        path = cache_name + _vstar_stem(request, idx, hparams, naming) + suffix + ".npz" if cache_name is not None else None
         try:
             if path is None:
                 raise FileNotFoundError
@@ -209,6 +268,10 @@ def _load_vstars(requests, hparams, cache_name, device, suffix=""):
             raise NotImplementedError(
                 f"v_star cache miss for request {request['source']!r} ({path}): stage 1 (compute_z, UNet/VAE "
                 "optimisation) is outside the B200 hot path — precompute v_star with the reference") from None
+        except (zipfile.BadZipFile, OSError, KeyError, ValueError, EOFError) as e:
+            raise NotImplementedError(
+                f"v_star cache miss for request {request['source']!r}: {path} is unreadable ({type(e).__name__}: {e}); "
+                "stage 1 (compute_z) is outside the B200 hot path — recompute v_star with the reference") from None
     # stacked on the host, one H2D copy (the reference moves every v* separately, :892-901)
     if getattr(hparams, "use_new_compute_z", False):
         z = torch.stack(zs, dim=0).to(device)           # [rq, num, h]
@@ -216,9 +279,64 @@ def _load_vstars(requests, hparams, cache_name, device, suffix=""):
     return torch.stack(zs, dim=1).to(device)            # [h, n]
 
 
+class _Background:
+    """Runs `fn` on a helper thread; result() joins and re-raises.  The v* files of an edit (1000 small reads) load while
+    the main thread tokenises the prompts and extracts the first layer's keys."""
+
+    def __init__(self, fn):
+        import threading
+
+        self._out = self._err = None
+
+        def run():
+            try:
+                self._out = fn()
+            except BaseException as e:          # re-raised by result()
+                self._err = e
+
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def join(self):
+        self._t.join()
+
+    def result(self):
+        self._t.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
+
+
+# fp32 [h, d] updates of the last insert loop, by weight name, still on the device: apply_* adds them in place instead of
+# re-forming adj_k @ resid^T from the host copies (reference :802-809; SURVEY.md §8 a11 "or skip: dW already known")
+_DEVICE_UPDATES: Dict[int, Dict[str, torch.Tensor]] = {}
+
+
+def _prefetch_covariances(text_encoder, tokenizer, hparams, layers, stat_dir, verbose):
+    """Cold COV_CACHE: every missing layer's statistics file is loaded — or, on a cold disk cache too, computed — by ONE
+    multi-layer pass (the reference's get_cov_text_encoder runs one pass per layer, :2263-2272)."""
+    model_name = text_encoder.config._name_or_path.replace("/", "_")
+    names = [hparams.rewrite_module_tmp.format(l) for l in layers]
+    missing = [n for n in names if (model_name, n) not in COV_CACHE]
+    if len(missing) < 2 or not all(n.endswith(".fc2") for n in missing):
+        return
+    stats = layer_stats_text_encoder_multi(text_encoder, tokenizer, missing, stat_dir, hparams.mom2_dataset,
+                                           to_collect=["mom2"], sample_size=hparams.mom2_n_samples,
+                                           precision=hparams.mom2_dtype, broadcast=True,
+                                           progress=None if not verbose else layer_stats_progress())
+    for n in missing:
+        COV_CACHE[(model_name, n)] = stats[n].mom2.moment().float().to(text_encoder.device)
+
+
+def layer_stats_progress():
+    from .layer_stats import tqdm
+
+    return tqdm
+
+
 def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_update_weight, stat_dir, verbose,
-                 refine_steps):
-    """The stage-2 loop of the reference (:980-1073) for one encoder."""
+                 refine_steps, host_deltas: bool = True):
+    """The stage-2 loop of the reference (:980-1073) for one encoder.  `zs`: [h, n] tensor or a _Background producing it."""
     device = text_encoder.device
     names = [f"{hparams.rewrite_module_tmp.format(l)}.weight" for l in layers]
     weights = {n: nethook.get_parameter(text_encoder, n) for n in names}
@@ -231,6 +349,8 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
     t = time.perf_counter()
     prepared = prepare_lookup(tokenizer, requests, hparams.num_edit_tokens, device)
     t = _tick(device, "tokenise_lookup_ms", t)
+    _prefetch_covariances(text_encoder, tokenizer, hparams, layers, stat_dir, verbose)
+    updates = _DEVICE_UPDATES[id(text_encoder)] = {}
     try:
         with torch.no_grad():
             for i, layer in enumerate(layers):
@@ -246,6 +366,9 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
                 if verbose:
                     print(f"\n\nLAYER {layer}\n")
                     print(f"Writing {layer_ks.size(0)} key/value pair(s) into layer {layer}")
+                if isinstance(zs, _Background):
+                    zs = zs.result()                                              # the v* reads ran beside tokenise + keys
+                    t = _tick(device, "vstar_wait_ms", t)
                 sources_t = zs.T.to(cur_zs.dtype) - cur_zs                       # (zs - cur_zs)^T, [n, h]
                 if verbose:
                     print("z error", torch.linalg.norm(sources_t, dim=1).mean())
@@ -261,9 +384,10 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
                     print("orig norm", torch.linalg.norm(weights[name]))
                     print("upd norm", torch.linalg.norm(upd))
                 weights[name][...] = weights_copy[name] + upd                     # :1061 — next layer sees it
+                updates[name] = upd
                 # the reference returns CPU tensors (:1062-1065); copy asynchronously into pinned memory so the transfer
                 # of layer i (30 MB of fp64) overlaps the key extraction and the solve of layer i + 1
-                deltas[name] = (_to_host_async(adj_k), _to_host_async(resid))
+                deltas[name] = (_to_host_async(adj_k), _to_host_async(resid)) if host_deltas else (adj_k, resid)
                 t = _tick(device, "write_and_d2h_ms", t)
         if torch.device(device).type == "cuda":
             torch.cuda.current_stream(device).synchronize()      # all delta copies have landed
@@ -286,25 +410,56 @@ def execute_emcid_text_encoder(pipe, requests: List[Dict], hparams, cache_name: 
     if verbose:
         for request in requests:
             print(f"EMCID request sample: [{request['source']}] -> [{request['dest']}]")
-    import time
+    return _execute_text_encoder(pipe, requests, hparams, cache_name, verbose, stat_dir, refine_steps, host_deltas=True)
 
+
+def _execute_text_encoder(pipe, requests, hparams, cache_name, verbose, stat_dir, refine_steps, host_deltas):
+    device = pipe.device
     LAST_EDIT_TIMING.clear()
-    t = time.perf_counter()
-    zs = _load_vstars(requests, hparams, cache_name, device)
-    _tick(device, "vstar_npz_read_ms", t)
-    deltas = _insert_loop(pipe.text_encoder, pipe.tokenizer, requests, hparams, hparams.layers, zs,
-                          hparams.mom2_update_weight, stat_dir, verbose, refine_steps)
+    del LAST_SOLVE_PATHS[:]
+    if TIMING:   # stage timing wants the read on the main thread, where it can be timed
+        import time
+
+        t = time.perf_counter()
+        zs = _load_vstars(requests, hparams, cache_name, device)
+        _tick(device, "vstar_npz_read_ms", t)
+    else:
+        zs = _Background(lambda: _load_vstars(requests, hparams, cache_name, device))
+    try:
+        deltas = _insert_loop(pipe.text_encoder, pipe.tokenizer, requests, hparams, hparams.layers, zs,
+                              hparams.mom2_update_weight, stat_dir, verbose, refine_steps, host_deltas=host_deltas)
+    finally:
+        if isinstance(zs, _Background):
+            zs.join()
     print(f"Deltas successfully computed for {list(deltas.keys())}")
     return deltas
 
 
 def _apply_deltas(model, deltas, device):
+    """w += (adj_k @ resid^T)^T.float() for every edited weight (reference :802-809).  The insert loop that produced
+    `deltas` left exactly that matrix — float(resid @ adj_k^T), formed in fp64 by the solver — on the device: it is
+    added in place.  Deltas that did not come from the last insert loop on this model (a caller replaying saved
+    deltas) take the reference's route: the fp64 product, on the library's DMMA GEMM."""
+    updates = _DEVICE_UPDATES.pop(id(model), {})
     with torch.no_grad():
         for w_name, (key_mat, val_mat) in deltas.items():
-            key_mat, val_mat = key_mat.to(device), val_mat.to(device)
-            upd_matrix = key_mat @ val_mat.T                                      # :805, fp64 on the device
             w = nethook.get_parameter(model, w_name)
-            w[...] += upd_matrix_match_shape(upd_matrix, w.shape).float()
+            upd = updates.get(w_name)
+            if upd is None or upd.device != w.device:
+                upd = _update_from_deltas(key_mat.to(w.device), val_mat.to(w.device))
+            w[...] += upd_matrix_match_shape(upd, w.shape).to(w.dtype)
+
+
+def _update_from_deltas(adj_k: torch.Tensor, resid: torch.Tensor) -> torch.Tensor:
+    """float(resid @ adj_k^T) [h, d] from fp64 CUDA deltas (adj_k [d, n], resid [h, n]) through emcid_delta_update."""
+    adj_k, resid = adj_k.double().contiguous(), resid.double().contiguous()
+    d, n = adj_k.shape
+    h = resid.shape[0]
+    out = torch.empty(h, d, dtype=torch.float32, device=adj_k.device)
+    with torch.cuda.device(adj_k.device):
+        _lib.check(_lib.lib().emcid_delta_update(h, d, n, _lib.ptr(resid), _lib.ptr(adj_k), _lib.ptr(out),
+                                                 _lib.current_stream_ptr()))
+    return out
 
 
 def apply_emcid_to_text_encoder(pipe, requests: List[Dict], hparams, device: str, mom2_weight: Optional[int] = None,
@@ -315,13 +470,40 @@ def apply_emcid_to_text_encoder(pipe, requests: List[Dict], hparams, device: str
     origin_text_encoder = None
     if return_orig_text_encoder:
         origin_text_encoder = deepcopy(pipe.text_encoder).to("cpu")
-    deltas = execute_emcid_text_encoder(pipe, requests, hparams, cache_name=cache_name, mom2_weight=mom2_weight,
-                                        edit_weight=edit_weight, verbose=verbose, stat_dir=stats_dir)
+    hparams.mom2_update_weight = mom2_weight if mom2_weight is not None else hparams.mom2_update_weight
+    hparams.edit_weight = edit_weight if edit_weight is not None else hparams.edit_weight
+    requests = deepcopy(requests)
+    if verbose:
+        for request in requests:
+            print(f"EMCID request sample: [{request['source']}] -> [{request['dest']}]")
+    # the deltas stay on the device: nothing here reads them on the host (execute_emcid_text_encoder returns CPU copies)
+    deltas = _execute_text_encoder(pipe, requests, hparams, cache_name, verbose, stats_dir, DEFAULT_REFINE_STEPS,
+                                   host_deltas=False)
     _apply_deltas(pipe.text_encoder, deltas, device)
     print(f"New weights successfully inserted into {list(deltas.keys())}")
     if return_orig_text_encoder:
         origin_text_encoder = origin_text_encoder.to(device)
     return pipe, origin_text_encoder
+
+
+def _execute_sdxl(pipe, requests, hparams, cache_name, verbose, stat_dir, stat_dir_2, refine_steps, host_deltas):
+    device = pipe.device
+    LAST_EDIT_TIMING.clear()
+    del LAST_SOLVE_PATHS[:]
+    zs = _load_vstars(requests, hparams, cache_name, device, naming="sdxl")
+    zs_2 = _load_vstars(requests, hparams, cache_name, device, suffix="_2", naming="sdxl")
+    deltas = _insert_loop(pipe.text_encoder, pipe.tokenizer, requests, hparams, hparams.layers, zs,
+                          hparams.mom2_update_weight, stat_dir, verbose, refine_steps, host_deltas=host_deltas)
+    deltas_2 = _insert_loop(pipe.text_encoder_2, pipe.tokenizer_2, requests, hparams, hparams.layers_2, zs_2,
+                            hparams.mom2_update_weight_2, stat_dir_2, verbose, refine_steps, host_deltas=host_deltas)
+    print(f"Deltas successfully computed for {list(deltas.keys())} and {list(deltas_2.keys())}")
+    return deltas, deltas_2
+
+
+def _set_sdxl_hparams(hparams, mom2_weight, mom2_weight_2, edit_weight):
+    hparams.mom2_update_weight = mom2_weight if mom2_weight is not None else hparams.mom2_update_weight
+    hparams.mom2_update_weight_2 = mom2_weight_2 if mom2_weight_2 is not None else hparams.mom2_update_weight_2
+    hparams.edit_weight = edit_weight if edit_weight is not None else hparams.edit_weight
 
 
 def execute_emcid_sd_xl_text_encoders(pipe, requests: List[Dict], hparams, cache_name: Optional[str] = None,
@@ -331,19 +513,8 @@ def execute_emcid_sd_xl_text_encoders(pipe, requests: List[Dict], hparams, cache
                                       refine_steps: int = DEFAULT_REFINE_STEPS):
     """Both SDXL text encoders: `layers` / `mom2_update_weight` / stat_dir for text_encoder,
     `layers_2` / `mom2_update_weight_2` / stat_dir_2 for text_encoder_2 (v_star files end in _2)."""
-    device = pipe.device
-    hparams.mom2_update_weight = mom2_weight if mom2_weight is not None else hparams.mom2_update_weight
-    hparams.mom2_update_weight_2 = mom2_weight_2 if mom2_weight_2 is not None else hparams.mom2_update_weight_2
-    hparams.edit_weight = edit_weight if edit_weight is not None else hparams.edit_weight
-    requests = deepcopy(requests)
-    zs = _load_vstars(requests, hparams, cache_name, device)
-    zs_2 = _load_vstars(requests, hparams, cache_name, device, suffix="_2")
-    deltas = _insert_loop(pipe.text_encoder, pipe.tokenizer, requests, hparams, hparams.layers, zs,
-                          hparams.mom2_update_weight, stat_dir, verbose, refine_steps)
-    deltas_2 = _insert_loop(pipe.text_encoder_2, pipe.tokenizer_2, requests, hparams, hparams.layers_2, zs_2,
-                            hparams.mom2_update_weight_2, stat_dir_2, verbose, refine_steps)
-    print(f"Deltas successfully computed for {list(deltas.keys())} and {list(deltas_2.keys())}")
-    return deltas, deltas_2
+    _set_sdxl_hparams(hparams, mom2_weight, mom2_weight_2, edit_weight)
+    return _execute_sdxl(pipe, deepcopy(requests), hparams, cache_name, verbose, stat_dir, stat_dir_2, refine_steps, True)
 
 
 def apply_emcid_to_sdxl_text_encoders(pipe, requests: List[Dict], hparams, device: str,
@@ -355,12 +526,190 @@ def apply_emcid_to_sdxl_text_encoders(pipe, requests: List[Dict], hparams, devic
     if return_orig_text_encoder:
         origin_1 = deepcopy(pipe.text_encoder).to("cpu")
         origin_2 = deepcopy(pipe.text_encoder_2).to("cpu")
-    deltas, deltas_2 = execute_emcid_sd_xl_text_encoders(
-        pipe, requests, hparams, cache_name=cache_name, mom2_weight=mom2_weight, mom2_weight_2=mom2_weight_2,
-        edit_weight=edit_weight, verbose=verbose, stat_dir=stat_dir, stat_dir_2=stat_dir_2)
+    _set_sdxl_hparams(hparams, mom2_weight, mom2_weight_2, edit_weight)
+    deltas, deltas_2 = _execute_sdxl(pipe, deepcopy(requests), hparams, cache_name, verbose, stat_dir, stat_dir_2,
+                                     DEFAULT_REFINE_STEPS, False)
     _apply_deltas(pipe.text_encoder, deltas, device)
     _apply_deltas(pipe.text_encoder_2, deltas_2, device)
     print(f"New weights successfully inserted into {list(deltas.keys())}")
     if return_orig_text_encoder:
         origin_1, origin_2 = origin_1.to(device), origin_2.to(device)
     return pipe, origin_1, origin_2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the text tower of a whole CLIPModel (reference :109-311)
+# ---------------------------------------------------------------------------------------------------------
+def execute_emcid_clip(model, processor, requests: List[Dict], hparams, cache_name: Optional[str] = None,
+                       verbose: bool = True, stat_dir=STATS_DIR, refine_steps: int = DEFAULT_REFINE_STEPS):
+    """execute_emcid_clip (:151-311): the same stage-2 loop on `model` (a transformers CLIPModel whose
+    hparams.rewrite_module_tmp names text_model.encoder.layers.{}.mlp.fc2), tokenizer = processor.tokenizer; v* files
+    named source_{source}_dest_{dest}.npz.  Invariant: model weights at return == at entry."""
+    requests = deepcopy(requests)
+    for request in requests:
+        print(f"EMCID request sample: [{request['source']}] -> [{request['dest']}]")
+    pipe = _ClipAsPipe(model, processor)
+    LAST_EDIT_TIMING.clear()
+    del LAST_SOLVE_PATHS[:]
+    zs = _load_vstars(requests, hparams, cache_name, pipe.device, naming="clip")
+    deltas = _insert_loop(model, pipe.tokenizer, requests, hparams, hparams.layers, zs, hparams.mom2_update_weight, stat_dir,
+                          verbose, refine_steps)
+    print(f"Deltas successfully computed for {list(deltas.keys())}")
+    return deltas
+
+
+class _ClipAsPipe:
+    def __init__(self, model, processor):
+        self.text_encoder, self.tokenizer, self.device = model, processor.tokenizer, model.device
+
+
+def apply_emcid_to_clip(model, processor, requests: List[Dict], hparams, device: str, mom2_weight: Optional[int] = None,
+                        edit_weight: Optional[float] = None, return_orig_text_model=False,
+                        cache_name: Optional[str] = None, stat_dir=STATS_DIR):
+    """Returns (the updated model, the original model or None) — apply_emcid_to_clip (:109-148)."""
+    hparams.mom2_update_weight = mom2_weight if mom2_weight is not None else hparams.mom2_update_weight
+    hparams.edit_weight = edit_weight if edit_weight is not None else hparams.edit_weight
+    origin = deepcopy(model).to("cpu") if return_orig_text_model else None
+    deltas = execute_emcid_clip(model, processor, requests, hparams, cache_name=cache_name, stat_dir=stat_dir)
+    _apply_deltas(model, deltas, device)
+    print(f"New weights successfully inserted into {list(deltas.keys())}")
+    if origin is not None:
+        origin = origin.to(device)
+    return model, origin
+
+
+# ---------------------------------------------------------------------------------------------------------
+# UNet cross-attention to_k / to_v (reference :314-547; SURVEY.md §8 f4)
+# ---------------------------------------------------------------------------------------------------------
+def get_cov_cross_attn(pipe, layer_name: str, mom2_dataset: str, sample_size: int, mom2_dtype: str, inv: bool = False,
+                       force_recompute: bool = False, verbose: bool = False, stat_dir: str = STATS_DIR) -> torch.Tensor:
+    """C = mom2 / count of the module's input (the text encoder's last_hidden_state), fp32 on pipe.device, cached per
+    (unet name, layer) like the reference (:2203-2236)."""
+    model_name = pipe.unet.config._name_or_path.replace("/", "_")
+    key = (model_name, layer_name)
+    if verbose:
+        print(f"Retrieving covariance statistics for {model_name} @ {layer_name}.")
+    if key not in COV_CACHE or force_recompute:
+        stat = layer_stats_cross_attn_kv(pipe, layer_name, stat_dir, mom2_dataset, to_collect=["mom2"],
+                                         sample_size=sample_size, precision=mom2_dtype, force_recompute=force_recompute)
+        COV_CACHE[key] = stat.mom2.moment().float().to(pipe.device)
+    cov = COV_CACHE[key].to(pipe.device)
+    return torch.inverse(cov) if inv else cov
+
+
+def _cross_attn_keys(pipe, requests):
+    """K [n, hidden]: last_hidden_state at the last subject token of every source prompt, averaged over each request's
+    prompts (emcid/compute_ks.py:52-139 reads it as the traced input of every attn2.to_k / to_v — the same tensor for all
+    of them, so it is taken once, from the text encoder, and the UNet is not run)."""
+    from .compute_ks import last_hidden_at_words
+
+    return last_hidden_at_words(pipe.text_encoder, pipe.tokenizer, requests)
+
+
+def _load_cross_attn_vstars(requests, cache_name, layer_names, device):
+    """{layer: zs [out_features, n]} from source_{source}.npz files holding one pickled {"v_star": array} per layer
+    (:365-396).  A miss is an error: computing them (compute_z_unet_x_kv) is stage 1."""
+    per_layer = {n: [] for n in layer_names}
+    for request in requests:
+        path = cache_name + f"source_{request['source']}.npz" if cache_name is not None else None
+        try:
+            if path is None:
+                raise FileNotFoundError
+            data = np.load(path, allow_pickle=True)
+            for n in layer_names:
+                per_layer[n].append(torch.from_numpy(np.asarray(data[n].item()["v_star"])))
+        except Exception as e:
+            raise NotImplementedError(
+                f"v_star cache miss for request {request['source']!r} ({path}: {type(e).__name__}): stage 1 "
+                "(compute_z_unet_x_kv) is outside the B200 hot path — precompute v_star with the reference") from None
+    return {n: torch.stack(v, dim=1).to(device) for n, v in per_layer.items()}
+
+
+def execute_emcid_cross_attn(pipe, requests: List[Dict], hparams, cache_name: Optional[str] = None,
+                             mom2_weight: Optional[int] = None, edit_weight: Optional[float] = None, verbose: bool = True,
+                             stat_dir: str = STATS_DIR, refine_steps: int = DEFAULT_REFINE_STEPS):
+    """execute_emcid_cross_attn (:314-508): closed-form update of every attn2.to_k / attn2.to_v of pipe.unet.
+
+    Unlike the text-encoder edit the modules are INDEPENDENT (no module sees another's update, `resid = sources`,
+    :470) and all of them read the same input, so there is one key matrix K and one system matrix
+    M = lambda * C32 + Ks Ks^T for all 32 of them; only the right-hand sides (zs_l - W_l K) and the output widths differ.
+    The modules are grouped by output width and each group goes through ONE batched library solve."""
+    device = pipe.device
+    hparams.mom2_update_weight = mom2_weight if mom2_weight is not None else hparams.mom2_update_weight
+    hparams.edit_weight = edit_weight if edit_weight is not None else hparams.edit_weight
+    requests = deepcopy(requests)
+    for request in requests:
+        if "dest" in request:
+            print(f"EMCID request sample: [{request['source']}] -> [{request['dest']}]")
+        else:
+            print(f"EMCID request sample: erasing [{request['source']}]")
+    names = get_all_cross_attn_kv_layer_names(pipe)
+    weights = {f"{n}.weight": nethook.get_parameter(pipe.unet, f"{n}.weight") for n in names}
+    zs = _load_cross_attn_vstars(requests, cache_name, names, device)
+    ew = hparams.edit_weight
+    scale = (ew / 0.5) ** 0.5
+    deltas = {}
+    updates = _DEVICE_UPDATES[id(pipe.unet)] = {}
+    del LAST_SOLVE_PATHS[:]
+    with torch.no_grad():
+        K = _cross_attn_keys(pipe, requests).float().contiguous()                  # [n, hidden]
+        groups: Dict[int, List[str]] = {}
+        for n in names:
+            groups.setdefault(weights[f"{n}.weight"].shape[0], []).append(n)
+        for out_features, members in groups.items():
+            covs, raw_covs, sources = [], [], []
+            for n in members:
+                w = weights[f"{n}.weight"]
+                bias = getattr(nethook.get_module(pipe.unet, n), "bias", None)
+                cur = _lib.gemm3x_nt(K, w.detach().float().contiguous())           # W_l K: the module's current output, [n, out]
+                if bias is not None:
+                    cur = cur + bias
+                sources.append(zs[n].T.float() - cur)                              # (zs - cur_zs)^T, [n, out]
+                if verbose:
+                    print(f"Writing {K.shape[0]} key/value pair(s) into layer {n}")
+                    print("z error", torch.linalg.norm(sources[-1], dim=1).mean())
+                raw_covs.append(get_cov_cross_attn(pipe, n, hparams.mom2_dataset, hparams.mom2_n_samples, hparams.mom2_dtype,
+                                                   verbose=verbose, stat_dir=stat_dir))
+                covs.append(raw_covs[-1] * (1 - ew) / 0.5)                         # fp32 scaling, as the reference forms it (:455)
+            B = len(members)
+            try:
+                adj_k, resid, dW = solve_layers(torch.stack(covs), K[None].expand(B, -1, -1), torch.stack(sources),
+                                                hparams.mom2_update_weight, scale, [1] * B, refine_steps=refine_steps,
+                                                strict=True)
+                LAST_SOLVE_PATHS.extend(["direct"] * B)
+                adj_k, resid, dW = list(adj_k), list(resid), list(dW)
+            except _lib.EmcidError as e:
+                if e.code != -4:
+                    raise
+                import warnings
+
+                warnings.warn(f"emcid_b200: cross-attention modules of width {out_features}: {e}; solving with fp64 LU on "
+                              "the device instead", RuntimeWarning)
+                trip = [_fp64_lu_on_device(c, K, s_, hparams.mom2_update_weight, ew, 1) for c, s_ in zip(raw_covs, sources)]
+                adj_k, resid, dW = zip(*trip)
+                LAST_SOLVE_PATHS.extend(["fp64_lu"] * B)
+            for i, n in enumerate(members):
+                name = f"{n}.weight"
+                upd = upd_matrix_match_shape(dW[i], weights[name].shape)
+                if verbose:
+                    print("orig norm", torch.linalg.norm(weights[name]))
+                    print("upd norm", torch.linalg.norm(upd))
+                updates[name] = upd
+                deltas[name] = (_to_host_async(adj_k[i]), _to_host_async(resid[i]))
+        if torch.device(device).type == "cuda":
+            torch.cuda.current_stream(device).synchronize()
+    deltas = {f"{n}.weight": deltas[f"{n}.weight"] for n in names}                 # the reference's order
+    print(f"Deltas successfully computed for {list(deltas.keys())}")
+    return deltas
+
+
+def apply_emcid_to_cross_attn(pipe, requests: List[Dict], hparams, device: str, mom2_weight: Optional[int] = None,
+                              edit_weight: Optional[float] = None, return_orig_text_model=False,
+                              cache_name: Optional[str] = None, stat_dir: str = STATS_DIR):
+    """Returns (pipe with edited UNet cross-attention K/V projections, original unet or None) — :511-547."""
+    orig_unet = deepcopy(pipe.unet) if return_orig_text_model else None
+    deltas = execute_emcid_cross_attn(pipe, requests, hparams, cache_name=cache_name, mom2_weight=mom2_weight,
+                                      edit_weight=edit_weight, stat_dir=stat_dir)
+    _apply_deltas(pipe.unet, deltas, device)
+    print(f"New weights successfully inserted into {list(deltas.keys())}")
+    return pipe, orig_unet

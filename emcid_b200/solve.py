@@ -28,11 +28,18 @@ def release_workspace() -> None:
     _WS.clear()
 
 
+class SolveNotConverged(_lib.EmcidError):
+    """The fp32-class factorisation did not contract: the system is too ill-conditioned for it (status bit 1)."""
+
+
 def solve_layers(C32: torch.Tensor, Kt: torch.Tensor, St: torch.Tensor, mom2_update_weight: float,
                  scale: float, layers_left: Sequence[int], refine_steps: int = DEFAULT_REFINE_STEPS,
-                 check: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                 check: bool = True, strict: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """C32 [B, d, d] fp32, Kt [B, n, d] fp32, St [B, n, h] fp32 (CUDA).  layers_left[b] = L - i.
-    Returns (adj_k [B, d, n] fp64, resid [B, h, n] fp64, dW [B, h, d] fp32) on the same device."""
+    Returns (adj_k [B, d, n] fp64, resid [B, h, n] fp64, dW [B, h, d] fp32) on the same device.
+    check: read the status word (one D2H sync) and raise EmcidError on a Cholesky breakdown; a refinement that used all
+    its sweeps without reaching its target is a RuntimeWarning, or SolveNotConverged with `strict` (callers that have a
+    fallback, emcid_main._solve_one_layer)."""
     if C32.dim() == 2:
         C32, Kt, St = C32[None], Kt[None], St[None]
     assert C32.is_cuda and Kt.is_cuda and St.is_cuda, "emcid_b200.solve needs CUDA tensors (no CPU path)"
@@ -42,6 +49,18 @@ def solve_layers(C32: torch.Tensor, Kt: torch.Tensor, St: torch.Tensor, mom2_upd
     B, d, _ = C32.shape
     n, h = Kt.shape[1], St.shape[2]
     assert Kt.shape == (B, n, d) and St.shape == (B, n, h) and len(layers_left) == B
+    if d % 128:
+        # the blocked factorisation works on 128-wide panels: embed the system in the next multiple of 128 with a
+        # decoupled identity block (zero key columns there), solve, and cut the padding off again
+        dp = -(-d // 128) * 128
+        Cp = torch.zeros(B, dp, dp, dtype=torch.float32, device=C32.device)
+        Cp[:, :d, :d] = C32
+        idx = torch.arange(d, dp, device=C32.device)
+        Cp[:, idx, idx] = 1.0
+        Kp = torch.zeros(B, n, dp, dtype=torch.float32, device=C32.device)
+        Kp[:, :, :d] = Kt
+        adj_k, resid, dW = solve_layers(Cp, Kp, St, mom2_update_weight, scale, layers_left, refine_steps, check, strict)
+        return adj_k[:, :d].contiguous(), resid, dW[:, :, :d].contiguous()
     dev = C32.device
     adj_k = torch.empty(B, d, n, dtype=torch.float64, device=dev)
     resid = torch.empty(B, h, n, dtype=torch.float64, device=dev)
@@ -57,15 +76,18 @@ def solve_layers(C32: torch.Tensor, Kt: torch.Tensor, St: torch.Tensor, mom2_upd
                                           _lib.ptr(resid), _lib.ptr(dW), int(refine_steps), _lib.ptr(ws), ws.numel(),
                                           _lib.ptr(status), _lib.current_stream_ptr()))
     if check:
-        _check_status(int(status.item()), "lambda*C + K K^T")
+        _check_status(int(status.item()), "lambda*C + K K^T", strict)
     return adj_k, resid, dW
 
 
-def _check_status(st: int, what: str) -> None:
-    """status bits of include/emcid_b200.h: bit 0 = breakdown (raise), bit 1 = refinement target not reached (warn)."""
+def _check_status(st: int, what: str, strict: bool = False) -> None:
+    """status bits of include/emcid_b200.h: bit 0 = breakdown (raise), bit 1 = refinement target not reached (warn, or
+    raise SolveNotConverged when `strict`)."""
     if st & 1:
-        raise _lib.EmcidError(-4, f"Cholesky breakdown: {what} is not positive definite (status {st})")
+        raise _lib.EmcidError(-4, f"Cholesky breakdown: {what} is not positive definite in fp32-class arithmetic (status {st})")
     if st & 2:
+        if strict:
+            raise SolveNotConverged(-4, f"iterative refinement of {what} did not reach its target (status {st})")
         import warnings
 
         warnings.warn(f"emcid_b200.solve: the iterative refinement of {what} did not reach its target "
@@ -100,7 +122,7 @@ class CachedFactor:
             raise _lib.EmcidError(-4, f"Cholesky breakdown: lambda*C is not positive definite (status {st})")
 
     def solve(self, Kt: torch.Tensor, St: torch.Tensor, scale: float, layers_left: int,
-              refine_steps: int = DEFAULT_REFINE_STEPS, check: bool = True
+              refine_steps: int = DEFAULT_REFINE_STEPS, check: bool = True, strict: bool = False
               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Kt [n, d] fp32, St [n, h] fp32 (CUDA) -> (adj_k [d, n] fp64, resid [h, n] fp64, dW [h, d] fp32)."""
         assert self._handle, "CachedFactor is closed"
@@ -123,7 +145,7 @@ class CachedFactor:
                                               int(refine_steps), _lib.ptr(ws), ws.numel(), _lib.ptr(status),
                                               _lib.current_stream_ptr()))
         if check:
-            _check_status(int(status.item()), "lambda*C / I + Ks^T A^-1 Ks")
+            _check_status(int(status.item()), "lambda*C / I + Ks^T A^-1 Ks", strict)
         return adj_k, resid, dW
 
     def close(self) -> None:

@@ -212,6 +212,11 @@ int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* 
                        const double* inv_layers_left, double* adj_k, double* resid, float* dW,
                        int refine_steps, void* workspace, size_t workspace_bytes, int* status_dev, void* stream);
 
+/* dW [h x d] fp32 = float(resid [h x n] * adj_k [d x n]^T), both fp64 row-major on the device: the product
+ * apply_emcid_to_text_encoder forms from the deltas (emcid/emcid_main.py:802-809: `upd = adj_k @ resid.T` in fp64, then
+ * `.float()`, transposed to the weight's shape) on the DMMA GEMM of the solver. */
+int emcid_delta_update(int h, int d, int n, const double* resid, const double* adj_k, float* dW, void* stream);
+
 /* ---- cached factorisation: repeated edits with the same covariance ------------------------------------
  * The reference re-runs torch.linalg.solve on a fresh d x d matrix for every edit even when lambda * C has not changed:
  * sequential editing (experiments/sequential_editing.py:98-171 -> emcid_main.py:1037-1050 once per edit and layer), the

@@ -285,3 +285,159 @@ def run_reference_apply(model, tokenizer, requests, hparams, cache_name: str, st
         ref.emcid_main.apply_emcid_to_text_encoder(
             pipe, requests, hparams, device=pipe.device, cache_name=cache_name, stats_dir=stat_dir, verbose=False)
     return model
+
+
+# ---------------------------------------------------------------------------------------------
+# UNet cross-attention K/V modules and the whole-CLIPModel variant (tiny stand-ins)
+# ---------------------------------------------------------------------------------------------
+class _Attn2(torch.nn.Module):
+    def __init__(self, hidden, width):
+        super().__init__()
+        self.to_k = torch.nn.Linear(hidden, width, bias=False)
+        self.to_v = torch.nn.Linear(hidden, width, bias=False)
+
+
+class _TBlock(torch.nn.Module):
+    def __init__(self, hidden, width):
+        super().__init__()
+        self.attn2 = _Attn2(hidden, width)
+
+
+class _AttnHolder(torch.nn.Module):
+    def __init__(self, hidden, width):
+        super().__init__()
+        self.transformer_blocks = torch.nn.ModuleList([_TBlock(hidden, width)])
+
+
+class _Block(torch.nn.Module):
+    def __init__(self, hidden, widths):
+        super().__init__()
+        if widths:
+            self.attentions = torch.nn.ModuleList([_AttnHolder(hidden, w) for w in widths])
+
+
+class TinyUNet(torch.nn.Module):
+    """The part of diffusers' UNet2DConditionModel the cross-attention path touches: modules named
+    {down,up}_blocks.i.attentions.j.transformer_blocks.0.attn2.to_{k,v} and mid_block.attentions.0... (util/globals.py:37-38)
+    that all read `encoder_hidden_states`, plus the config fields the reference's dummy forward needs
+    (emcid/layer_stats.py:397-403).  Block layout follows SD-v1.4 in miniature: some blocks have no attention."""
+
+    def __init__(self, hidden=64, seed=0):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.down_blocks = torch.nn.ModuleList([_Block(hidden, [32, 32]), _Block(hidden, [])])
+        self.up_blocks = torch.nn.ModuleList([_Block(hidden, []), _Block(hidden, [48])])
+        self.mid_block = _Block(hidden, [64])
+        self.config = SimpleNamespace(in_channels=4, sample_size=8, _name_or_path="synthetic/tiny-unet")
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def forward(self, latents, timesteps, encoder_hidden_states=None):
+        out = []
+        for blocks in (self.down_blocks, self.up_blocks, [self.mid_block]):
+            for b in blocks:
+                for a in getattr(b, "attentions", []):
+                    attn = a.transformer_blocks[0].attn2
+                    out.append((attn.to_k(encoder_hidden_states), attn.to_v(encoder_hidden_states)))
+        return out
+
+
+def make_cross_attn_pipe(seed: int = 0, device="cpu"):
+    """Stand-in for the StableDiffusionPipeline fields the cross-attention path reads."""
+    text = make_clip_text_model("tiny", seed=seed).to(device)
+    unet = TinyUNet(text.config.hidden_size, seed=seed + 100).to(device)
+    return SimpleNamespace(text_encoder=text, unet=unet, tokenizer=FakeTokenizer(text.config.vocab_size),
+                           scheduler=SimpleNamespace(config=SimpleNamespace(num_train_timesteps=1000)),
+                           device=torch.device(device))
+
+
+def write_cross_attn_vstar_cache(cache_name: str, requests, pipe, layer_names, seed: int = 2):
+    """source_{source}.npz holding one pickled {"v_star": array} per K/V module (emcid/emcid_main.py:365-420)."""
+    g = torch.Generator().manual_seed(seed)
+    os.makedirs(os.path.dirname(cache_name) or ".", exist_ok=True)
+    out = {n: [] for n in layer_names}
+    for r in requests:
+        payload = {}
+        for n in layer_names:
+            mod = pipe.unet
+            for part in n.split("."):
+                mod = getattr(mod, part)
+            v = torch.randn(mod.weight.shape[0], generator=g)
+            payload[n] = {"v_star": v.numpy()}
+            out[n].append(v)
+        np.savez(cache_name + f"source_{r['source']}.npz", **payload)
+    return {n: torch.stack(v, dim=1) for n, v in out.items()}
+
+
+def run_reference_cross_attn_stats(pipe, captions, layer_name: str, stats_dir: str, sample_size: int):
+    """Reference emcid/layer_stats.py::layer_stats_cross_attn_kv (:333-427), unmodified."""
+    ref = import_reference()
+    ref.layer_stats.get_ccs_filtered_ds = lambda tokenizer: SynthTokenDataset(captions)
+    return ref.layer_stats.layer_stats_cross_attn_kv(pipe, layer_name, stats_dir=stats_dir, sample_size=sample_size,
+                                                     precision="float32", progress=lambda x, total=None: x)
+
+
+def run_reference_cross_attn_edit(pipe, requests, hparams, cache_name: str, stats_dir: str, apply: bool):
+    """Reference execute_emcid_cross_attn / apply_emcid_to_cross_attn (emcid/emcid_main.py:314-547); statistics come
+    from `stats_dir` (the reference reads its module-level STATS_DIR, :2225)."""
+    ref = import_reference()
+    ref.emcid_main.COV_CACHE.clear()
+    saved = ref.emcid_main.STATS_DIR
+    ref.emcid_main.STATS_DIR = stats_dir
+    try:
+        with cpu_cuda_patches():
+            if apply:
+                return ref.emcid_main.apply_emcid_to_cross_attn(pipe, requests, hparams, device=pipe.device,
+                                                                cache_name=cache_name)
+            return ref.emcid_main.execute_emcid_cross_attn(pipe, requests, hparams, cache_name=cache_name, verbose=False)
+    finally:
+        ref.emcid_main.STATS_DIR = saved
+
+
+def make_clip_model(seed: int = 0):
+    """Tiny transformers.CLIPModel (text tower of the 'tiny' preset + a minimal vision tower) for the
+    apply_emcid_to_clip variant (emcid/emcid_main.py:109-311)."""
+    from transformers import CLIPConfig, CLIPModel
+
+    text = dict(vocab_size=1000, hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                max_position_embeddings=77, hidden_act="quick_gelu", bos_token_id=998, eos_token_id=999)
+    vision = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=2, image_size=16,
+                  patch_size=8)
+    torch.manual_seed(seed)
+    model = CLIPModel(CLIPConfig(text_config=text, vision_config=vision, projection_dim=32)).eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    model.config._name_or_path = f"synthetic/tiny-clipmodel-seed{seed}"
+    return model
+
+
+def text_tower_of(clip_model):
+    """A CLIPTextModel sharing the CLIPModel's text weights: the reference's statistics pass calls model(**batch),
+    which a whole CLIPModel cannot serve without pixel values, so its statistics files are made from the tower alone."""
+    from transformers import CLIPTextModel
+
+    tower = CLIPTextModel(clip_model.config.text_config).eval()
+    tower.text_model.load_state_dict(clip_model.text_model.state_dict())
+    for p in tower.parameters():
+        p.requires_grad_(False)
+    tower.config._name_or_path = clip_model.config._name_or_path
+    return tower
+
+
+def run_reference_clip_edit(model, tokenizer, requests, hparams, cache_name: str, stats_dir: str, apply: bool):
+    """Reference execute_emcid_clip / apply_emcid_to_clip (emcid/emcid_main.py:109-311) on CPU."""
+    ref = import_reference()
+    ref.emcid_main.COV_CACHE.clear()
+    processor = SimpleNamespace(tokenizer=tokenizer)
+    # get_cov_text_encoder's stat_dir default was bound at definition time: point it at the fixture's directory
+    fn = ref.emcid_main.get_cov_text_encoder
+    saved = fn.__defaults__
+    fn.__defaults__ = saved[:-1] + (stats_dir,)
+    try:
+        with cpu_cuda_patches():
+            if apply:
+                return ref.emcid_main.apply_emcid_to_clip(model, processor, requests, hparams, device=model.device,
+                                                          cache_name=cache_name)
+            return ref.emcid_main.execute_emcid_clip(model, processor, requests, hparams, cache_name=cache_name, verbose=False)
+    finally:
+        fn.__defaults__ = saved

@@ -232,6 +232,13 @@ def test_edit_api_error_behaviour(tmp_path):
     hp = rh.make_hparams([0, 1], 8)
     with pytest.raises(NotImplementedError, match="v_star cache miss"):
         emcid_main._load_vstars(rh.make_requests(1), hp, str(tmp_path / "c_"), "cpu")
+    (tmp_path / "bad_source_artist0 name0_dest_art.npz").write_bytes(b"PK\x03\x04 not a zip file at all")
+    with pytest.raises(NotImplementedError, match="unreadable"):             # a corrupt file is a miss too, named
+        emcid_main._load_vstars(rh.make_requests(1), hp, str(tmp_path / "bad_"), "cpu")
+    hp_esd = rh.make_hparams([0, 1], 8)
+    hp_esd.objective = "esd-3.0"
+    assert emcid_main._vstar_stem(rh.make_requests(1)[0], 0, hp_esd, "sd") == "source_artist0 name0"
+    assert emcid_main._vstar_stem(rh.make_requests(1)[0], 0, hp_esd, "sdxl") == "source_artist0 name0_dest_art"
     zs = rh.write_vstar_cache(str(tmp_path / "c_"), rh.make_requests(3), 64)
     got = emcid_main._load_vstars(rh.make_requests(3), hp, str(tmp_path / "c_"), "cpu")
     assert torch.equal(got, zs) and got.shape == (64, 3)
@@ -394,14 +401,14 @@ def test_factor_cache_policy(monkeypatch):
             calls.append(("create", float(lam), float(C32[0, 0])))
             self.closed = False
 
-        def solve(self, Kt, St, scale, left, refine_steps=-1):
+        def solve(self, Kt, St, scale, left, refine_steps=-1, strict=False):
             calls.append(("cached", Kt.shape[0], left))
             return "adj", "resid", "dW"
 
         def close(self):
             self.closed = True
 
-    def fake_direct(C32, Kt, St, lam, scale, left, refine_steps=-1):
+    def fake_direct(C32, Kt, St, lam, scale, left, refine_steps=-1, strict=False):
         calls.append(("direct", Kt.shape[0], tuple(left)))
         return ["adj"], ["resid"], ["dW"]
 
@@ -435,6 +442,37 @@ def test_factor_cache_policy(monkeypatch):
     assert len(emcid_main.FACTOR_CACHE) == 2 and first.closed
     emcid_main.clear_factor_cache()
     assert len(emcid_main.FACTOR_CACHE) == 0
+
+    # a factorisation that breaks down, or a refinement that misses its target, falls through:
+    # cached factor -> direct solve -> the reference's fp64 LU (the reference's LU never fails this way)
+    from emcid_b200 import _lib
+    from emcid_b200.solve import SolveNotConverged
+
+    class BrokenFactor(FakeFactor):
+        def solve(self, *a, **k):
+            raise SolveNotConverged(-4, "refinement did not reach its target")
+
+    def broken_direct(*a, **k):
+        raise _lib.EmcidError(-4, "Cholesky breakdown")
+
+    lu_calls = []
+    monkeypatch.setattr(emcid_main, "CachedFactor", BrokenFactor)
+    monkeypatch.setattr(emcid_main, "_fp64_lu_on_device", lambda *a: lu_calls.append(1) or ("adj", "resid", "dW"))
+    calls.clear()
+    assert run("l7", cov, k100) == ("adj", "resid", "dW") and calls[-1][0] == "direct" and not lu_calls
+    assert emcid_main.LAST_SOLVE_PATHS[-1] == "direct" and len(emcid_main.FACTOR_CACHE) == 0
+    monkeypatch.setattr(emcid_main, "solve_layers", broken_direct)
+    with pytest.warns(RuntimeWarning, match="fp64 LU"):
+        assert run("l7", cov, k100) == ("adj", "resid", "dW")
+    assert lu_calls == [1] and emcid_main.LAST_SOLVE_PATHS[-1] == "fp64_lu"
+
+    def other_error(*a, **k):
+        raise _lib.EmcidError(-2, "cuda failure")
+
+    monkeypatch.setattr(emcid_main, "solve_layers", other_error)
+    with pytest.raises(_lib.EmcidError):
+        run("l7", cov, torch.zeros(600, d))                     # anything but a numerical failure is not swallowed
+    emcid_main.clear_factor_cache()
 
 
 def test_token_range_fast_path_equals_whole_array_decode():

@@ -148,6 +148,66 @@ def test_execute_oracle_matches_reference_digest_at_clipl_size(golden_dir):
         assert abs(np.linalg.norm(dW) / float(g[f"cum.0.{l}.fro"]) - 1) < 1e-6, l
 
 
+def _get(obj, name):
+    for part in name.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+def test_cross_attn_oracle_matches_reference_fixture(golden_dir):
+    """statistics of the cross-attention K/V input and the independent per-module edit, against the
+    unmodified reference (oracle/gen_golden_f4.py::tiny_cross_attn)."""
+    from emcid_b200 import layer_stats
+    g = np.load(os.path.join(golden_dir, "tiny_cross_attn.npz"))
+    names = [str(n) for n in g["names"]]
+    pipe = rh.make_cross_attn_pipe(seed=0)
+    assert float(pipe.text_encoder.text_model.encoder.layers[1].mlp.fc2.weight.double().abs().sum()) == float(g["text_fc2_checksum"])
+    assert layer_stats.get_all_cross_attn_kv_layer_names(pipe) == names          # same modules, the reference's order
+    for n in names:
+        assert np.array_equal(_get(pipe.unet, n).weight.numpy(), g[f"w_before.{n}"])
+    caps = [c.numpy() for c in rh.make_captions(int(g["n_caps"]), 1000, seed=int(g["seed_caps"]))]
+    stat = orc.cross_attn_kv_stats_oracle(pipe.text_encoder, caps, int(g["sample_size"]))
+    for n in (names[0], names[-1]):                                              # one matrix whatever the module
+        assert stat.count == int(g[f"count.{n}"])
+        assert rel_fro(stat.mom2, g[f"mom2.{n}"]) < 1e-6
+    assert [str(f) for f in g["stat_files"]] == sorted(
+        orc.stats_filename("", "unet", "ccs_filtered", n, "float32", ["mom2"], 3072, int(g["sample_size"])).lstrip("/")
+        for n in (names[0], names[-1]))
+    reqs = rh.make_requests(int(g["n_req"]))
+    g_v = torch.Generator().manual_seed(2)                                       # ref_harness.write_cross_attn_vstar_cache
+    zs = {n: [] for n in names}
+    for _ in reqs:
+        for n in names:
+            zs[n].append(torch.randn(g[f"w_before.{n}"].shape[0], generator=g_v))
+    zs = {n: torch.stack(v, dim=1).numpy() for n, v in zs.items()}
+    cov = orc.cov_from_state(g[f"mom2.{names[0]}"], int(g[f"count.{names[0]}"]))
+    deltas = orc.execute_cross_attn_oracle(pipe.text_encoder, pipe.tokenizer, reqs, {n: g[f"w_before.{n}"] for n in names},
+                                           zs, cov, float(g["lam"]), float(g["edit_weight"]))
+    for n in names:
+        assert rel_fro(deltas[n][0], g[f"adj_k.{n}"]) < 1e-5
+        assert rel_fro(deltas[n][1], g[f"resid.{n}"]) < 1e-5
+        w_after = orc.apply_delta(g[f"w_before.{n}"], g[f"adj_k.{n}"], g[f"resid.{n}"])
+        assert rel_fro(w_after, g[f"w_after.{n}"]) < 1e-7
+
+
+def test_clip_model_variant_matches_reference_fixture(golden_dir):
+    """apply_emcid_to_clip (emcid/emcid_main.py:109-311) runs the text-encoder loop on a whole CLIPModel: the oracle's
+    stage-2 restatement on the model's text tower reproduces the reference's deltas and weights."""
+    g = np.load(os.path.join(golden_dir, "tiny_clip_model.npz"))
+    layers = [int(l) for l in g["layers"]]
+    model = rh.make_clip_model(seed=5)
+    for l in layers:
+        assert np.array_equal(model.text_model.encoder.layers[l].mlp.fc2.weight.numpy(), g[f"w_before.{l}"])
+    tower = rh.text_tower_of(model)
+    tok = rh.FakeTokenizer(1000)
+    reqs = rh.make_requests(int(g["n_req"]))
+    covs = {l: orc.cov_from_state(g[f"mom2.{l}"], int(g[f"count.{l}"])) for l in layers}
+    deltas = orc.execute_oracle(tower, tok, reqs, layers, g["zs"], covs, float(g["lam"]), float(g["edit_weight"]))
+    for l in layers:
+        assert rel_fro(deltas[l][1] @ deltas[l][0].T, g[f"resid.{l}"] @ g[f"adj_k.{l}"].T) < 1e-5
+        assert rel_fro(orc.apply_delta(g[f"w_before.{l}"], g[f"adj_k.{l}"], g[f"resid.{l}"]), g[f"w_after.{l}"]) < 1e-7
+
+
 def test_exact_spd_matrix_is_reproducible():
     a = orc.exact_spd_matrix(64, 128, seed=3)
     b = orc.exact_spd_matrix(64, 128, seed=3)
