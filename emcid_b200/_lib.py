@@ -58,6 +58,7 @@ SIGNATURES = {
     "emcid_mom2_export_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "emcid_mom2_import_state": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "emcid_symmetrize_lower": (c_int, [c_void_p, c_int, c_longlong, c_void_p]),
+    "emcid_checksum_tensors": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "emcid_fixed_random_subset": (c_int, [c_longlong, c_longlong, ctypes.POINTER(c_longlong), c_longlong]),
     "emcid_clip_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                   c_longlong, c_int]),

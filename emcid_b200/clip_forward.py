@@ -43,6 +43,8 @@ def supports(model) -> bool:
             return False
         if cfg.hidden_size % 4 or cfg.intermediate_size % 4:
             return False
+        if cfg.hidden_size // cfg.num_attention_heads not in (16, 32, 64, 128):
+            return False
         ly = layers[0]
         for mod in (ly.self_attn.q_proj, ly.self_attn.k_proj, ly.self_attn.v_proj, ly.self_attn.out_proj, ly.mlp.fc1,
                     ly.mlp.fc2):
@@ -118,12 +120,24 @@ class NativeClipTextEncoder:
     def _signature(tensors) -> tuple:
         return tuple((0, 0) if t is None else (t.data_ptr(), t._version) for t in tensors)
 
-    @staticmethod
-    def _checksums(tensors) -> torch.Tensor:
-        """One int64 per tensor: the wrapping sum of its 32-bit words (exact, order independent; any realistic edit of
-        a weight changes it)."""
-        return torch.stack([torch.zeros((), dtype=torch.int64, device=tensors[0].device) if t is None else
-                            t.detach().reshape(-1).view(torch.int32).sum(dtype=torch.int64) for t in tensors])
+    def _checksums(self, tensors) -> torch.Tensor:
+        """One int64 per tensor (host): the wrapping sum of its 32-bit words (exact, order independent; any realistic
+        edit of a weight changes it), all tensors in ONE launch (emcid_checksum_tensors) and one D2H copy."""
+        table = []
+        keep = []
+        for t in tensors:
+            if t is None:
+                table += [0, 0]
+            else:
+                t = t.detach()
+                if not t.is_contiguous():
+                    t = t.contiguous()
+                    keep.append(t)
+                table += [t.data_ptr(), t.numel() * t.element_size() // 4]
+        table_dev = torch.tensor(table, dtype=torch.int64).to(self.device, non_blocking=True)
+        out = torch.empty(len(tensors), dtype=torch.int64, device=self.device)
+        _lib.check(_lib.lib().emcid_checksum_tensors(_lib.ptr(table_dev), len(tensors), _lib.ptr(out), self._stream()))
+        return out.cpu()
 
     def invalidate(self) -> None:
         """Forget what was uploaded: the next sync re-uploads everything it needs."""
@@ -153,8 +167,7 @@ class NativeClipTextEncoder:
         stale: Dict[object, list] = {}       # group -> indices of the tensors whose content changed behind the version counter
         if verify:
             with torch.cuda.device(self.device):
-                sums = {k: self._checksums(v) for k, v in groups.items()}
-                flat = torch.cat([sums[k] for k in groups]).cpu()
+                flat = self._checksums([t for v in groups.values() for t in v])
             at = 0
             for k, v in groups.items():
                 cur = flat[at: at + len(v)]

@@ -59,7 +59,6 @@ struct ClipHandle {
   float* qkv;                  // [cap x 3h]   fp32 q|k|v (CUDA-core attention path)
   uint16_t *qp_hi, *qp_lo;     // [cap x 3h]   q|k|v planes (tensor-core attention path)
   bool attn_tc;
-  int rowb;                    // bytes per smem row of the GEMM operand tiles: 128 (2 stages) or 64 (4 stages)
   uint16_t *x_hi, *x_lo;       // [cap x hp]   LN output
   uint16_t *a_hi, *a_lo;       // [cap x hp]   attention output
   uint16_t *f_hi, *f_lo;       // [cap x dp]   act(fc1)
@@ -116,55 +115,10 @@ __global__ void clip_embed_kernel(const int* __restrict__ ids, const int* __rest
   }
 }
 
-// One warp per token: y = (x - mean) * rsqrt(var + eps) * w + b (biased variance, like torch.nn.LayerNorm),
-// written as fp16 hi/lo planes.  NV = ceil(h / 32) values per lane stay in registers between the passes.
-template <int NV>
-__global__ void clip_layernorm_kernel(const float* __restrict__ x, int T, int h, const float* __restrict__ w,
-                                      const float* __restrict__ b, float eps, uint16_t* __restrict__ o_hi,
-                                      uint16_t* __restrict__ o_lo, int ldo) {
-  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
-  const float inv_h = 1.0f / static_cast<float>(h);
-  for (int t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
-    const float* src = x + static_cast<long long>(t) * h;
-    float v[NV];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = c < h ? src[c] : 0.f;
-      s += v[i];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * inv_h;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      const float dlt = c < h ? v[i] - mean : 0.f;
-      q += dlt * dlt;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * inv_h + eps);
-    uint16_t* oh = o_hi + static_cast<long long>(t) * ldo;
-    uint16_t* ol = o_lo + static_cast<long long>(t) * ldo;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < h) {
-        const float y = (v[i] - mean) * rstd * w[c] + b[c];
-        uint16_t hh, ll;
-        split_f16(y, FMT_F16, hh, ll);
-        oh[c] = hh;
-        ol[c] = ll;
-      }
-    }
-  }
-}
-
-// Same, four consecutive columns per lane: float4 loads, one 8-byte store per plane (h % 4 == 0, ldo % 4 == 0).
-// NV4 = ceil(h / 128) float4 per lane.
+// One warp per token: y = (x - mean) * rsqrt(var + eps) * w + b (biased variance, like torch.nn.LayerNorm), written as
+// fp16 hi/lo planes.  Four consecutive columns per lane: float4 loads, one 8-byte store per plane (h % 4 == 0, ldo % 4 == 0;
+// the scalar first version ran at 48.6 us per 39 424 tokens against 34 us).  NV4 = ceil(h / 128) float4 per lane stay in
+// registers between the passes.
 template <int NV4>
 __global__ void clip_layernorm4_kernel(const float* __restrict__ x, int T, int h, const float* __restrict__ w,
                                        const float* __restrict__ b, float eps, uint16_t* __restrict__ o_hi,
@@ -215,85 +169,10 @@ __global__ void clip_layernorm4_kernel(const float* __restrict__ x, int T, int h
   }
 }
 
-// Causal softmax attention of one (caption, head): fp32, K/V of the caption staged in shared memory,
-// one warp per query row.  qkv: [T x 3h] (q | k | v), output planes [T x ldo] at columns head*dh...
-__global__ void __launch_bounds__(128) clip_attention_kernel(const float* __restrict__ qkv, const int* __restrict__ cu,
-                                                             int h, int dh, int lmax, float scale,
-                                                             uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo,
-                                                             int ldo) {
-  extern __shared__ float attn_sm[];
-  const int ldk = dh + 1;
-  float* Ks = attn_sm;                        // [lmax][dh + 1]
-  float* Vs = Ks + lmax * ldk;            // [lmax][dh + 1]
-  float* Qs = Vs + lmax * ldk;            // [4][dh]
-  float* Ps = Qs + 4 * dh;                // [4][lmax]
-  const int head = blockIdx.x, seq = blockIdx.y;
-  const int t0 = cu[seq];
-  int Ls = cu[seq + 1] - t0;
-  if (Ls > lmax) Ls = lmax;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long ld = 3ll * h;
-  const float* base = qkv + static_cast<long long>(t0) * ld + head * dh;
-  for (int e = tid; e < Ls * dh; e += blockDim.x) {
-    const int j = e / dh, c = e - j * dh;
-    Ks[j * ldk + c] = base[j * ld + h + c];
-    Vs[j * ldk + c] = base[j * ld + 2 * h + c];
-  }
-  __syncthreads();
-  float* q = Qs + warp * dh;
-  float* pr = Ps + warp * lmax;
-  for (int i = warp; i < Ls; i += 4) {
-    for (int c = lane; c < dh; c += 32) q[c] = base[i * ld + c];
-    __syncwarp();
-    float sc[4];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int j = lane + 32 * m;
-      float dot = -INFINITY;
-      if (j <= i) {
-        dot = 0.f;
-        const float* kr = Ks + j * ldk;
-        for (int c = 0; c < dh; ++c) dot = fmaf(q[c], kr[c], dot);
-        dot *= scale;
-      }
-      sc[m] = dot;
-      mx = fmaxf(mx, dot);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int j = lane + 32 * m;
-      const float e = j <= i ? expf(sc[m] - mx) : 0.f;
-      sc[m] = e;
-      sum += e;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int j = lane + 32 * m;
-      if (j <= i) pr[j] = sc[m] * inv;
-    }
-    __syncwarp();
-    uint16_t* oh = o_hi + static_cast<long long>(t0 + i) * ldo + head * dh;
-    uint16_t* ol = o_lo + static_cast<long long>(t0 + i) * ldo + head * dh;
-    for (int c = lane; c < dh; c += 32) {
-      float acc = 0.f;
-      for (int j = 0; j <= i; ++j) acc = fmaf(pr[j], Vs[j * ldk + c], acc);
-      uint16_t hh, ll;
-      split_f16(acc, FMT_F16, hh, ll);
-      oh[c] = hh;
-      ol[c] = ll;
-    }
-    __syncwarp();
-  }
-}
-
-// Register-tiled variant for head dims 16/32/64/128: a warp handles TWO adjacent query rows at once, keeps both
+// Causal softmax attention of one (caption, head) in fp32 on the CUDA cores, for head dims the tensor-core kernel
+// (attn.cuh, head dim 64) does not cover: K/V of the caption staged in shared memory; qkv: [T x 3h] (q | k | v), output planes
+// [T x ldo] at columns head*dh...
+// Register-tiled for head dims 16/32/64/128: a warp handles TWO adjacent query rows at once, keeps both
 // q rows in registers and reads K/V as float4 from shared memory (row pitch DH + 4: conflict-free LDS.128), so
 // every K/V element fetched feeds two FMAs and the kernel is FMA- rather than LDS-bound.
 template <int DH>
@@ -505,30 +384,23 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
   }
   {
     const int dh = H->dh;
-    const bool tiled = dh == 16 || dh == 32 || dh == 64 || dh == 128;
+    if (!(dh == 16 || dh == 32 || dh == 64 || dh == 128)) {
+      clip_destroy(H);
+      return set_error(EMCID_ERR_UNSUPPORTED, "clip_create: head dim %d (supported: 16, 32, 64, 128)", dh);
+    }
     const int lp = (max_pos + 7) & ~3;
-    H->attn_smem = tiled ? (2 * lp * (dh + 4) + 8 * lp) * static_cast<int>(sizeof(float))
-                         : (2 * max_pos * (dh + 1) + 4 * dh + 4 * max_pos) * static_cast<int>(sizeof(float));
+    H->attn_smem = (2 * lp * (dh + 4) + 8 * lp) * static_cast<int>(sizeof(float));
     cudaError_t e = cudaSuccess;
     if (H->attn_smem > 48 * 1024) {
       if (dh == 16) e = cudaFuncSetAttribute(clip_attention2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
       else if (dh == 32) e = cudaFuncSetAttribute(clip_attention2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
       else if (dh == 64) e = cudaFuncSetAttribute(clip_attention2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
-      else if (dh == 128) e = cudaFuncSetAttribute(clip_attention2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
-      else e = cudaFuncSetAttribute(clip_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
+      else e = cudaFuncSetAttribute(clip_attention2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, H->attn_smem);
     }
     if (e != cudaSuccess) {
       clip_destroy(H);
       return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", H->attn_smem, cudaGetErrorString(e));
     }
-  }
-  {
-    // experiment switch: 64-byte operand rows / 4 pipeline stages (needs the staged TMA epilogue).  Measured on
-    // B200: within 2 % of the default 128-byte / 2-stage pipeline (only the K = 3072 fc2 gains ~10 %), i.e. the
-    // mainloop is not TMA-latency bound; kept off.
-    const char* e = getenv("EMCID_GEMM_S64");
-    const char* t = getenv("EMCID_LINEAR_TMA");
-    H->rowb = (e && e[0] == '1' && !(t && t[0] == '0')) ? 64 : 128;
   }
   {
     // tensor-core attention: head dim 64 (CLIP-L, OpenCLIP bigG), captions up to 128 tokens; EMCID_ATTN_TC=0 disables
@@ -586,8 +458,8 @@ inline int clip_prepare_weight(ClipHandle* H, ClipWeight* W, int parts, const fl
       EMCID_CUDA_CHECK(cudaMemsetAsync(W->bias + static_cast<size_t>(i) * rows_each, 0, rows_each * sizeof(float), stream));
     }
   }
-  if ((rc = make_tmap_2d(&W->m_hi, W->hi, N, K, Kp, 128, 2, 0, H->rowb)) ||
-      (rc = make_tmap_2d(&W->m_lo, W->lo, N, K, Kp, 128, 2, 0, H->rowb)))
+  if ((rc = make_tmap_2d(&W->m_hi, W->hi, N, K, Kp, 128, 2)) ||
+      (rc = make_tmap_2d(&W->m_lo, W->lo, N, K, Kp, 128, 2)))
     return rc;
   return EMCID_OK;
 }
@@ -661,22 +533,19 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   H->launches += 1;
   // the epilogue variant is a compile-time option (see EF_* in gemm3x.cuh): only the combinations the forward uses
   const int ef = act | (C ? EF_C : 0) | (Cin ? EF_CIN : 0) | (P_hi ? EF_P : 0) | (Pt_hi ? EF_PT : 0);
-  if (om && H->rowb == 64) p.chunk_kblocks *= 2;   // k-blocks are half as deep
-  const bool cta2 = om && H->rowb == 128 && gemm_cta2_enabled();
+  const bool cta2 = om && gemm_cta2_enabled();
   const int pair_tiles = ((T + 255) / 256) * ((W.N + 255) / 256);
   const int grid2 = 2 * pair_tiles < (H->info.sm_count & ~1) ? 2 * pair_tiles : (H->info.sm_count & ~1);
 #define EMCID_LIN_CASE(F)                                                                                     \
   if (ef == (F))                                                                                              \
     return !om            ? launch_gemm3x<256, 2, EPI_LINEAR, KIND_F16, (F)>(ops, p, grid, stream)            \
            : cta2          ? launch_gemm3x<256, 3, EPI_LINEAR_TMA, KIND_F16, (F), 1>(ops, p, grid2, stream, 1, om) \
-           : H->rowb == 64 ? launch_gemm3x<256, 4, EPI_LINEAR_TMA, KIND_F16_S64, (F)>(ops, p, grid, stream, 1, om) \
                            : launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (F)>(ops, p, grid, stream, 1, om);
   EMCID_LIN_CASE(ACT_NONE | EF_C)                       // q/k/v projection (fp32, CUDA-core attention)
   if (cta2 && ef == (ACT_NONE | EF_P))
     return launch_gemm3x<256, 3, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P), 1>(ops, p, grid2, stream, 1, om);
   if (om && ef == (ACT_NONE | EF_P))                    // q/k/v projection as planes (tensor-core attention)
-    return H->rowb == 64 ? launch_gemm3x<256, 4, EPI_LINEAR_TMA, KIND_F16_S64, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om)
-                         : launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om);
+    return launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om);
   EMCID_LIN_CASE(ACT_NONE | EF_C | EF_CIN)              // out projection / fc2 with residual
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P)                 // fc1
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P | EF_PT)         // fc1 of an edited layer
@@ -691,7 +560,6 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
 inline int clip_layernorm(ClipHandle* H, const float* x, int T, const float* w, const float* b, uint16_t* o_hi,
                           uint16_t* o_lo, cudaStream_t stream) {
   ClipProfScope prof(H, stream, CLIP_TAG_LN, 0.0);
-  const int nv = (H->h + 31) / 32;
   int blocks = (T + 7) / 8;
   if (blocks > H->info.sm_count * 16) blocks = H->info.sm_count * 16;
   H->launches += 1;
@@ -708,15 +576,6 @@ inline int clip_layernorm(ClipHandle* H, const float* x, int T, const float* w, 
     EMCID_LN4_CASE(16)
 #undef EMCID_LN4_CASE
   }
-#define EMCID_LN_CASE(NV)                                                                                         \
-  if (nv <= NV) {                                                                                                 \
-    clip_layernorm_kernel<NV><<<blocks, 256, 0, stream>>>(x, T, H->h, w, b, H->eps, o_hi, o_lo, H->hp);          \
-    EMCID_CUDA_CHECK(cudaGetLastError());                                                                         \
-    return EMCID_OK;                                                                                              \
-  }
-  EMCID_LN_CASE(2) EMCID_LN_CASE(4) EMCID_LN_CASE(8) EMCID_LN_CASE(16) EMCID_LN_CASE(24) EMCID_LN_CASE(32)
-  EMCID_LN_CASE(40) EMCID_LN_CASE(64)
-#undef EMCID_LN_CASE
   return set_error(EMCID_ERR_UNSUPPORTED, "clip_layernorm: hidden size %d too large", H->h);
 }
 
@@ -808,13 +667,12 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   // per-call TMA maps over exactly T rows: out-of-range rows of the last tile read as zeros
   CUtensorMap mx_hi, mx_lo, ma_hi, ma_lo, mf_hi, mf_lo;
   GemmOperands ft;
-  const int rb = H->rowb;
   CUtensorMap sf_hi, sf_lo;   // store maps of the f planes (always 128-byte swizzled staging tiles)
-  if ((rc = make_tmap_2d(&mx_hi, H->x_hi, T, H->h, H->hp, 128, 2, 0, rb)) || (rc = make_tmap_2d(&mx_lo, H->x_lo, T, H->h, H->hp, 128, 2, 0, rb)) ||
-      (rc = make_tmap_2d(&ma_hi, H->a_hi, T, H->h, H->hp, 128, 2, 0, rb)) || (rc = make_tmap_2d(&ma_lo, H->a_lo, T, H->h, H->hp, 128, 2, 0, rb)) ||
-      (rc = make_tmap_2d(&mf_hi, H->f_hi, T, H->d, H->dp, 128, 2, 0, rb)) || (rc = make_tmap_2d(&mf_lo, H->f_lo, T, H->d, H->dp, 128, 2, 0, rb)) ||
+  if ((rc = make_tmap_2d(&mx_hi, H->x_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&mx_lo, H->x_lo, T, H->h, H->hp, 128, 2)) ||
+      (rc = make_tmap_2d(&ma_hi, H->a_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&ma_lo, H->a_lo, T, H->h, H->hp, 128, 2)) ||
+      (rc = make_tmap_2d(&mf_hi, H->f_hi, T, H->d, H->dp, 128, 2)) || (rc = make_tmap_2d(&mf_lo, H->f_lo, T, H->d, H->dp, 128, 2)) ||
       (rc = make_tmap_2d(&sf_hi, H->f_hi, T, H->d, H->dp, 128, 2)) || (rc = make_tmap_2d(&sf_lo, H->f_lo, T, H->d, H->dp, 128, 2)) ||
-      (rc = make_tmap_2d(&ft.a_hi, H->ft_hi, H->d, T, H->tp, 128, 2, 0, rb)) || (rc = make_tmap_2d(&ft.a_lo, H->ft_lo, H->d, T, H->tp, 128, 2, 0, rb)))
+      (rc = make_tmap_2d(&ft.a_hi, H->ft_hi, H->d, T, H->tp, 128, 2)) || (rc = make_tmap_2d(&ft.a_lo, H->ft_lo, H->d, T, H->tp, 128, 2)))
     return rc;
   ft.b_hi = ft.a_hi; ft.b_lo = ft.a_lo;
   // store maps of the staged (TMA) epilogue; EMCID_LINEAR_TMA=0 keeps the direct-store epilogue
@@ -886,9 +744,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   if (H->dh == D)                                                                                                      \
     clip_attention2_kernel<D><<<ag, 128, H->attn_smem, stream>>>(H->qkv, cu_seqlens, H->h, H->max_pos, scale, H->a_hi, \
                                                                  H->a_lo, H->hp);
-      EMCID_ATTN_CASE(16) else EMCID_ATTN_CASE(32) else EMCID_ATTN_CASE(64) else EMCID_ATTN_CASE(128) else
-        clip_attention_kernel<<<ag, 128, H->attn_smem, stream>>>(H->qkv, cu_seqlens, H->h, H->dh, H->max_pos, scale,
-                                                                 H->a_hi, H->a_lo, H->hp);
+      EMCID_ATTN_CASE(16) else EMCID_ATTN_CASE(32) else EMCID_ATTN_CASE(64) else EMCID_ATTN_CASE(128)
 #undef EMCID_ATTN_CASE
     }
     }
@@ -904,7 +760,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     // planes fc2 reads as well, so an edited layer's fc1 is an ordinary fc1.  EMCID_SYRK_MN=0: the SYRK reads K-major
     // tiles of a transposed copy f^T, which fc1 of an edited layer then has to write as well (+100 us per launch).
     static const bool syrk_mn = [] { const char* e = getenv("EMCID_SYRK_MN"); return !(e && e[0] == '0'); }();
-    const bool mn = syrk_mn && rb == 128 && use_tma_epi;
+    const bool mn = syrk_mn && use_tma_epi;
     const bool want_p = mn || !is_last, want_pt = is_stat && !mn;
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.fc1, T, H->act, nullptr, nullptr, 0, want_p ? H->f_hi : nullptr,
                           want_p ? H->f_lo : nullptr, H->dp, want_pt ? H->ft_hi : nullptr, want_pt ? H->ft_lo : nullptr,
@@ -925,7 +781,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
         if ((rc = mom2_syrk_slab(A, fm, KIND_F16_MN, 0, T, nullptr, stream, hybrid ? 2 : 1))) return rc;
         A->slabs_since_fold += 4;
         if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
-      } else if (hybrid && rb == 128) {
+      } else if (hybrid) {
         if ((rc = mom2_syrk_slab(A, ft, KIND_F16, 0, T, nullptr, stream, 2))) return rc;
         A->slabs_since_fold += 4;
         if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
@@ -936,7 +792,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       if (per > slab) per = slab;
       for (long long c0 = 0; c0 < T; c0 += per) {
         const int t = static_cast<int>(T - c0 < per ? T - c0 : per);
-        if ((rc = mom2_syrk_slab(A, ft, rb == 64 ? KIND_F16_S64 : KIND_F16, static_cast<int>(c0), t, nullptr, stream))) return rc;
+        if ((rc = mom2_syrk_slab(A, ft, KIND_F16, static_cast<int>(c0), t, nullptr, stream))) return rc;
         if (++A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
       }
       }
@@ -954,8 +810,8 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       H->launches += 1;
       CUtensorMap mg_hi, mg_lo;
       GemmOutMaps om_z = {};
-      if ((rc = make_tmap_2d(&mg_hi, g_hi, n_keys, H->d, H->dp, 128, 2, 0, rb)) ||
-          (rc = make_tmap_2d(&mg_lo, g_lo, n_keys, H->d, H->dp, 128, 2, 0, rb)) ||
+      if ((rc = make_tmap_2d(&mg_hi, g_hi, n_keys, H->d, H->dp, 128, 2)) ||
+          (rc = make_tmap_2d(&mg_lo, g_lo, n_keys, H->d, H->dp, 128, 2)) ||
           (use_tma_epi && (rc = make_tmap_2d(&om_z.c, z_out, n_keys, H->h, H->h, 128, 4))))
         return rc;
       if ((rc = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, nullptr,

@@ -121,6 +121,10 @@ int emcid_symmetrize_lower(float* C, int d, long long ldc, void* stream) {
   return symmetrize_lower(C, d, ldc, static_cast<cudaStream_t>(stream));
 }
 
+int emcid_checksum_tensors(const void* table_dev, int n, unsigned long long* out_dev, void* stream) {
+  return checksum_tensors(table_dev, n, out_dev, static_cast<cudaStream_t>(stream));
+}
+
 int emcid_fixed_random_subset(long long n_items, long long seed, long long* out, long long n_out) {
   return fixed_random_subset(n_items, seed, out, n_out);
 }

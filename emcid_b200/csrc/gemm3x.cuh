@@ -42,16 +42,14 @@ constexpr int GEMM_BLOCK_K = 32;  // tf32 kind: 32 fp32 = 128 bytes = one swizzl
 // tcgen05.mma.kind::tf32 (K = 8 per instruction).  KIND_F16: planes are 16-bit (hi = fp16, lo = bf16
 // or fp16, see split_f16), tcgen05.mma.kind::f16 (K = 16 per instruction): the same three MMAs per
 // 128-byte k-step retire twice the contraction depth and every plane moves half the bytes.
-// KIND_F16_S64: the same fp16 planes and MMAs as KIND_F16, staged as 64-byte rows (TMA SWIZZLE_64B, 32 elements
-// per k-block): stages are half the size, so twice as many fit in shared memory and the TMA round trip has
-// (stages - 1) x 768 instead of 1 x 1536 MMA cycles to hide behind.
+// (A variant staged as 64-byte rows with four pipeline stages was measured within 2 % of this one — the mainloop is not
+// TMA-latency bound — and dropped.)
 // KIND_F16_MN: fp16 planes stored [K x MN] row-major (MN contiguous) — the SYRK reads act(fc1) planes [tokens x
 // features] directly: both operands are MN-major tiles of 64 tokens (K) x 64-feature atoms, no transposed copy needed.
-enum GemmKind : int { KIND_TF32 = 0, KIND_F16 = 1, KIND_F16_S64 = 2, KIND_F16_MN = 3 };
+enum GemmKind : int { KIND_TF32 = 0, KIND_F16 = 1, KIND_F16_MN = 3 };
 template <int KIND> struct KindTraits;
 template <> struct KindTraits<KIND_TF32> { static constexpr int kBlockK = 32, kElemBytes = 4, kRowBytes = 128; };
 template <> struct KindTraits<KIND_F16> { static constexpr int kBlockK = 64, kElemBytes = 2, kRowBytes = 128; };
-template <> struct KindTraits<KIND_F16_S64> { static constexpr int kBlockK = 32, kElemBytes = 2, kRowBytes = 64; };
 template <> struct KindTraits<KIND_F16_MN> { static constexpr int kBlockK = 64, kElemBytes = 2, kRowBytes = 128; };
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_THREADS = 256;

@@ -405,11 +405,9 @@ inline int mom2_syrk_slab(Mom2Handle* H, const GemmOperands& ops, int kind, int 
     EMCID_CUDA_CHECK(cudaEventRecord(e0, stream));
   }
   const int sms = H->info.sm_count;
-  if (kind == KIND_F16_S64) p.chunk_kblocks *= 2;   // k-blocks are half as deep
   int rc = kind == KIND_F16_MN
                ? (gemm_cta2_enabled() ? launch_gemm3x<256, 3, EPI_RED, KIND_F16_MN, EF_DEFAULT, 1>(ops, p, sms & ~1, stream)
                                       : launch_gemm3x<256, 2, EPI_RED, KIND_F16_MN>(ops, p, sms, stream))
-           : kind == KIND_F16_S64 ? launch_gemm3x<256, 4, EPI_RED, KIND_F16_S64>(ops, p, sms, stream)
            : kind == KIND_F16
                ? (gemm_cta2_enabled() ? launch_gemm3x<256, 3, EPI_RED, KIND_F16, EF_DEFAULT, 1>(ops, p, sms & ~1, stream)
                                       : launch_gemm3x<256, 2, EPI_RED, KIND_F16>(ops, p, sms, stream))

@@ -166,6 +166,31 @@ inline int symmetrize_lower(float* C, int d, long long ldc, cudaStream_t stream)
   return EMCID_OK;
 }
 
+// ---- content checksums of a set of device tensors, one launch ---------------------------------------------------------
+// out[i] = wrapping sum of the 32-bit words of tensor i.  The weight-change detection of the key extraction compares these
+// with the values recorded at upload time: `Tensor._version` misses writes through `param.data`, and ~200 separate
+// reductions per edit cost more host time than a layer's solve.  table: device array of n (pointer, word count) pairs.
+struct ChecksumEntry { const uint32_t* ptr; long long words; };
+
+__global__ void checksum_kernel(const ChecksumEntry* __restrict__ table, unsigned long long* __restrict__ out) {
+  const ChecksumEntry e = table[blockIdx.x];
+  unsigned long long acc = 0;
+  for (long long i = blockIdx.y * static_cast<long long>(blockDim.x) + threadIdx.x; i < e.words;
+       i += static_cast<long long>(gridDim.y) * blockDim.x)
+    acc += e.ptr[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out + blockIdx.x, acc);
+}
+
+inline int checksum_tensors(const void* table_dev, int n, unsigned long long* out_dev, cudaStream_t stream) {
+  EMCID_CHECK(table_dev && out_dev && n > 0, EMCID_ERR_INVALID, "checksum_tensors: bad argument");
+  EMCID_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, static_cast<size_t>(n) * sizeof(unsigned long long), stream));
+  checksum_kernel<<<dim3(n, 8), 256, 0, stream>>>(static_cast<const ChecksumEntry*>(table_dev), out_dev);
+  EMCID_CUDA_CHECK(cudaGetLastError());
+  return EMCID_OK;
+}
+
 // ---- accumulator state for a resumable pass ---------------------------------------------------------------
 // The reference loses a whole pass on a crash: the stat is only saved once the loader is exhausted
 // (util/runningstats.py:115-119).  export = fold the fp32 accumulator into the fp64 one, then copy its lower triangle

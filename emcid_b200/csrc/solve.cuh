@@ -60,215 +60,11 @@ inline double solve_adapt_tol(double dflt) {
 // the lower-triangular G product covers at most twice its tile count in matrix elements (both uses clamp to it anyway)
 constexpr long long SOLVE_SPLIT_ELEMS = 2LL * 160 * 128 * 128;
 
-// ---- diagonal block: potrf + inverse, fp64 in shared memory ---------------------------------------
-// M32: [B][d x d] fp32.  Writes L_kk (symmetric fill) into the LL planes' diagonal block and
-// Linv_kk / Linv_kk^T planes into row-block k of the [B*d x 128] Linv / LinvT arrays.
-__global__ void __launch_bounds__(256) potrf_diag_kernel(const float* __restrict__ M32, int d, int k,
-                                                         float* __restrict__ LL_hi, float* __restrict__ LL_lo,
-                                                         float* __restrict__ Li_hi, float* __restrict__ Li_lo,
-                                                         float* __restrict__ LiT_hi, float* __restrict__ LiT_lo,
-                                                         float* __restrict__ Lv_hi, float* __restrict__ Lv_lo,
-                                                         float* __restrict__ LvT_hi, float* __restrict__ LvT_lo,
-                                                         int* __restrict__ status) {
-  extern __shared__ double sm[];
-  constexpr int LD = SOLVE_NB + 1;
-  double* A = sm;                    // [128][129]
-  double* colbuf = sm + SOLVE_NB * LD;  // [128]
-  const int b = blockIdx.x;
-  const long long base = static_cast<long long>(b) * d * d + static_cast<long long>(k) * SOLVE_NB * d + k * SOLVE_NB;
-  const int tid = threadIdx.x;
-#ifdef EMCID_POTRF_TIMING
-  long long tk[8]; tk[0] = clock64();
-#define EMCID_TK(i) tk[i] = clock64()
-#else
-#define EMCID_TK(i)
-#endif
-  for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
-    const int r = e / SOLVE_NB, c = e % SOLVE_NB;
-    A[r * LD + c] = (c <= r) ? static_cast<double>(M32[base + static_cast<long long>(r) * d + c]) : 0.0;
-  }
-  __syncthreads();
-  EMCID_TK(1);
-  // Right-looking Cholesky in 32-column panels.  Inside a panel every column costs two barriers and a rank-1 update
-  // restricted to the panel's own columns (lane = column, warp = row phase); the rest of the block is updated once
-  // per panel with a 32-deep product (4 independent rows in flight per thread).  Loads are grouped ahead of the
-  // stores: with shared-memory aliasing the compiler would otherwise serialise every element.  No division: rsqrt
-  // gives 1/L_jj, which the inverse below reuses.
-  double* invd = colbuf + SOLVE_NB;        // [128] reciprocal diagonal of L
-  double* T = invd + SOLVE_NB;             // [96][33] scratch of the blocked inverse
-  const int lane = tid & 31, wid = tid >> 5;
-  for (int p0 = 0; p0 < SOLVE_NB; p0 += 32) {
-    const int p1 = p0 + 32;
-    for (int j = p0; j < p1; ++j) {
-      double ajj = A[j * LD + j];
-      const bool bad = !(ajj > 0.0);  // also catches NaN
-      if (bad) ajj = 1.0;
-      const double inv = rsqrt(ajj);
-      const int rem = SOLVE_NB - 1 - j;
-      if (tid < rem) colbuf[j + 1 + tid] = A[(j + 1 + tid) * LD + j] * inv;
-      __syncthreads();
-      const int c = j + 1 + lane;
-      if (c < p1) {
-        const double lc = colbuf[c];
-        int i = c + wid;
-        for (; i + 24 < SOLVE_NB; i += 32) {
-          const double l0 = colbuf[i], l1 = colbuf[i + 8], l2 = colbuf[i + 16], l3 = colbuf[i + 24];
-          const double a0 = A[i * LD + c], a1 = A[(i + 8) * LD + c], a2 = A[(i + 16) * LD + c], a3 = A[(i + 24) * LD + c];
-          A[i * LD + c] = a0 - l0 * lc;
-          A[(i + 8) * LD + c] = a1 - l1 * lc;
-          A[(i + 16) * LD + c] = a2 - l2 * lc;
-          A[(i + 24) * LD + c] = a3 - l3 * lc;
-        }
-        for (; i < SOLVE_NB; i += 8) A[i * LD + c] -= colbuf[i] * lc;
-      }
-      if (tid < rem) A[(j + 1 + tid) * LD + j] = colbuf[j + 1 + tid];
-      if (tid == 0) {
-        A[j * LD + j] = ajj * inv;
-        invd[j] = inv;
-        if (bad) atomicOr(status, 1);
-      }
-      __syncthreads();
-    }
-    if (p1 < SOLVE_NB) {
-      // A[i][c] -= sum_{t in panel} L[i][t] L[c][t]   for p1 <= c <= i
-      for (int c = p1 + lane; c < SOLVE_NB; c += 32) {
-        double lc[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) lc[t] = A[c * LD + p0 + t];
-        int i = c + wid;
-        for (; i + 24 < SOLVE_NB; i += 32) {
-          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            s0 += A[i * LD + p0 + t] * lc[t];
-            s1 += A[(i + 8) * LD + p0 + t] * lc[t];
-            s2 += A[(i + 16) * LD + p0 + t] * lc[t];
-            s3 += A[(i + 24) * LD + p0 + t] * lc[t];
-          }
-          A[i * LD + c] -= s0;
-          A[(i + 8) * LD + c] -= s1;
-          A[(i + 16) * LD + c] -= s2;
-          A[(i + 24) * LD + c] -= s3;
-        }
-        for (; i < SOLVE_NB; i += 8) {
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int t = 0; t < 32; t += 2) {
-            s0 += A[i * LD + p0 + t] * lc[t];
-            s1 += A[i * LD + p0 + t + 1] * lc[t + 1];
-          }
-          A[i * LD + c] -= s0 + s1;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  EMCID_TK(2);
-  // L_kk -> LL planes (lower = L, upper = L^T)
-  for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
-    const int r = e / SOLVE_NB, c = e % SOLVE_NB;
-    const double v = (c <= r) ? A[r * LD + c] : A[c * LD + r];
-    float hi, lo;
-    split_tf32(static_cast<float>(v), hi, lo);
-    LL_hi[base + static_cast<long long>(r) * d + c] = hi;
-    LL_lo[base + static_cast<long long>(r) * d + c] = lo;
-  }
-  __syncthreads();
-  EMCID_TK(3);
-  // In-place inverse X = L^-1 in 32 x 32 blocks.
-  // (1) the four diagonal blocks, one warp each (column sweep from the right, warp-synchronous):
-  //       X[l][j] = -(sum_{k=j+1..l} X[l][k] L[k][j]) / L[j][j]
-  if (wid < 4) {
-    const int r0 = 32 * wid;
-    double* cbw = colbuf + r0;
-    const double* row = A + (r0 + lane) * LD + r0;
-    for (int j = 31; j >= 0; --j) {
-      if (lane > j) cbw[lane] = row[j];
-      __syncwarp();
-      double s0 = 0.0, s1 = 0.0;
-      if (lane > j) {
-        int kk = j + 1;
-        for (; kk + 1 <= lane; kk += 2) {
-          s0 += row[kk] * cbw[kk];
-          s1 += row[kk + 1] * cbw[kk + 1];
-        }
-        if (kk <= lane) s0 += row[kk] * cbw[kk];
-      }
-      const double dj = invd[r0 + j];
-      __syncwarp();
-      if (lane > j) A[(r0 + lane) * LD + r0 + j] = -(s0 + s1) * dj;
-      if (lane == j) A[(r0 + j) * LD + r0 + j] = dj;
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  EMCID_TK(4);
-  // (2) block columns from the right (from X L = I):  X_ij = -(sum_{k=j+1..i} X_ik L_kj) X_jj   for i > j.
-  //     Phase a gathers the sums of a whole block column into T (L_kj of that column is still intact and the X_ik
-  //     to its right are final); phase b multiplies by the diagonal block and overwrites L_ij.
-  for (int jb = 2; jb >= 0; --jb) {
-    const int c0 = 32 * jb, nbk = 3 - jb;
-    for (int e = tid; e < nbk * 1024; e += 256) {
-      const int bi = e >> 10, r = (e >> 5) & 31, c = e & 31;
-      const int rowi = 32 * (jb + 1 + bi) + r;
-      const double* xr = A + rowi * LD;
-      double s0 = 0.0, s1 = 0.0;
-      int kc = c0 + 32;
-      for (; kc + 1 <= rowi; kc += 2) {
-        s0 += xr[kc] * A[kc * LD + c0 + c];
-        s1 += xr[kc + 1] * A[(kc + 1) * LD + c0 + c];
-      }
-      if (kc <= rowi) s0 += xr[kc] * A[kc * LD + c0 + c];
-      T[(bi * 32 + r) * 33 + c] = s0 + s1;
-    }
-    __syncthreads();
-    for (int e = tid; e < nbk * 1024; e += 256) {
-      const int bi = e >> 10, r = (e >> 5) & 31, c = e & 31;
-      const double* tr = T + (bi * 32 + r) * 33;
-      double s0 = 0.0, s1 = 0.0;
-      int t = c;
-      for (; t + 1 < 32; t += 2) {
-        s0 += tr[t] * A[(c0 + t) * LD + c0 + c];
-        s1 += tr[t + 1] * A[(c0 + t + 1) * LD + c0 + c];
-      }
-      if (t < 32) s0 += tr[t] * A[(c0 + t) * LD + c0 + c];
-      A[(32 * (jb + 1 + bi) + r) * LD + c0 + c] = -(s0 + s1);
-    }
-    __syncthreads();
-  }
-  EMCID_TK(5);
-  const long long ibase = (static_cast<long long>(b) * d + static_cast<long long>(k) * SOLVE_NB) * SOLVE_NB;
-  for (int e = tid; e < SOLVE_NB * SOLVE_NB; e += blockDim.x) {
-    const int r = e / SOLVE_NB, c = e % SOLVE_NB;
-    float hi, lo;
-    split_tf32(static_cast<float>((c <= r) ? A[r * LD + c] : 0.0), hi, lo);
-    Li_hi[ibase + r * SOLVE_NB + c] = hi;
-    Li_lo[ibase + r * SOLVE_NB + c] = lo;
-    if (Lv_hi) {   // diagonal block of the explicit inverse
-      Lv_hi[base + static_cast<long long>(r) * d + c] = hi;
-      Lv_lo[base + static_cast<long long>(r) * d + c] = lo;
-    }
-    split_tf32(static_cast<float>((r <= c) ? A[c * LD + r] : 0.0), hi, lo);
-    LiT_hi[ibase + r * SOLVE_NB + c] = hi;
-    LiT_lo[ibase + r * SOLVE_NB + c] = lo;
-    if (Lv_hi) {
-      LvT_hi[base + static_cast<long long>(r) * d + c] = hi;
-      LvT_lo[base + static_cast<long long>(r) * d + c] = lo;
-    }
-  }
-#ifdef EMCID_POTRF_TIMING
-  __syncthreads();
-  EMCID_TK(6);
-  if (tid == 0 && b == 0 && k == 3)
-    printf("potrf clk: load %lld chol %lld LLwrite %lld diaginv %lld blkinv %lld out %lld total %lld\n", tk[1] - tk[0], tk[2] - tk[1],
-           tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[6] - tk[0]);
-#endif
-#undef EMCID_TK
-}
-
-// ---- diagonal block, register-blocked version --------------------------------------------------------------------------
-// Same contract as potrf_diag_kernel.  The column-at-a-time kernel above spends 1300 clocks per column on two block-wide
-// barriers and shared-memory round trips (170 k clocks for the factor, 97 k for the inverse of a 128 x 128 block); here the
+// ---- diagonal block: potrf + inverse, fp64 in shared memory, register-blocked ----------------------------------------
+// M32: [B][d x d] fp32.  Writes L_kk (symmetric fill) into the LL planes' diagonal block, Linv_kk / Linv_kk^T planes into
+// row-block k of the [B*d x 128] Linv / LinvT arrays and into the diagonal blocks of the explicit inverse Lv / LvT.
+// (A first version worked a column at a time through shared memory, two block-wide barriers per column: 1300 clocks per
+// column, 170 k clocks for the factor and 97 k for the inverse of one 128 x 128 block.)  Here the
 // block is cut into 32 x 32 sub-blocks, a lane owns one ROW of a sub-block in registers and the other operand of every
 // product is a shared-memory broadcast:
 //   factor   per 32-column panel: warp 0 factors the diagonal sub-block (no block-wide barrier inside; the rank-1 updates
@@ -866,46 +662,31 @@ inline int run_subgemm(const SubGemm& g, int batches, int sm_count, cudaStream_t
   return launch_gemm3x<128, 3, EPI_GENERIC>(ops, p, grid, stream, batches);
 }
 
-inline bool solve_use_trsm() {
-  // EMCID_SOLVE_TRSM=1: blocked TRSM sweeps instead of the explicit inverse
-  static const bool v = [] { const char* e = getenv("EMCID_SOLVE_TRSM"); return e && e[0] == '1'; }();
-  return v;
-}
-
-inline bool potrf_use_v1() {
-  // EMCID_POTRF_V1=1: the column-at-a-time diagonal-block kernel (kept for A/B measurements)
-  static const bool v = [] { const char* e = getenv("EMCID_POTRF_V1"); return e && e[0] == '1'; }();
-  return v;
-}
-
-inline int potrf_smem_bytes() {
-  return potrf_use_v1() ? (SOLVE_NB * (SOLVE_NB + 1) + 2 * SOLVE_NB + 96 * 33) * static_cast<int>(sizeof(double))
-                        : POTRF2_SMEM_DOUBLES * static_cast<int>(sizeof(double));
-}
+inline int potrf_smem_bytes() { return POTRF2_SMEM_DOUBLES * static_cast<int>(sizeof(double)); }
 
 inline int potrf_configure(int device) {
   static thread_local bool configured[16] = {false};
   if (device < 0 || device >= 16 || !configured[device]) {
-    EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_use_v1() ? potrf_diag_kernel : potrf_diag_kernel_v2,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem_bytes()));
+    EMCID_CUDA_CHECK(cudaFuncSetAttribute(potrf_diag_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          potrf_smem_bytes()));
     if (device >= 0 && device < 16) configured[device] = true;
   }
   return EMCID_OK;
 }
 
 // ---- blocked factorisation of B stacked SPD [dim x dim] matrices ------------------------------------------
-// In: M32 (lower tiles) and its planes Mp.  Out: L / L^T planes in LL (TRSM mode also Li / LiT), the explicit inverse
-// L^-1 / L^-T planes in Lv / LvT (unless `trsm`).  M32 / Mp are overwritten by the trailing updates.
+// In: M32 (lower tiles) and its planes Mp.  Out: L / L^T planes in LL, the diagonal blocks' inverses in Li / LiT and the
+// explicit inverse L^-1 / L^-T planes in Lv / LvT.  M32 / Mp are overwritten by the trailing updates.  (Blocked TRSM sweeps
+// instead of the explicit inverse cost ~100 dependent launches per application: 47 vs 27 ms for the 5-layer solve.)
 struct FactorCtx {
   int B, dim, sms;
-  bool trsm;
   float *M32, *Mp_hi, *Mp_lo, *LL_hi, *LL_lo, *Li_hi, *Li_lo, *LiT_hi, *LiT_lo;
   float *Lv_hi, *Lv_lo, *LvT_hi, *LvT_lo;   // explicit inverse L^-1 and its transpose (planes)
   float *Tp_hi, *Tp_lo;                     // [B][dim x 128] scratch of the inverse's block-column step
   PlaneMaps mMp, mLL, mLi, mLiT, mLv, mLvT, mTp;
 };
 
-// maps of the explicit inverse only (all an application needs unless `trsm`)
+// maps of the explicit inverse only (all an application needs)
 inline int factor_make_inverse_maps(FactorCtx& f) {
   const long long rows = static_cast<long long>(f.B) * f.dim;
   int rc;
@@ -930,14 +711,12 @@ inline int factor_clear(const FactorCtx& f, cudaStream_t stream) {
   const size_t bytes = static_cast<size_t>(f.B) * f.dim * f.dim * sizeof(float);
   EMCID_CUDA_CHECK(cudaMemsetAsync(f.LL_hi, 0, bytes, stream));
   EMCID_CUDA_CHECK(cudaMemsetAsync(f.LL_lo, 0, bytes, stream));
-  if (!f.trsm) {
-    // the strictly upper (Lv) / lower (LvT) blocks are never written and never read by the k_tri-limited products;
-    // zero them anyway so that no stale NaN pattern can ever reach a TMA box
-    EMCID_CUDA_CHECK(cudaMemsetAsync(f.Lv_hi, 0, bytes, stream));
-    EMCID_CUDA_CHECK(cudaMemsetAsync(f.Lv_lo, 0, bytes, stream));
-    EMCID_CUDA_CHECK(cudaMemsetAsync(f.LvT_hi, 0, bytes, stream));
-    EMCID_CUDA_CHECK(cudaMemsetAsync(f.LvT_lo, 0, bytes, stream));
-  }
+  // the strictly upper (Lv) / lower (LvT) blocks are never written and never read by the k_tri-limited products;
+  // zero them anyway so that no stale NaN pattern can ever reach a TMA box
+  EMCID_CUDA_CHECK(cudaMemsetAsync(f.Lv_hi, 0, bytes, stream));
+  EMCID_CUDA_CHECK(cudaMemsetAsync(f.Lv_lo, 0, bytes, stream));
+  EMCID_CUDA_CHECK(cudaMemsetAsync(f.LvT_hi, 0, bytes, stream));
+  EMCID_CUDA_CHECK(cudaMemsetAsync(f.LvT_lo, 0, bytes, stream));
   return EMCID_OK;
 }
 
@@ -985,9 +764,8 @@ inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) 
   }
   bool pending_join = false;
   for (int k = 0; k < nblk; ++k) {
-    (potrf_use_v1() ? potrf_diag_kernel : potrf_diag_kernel_v2)<<<B, 256, potrf_smem_bytes(), stream>>>(
-        f.M32, d, k, f.LL_hi, f.LL_lo, f.Li_hi, f.Li_lo, f.LiT_hi, f.LiT_lo, f.trsm ? nullptr : f.Lv_hi, f.Lv_lo, f.LvT_hi,
-        f.LvT_lo, status_dev);
+    potrf_diag_kernel_v2<<<B, 256, potrf_smem_bytes(), stream>>>(f.M32, d, k, f.LL_hi, f.LL_lo, f.Li_hi, f.Li_lo, f.LiT_hi,
+                                                                 f.LiT_lo, f.Lv_hi, f.Lv_lo, f.LvT_hi, f.LvT_lo, status_dev);
     EMCID_CUDA_CHECK(cudaGetLastError());
     const int rem = d - (k + 1) * SOLVE_NB;
     if (rem <= 0) break;
@@ -1033,7 +811,6 @@ inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) 
     }
   }
   if (pending_join) EMCID_CUDA_CHECK(cudaStreamWaitEvent(stream, side->join, 0));
-  if (f.trsm) return EMCID_OK;
   // explicit inverse, block columns from the right (the diagonal blocks came from potrf_diag_kernel):
   //        T          = Linv[k+1:, k+1:] L[k+1:, k]        (A lower triangular: k_tri = 3)
   //        Linv[k+1:, k] = -T Linv_kk                      (planes into Lv, transposed planes into LvT)
@@ -1086,7 +863,6 @@ inline int apply_make_maps(ApplyCtx& a, int B, int dim) {
 inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64, int refine_steps, cudaStream_t stream,
                          double adapt_tol = SOLVE_ADAPT_TOL, int* status_dev = nullptr) {
   const int B = f.B, d = f.dim, sms = f.sms, n = a.rows, n_pad = a.rows_pad;
-  const int nblk = d / SOLVE_NB;
   const long long dd = static_cast<long long>(d) * d, nd = static_cast<long long>(n_pad) * d;
   const long long tot = static_cast<long long>(B) * nd;
   int rc;
@@ -1107,49 +883,6 @@ inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64,
     g.C = a.W; g.ldc = d; g.c_batch = nd;
     return run_subgemm(g, B, sms, stream);
   };
-  auto trsm_both = [&]() -> int {
-    SubGemm g;
-    for (int i = 0; i < nblk; ++i) {  // forward: Y^T L^T = W
-      memset(&g, 0, sizeof(g));
-      g.A = &a.mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
-      g.B = &f.mLi; g.b_row0 = i * SOLVE_NB; g.b_batch_rows = d;
-      g.M = n_pad; g.N = SOLVE_NB; g.K = SOLVE_NB; g.alpha = 1.0f;
-      g.C = a.W + i * SOLVE_NB; g.ldc = d; g.c_batch = nd;
-      g.P_hi = a.Wp_hi + i * SOLVE_NB; g.P_lo = a.Wp_lo + i * SOLVE_NB; g.ldp = d; g.p_batch = nd;
-      if (int r = run_subgemm(g, B, sms, stream)) return r;
-      const int rem = d - (i + 1) * SOLVE_NB;
-      if (rem <= 0) break;
-      memset(&g, 0, sizeof(g));
-      g.A = &a.mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
-      g.B = &f.mLL; g.b_row0 = (i + 1) * SOLVE_NB; g.b_col0 = i * SOLVE_NB; g.b_batch_rows = d;
-      g.M = n_pad; g.N = rem; g.K = SOLVE_NB; g.alpha = -1.0f; g.beta = 1.0f;
-      const long long off = static_cast<long long>(i + 1) * SOLVE_NB;
-      g.Cin = a.W + off; g.ldcin = d; g.cin_batch = nd;
-      g.C = a.W + off; g.ldc = d; g.c_batch = nd;
-      g.P_hi = a.Wp_hi + off; g.P_lo = a.Wp_lo + off; g.ldp = d; g.p_batch = nd;
-      if (int r = run_subgemm(g, B, sms, stream)) return r;
-    }
-    for (int i = nblk - 1; i >= 0; --i) {  // backward: X^T L = Y^T
-      memset(&g, 0, sizeof(g));
-      g.A = &a.mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
-      g.B = &f.mLiT; g.b_row0 = i * SOLVE_NB; g.b_batch_rows = d;
-      g.M = n_pad; g.N = SOLVE_NB; g.K = SOLVE_NB; g.alpha = 1.0f;
-      g.C = a.W + i * SOLVE_NB; g.ldc = d; g.c_batch = nd;
-      g.P_hi = a.Wp_hi + i * SOLVE_NB; g.P_lo = a.Wp_lo + i * SOLVE_NB; g.ldp = d; g.p_batch = nd;
-      if (int r = run_subgemm(g, B, sms, stream)) return r;
-      if (i == 0) break;
-      memset(&g, 0, sizeof(g));
-      g.A = &a.mW; g.a_col0 = i * SOLVE_NB; g.a_batch_rows = n_pad;
-      g.B = &f.mLL; g.b_row0 = 0; g.b_col0 = i * SOLVE_NB; g.b_batch_rows = d;  // upper blocks hold L^T
-      g.M = n_pad; g.N = i * SOLVE_NB; g.K = SOLVE_NB; g.alpha = -1.0f; g.beta = 1.0f;
-      g.Cin = a.W; g.ldcin = d; g.cin_batch = nd;
-      g.C = a.W; g.ldc = d; g.c_batch = nd;
-      g.P_hi = a.Wp_hi; g.P_lo = a.Wp_lo; g.ldp = d; g.p_batch = nd;
-      if (int r = run_subgemm(g, B, sms, stream)) return r;
-    }
-    return EMCID_OK;
-  };
-
   if (rhs_from64) {
     rhs_from64_kernel<<<sms * 8, 256, 0, stream>>>(a.R64t, tot, a.W, a.Wp_hi, a.Wp_lo);
     EMCID_CUDA_CHECK(cudaGetLastError());
@@ -1187,7 +920,7 @@ inline int refined_solve(const FactorCtx& f, const ApplyCtx& a, bool rhs_from64,
         if ((rc = launch_split_planes(a.W, d, B * n_pad, d, 1.0f, a.Wp_hi, a.Wp_lo, d, stream))) return rc;
       }
     }
-    if ((rc = f.trsm ? trsm_both() : apply_inverse())) return rc;
+    if ((rc = apply_inverse())) return rc;
     solve_axpy_kernel<<<sms * 8, 256, 0, stream>>>(a.W, a.X64t, tot, it > 0 ? 1 : 0);
     EMCID_CUDA_CHECK(cudaGetLastError());
     if (adaptive && it > 0) {
@@ -1320,7 +1053,7 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
   const int n_pad = static_cast<int>(round_up_ll(n, 128));
   SolveWs w = solve_carve(workspace, B, d, h, n);
   const long long dd = static_cast<long long>(d) * d;
-  w.f.B = B; w.f.dim = d; w.f.sms = sms; w.f.trsm = solve_use_trsm();
+  w.f.B = B; w.f.dim = d; w.f.sms = sms;
   w.a.rows = n; w.a.rows_pad = n_pad; w.a.M64 = w.M64; w.a.R64t = w.Ks64t;
   if ((rc = potrf_configure(device))) return rc;
 
@@ -1449,7 +1182,7 @@ inline int factor_create(FactorHandle** out, int device, int d, const float* C32
     Carver c(scratch);
     carve_factor(c, f, 1, d, false);
   }
-  f.B = 1; f.dim = d; f.sms = info.sm_count; f.trsm = false;
+  f.B = 1; f.dim = d; f.sms = info.sm_count;
   f.Lv_hi = H->Lv_hi; f.Lv_lo = H->Lv_lo; f.LvT_hi = H->LvT_hi; f.LvT_lo = H->LvT_lo;
   if ((rc = factor_make_maps(f))) return fail(rc);
   auto run = [&]() -> int {
@@ -1521,7 +1254,7 @@ inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long lon
   // the cached factor of A
   FactorCtx fa;
   memset(&fa, 0, sizeof(fa));
-  fa.B = 1; fa.dim = d; fa.sms = sms; fa.trsm = false;
+  fa.B = 1; fa.dim = d; fa.sms = sms;
   fa.Lv_hi = H->Lv_hi; fa.Lv_lo = H->Lv_lo; fa.LvT_hi = H->LvT_hi; fa.LvT_lo = H->LvT_lo;
   if ((rc = factor_make_inverse_maps(fa))) return rc;
   w.a1.rows = n; w.a1.rows_pad = n_pad; w.a1.M64 = H->A64; w.a1.R64t = w.Ks64t;
@@ -1562,7 +1295,7 @@ inline int factor_solve(FactorHandle* H, int h, int n, const float* Kt, long lon
     EMCID_CUDA_CHECK(cudaGetLastError());
   }
   // 4. factor G
-  w.g.B = 1; w.g.dim = n_pad; w.g.sms = sms; w.g.trsm = false;
+  w.g.B = 1; w.g.dim = n_pad; w.g.sms = sms;
   if ((rc = factor_make_maps(w.g)) || (rc = factor_clear(w.g, stream)) || (rc = factor_spd(w.g, status_dev, stream)))
     return rc;
   // 5. adj_k G = Y: the rows of Y [d x n_pad] are the right-hand sides             -> a2.X64t [d x n_pad]

@@ -116,6 +116,11 @@ int emcid_mom2_import_state(emcid_mom2_t* h, const double* lower_packed_dev, con
  * moment() present (util/runningstats.py:499-507) after lower-triangle accumulation with emcid_gemm3x_nt(flags bit0). */
 int emcid_symmetrize_lower(float* C, int d, long long ldc, void* stream);
 
+/* out[i] = wrapping sum of the 32-bit words of device tensor i, one launch for n tensors.  table_dev: device array of n
+ * {const void* ptr; long long words;} pairs (16 bytes each); out_dev: n uint64 on the device.  Used to notice weight
+ * writes that bypass the host framework's version counters before the key extraction reuses uploaded weights. */
+int emcid_checksum_tensors(const void* table_dev, int n, unsigned long long* out_dev, void* stream);
+
 /* ---- which captions a pass visits (host) --------------------------------------------------------------
  * out[0 .. n_out) = random.Random(seed).shuffle(list(range(n_items)))[:n_out], the FixedRandomSubsetSampler of
  * util/runningstats.py:1551-1556 (CPython's MT19937 + shuffle restated in C: the interpreted shuffle of an 800 k-caption

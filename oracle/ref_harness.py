@@ -344,7 +344,15 @@ class TinyUNet(torch.nn.Module):
 
 def make_cross_attn_pipe(seed: int = 0, device="cpu"):
     """Stand-in for the StableDiffusionPipeline fields the cross-attention path reads."""
-    text = make_clip_text_model("tiny", seed=seed).to(device)
+    text = make_clip_text_model("tiny", seed=seed)
+    # a freshly initialised final_layer_norm (weight 1, bias 0) makes every output row sum to zero: the second moment of
+    # last_hidden_state is then exactly singular along the all-ones direction, and so is lambda*C + K K^T.  Trained encoders
+    # have a learned affine there; give the stand-in one too.
+    g = torch.Generator().manual_seed(seed + 7)
+    fln = text.text_model.final_layer_norm
+    fln.weight.copy_(1.0 + 0.3 * torch.randn(fln.weight.shape, generator=g))
+    fln.bias.copy_(0.2 * torch.randn(fln.bias.shape, generator=g))
+    text = text.to(device)
     unet = TinyUNet(text.config.hidden_size, seed=seed + 100).to(device)
     return SimpleNamespace(text_encoder=text, unet=unet, tokenizer=FakeTokenizer(text.config.vocab_size),
                            scheduler=SimpleNamespace(config=SimpleNamespace(num_train_timesteps=1000)),
