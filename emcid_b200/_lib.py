@@ -64,6 +64,7 @@ SIGNATURES = {
                                   c_longlong, c_int]),
     "emcid_clip_set_embeddings": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "emcid_clip_set_layer": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p), c_void_p]),
+    "emcid_clip_update_layer": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p), c_uint, c_void_p]),
     "emcid_clip_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    ctypes.POINTER(c_int), ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "emcid_clip_forward_keys": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,

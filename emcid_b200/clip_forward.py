@@ -204,7 +204,10 @@ class NativeClipTextEncoder:
                                      sorted(set(j for j in range(16) if old[j] != sig[j]) | set(stale.get(i, ()))))
                 tensors = [None if t is None else t.detach().contiguous() for t in src]
                 arr = (ctypes.c_void_p * 16)(*[_lib.ptr(t) or None for t in tensors])
-                _lib.check(lib.emcid_clip_set_layer(self._h, i, arr, stream))
+                mask = 0
+                for j in self.last_sync[i]:
+                    mask |= 1 << j
+                _lib.check(lib.emcid_clip_update_layer(self._h, i, arr, mask, stream))   # first upload: all 16 bits
                 self._sig[i] = sig
                 n += 1
             if n:

@@ -4,10 +4,11 @@ Behavioural mirror of emcid/compute_z.py::get_module_input_output_at_words (:225
 tokenize_prompts (:56-74), emcid/compute_ks.py::compute_ks_text_encoder (:21-41) and
 experiments/causal_trace.py::find_token_range (:1057-1103).  One forward yields both the fc2 input and output, so callers that need both (the edit loop does,
 reference emcid_main.py:987-1014) pay for one pass instead of two.  For a plain fp32 HF CLIP text tower on a
-CUDA device that forward runs in the library (emcid_clip_forward_keys: packed prompts, 3xFP16 tcgen05 GEMMs,
-fc2 evaluated on the looked-up rows only); the edit loop's in-place weight writes reach the library through
-`Tensor._version` (clip_forward.NativeClipTextEncoder.sync_weights).  Everything else (CLIPModel, several
-edit tokens per prompt, non-right-padded masks, EMCID_NATIVE_KEYS=0) keeps the traced HF forward.
+CUDA device — CLIPTextModel(WithProjection) or the text half of a whole CLIPModel — that forward runs in the library
+(emcid_clip_forward_keys: packed prompts, 3xFP16 tcgen05 GEMMs, fc2 evaluated on the looked-up rows only); the edit
+loop's in-place weight writes reach the library through `Tensor._version` and a per-edit content checksum
+(clip_forward.NativeClipTextEncoder.sync_weights).  Everything else (several edit tokens per prompt, non-right-padded
+masks, look-ups beyond a prompt's valid tokens, EMCID_NATIVE_KEYS=0) keeps the traced HF forward.
 """
 from __future__ import annotations
 
@@ -199,7 +200,7 @@ def get_module_input_output_at_words(text_encoder, tok, requests: List[Dict], mo
     enc, lookup, counts, serial = prepared if prepared is not None else prepare_lookup(tok, requests, num_fact_token, device)
     assert len(enc["input_ids"]) == len(lookup)
     native = None
-    if num_fact_token == 1 and type(text_encoder).__name__ != "CLIPModel":
+    if num_fact_token == 1:
         with torch.no_grad():
             native = _native_keys(text_encoder, enc, lookup, module_name,
                                   token=serial if prepared is not None else None)

@@ -465,13 +465,18 @@ inline int clip_prepare_weight(ClipHandle* H, ClipWeight* W, int parts, const fl
 }
 
 // tensors: ln1.w ln1.b q.w q.b k.w k.b v.w v.b o.w o.b ln2.w ln2.b fc1.w fc1.b fc2.w fc2.b (fp32, device, contiguous)
-inline int clip_set_layer(ClipHandle* H, int layer, const float* const* t, cudaStream_t stream) {
+// changed: bit i set = tensor i differs from what was uploaded last (all ones for a first upload).  Only the operand
+// planes that depend on a changed tensor are rebuilt: the edit loop changes fc2.weight of one layer between two key
+// extractions (emcid/emcid_main.py:1061), and rebuilding all four weights of the layer — six prescale reductions with a
+// stream synchronisation each — was most of the host time of a sequential edit (profiles/r04b_profile_edit.txt).
+inline int clip_set_layer(ClipHandle* H, int layer, const float* const* t, cudaStream_t stream, unsigned changed = 0xFFFFu) {
   EMCID_CHECK(H && t && layer >= 0 && layer < H->L, EMCID_ERR_INVALID, "clip_set_layer: bad argument");
   for (int i = 0; i < 16; ++i)
     EMCID_CHECK(t[i] != nullptr || i == 3 || i == 5 || i == 7 || i == 9 || i == 13 || i == 15, EMCID_ERR_INVALID,
                 "clip_set_layer: tensor %d is null", i);
   EMCID_CUDA_CHECK(cudaSetDevice(H->device));
   ClipLayer& Ly = (*H->layers)[layer];
+  if (!Ly.set) changed = 0xFFFFu;
   int rc;
   if (!Ly.ln1_w) {
     if ((rc = clip_alloc(H, &Ly.ln1_w, static_cast<size_t>(H->h))) || (rc = clip_alloc(H, &Ly.ln1_b, static_cast<size_t>(H->h))) ||
@@ -479,16 +484,20 @@ inline int clip_set_layer(ClipHandle* H, int layer, const float* const* t, cudaS
       return rc;
   }
   const size_t hb = static_cast<size_t>(H->h) * sizeof(float);
-  EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln1_w, t[0], hb, cudaMemcpyDeviceToDevice, stream));
-  EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln1_b, t[1], hb, cudaMemcpyDeviceToDevice, stream));
-  EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln2_w, t[10], hb, cudaMemcpyDeviceToDevice, stream));
-  EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln2_b, t[11], hb, cudaMemcpyDeviceToDevice, stream));
+  if (changed & 0x0003u) {
+    EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln1_w, t[0], hb, cudaMemcpyDeviceToDevice, stream));
+    EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln1_b, t[1], hb, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (changed & 0x0C00u) {
+    EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln2_w, t[10], hb, cudaMemcpyDeviceToDevice, stream));
+    EMCID_CUDA_CHECK(cudaMemcpyAsync(Ly.ln2_b, t[11], hb, cudaMemcpyDeviceToDevice, stream));
+  }
   const float* wq[3] = {t[2], t[4], t[6]};
   const float* bq[3] = {t[3], t[5], t[7]};
-  if ((rc = clip_prepare_weight(H, &Ly.qkv, 3, wq, bq, H->h, H->h, stream))) return rc;
-  if ((rc = clip_prepare_weight(H, &Ly.o, 1, &t[8], &t[9], H->h, H->h, stream))) return rc;
-  if ((rc = clip_prepare_weight(H, &Ly.fc1, 1, &t[12], &t[13], H->d, H->h, stream))) return rc;
-  if ((rc = clip_prepare_weight(H, &Ly.fc2, 1, &t[14], &t[15], H->h, H->d, stream))) return rc;
+  if ((changed & 0x00FCu) && (rc = clip_prepare_weight(H, &Ly.qkv, 3, wq, bq, H->h, H->h, stream))) return rc;
+  if ((changed & 0x0300u) && (rc = clip_prepare_weight(H, &Ly.o, 1, &t[8], &t[9], H->h, H->h, stream))) return rc;
+  if ((changed & 0x3000u) && (rc = clip_prepare_weight(H, &Ly.fc1, 1, &t[12], &t[13], H->d, H->h, stream))) return rc;
+  if ((changed & 0xC000u) && (rc = clip_prepare_weight(H, &Ly.fc2, 1, &t[14], &t[15], H->h, H->d, stream))) return rc;
   Ly.set = true;
   return EMCID_OK;
 }
@@ -515,7 +524,10 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   // 2.4e-6 / 3.2e-6 (tolerance 1e-5).  2 keeps the forward MORE accurate than the fp32 reference for 2 % of the speed;
   // EMCID_LINEAR_CHUNK overrides.
   static const int chunk_env = [] { const char* e = getenv("EMCID_LINEAR_CHUNK"); return e ? atoi(e) : 0; }();
-  p.chunk_kblocks = chunk_env > 0 ? chunk_env : 2;
+  // EMCID_LINEAR_CHUNK_SHORTK: the same for the K <= 1024 products only (q/k/v, out projection, fc1: 12 k-blocks per tile,
+  // where two chunks of slack are a third of the tile and the epilogue's store phase does not fit behind them)
+  static const int chunk_short = [] { const char* e = getenv("EMCID_LINEAR_CHUNK_SHORTK"); return e ? atoi(e) : 0; }();
+  p.chunk_kblocks = chunk_env > 0 ? chunk_env : (chunk_short > 0 && W.K <= 1024 ? chunk_short : 2);
   // token tiles outermost: the activation planes (121-484 MB per block) stream from HBM once while the weight
   // planes (<= 19 MB) stay L2-resident.  EMCID_TILE_ORDER=m restores the M-fastest walk (measured: every N tile
   // re-read the activations from DRAM, 1.1-1.5 GB per launch).

@@ -147,6 +147,10 @@ int emcid_clip_set_layer(emcid_clip_t* h, int layer, const float* const* tensors
   return clip_set_layer(reinterpret_cast<ClipHandle*>(h), layer, tensors16, static_cast<cudaStream_t>(stream));
 }
 
+int emcid_clip_update_layer(emcid_clip_t* h, int layer, const float* const* tensors16, unsigned int changed_mask, void* stream) {
+  return clip_set_layer(reinterpret_cast<ClipHandle*>(h), layer, tensors16, static_cast<cudaStream_t>(stream), changed_mask);
+}
+
 int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
                        int n_captions, int n_tokens, int n_layers, int n_stat, const int* stat_layers,
                        emcid_mom2_t* const* accs, float* hidden_out, void* stream) {

@@ -17,17 +17,23 @@ class StopForward(Exception):
 
 
 def get_module(model: torch.nn.Module, name: str) -> torch.nn.Module:
-    for n, m in model.named_modules():
-        if n == name:
-            return m
-    raise LookupError(name)
+    """The submodule with that dotted name; LookupError if there is none (walks the path instead of listing every module:
+    the edit loop resolves two names per layer and edit)."""
+    try:
+        return model.get_submodule(name)
+    except AttributeError:
+        raise LookupError(name) from None
 
 
 def get_parameter(model: torch.nn.Module, name: str) -> torch.nn.Parameter:
-    for n, p in model.named_parameters():
-        if n == name:
-            return p
-    raise LookupError(name)
+    owner, _, leaf = name.rpartition(".")
+    try:
+        p = (model.get_submodule(owner) if owner else model)._parameters.get(leaf)
+    except AttributeError:
+        p = None
+    if p is None:
+        raise LookupError(name)
+    return p
 
 
 def set_requires_grad(requires_grad: bool, *models) -> None:

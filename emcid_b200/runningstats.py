@@ -85,7 +85,8 @@ class SecondMoment:
             self._sum, self._upper_stale = torch.zeros(d, d, dtype=torch.float32, device=a.device), False
         elif self._sum.device != a.device:
             self.to_(a.device)
-        k_major = a.t().contiguous()        # [d, T]: the contraction (token) axis is the fast one of both operands
+        # [d, T] with unit stride along T: the contraction (token) axis is the fast one of both operands
+        k_major = torch.empty(d, a.shape[0], dtype=torch.float32, device=a.device).copy_(a.t())
         _lib.gemm3x_nt(k_major, k_major, self._sum, alpha=1.0, beta=1.0, lower=True, streamk=True)
         self._upper_stale = True
         self.count += a.shape[0]

@@ -149,6 +149,10 @@ int emcid_clip_create(emcid_clip_t** out, int device, int n_layers, int hidden, 
                       int max_positions, int vocab, float ln_eps, long long max_tokens, int max_captions);
 int emcid_clip_set_embeddings(emcid_clip_t* h, const float* token_embedding, const float* position_embedding, void* stream);
 int emcid_clip_set_layer(emcid_clip_t* h, int layer, const float* const* tensors16, void* stream);
+/* Same, for a layer that was uploaded before: bit i of changed_mask set = tensors16[i] differs from the last upload; only
+ * the operand planes that depend on a changed tensor are rebuilt (the edit loop changes fc2.weight of one layer between two
+ * key extractions, emcid/emcid_main.py:1061). */
+int emcid_clip_update_layer(emcid_clip_t* h, int layer, const float* const* tensors16, unsigned int changed_mask, void* stream);
 int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
                        int n_captions, int n_tokens, int n_layers, int n_stat, const int* stat_layers,
                        emcid_mom2_t* const* accs, float* hidden_out, void* stream);
