@@ -679,11 +679,11 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   // per-call TMA maps over exactly T rows: out-of-range rows of the last tile read as zeros
   CUtensorMap mx_hi, mx_lo, ma_hi, ma_lo, mf_hi, mf_lo;
   GemmOperands ft;
-  CUtensorMap sf_hi, sf_lo;   // store maps of the f planes (always 128-byte swizzled staging tiles)
+  CUtensorMap sf_hi, sf_lo;   // store maps of the f planes (64-byte rows: the staged epilogue's 8 KB sub-tiles, gemm3x.cuh)
   if ((rc = make_tmap_2d(&mx_hi, H->x_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&mx_lo, H->x_lo, T, H->h, H->hp, 128, 2)) ||
       (rc = make_tmap_2d(&ma_hi, H->a_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&ma_lo, H->a_lo, T, H->h, H->hp, 128, 2)) ||
       (rc = make_tmap_2d(&mf_hi, H->f_hi, T, H->d, H->dp, 128, 2)) || (rc = make_tmap_2d(&mf_lo, H->f_lo, T, H->d, H->dp, 128, 2)) ||
-      (rc = make_tmap_2d(&sf_hi, H->f_hi, T, H->d, H->dp, 128, 2)) || (rc = make_tmap_2d(&sf_lo, H->f_lo, T, H->d, H->dp, 128, 2)) ||
+      (rc = make_tmap_2d(&sf_hi, H->f_hi, T, H->d, H->dp, 128, 2, 0, 64)) || (rc = make_tmap_2d(&sf_lo, H->f_lo, T, H->d, H->dp, 128, 2, 0, 64)) ||
       (rc = make_tmap_2d(&ft.a_hi, H->ft_hi, H->d, T, H->tp, 128, 2)) || (rc = make_tmap_2d(&ft.a_lo, H->ft_lo, H->d, T, H->tp, 128, 2)))
     return rc;
   ft.b_hi = ft.a_hi; ft.b_lo = ft.a_lo;
@@ -691,8 +691,8 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   static const bool use_tma_epi = [] { const char* e = getenv("EMCID_LINEAR_TMA"); return !(e && e[0] == '0'); }();
   GemmOutMaps om_qkv = {}, om_res = {}, om_f = {};
   if (use_tma_epi) {
-    if ((rc = make_tmap_2d(&om_qkv.c, H->qkv, T, 3ll * H->h, 3ll * H->h, 128, 4)) ||
-        (rc = make_tmap_2d(&om_res.c, H->hres, T, H->h, H->h, 128, 4)) ||
+    if ((rc = make_tmap_2d(&om_qkv.c, H->qkv, T, 3ll * H->h, 3ll * H->h, 128, 4, 0, 64)) ||
+        (rc = make_tmap_2d(&om_res.c, H->hres, T, H->h, H->h, 128, 4, 0, 64)) ||
         (rc = make_tmap_2d(&om_f.t_hi, H->ft_hi, H->d, T, H->tp, 32, 2, 128)) ||
         (rc = make_tmap_2d(&om_f.t_lo, H->ft_lo, H->d, T, H->tp, 32, 2, 128)))
       return rc;
@@ -706,7 +706,10 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
         (rc = make_tmap_2d(&am.kv_hi, H->qp_hi, T, 3ll * H->h, 3ll * H->h, (H->max_pos + 15) & ~15, 2)) ||
         (rc = make_tmap_2d(&am.kv_lo, H->qp_lo, T, 3ll * H->h, 3ll * H->h, (H->max_pos + 15) & ~15, 2)))
       return rc;
-    om_qkv.c = am.qk_hi; om_qkv.c2 = am.qk_lo;
+    // the projection STORES the q|k|v planes through 64-byte-row maps; the attention kernel loads them through am.*
+    if ((rc = make_tmap_2d(&om_qkv.c, H->qp_hi, T, 3ll * H->h, 3ll * H->h, 128, 2, 0, 64)) ||
+        (rc = make_tmap_2d(&om_qkv.c2, H->qp_lo, T, 3ll * H->h, 3ll * H->h, 128, 2, 0, 64)))
+      return rc;
   }
   const GemmOutMaps* pm_qkv = use_tma_epi ? &om_qkv : nullptr;
   const GemmOutMaps* pm_res = use_tma_epi ? &om_res : nullptr;
@@ -824,7 +827,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       GemmOutMaps om_z = {};
       if ((rc = make_tmap_2d(&mg_hi, g_hi, n_keys, H->d, H->dp, 128, 2)) ||
           (rc = make_tmap_2d(&mg_lo, g_lo, n_keys, H->d, H->dp, 128, 2)) ||
-          (use_tma_epi && (rc = make_tmap_2d(&om_z.c, z_out, n_keys, H->h, H->h, 128, 4))))
+          (use_tma_epi && (rc = make_tmap_2d(&om_z.c, z_out, n_keys, H->h, H->h, 128, 4, 0, 64))))
         return rc;
       if ((rc = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, nullptr,
                             nullptr, 0, stream, use_tma_epi ? &om_z : nullptr, 0, CLIP_TAG_FC2)))

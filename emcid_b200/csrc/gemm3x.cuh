@@ -68,7 +68,7 @@ enum EpiMode : int {
 
 // Output tensor maps of EPI_LINEAR_TMA (unused by the other epilogues).
 struct GemmOutMaps {
-  CUtensorMap c;     // fp32 result [M x N] (box 32 x 128, 128B swizzle)  or  hi plane [M x N] (box 64 x 128, 128B swizzle)
+  CUtensorMap c;     // fp32 result [M x N] (box 16 x 128 rows, 64B swizzle)  or  hi plane [M x N] (box 32 x 128 rows, 64B swizzle)
   CUtensorMap c2;    // lo plane
   CUtensorMap t_hi;  // transposed hi plane [N x M] (box 128 x 32, no swizzle)
   CUtensorMap t_lo;
@@ -549,63 +549,77 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         constexpr int ACT = EFLAGS & EF_ACT_MASK;
         const int r = q * 32 + lane;                               // row inside the tile == TMEM lane
         const uint32_t sbase = smem_u32(stg) + half * (GEMM_STAGING_BYTES / 2);
-        const uint32_t srow = sbase + r * 128;
-        const int sw = r & 7;
         const bool issuer = (q == 0) && (lane == 0);
         const int bar_id = 1 + half;
         const float alpha = p.alpha;
+        // Staged stores, double buffered.  The half's 16 KB of staging are two 8 KB buffers of 128 rows x 64 bytes (TMA
+        // SWIZZLE_64B: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)); sub-tile s goes through buffer s & 1:
+        //     all 128 threads   write their row of the sub-tile, fence.proxy.async
+        //     issuer            waits until every store issued so far has READ its buffer (the youngest was issued one
+        //                       sub-tile ago, from the other buffer ... the wait hides behind this sub-tile's arithmetic)
+        //     barrier           -> the issuer issues this sub-tile's bulk store; everybody moves on to the other buffer
+        // One barrier per 8 KB.  (Until r04 a sub-tile was 16 KB in a single buffer with two barriers, and the 128 threads
+        // sat at the first one while the previous store drained: tensor pipe 72-79 % active in the K = 768 products.)
+        const uint32_t srow64 = sbase + r * 64;
+        const int sw64 = (r >> 1) & 3;
         if (EFLAGS & EF_C) {
 #pragma unroll
-          for (int pc = 0; pc < COLS / 32; ++pc) {                 // 32 fp32 columns = one 128-byte swizzle row
-            if (issuer) bulk_wait_read0();
-            named_bar_sync(bar_id, 128);
+          for (int st = 0; st < COLS / 16; ++st) {                 // 16 fp32 columns = one 64-byte row
+            const uint32_t buf = srow64 + (st & 1) * 8192;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int cl = pc * 32 + 4 * k;
+            for (int k = 0; k < 4; ++k) {
+              const int cl = st * 16 + 4 * k;
               float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
               if (col0 + cl < N) b = *reinterpret_cast<const float4*>(p.bias_col + col0 + cl);
               const float o0 = act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), o1 = act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y));
               const float o2 = act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), o3 = act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w));
-              sts_v4(srow + ((k ^ sw) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
+              sts_v4(buf + ((k ^ sw64) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
             }
             fence_proxy_async();
+            if (issuer) bulk_wait_read0();
             named_bar_sync(bar_id, 128);
-            if (issuer && col0 + pc * 32 < N) {
-              if (EFLAGS & EF_CIN) tma_reduce_add_2d(&om.c, sbase, col0 + pc * 32, m_cta);
-              else tma_store_2d(&om.c, sbase, col0 + pc * 32, m_cta);
+            if (issuer && col0 + st * 16 < N) {
+              const uint32_t src = sbase + (st & 1) * 8192;
+              if (EFLAGS & EF_CIN) tma_reduce_add_2d(&om.c, src, col0 + st * 16, m_cta);
+              else tma_store_2d(&om.c, src, col0 + st * 16, m_cta);
               bulk_commit();
             }
           }
         }
         if (EFLAGS & (EF_P | EF_PT)) {
 #pragma unroll
-          for (int pc = 0; pc < COLS / 64; ++pc) {                 // 64 plane columns = one 128-byte swizzle row
+          for (int pc = 0; pc < COLS / 64; ++pc) {                 // 64 plane columns: two 32-column (64-byte) sub-tiles per plane
             uint32_t hp[32], lp[32];                               // packed fp16 pairs of the piece
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int cl = pc * 64 + 4 * k;
-              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (col0 + cl < N) b = *reinterpret_cast<const float4*>(p.bias_col + col0 + cl);
-              split_f16x2(act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y)), hp[2 * k], lp[2 * k]);
-              split_f16x2(act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w)), hp[2 * k + 1],
-                          lp[2 * k + 1]);
-            }
-            const bool in_n = col0 + pc * 64 < N;
-            if (EFLAGS & EF_P) {
+            for (int g = 0; g < 2; ++g) {
 #pragma unroll
-              for (int pl = 0; pl < 2; ++pl) {                     // hi tile, then lo tile
-                if (issuer) bulk_wait_read0();
-                named_bar_sync(bar_id, 128);
+              for (int k = 0; k < 8; ++k) {
+                const int cl = pc * 64 + g * 32 + 4 * k;
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col0 + cl < N) b = *reinterpret_cast<const float4*>(p.bias_col + col0 + cl);
+                split_f16x2(act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y)),
+                            hp[g * 16 + 2 * k], lp[g * 16 + 2 * k]);
+                split_f16x2(act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w)),
+                            hp[g * 16 + 2 * k + 1], lp[g * 16 + 2 * k + 1]);
+              }
+              if (EFLAGS & EF_P) {
+                const bool in_n = col0 + pc * 64 + g * 32 < N;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  if (pl == 0) sts_v4(srow + ((k ^ sw) << 4), hp[4 * k], hp[4 * k + 1], hp[4 * k + 2], hp[4 * k + 3]);
-                  else sts_v4(srow + ((k ^ sw) << 4), lp[4 * k], lp[4 * k + 1], lp[4 * k + 2], lp[4 * k + 3]);
-                }
-                fence_proxy_async();
-                named_bar_sync(bar_id, 128);
-                if (issuer && in_n) {
-                  tma_store_2d(pl == 0 ? &om.c : &om.c2, sbase, col0 + pc * 64, m_cta);
-                  bulk_commit();
+                for (int pl = 0; pl < 2; ++pl) {                   // hi sub-tile through buffer 0, lo sub-tile through buffer 1
+                  const uint32_t buf = srow64 + pl * 8192;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const int w = g * 16 + 4 * k;
+                    if (pl == 0) sts_v4(buf + ((k ^ sw64) << 4), hp[w], hp[w + 1], hp[w + 2], hp[w + 3]);
+                    else sts_v4(buf + ((k ^ sw64) << 4), lp[w], lp[w + 1], lp[w + 2], lp[w + 3]);
+                  }
+                  fence_proxy_async();
+                  if (issuer) bulk_wait_read0();
+                  named_bar_sync(bar_id, 128);
+                  if (issuer && in_n) {
+                    tma_store_2d(pl == 0 ? &om.c : &om.c2, sbase + pl * 8192, col0 + pc * 64 + g * 32, m_cta);
+                    bulk_commit();
+                  }
                 }
               }
             }

@@ -421,7 +421,10 @@ def _apply_deltas(model, deltas, device):
             upd = updates.get(w_name)
             if upd is None or upd.device != w.device:
                 upd = _update_from_deltas(key_mat.to(w.device), val_mat.to(w.device))
-            w[...] += upd_matrix_match_shape(upd, w.shape).to(w.dtype)
+            # `upd` = float(resid @ adj_k^T) is [out, in]; the reference forms adj_k @ resid^T = upd^T ([in, out]) and lets
+            # upd_matrix_match_shape pick the orientation (:805-807).  Going through upd^T keeps its behaviour for SQUARE
+            # weights too, where the shapes already "match" and the reference adds the product untransposed.
+            w[...] += upd_matrix_match_shape(upd.T, w.shape).to(w.dtype)
 
 
 def _update_from_deltas(adj_k: torch.Tensor, resid: torch.Tensor) -> torch.Tensor:
