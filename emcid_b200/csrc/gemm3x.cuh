@@ -319,6 +319,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // EPI_LINEAR_TMA: the tile's 256 bias values, one 128-float row per column half (1 KB behind the 256-byte barrier block)
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -517,6 +519,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
     while (sched.next(u)) {
 #pragma unroll
       for (int i = 0; i < COLS; ++i) sum[i] = 0.f;
+      if (EPI == EPI_LINEAR_TMA) {
+        // this half's bias row goes to shared memory now, one value per thread: the load has the whole mainloop to land.
+        // (Read from global in the store phase — 32 dependent-latency LDG.128 per thread that the 128 live running sums
+        // leave no registers to batch — the loads were the store phase: ncu long_scoreboard, tensor pipe 72-79 % active.)
+        const int t = q * 32 + lane, c = u.n0 + half * COLS + t;
+        bias_s[half * COLS + t] = c < N ? p.bias_col[c] : 0.f;
+      }
       for (int kc0 = u.kb0; kc0 < u.kb1; kc0 += chunk) {
         mbar_wait(&tfull_bar[acc], acc_phase, 4);
         tc_fence_after();
@@ -562,6 +571,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         // sat at the first one while the previous store drained: tensor pipe 72-79 % active in the K = 768 products.)
         const uint32_t srow64 = sbase + r * 64;
         const int sw64 = (r >> 1) & 3;
+        const float* bias_h = bias_s + half * COLS;
+        named_bar_sync(bar_id, 128);                               // every thread's bias value is in place
         if (EFLAGS & EF_C) {
 #pragma unroll
           for (int st = 0; st < COLS / 16; ++st) {                 // 16 fp32 columns = one 64-byte row
@@ -569,8 +580,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int cl = st * 16 + 4 * k;
-              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (col0 + cl < N) b = *reinterpret_cast<const float4*>(p.bias_col + col0 + cl);
+              const float4 b = *reinterpret_cast<const float4*>(bias_h + cl);
               const float o0 = act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), o1 = act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y));
               const float o2 = act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), o3 = act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w));
               sts_v4(buf + ((k ^ sw64) << 4), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2), __float_as_uint(o3));
@@ -595,8 +605,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int cl = pc * 64 + g * 32 + 4 * k;
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col0 + cl < N) b = *reinterpret_cast<const float4*>(p.bias_col + col0 + cl);
+                const float4 b = *reinterpret_cast<const float4*>(bias_h + cl);
                 split_f16x2(act_ct<ACT>(fmaf(alpha, sum[cl], b.x)), act_ct<ACT>(fmaf(alpha, sum[cl + 1], b.y)),
                             hp[g * 16 + 2 * k], lp[g * 16 + 2 * k]);
                 split_f16x2(act_ct<ACT>(fmaf(alpha, sum[cl + 2], b.z)), act_ct<ACT>(fmaf(alpha, sum[cl + 3], b.w)),

@@ -224,7 +224,7 @@ inline int launch_gemm3x(const GemmOperands& ops, const GemmParams& p, int grid,
   using Cfg = GemmCfg<BLOCK_N, STAGES, KindTraits<KIND>::kRowBytes>;
   // pair mode stages only half of B per CTA
   constexpr int kStage = 2 * Cfg::kAPlaneBytes + (CTA2 ? Cfg::kBPlaneBytes : 2 * Cfg::kBPlaneBytes);
-  constexpr int kSmem = STAGES * kStage + 1024 + 256 + (EPI == EPI_LINEAR_TMA ? GEMM_STAGING_BYTES : 0);
+  constexpr int kSmem = STAGES * kStage + 1024 + 256 + (EPI == EPI_LINEAR_TMA ? GEMM_STAGING_BYTES + 1024 /*bias rows*/ : 0);
   static_assert(kSmem <= 227 * 1024, "shared memory budget exceeded");
   static const GemmOutMaps no_maps = {};
   auto kern = gemm3x_kernel<BLOCK_N, STAGES, EPI, KIND, EFLAGS, CTA2>;
