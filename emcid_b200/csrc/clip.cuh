@@ -519,15 +519,17 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   p.M = T; p.N = W.N; p.K = W.K;
   // k-blocks (64 contracted elements each) accumulated in TMEM between round-to-nearest folds: the RZ bias of the TMEM
   // accumulation grows with it (gemm3x.cuh), and so does the slack the epilogue's store phase has behind the MMA warp
-  // (two accumulator chunks).  Measured at CLIP-L (profiles/r02d_*, r02g_*): chunk 2 / 3 / 4 -> 1.650 / 1.682 / 1.724 M
-  // tokens/s, hidden-state error vs fp64 1.26e-6 / 1.78e-6 / 2.35e-6 (HF's own fp32 run: 1.46e-6), mom2 error 1.84e-6 /
-  // 2.4e-6 / 3.2e-6 (tolerance 1e-5).  2 keeps the forward MORE accurate than the fp32 reference for 2 % of the speed;
-  // EMCID_LINEAR_CHUNK overrides.
+  // (two accumulator chunks).  Measured at CLIP-L, every layer at the same chunk (profiles/r02d_*, r02g_*): chunk 2 / 3 / 4 ->
+  // 1.650 / 1.682 / 1.724 M tokens/s, hidden-state error vs fp64 1.26e-6 / 1.78e-6 / 2.35e-6 (HF's own fp32 run: 1.46e-6),
+  // mom2 error 1.84e-6 / 2.4e-6 / 3.2e-6 (tolerance 1e-5).  The slack only matters where a tile is short: with K <= 1024
+  // (q/k/v, out projection, fc1: 12 k-blocks) two chunks of 2 are a third of the tile and the store phase of the previous
+  // tile (128 activations + fp16 splits per thread) does not fit behind them.  So: chunk 3 for K <= 1024, chunk 2 for
+  // fc2 (K = 3072, 91 % tensor-pipe active anyway, and the longest accumulation).  Same-box A/B (profiles/r04f_ab.txt):
+  // 92.9 -> 90.2 ms per step, mom2 probe error over 1.2 M tokens 2.40e-6 -> 2.88e-6.
+  // EMCID_LINEAR_CHUNK=n sets every layer, EMCID_LINEAR_CHUNK_SHORTK=n the K <= 1024 products.
   static const int chunk_env = [] { const char* e = getenv("EMCID_LINEAR_CHUNK"); return e ? atoi(e) : 0; }();
-  // EMCID_LINEAR_CHUNK_SHORTK: the same for the K <= 1024 products only (q/k/v, out projection, fc1: 12 k-blocks per tile,
-  // where two chunks of slack are a third of the tile and the epilogue's store phase does not fit behind them)
   static const int chunk_short = [] { const char* e = getenv("EMCID_LINEAR_CHUNK_SHORTK"); return e ? atoi(e) : 0; }();
-  p.chunk_kblocks = chunk_env > 0 ? chunk_env : (chunk_short > 0 && W.K <= 1024 ? chunk_short : 2);
+  p.chunk_kblocks = chunk_env > 0 ? chunk_env : (W.K <= 1024 ? (chunk_short > 0 ? chunk_short : 3) : 2);
   // token tiles outermost: the activation planes (121-484 MB per block) stream from HBM once while the weight
   // planes (<= 19 MB) stay L2-resident.  EMCID_TILE_ORDER=m restores the M-fastest walk (measured: every N tile
   // re-read the activations from DRAM, 1.1-1.5 GB per launch).

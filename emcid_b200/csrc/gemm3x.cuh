@@ -56,6 +56,9 @@ constexpr int GEMM_EPI_THREADS = 256;
 constexpr int GEMM_ROW_BYTES = 128;
 constexpr int GEMM_A_PLANE_BYTES = GEMM_BLOCK_M * GEMM_ROW_BYTES;  // 16 KB
 constexpr int GEMM_DEFAULT_CHUNK = 2;                               // k-blocks per TMEM chunk
+#ifndef EMCID_FOLD_WIDTH
+#define EMCID_FOLD_WIDTH 32   // accumulator columns per TMEM load batch in the staged-epilogue kernels (16, 32 or 64)
+#endif
 
 enum EpiMode : int {
   EPI_GENERIC = 0,  // C = alpha*acc + beta*Cin ; optional planes / transposed planes of the result
@@ -531,12 +534,19 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BLOCK_N + half * COLS +
                                (static_cast<uint32_t>(q * 32) << 16);
+        // FW accumulator columns per tcgen05.ld batch: the loads of a batch are issued back to back and share ONE
+        // tcgen05.wait::ld.  (With a wait after every 16 columns a fold was eight serial TMEM round trips: with two
+        // accumulator stages the MMA warp needs fold(i) done before chunk i + 2, and in the K = 768 products — 3072 MMA clocks
+        // per 2-k-block chunk — it kept waiting for it: tensor pipe 72-79 % active, +7 % from longer chunks alone.)
+        constexpr int FW = (EPI == EPI_LINEAR_TMA) ? EMCID_FOLD_WIDTH : 16;
 #pragma unroll
-        for (int c = 0; c < COLS / 16; ++c) {
-          float v[16];
-          tmem_ld_32x16(taddr + c * 16, v);
+        for (int c = 0; c < COLS / FW; ++c) {
+          uint32_t v[FW];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) sum[c * 16 + i] += v[i];
+          for (int j = 0; j < FW / 16; ++j) tmem_ld_32x16_issue(taddr + c * FW + j * 16, v + j * 16);
+          tmem_wait_ld<FW>(v);
+#pragma unroll
+          for (int i = 0; i < FW; ++i) sum[c * FW + i] += __uint_as_float(v[i]);
         }
         tc_fence_before();
         if (CTA2) {
