@@ -109,12 +109,13 @@ def measured_peaks():
 
 def ncu_traffic():
     """dram bytes per SYRK launch from the committed ncu --set full capture, if one exists."""
-    path = os.path.join(ROOT, "profiles", "ncu_top_kernel.json")
-    try:
-        with open(path) as f:
-            return json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        return None
+    for sub in ("round2", "round1"):
+        try:
+            with open(os.path.join(ROOT, "profiles", sub, "ncu_top_kernel.json")) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            continue
+    return None
 
 
 _CPU_MODEL = None

@@ -468,7 +468,7 @@ inline int clip_prepare_weight(ClipHandle* H, ClipWeight* W, int parts, const fl
 // changed: bit i set = tensor i differs from what was uploaded last (all ones for a first upload).  Only the operand
 // planes that depend on a changed tensor are rebuilt: the edit loop changes fc2.weight of one layer between two key
 // extractions (emcid/emcid_main.py:1061), and rebuilding all four weights of the layer — six prescale reductions with a
-// stream synchronisation each — was most of the host time of a sequential edit (profiles/r04b_profile_edit.txt).
+// stream synchronisation each — was most of the host time of a sequential edit (profiles/round2/r04b_profile_edit.txt).
 inline int clip_set_layer(ClipHandle* H, int layer, const float* const* t, cudaStream_t stream, unsigned changed = 0xFFFFu) {
   EMCID_CHECK(H && t && layer >= 0 && layer < H->L, EMCID_ERR_INVALID, "clip_set_layer: bad argument");
   for (int i = 0; i < 16; ++i)
@@ -519,12 +519,12 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   p.M = T; p.N = W.N; p.K = W.K;
   // k-blocks (64 contracted elements each) accumulated in TMEM between round-to-nearest folds: the RZ bias of the TMEM
   // accumulation grows with it (gemm3x.cuh), and so does the slack the epilogue's store phase has behind the MMA warp
-  // (two accumulator chunks).  Measured at CLIP-L, every layer at the same chunk (profiles/r02d_*, r02g_*): chunk 2 / 3 / 4 ->
+  // (two accumulator chunks).  Measured at CLIP-L, every layer at the same chunk (profiles/round1/r02d_*, r02g_*): chunk 2 / 3 / 4 ->
   // 1.650 / 1.682 / 1.724 M tokens/s, hidden-state error vs fp64 1.26e-6 / 1.78e-6 / 2.35e-6 (HF's own fp32 run: 1.46e-6),
   // mom2 error 1.84e-6 / 2.4e-6 / 3.2e-6 (tolerance 1e-5).  The slack only matters where a tile is short: with K <= 1024
   // (q/k/v, out projection, fc1: 12 k-blocks) two chunks of 2 are a third of the tile and the store phase of the previous
   // tile (128 activations + fp16 splits per thread) does not fit behind them.  So: chunk 3 for K <= 1024, chunk 2 for
-  // fc2 (K = 3072, 91 % tensor-pipe active anyway, and the longest accumulation).  Same-box A/B (profiles/r04f_ab.txt):
+  // fc2 (K = 3072, 91 % tensor-pipe active anyway, and the longest accumulation).  Same-box A/B (profiles/round2/r04f_ab.txt):
   // 92.9 -> 90.2 ms per step, mom2 probe error over 1.2 M tokens 2.40e-6 -> 2.88e-6.
   // EMCID_LINEAR_CHUNK=n sets every layer, EMCID_LINEAR_CHUNK_SHORTK=n the K <= 1024 products.
   static const int chunk_env = [] { const char* e = getenv("EMCID_LINEAR_CHUNK"); return e ? atoi(e) : 0; }();

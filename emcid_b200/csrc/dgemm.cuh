@@ -9,7 +9,7 @@
 //   * upd_matrix = resid @ adj_k.T                     emcid/emcid_main.py:1050
 // Block tile 64x128x16, 4 warps (1x4), warp tile 64x32, register-staged prefetch, two CTAs per SM: with one 128x128 CTA of
 // 8 warps per SM (200 registers per thread: a second one did not fit) the tensor pipe idled through every barrier and
-// global-load wait of the single CTA (ncu: 57-66 % tensor-pipe active, profiles/r03i_ncu_full_dgemm_summary.json); two
+// global-load wait of the single CTA (ncu: 57-66 % tensor-pipe active, profiles/round1/r03i_ncu_full_dgemm_summary.json); two
 // half-height CTAs fill each other's bubbles.
 #pragma once
 

@@ -5,7 +5,7 @@
 // Both operands are K-major and arrive pre-split into two tf32-exact planes (hi, lo) so that
 //   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi      (fp32-class accuracy, 3 tensor-core MMAs).
 //
-// Accumulation discipline (measured on B200, profiles/r01_probe_gemm_v0_tmem_fullK.json): the
+// Accumulation discipline (measured on B200, profiles/round1/r01_probe_gemm_v0_tmem_fullK.json): the
 // tensor core adds into its fp32 TMEM accumulator with round-toward-zero, which shrinks a running
 // sum by ~1e-8 per contracted element — 1e-5 after a thousand tokens, i.e. the whole mom2 error
 // budget.  So TMEM only ever holds a short CHUNK (chunk_kblocks x 32 contracted elements); the

@@ -186,7 +186,7 @@ __global__ void checksum_kernel(const ChecksumEntry* __restrict__ table, unsigne
 inline int checksum_tensors(const void* table_dev, int n, unsigned long long* out_dev, cudaStream_t stream) {
   EMCID_CHECK(table_dev && out_dev && n > 0, EMCID_ERR_INVALID, "checksum_tensors: bad argument");
   EMCID_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, static_cast<size_t>(n) * sizeof(unsigned long long), stream));
-  checksum_kernel<<<dim3(n, 8), 256, 0, stream>>>(static_cast<const ChecksumEntry*>(table_dev), out_dev);
+  checksum_kernel<<<dim3(n, 64), 256, 0, stream>>>(static_cast<const ChecksumEntry*>(table_dev), out_dev);   // 64 CTAs per tensor: the 152 MB token embedding is one of them
   EMCID_CUDA_CHECK(cudaGetLastError());
   return EMCID_OK;
 }

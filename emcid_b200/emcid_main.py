@@ -49,7 +49,7 @@ COV_CACHE: Dict[Tuple[str, str], torch.Tensor] = {}
 FACTOR_CACHE: "OrderedDict[Tuple[str, str, float, float], Tuple[torch.Tensor, CachedFactor]]" = OrderedDict()
 FACTOR_CACHE_MAX = 16
 # the cached path wins while the n_pad x n_pad system of the push-through identity stays small next to d x d
-# (measured on B200, ms cached / direct, profiles/r03e_probe_factor.json: d = 3072: n = 100 2.9 / 6.3, 300 4.8 / 6.7,
+# (measured on B200, ms cached / direct, profiles/round1/r03e_probe_factor.json: d = 3072: n = 100 2.9 / 6.3, 300 4.8 / 6.7,
 #  700 6.9 / 7.2, 1000 13.3 / 7.4;  d = 5120: n = 100 9.5 / 14.2, 1000 50 / 20)
 FACTOR_CACHE_MAX_FRACTION = 6
 
