@@ -1,24 +1,31 @@
-"""Minimal module-instrumentation helpers used on the hot path.
+"""The little module instrumentation the EMCID hot path needs.
 
-Behavioural mirror of the pieces of util/nethook.py the EMCID edit path touches:
-`get_module` (:375-382), `get_parameter` (:385-392), `Trace(..., stop=True)` (:22-128) and
-`TraceDict` (:131-200).  Implemented with plain forward hooks.
+The reference's util/nethook.py is a general tracing toolkit (Trace / TraceDict with output editing, gradient retention,
+subsequence extraction, ...).  The edit path touches three things of it, restated here from what callers observe:
+
+  get_module(model, "a.b.c")        the submodule, LookupError when there is none            (util/nethook.py:375-382)
+  get_parameter(model, "a.b.weight") the parameter, LookupError when there is none          (:385-392)
+  TraceDict(model, [names], retain_input=True, retain_output=True)                           (:131-200)
+                                    context manager; td[name].input / td[name].output hold what the named submodule
+                                    received (its first positional argument) and returned during the forward passes inside
+                                    the `with` block.  Used by the traced fallback of the key extraction only; the
+                                    statistics pass hooks the MLP itself (layer_stats.TextEncoderMom2Pass).
+  StopForward                       raised by a hook to abandon the rest of a forward pass    (:203-213)
 """
 from __future__ import annotations
 
-import contextlib
-from collections import OrderedDict
+from types import SimpleNamespace
+from typing import Dict, Iterable
 
 import torch
 
 
 class StopForward(Exception):
-    """Raised by a hook to abandon the rest of a forward pass (reference :203-213)."""
+    """Raised inside a forward hook: nothing after the hooked module needs to run."""
 
 
 def get_module(model: torch.nn.Module, name: str) -> torch.nn.Module:
-    """The submodule with that dotted name; LookupError if there is none (walks the path instead of listing every module:
-    the edit loop resolves two names per layer and edit)."""
+    """Walks the dotted path (O(depth)): the edit loop resolves two names per layer and edit."""
     try:
         return model.get_submodule(name)
     except AttributeError:
@@ -36,87 +43,38 @@ def get_parameter(model: torch.nn.Module, name: str) -> torch.nn.Parameter:
     return p
 
 
-def set_requires_grad(requires_grad: bool, *models) -> None:
-    for model in models:
-        if isinstance(model, torch.nn.Module):
-            for p in model.parameters():
-                p.requires_grad = requires_grad
-        elif isinstance(model, (torch.nn.Parameter, torch.Tensor)):
-            model.requires_grad = requires_grad
-        else:
-            raise AssertionError("unknown type %r" % type(model))
+class TraceDict(dict):
+    """{name: record} with record.input / record.output of every named submodule, refreshed by each forward pass run inside
+    the `with` block; `stop=True` abandons a forward once the LAST named submodule has run."""
 
-
-def _keep(x, clone: bool, detach: bool):
-    if isinstance(x, torch.Tensor):
-        if detach:
-            x = x.detach()
-        if clone:
-            x = x.clone()
-        return x
-    if isinstance(x, (tuple, list)):
-        return type(x)(_keep(v, clone, detach) for v in x)
-    if isinstance(x, dict):
-        return type(x)((k, _keep(v, clone, detach)) for k, v in x.items())
-    return x
-
-
-class Trace(contextlib.AbstractContextManager):
-    """Retain input and/or output of one named submodule during a forward pass; with stop=True the
-    forward is abandoned right after that submodule ran and the StopForward is swallowed on exit."""
-
-    def __init__(self, module, layer=None, retain_output=True, retain_input=False, clone=False,
-                 detach=False, retain_grad=False, edit_output=None, stop=False):
-        self.layer = layer
-        self.stop = stop
-        target = get_module(module, layer) if layer is not None else module
-
-        def hook(_m, inputs, output):
-            if retain_input:
-                self.input = _keep(inputs[0] if len(inputs) == 1 else inputs, clone, detach)
-            if edit_output is not None:
-                try:
-                    output = edit_output(output=output, layer=self.layer)
-                except TypeError:
-                    output = edit_output(output)
-            if retain_output:
-                self.output = _keep(output, clone, detach)
-                if retain_grad and isinstance(self.output, torch.Tensor):
-                    self.output.requires_grad_(True)
-                    self.output.retain_grad()
-            if stop:
-                raise StopForward()
-            return output
-
-        self._handle = target.register_forward_hook(hook)
-
-    def __exit__(self, exc_type, exc, tb):
-        self.close()
-        if self.stop and exc_type is not None and issubclass(exc_type, StopForward):
-            return True
-
-    def close(self):
-        self._handle.remove()
-
-
-class TraceDict(OrderedDict, contextlib.AbstractContextManager):
-    """One Trace per named layer; the last layer carries the stop flag."""
-
-    def __init__(self, module, layers=None, retain_output=True, retain_input=False, clone=False,
-                 detach=False, retain_grad=False, edit_output=None, stop=False):
+    def __init__(self, module: torch.nn.Module, layers: Iterable[str] = (), retain_output: bool = True,
+                 retain_input: bool = False, stop: bool = False):
         super().__init__()
-        self.stop = stop
-        layers = list(dict.fromkeys(layers or []))
-        for i, name in enumerate(layers):
-            self[name] = Trace(module, name, retain_output=retain_output, retain_input=retain_input,
-                               clone=clone, detach=detach, retain_grad=retain_grad, edit_output=edit_output,
-                               stop=stop and i == len(layers) - 1)
+        self._handles = []
+        self._stop = stop
+        names = list(dict.fromkeys(layers))
+        for i, name in enumerate(names):
+            record = self[name] = SimpleNamespace(input=None, output=None)
+            last = stop and i == len(names) - 1
 
-    def __exit__(self, exc_type, exc, tb):
+            def hook(_mod, args, out, record=record, last=last):
+                if retain_input:
+                    record.input = args[0] if len(args) == 1 else args
+                if retain_output:
+                    record.output = out
+                if last:
+                    raise StopForward()
+
+            self._handles.append(get_module(module, name).register_forward_hook(hook))
+
+    def __enter__(self) -> "TraceDict":
+        return self
+
+    def __exit__(self, exc_type, exc, tb) -> bool:
         self.close()
-        if self.stop and exc_type is not None and issubclass(exc_type, StopForward):
-            return True
+        return bool(self._stop and exc_type is not None and issubclass(exc_type, StopForward))
 
-    def close(self):
-        for tr in reversed(list(self.values())):
-            tr.close()
+    def close(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
