@@ -523,9 +523,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < COLS; ++i) sum[i] = 0.f;
       if (EPI == EPI_LINEAR_TMA) {
-        // this half's bias row goes to shared memory now, one value per thread: the load has the whole mainloop to land.
-        // (Read from global in the store phase — 32 dependent-latency LDG.128 per thread that the 128 live running sums
-        // leave no registers to batch — the loads were the store phase: ncu long_scoreboard, tensor pipe 72-79 % active.)
+        // this half's bias row goes to shared memory now, one value per thread: the load has the whole mainloop to land
+        // (read from global in the store phase it was 32 LDG.128 per thread, four exposed L2 round trips per tile).  Safe
+        // against the previous tile's readers: every thread passes the last named barrier of its store phase after its
+        // last read of the row.
         const int t = q * 32 + lane, c = u.n0 + half * COLS + t;
         bias_s[half * COLS + t] = c < N ? p.bias_col[c] : 0.f;
       }
@@ -535,9 +536,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         const uint32_t taddr = tmem_base + acc * BLOCK_N + half * COLS +
                                (static_cast<uint32_t>(q * 32) << 16);
         // FW accumulator columns per tcgen05.ld batch: the loads of a batch are issued back to back and share ONE
-        // tcgen05.wait::ld.  (With a wait after every 16 columns a fold was eight serial TMEM round trips: with two
-        // accumulator stages the MMA warp needs fold(i) done before chunk i + 2, and in the K = 768 products — 3072 MMA clocks
-        // per 2-k-block chunk — it kept waiting for it: tensor pipe 72-79 % active, +7 % from longer chunks alone.)
+        // tcgen05.wait::ld.  (ptxas turns the wait into scoreboard dependencies and rotates three register sets through
+        // the LDTM.x16s either way — profiles/round2/r04_sass_fc1.txt; the batch width measured within 1 %.)
         constexpr int FW = (EPI == EPI_LINEAR_TMA) ? EMCID_FOLD_WIDTH : 16;
 #pragma unroll
         for (int c = 0; c < COLS / FW; ++c) {
@@ -578,7 +578,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
         //                       sub-tile ago, from the other buffer ... the wait hides behind this sub-tile's arithmetic)
         //     barrier           -> the issuer issues this sub-tile's bulk store; everybody moves on to the other buffer
         // One barrier per 8 KB.  (Until r04 a sub-tile was 16 KB in a single buffer with two barriers, and the 128 threads
-        // sat at the first one while the previous store drained: tensor pipe 72-79 % active in the K = 768 products.)
+        // sat at the first one while the previous store drained.  Measured: no faster — the store phase is arithmetic,
+        // not waiting, see DESIGN.md §3 — but half the barriers.  A per-warp variant without any block-level barrier, 2 KB
+        // sub-tiles stored by each warp's lane 0, was tried on top: +0.3 % and a race in the shared bias row; dropped.)
         const uint32_t srow64 = sbase + r * 64;
         const int sw64 = (r >> 1) & 3;
         const float* bias_h = bias_s + half * COLS;

@@ -429,10 +429,19 @@ class _Checkpointer:
 
     def _write(self, payload) -> None:
         self.path.parent.mkdir(parents=True, exist_ok=True)
-        tmp = f"{self.path}.{os.getpid()}.tmp.npz"
-        np.savez(tmp, **payload)
+        tmp = f"{self.path}.{os.getpid()}.tmp"
+        with open(tmp, "wb") as f:              # a file object: numpy must not append ".npz" to the temporary name
+            np.savez(f, **payload)
         os.replace(tmp, self.path)
         self.written += 1
+
+    def _sweep_temporaries(self) -> None:
+        """Half-written files of workers that died inside _write."""
+        for stale in self.path.parent.glob(self.path.name + ".*.tmp"):
+            try:
+                os.remove(stale)
+            except OSError:
+                pass
 
     def wait(self) -> None:
         if self._thread is not None:
@@ -441,6 +450,7 @@ class _Checkpointer:
 
     def discard(self) -> None:
         self.wait()
+        self._sweep_temporaries()
         try:
             os.remove(self.path)
         except FileNotFoundError:
