@@ -545,9 +545,6 @@ def run_ours(args):
         "peak_source": f"{peaks['source']}: bf16_tflops_sustained (cuBLAS dense 16-bit GEMM); achieved counts "
                        "ALGORITHMIC flops d(d+1) per token, the 3-term split issues 3x that",
         "issued_frac": 3.0 * syrk_tflops / tf32_peak,
-        # BASELINE.json's wording ("fraction of the dense-TF32 tensor-core roofline", SURVEY.md §8d: bf16 / 2 until a TF32
-        # figure is measured): the fp32-accurate product against what one single-pass TF32 GEMM could deliver
-        "frac_of_dense_tf32_roofline": syrk_tflops / (0.5 * tf32_peak),
         "avg_launch_ms": prof["syrk_ms"] / max(prof["syrk_launches"], 1.0),
         "rows_per_launch": prof["syrk_rows"] / max(prof["syrk_launches"], 1.0),
         "fc1": ({"achieved": fc1_tflops, "frac": fc1_tflops / tf32_peak,
