@@ -62,7 +62,7 @@ struct ClipHandle {
   uint16_t *x_hi, *x_lo;       // [cap x hp]   LN output
   uint16_t *a_hi, *a_lo;       // [cap x hp]   attention output
   uint16_t *f_hi, *f_lo;       // [cap x dp]   act(fc1)
-  uint16_t *ft_hi, *ft_lo;     // [d x tp]     act(fc1)^T (edited layers)
+  uint16_t *ft_hi, *ft_lo;     // [d x tp]     scratch planes: the gathered key rows [n_keys x dp] of the key extraction
   unsigned int* scratch;
   std::vector<void*>* allocs;
   DeviceInfo info;
@@ -509,8 +509,7 @@ struct ClipActMaps {
 // out[T x N] = act(X[T x K] W^T / scale + bias) (+ residual), optionally as fp32 / planes / transposed planes.
 inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap& x_lo, const ClipWeight& W, int T,
                        int act, const float* Cin, float* C, long long ldc, uint16_t* P_hi, uint16_t* P_lo, long long ldp,
-                       uint16_t* Pt_hi, uint16_t* Pt_lo, long long ldpt, cudaStream_t stream,
-                       const GemmOutMaps* om = nullptr, int pt_col_min = 0, int tag = CLIP_TAG_QKV) {
+                       cudaStream_t stream, const GemmOutMaps* om = nullptr, int tag = CLIP_TAG_QKV) {
   ClipProfScope prof(H, stream, tag, 2.0 * T * static_cast<double>(W.N) * W.K);
   GemmOperands ops;
   ops.a_hi = x_hi; ops.a_lo = x_lo; ops.b_hi = W.m_hi; ops.b_lo = W.m_lo;
@@ -540,13 +539,11 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   p.Cin = Cin; p.ldcin = ldc;
   p.C = C; p.ldc = ldc;
   p.P_hi = reinterpret_cast<float*>(P_hi); p.P_lo = reinterpret_cast<float*>(P_lo); p.ldp = ldp;
-  p.Pt_hi = reinterpret_cast<float*>(Pt_hi); p.Pt_lo = reinterpret_cast<float*>(Pt_lo); p.ldpt = ldpt;
-  p.pt_col_min = pt_col_min;
   const int tiles = gemm_num_tiles(T, W.N, 256, 0);
   const int grid = tiles < H->info.sm_count ? tiles : H->info.sm_count;
   H->launches += 1;
   // the epilogue variant is a compile-time option (see EF_* in gemm3x.cuh): only the combinations the forward uses
-  const int ef = act | (C ? EF_C : 0) | (Cin ? EF_CIN : 0) | (P_hi ? EF_P : 0) | (Pt_hi ? EF_PT : 0);
+  const int ef = act | (C ? EF_C : 0) | (Cin ? EF_CIN : 0) | (P_hi ? EF_P : 0);
   const bool cta2 = om && gemm_cta2_enabled();
   const int pair_tiles = ((T + 255) / 256) * ((W.N + 255) / 256);
   const int grid2 = 2 * pair_tiles < (H->info.sm_count & ~1) ? 2 * pair_tiles : (H->info.sm_count & ~1);
@@ -562,11 +559,7 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
     return launch_gemm3x<256, 2, EPI_LINEAR_TMA, KIND_F16, (ACT_NONE | EF_P)>(ops, p, grid, stream, 1, om);
   EMCID_LIN_CASE(ACT_NONE | EF_C | EF_CIN)              // out projection / fc2 with residual
   EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P)                 // fc1
-  EMCID_LIN_CASE(ACT_QUICK_GELU | EF_P | EF_PT)         // fc1 of an edited layer
-  EMCID_LIN_CASE(ACT_QUICK_GELU | EF_PT)                // fc1 of the deepest edited layer
   EMCID_LIN_CASE(ACT_GELU_ERF | EF_P)
-  EMCID_LIN_CASE(ACT_GELU_ERF | EF_P | EF_PT)
-  EMCID_LIN_CASE(ACT_GELU_ERF | EF_PT)
 #undef EMCID_LIN_CASE
   return set_error(EMCID_ERR_UNSUPPORTED, "clip_linear: epilogue variant %d is not instantiated", ef);
 }
@@ -680,23 +673,18 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   int rc;
   // per-call TMA maps over exactly T rows: out-of-range rows of the last tile read as zeros
   CUtensorMap mx_hi, mx_lo, ma_hi, ma_lo, mf_hi, mf_lo;
-  GemmOperands ft;
   CUtensorMap sf_hi, sf_lo;   // store maps of the f planes (64-byte rows: the staged epilogue's 8 KB sub-tiles, gemm3x.cuh)
   if ((rc = make_tmap_2d(&mx_hi, H->x_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&mx_lo, H->x_lo, T, H->h, H->hp, 128, 2)) ||
       (rc = make_tmap_2d(&ma_hi, H->a_hi, T, H->h, H->hp, 128, 2)) || (rc = make_tmap_2d(&ma_lo, H->a_lo, T, H->h, H->hp, 128, 2)) ||
       (rc = make_tmap_2d(&mf_hi, H->f_hi, T, H->d, H->dp, 128, 2)) || (rc = make_tmap_2d(&mf_lo, H->f_lo, T, H->d, H->dp, 128, 2)) ||
-      (rc = make_tmap_2d(&sf_hi, H->f_hi, T, H->d, H->dp, 128, 2, 0, 64)) || (rc = make_tmap_2d(&sf_lo, H->f_lo, T, H->d, H->dp, 128, 2, 0, 64)) ||
-      (rc = make_tmap_2d(&ft.a_hi, H->ft_hi, H->d, T, H->tp, 128, 2)) || (rc = make_tmap_2d(&ft.a_lo, H->ft_lo, H->d, T, H->tp, 128, 2)))
+      (rc = make_tmap_2d(&sf_hi, H->f_hi, T, H->d, H->dp, 128, 2, 0, 64)) || (rc = make_tmap_2d(&sf_lo, H->f_lo, T, H->d, H->dp, 128, 2, 0, 64)))
     return rc;
-  ft.b_hi = ft.a_hi; ft.b_lo = ft.a_lo;
   // store maps of the staged (TMA) epilogue; EMCID_LINEAR_TMA=0 keeps the direct-store epilogue
   static const bool use_tma_epi = [] { const char* e = getenv("EMCID_LINEAR_TMA"); return !(e && e[0] == '0'); }();
   GemmOutMaps om_qkv = {}, om_res = {}, om_f = {};
   if (use_tma_epi) {
     if ((rc = make_tmap_2d(&om_qkv.c, H->qkv, T, 3ll * H->h, 3ll * H->h, 128, 4, 0, 64)) ||
-        (rc = make_tmap_2d(&om_res.c, H->hres, T, H->h, H->h, 128, 4, 0, 64)) ||
-        (rc = make_tmap_2d(&om_f.t_hi, H->ft_hi, H->d, T, H->tp, 32, 2, 128)) ||
-        (rc = make_tmap_2d(&om_f.t_lo, H->ft_lo, H->d, T, H->tp, 32, 2, 128)))
+        (rc = make_tmap_2d(&om_res.c, H->hres, T, H->h, H->h, 128, 4, 0, 64)))
       return rc;
     om_f.c = sf_hi; om_f.c2 = sf_lo;
   }
@@ -730,15 +718,15 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     const ClipLayer& Ly = (*H->layers)[l];
     if (l == resume_layer) {
       // hres = h + attn(h) of this layer and f = act(fc1(LN2 hres)) are where the previous call left them
-      if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr,
-                            0, stream, pm_res, 0, CLIP_TAG_FC2)))
+      if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, stream, pm_res,
+                            CLIP_TAG_FC2)))
         return rc;
       continue;
     }
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln1_w, Ly.ln1_b, H->x_hi, H->x_lo, stream))) return rc;
     if (attn_tc) {
-      if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, nullptr, 0, H->qp_hi, H->qp_lo, 3ll * H->h, nullptr,
-                            nullptr, 0, stream, pm_qkv, 0, CLIP_TAG_QKV)))
+      if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, nullptr, 0, H->qp_hi, H->qp_lo, 3ll * H->h, stream,
+                            pm_qkv, CLIP_TAG_QKV)))
         return rc;
       ClipProfScope prof_attn(H, stream, CLIP_TAG_ATTN, 0.0);
       const int units = S * H->heads;
@@ -752,8 +740,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
         clip_attention_tc_kernel<8><<<grid, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
             am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
     } else {
-    if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, nullptr,
-                          nullptr, 0, stream, pm_qkv)))
+    if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, stream, pm_qkv)))
       return rc;
     {
       const dim3 ag(H->heads, S);
@@ -767,59 +754,39 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     }
     EMCID_CUDA_CHECK(cudaGetLastError());
     H->launches += 1;
-    if ((rc = clip_linear(H, ma_hi, ma_lo, Ly.o, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
-                          stream, pm_res, 0, CLIP_TAG_OUT)))
+    if ((rc = clip_linear(H, ma_hi, ma_lo, Ly.o, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, stream, pm_res,
+                          CLIP_TAG_OUT)))
       return rc;
     if ((rc = clip_layernorm(H, H->hres, T, Ly.ln2_w, Ly.ln2_b, H->x_hi, H->x_lo, stream))) return rc;
     const bool is_stat = si < n_stat && stat_layers[si] == l;
     const bool is_last = n_stat > 0 && l == last_stat;
-    // EMCID_SYRK_MN (default): the SYRK reads act(fc1) as MN-major operand tiles straight from the [tokens x features]
-    // planes fc2 reads as well, so an edited layer's fc1 is an ordinary fc1.  EMCID_SYRK_MN=0: the SYRK reads K-major
-    // tiles of a transposed copy f^T, which fc1 of an edited layer then has to write as well (+100 us per launch).
-    static const bool syrk_mn = [] { const char* e = getenv("EMCID_SYRK_MN"); return !(e && e[0] == '0'); }();
-    const bool mn = syrk_mn && use_tma_epi;
-    const bool want_p = mn || !is_last, want_pt = is_stat && !mn;
-    if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.fc1, T, H->act, nullptr, nullptr, 0, want_p ? H->f_hi : nullptr,
-                          want_p ? H->f_lo : nullptr, H->dp, want_pt ? H->ft_hi : nullptr, want_pt ? H->ft_lo : nullptr,
-                          H->tp, stream, pm_f, 0, is_stat ? CLIP_TAG_FC1_STAT : CLIP_TAG_FC1)))
+    // The SYRK reads act(fc1) as MN-major operand tiles straight from the [tokens x features] planes fc2 reads as well, so an
+    // edited layer's fc1 is an ordinary fc1.  (Until r04 a switch kept the first design alive — K-major tiles of a transposed
+    // copy f^T that fc1 of an edited layer wrote as well: +100 us per launch and 465 MB of extra HBM traffic per block.)
+    if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.fc1, T, H->act, nullptr, nullptr, 0, H->f_hi, H->f_lo, H->dp, stream, pm_f,
+                          is_stat ? CLIP_TAG_FC1_STAT : CLIP_TAG_FC1)))
       return rc;
     if (is_stat) {
       Mom2Handle* A = accs[si++];
       // One launch over the whole block (hybrid schedule, gemm3x.cuh: whole tiles march through the tokens together, so
       // each k-block of the planes is pulled from HBM once and shared through L2, and a tile is red.add'ed once per
       // block instead of once per 4096-token slab; the 4 leftover pair tiles are stream-K'd).  EMCID_SYRK_HYBRID=0
-      // restores the slab launches (measured: 10 x 102 us per block and layer, 40 MB of red.add traffic each).
+      // stream-K's every tile.
       static const bool hybrid = [] { const char* e = getenv("EMCID_SYRK_HYBRID"); return !(e && e[0] == '0'); }();
-      if (mn) {
-        GemmOperands fm;   // act(fc1) planes [T x d]: boxes of 64 tokens x 64 features
-        if ((rc = make_tmap_2d(&fm.a_hi, H->f_hi, T, H->d, H->dp, 64, 2)) || (rc = make_tmap_2d(&fm.a_lo, H->f_lo, T, H->d, H->dp, 64, 2)))
-          return rc;
-        fm.b_hi = fm.a_hi; fm.b_lo = fm.a_lo;
-        if ((rc = mom2_syrk_slab(A, fm, KIND_F16_MN, 0, T, nullptr, stream, hybrid ? 2 : 1))) return rc;
-        A->slabs_since_fold += 4;
-        if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
-      } else if (hybrid) {
-        if ((rc = mom2_syrk_slab(A, ft, KIND_F16, 0, T, nullptr, stream, 2))) return rc;
-        A->slabs_since_fold += 4;
-        if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
-      } else {
-      const int slab = A->slab;
-      const long long nslabs = (T + slab - 1) / slab;
-      long long per = round_up_ll((T + nslabs - 1) / nslabs, 64);
-      if (per > slab) per = slab;
-      for (long long c0 = 0; c0 < T; c0 += per) {
-        const int t = static_cast<int>(T - c0 < per ? T - c0 : per);
-        if ((rc = mom2_syrk_slab(A, ft, KIND_F16, static_cast<int>(c0), t, nullptr, stream))) return rc;
-        if (++A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
-      }
-      }
+      GemmOperands fm;   // act(fc1) planes [T x d]: boxes of 64 tokens x 64 features
+      if ((rc = make_tmap_2d(&fm.a_hi, H->f_hi, T, H->d, H->dp, 64, 2)) || (rc = make_tmap_2d(&fm.a_lo, H->f_lo, T, H->d, H->dp, 64, 2)))
+        return rc;
+      fm.b_hi = fm.a_hi; fm.b_lo = fm.a_lo;
+      if ((rc = mom2_syrk_slab(A, fm, KIND_F16_MN, 0, T, nullptr, stream, hybrid ? 2 : 1))) return rc;
+      A->slabs_since_fold += 4;
+      if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
       clip_add_count_kernel<<<1, 1, 0, stream>>>(A->count, static_cast<long long>(T));
       EMCID_CUDA_CHECK(cudaGetLastError());
       A->launches += 1;
     }
     if (is_last) break;
     if (l == keys_layer) {
-      uint16_t* g_hi = H->ft_hi;   // the transposed planes are idle in this mode: compact [n_keys x dp] copy of the key rows
+      uint16_t* g_hi = H->ft_hi;   // compact [n_keys x dp] copy of the key rows
       uint16_t* g_lo = H->ft_lo;
       clip_gather_keys_kernel<<<n_keys < sms * 8 ? n_keys : sms * 8, 256, 0, stream>>>(
           H->f_hi, H->f_lo, H->dp, key_rows, n_keys, T, H->d, H->dp, k_out, g_hi, g_lo);
@@ -831,15 +798,15 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
           (rc = make_tmap_2d(&mg_lo, g_lo, n_keys, H->d, H->dp, 128, 2)) ||
           (use_tma_epi && (rc = make_tmap_2d(&om_z.c, z_out, n_keys, H->h, H->h, 128, 4, 0, 64))))
         return rc;
-      if ((rc = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, nullptr,
-                            nullptr, 0, stream, use_tma_epi ? &om_z : nullptr, 0, CLIP_TAG_FC2)))
+      if ((rc = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, stream,
+                            use_tma_epi ? &om_z : nullptr, CLIP_TAG_FC2)))
         return rc;
       H->keys_state_layer = l;
       H->keys_state_tokens = T;
       break;
     }
-    if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, nullptr, nullptr, 0,
-                          stream, pm_res, 0, CLIP_TAG_FC2)))
+    if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, stream, pm_res,
+                          CLIP_TAG_FC2)))
       return rc;
   }
   if (hidden_out) {

@@ -73,8 +73,6 @@ enum EpiMode : int {
 struct GemmOutMaps {
   CUtensorMap c;     // fp32 result [M x N] (box 16 x 128 rows, 64B swizzle)  or  hi plane [M x N] (box 32 x 128 rows, 64B swizzle)
   CUtensorMap c2;    // lo plane
-  CUtensorMap t_hi;  // transposed hi plane [N x M] (box 128 x 32, no swizzle)
-  CUtensorMap t_lo;
 };
 constexpr int GEMM_STAGING_BYTES = 32768;
 
@@ -113,8 +111,6 @@ struct GemmParams {
   long long ldpt, pt_batch;
   const float* bias;           // [M], EPI_FC1
   const float* bias_col;       // [N], EPI_LINEAR (16-byte aligned)
-  int pt_col_min;              // EPI_LINEAR_TMA: transposed planes only for columns >= this (a multiple of 32);
-                               // the transposed tensor map starts at that column
   int act;
   int lo_fmt;                  // KIND_F16: format of the lo planes (FMT_BF16 default, FMT_F16)
 };
@@ -608,7 +604,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
             }
           }
         }
-        if (EFLAGS & (EF_P | EF_PT)) {
+        static_assert(EPI != EPI_LINEAR_TMA || !(EFLAGS & EF_PT), "the staged epilogue writes no transposed planes");
+        if (EFLAGS & EF_P) {
 #pragma unroll
           for (int pc = 0; pc < COLS / 64; ++pc) {                 // 64 plane columns: two 32-column (64-byte) sub-tiles per plane
             uint32_t hp[32], lp[32];                               // packed fp16 pairs of the piece
@@ -641,29 +638,6 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
                     tma_store_2d(pl == 0 ? &om.c : &om.c2, sbase + pl * 8192, col0 + pc * 64 + g * 32, m_cta);
                     bulk_commit();
                   }
-                }
-              }
-            }
-            if (EFLAGS & EF_PT) {
-#pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {                  // 32 features x 128 tokens per plane (8 KB each)
-                if (col0 + pc * 64 + sub * 32 < p.pt_col_min) continue;   // uniform over the 128 threads of the half
-                if (issuer) bulk_wait_read0();
-                named_bar_sync(bar_id, 128);
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                  const int idx = sub * 32 + c;
-                  const uint16_t hv = static_cast<uint16_t>(hp[idx >> 1] >> (16 * (idx & 1)));
-                  const uint16_t lv = static_cast<uint16_t>(lp[idx >> 1] >> (16 * (idx & 1)));
-                  sts_u16(sbase + c * 256 + r * 2, hv);
-                  sts_u16(sbase + 8192 + c * 256 + r * 2, lv);
-                }
-                fence_proxy_async();
-                named_bar_sync(bar_id, 128);
-                if (issuer && col0 + pc * 64 + sub * 32 < N) {
-                  tma_store_2d(&om.t_hi, sbase, m_cta, col0 + pc * 64 + sub * 32 - p.pt_col_min);
-                  tma_store_2d(&om.t_lo, sbase + 8192, m_cta, col0 + pc * 64 + sub * 32 - p.pt_col_min);
-                  bulk_commit();
                 }
               }
             }
