@@ -83,6 +83,7 @@ SIGNATURES = {
         [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_double, c_double,
          ctypes.POINTER(c_double), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p],
     ),
+    "emcid_read_npz_f32": (c_int, [ctypes.POINTER(c_char_p), c_int, c_char_p, c_void_p, c_longlong, ctypes.POINTER(c_int)]),
     "emcid_delta_update": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emcid_factor_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_void_p, c_double, c_void_p, c_void_p]),
     "emcid_factor_solve_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -24,6 +24,7 @@ from . import clip_forward, nethook
 _SERIAL = itertools.count(1)   # identity of a prepared prompt set (continuation token of the native key extraction)
 _FC2_NAME = re.compile(r"^(?:text_model\.)?encoder\.layers\.(\d+)\.mlp\.fc2$")
 LAST_PATH = {"native": False}   # which path served the last call (tests / bench read it)
+_PACKED: Dict[str, tuple] = {}  # packed prompts + looked-up rows of the last prepared prompt set
 
 
 def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name: str, token=None):
@@ -41,24 +42,30 @@ def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name
     if not clip_forward.supports(text_encoder):
         return None
     max_pos = tm.embeddings.position_embedding.weight.shape[0]
-    packed = clip_forward.pack_batch({"input_ids": enc["input_ids"], "attention_mask": enc["attention_mask"]}, max_pos)
-    if packed is None:
+    # the packed form of the prompts and the looked-up rows depend on the prompt set only: once per edit, not per layer
+    hit = _PACKED.get("last")
+    if token is not None and hit is not None and hit[0] == token and hit[1] is enc["input_ids"]:
+        packed, rows = hit[2], hit[3]
+    else:
+        packed = clip_forward.pack_batch({"input_ids": enc["input_ids"], "attention_mask": enc["attention_mask"]}, max_pos)
+        rows = None
+        if packed is not None and packed[4] > 0:
+            cu = packed[2]
+            first = torch.tensor([row[0] for row in lookup], dtype=torch.int32, device=cu.device)
+            if bool((first < cu[1:] - cu[:-1]).all()):
+                rows = cu[:-1] + first
+            # else: a looked-up position beyond a prompt's valid tokens (subjects "", " ", "[EOS]" with ragged prompts: the
+            # LAST COLUMN of the padded batch, causal_trace.py:1063-1064): that pad row does not exist in the packed forward
+        _PACKED["last"] = (token, enc["input_ids"], packed, rows)
+    if packed is None or rows is None:
         return None
     ids, pos, cu, S, T = packed
-    if T == 0:
-        return None
     prev_token = getattr(_native_keys, "_last_token", None)
     # once per edit (a new prompt set): compare content checksums too — writes through `.data` do not bump `_version`
     native = clip_forward.key_encoder(text_encoder, T, S, layer, verify=token is None or token != prev_token)
     _native_keys._last_token = token
     if native is None:
         return None
-    first = torch.tensor([row[0] for row in lookup], dtype=torch.int32, device=cu.device)
-    if not bool((first < cu[1:] - cu[:-1]).all()):
-        # a looked-up position beyond a prompt's valid tokens (subjects "", " ", "[EOS]" with ragged prompts: the LAST
-        # COLUMN of the padded batch, causal_trace.py:1063-1064): that pad row does not exist in the packed forward
-        return None
-    rows = cu[:-1] + first
     resume = -1
     prev = native.keys_token
     if token is not None and prev is not None and prev[0] == token and prev[1] < layer and prev[2] == T:

@@ -204,6 +204,10 @@ int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* 
                       dW, refine_steps, workspace, workspace_bytes, status_dev, static_cast<cudaStream_t>(stream));
 }
 
+int emcid_read_npz_f32(const char* const* paths, int n, const char* key, float* out, long long elems, int* bad) {
+  return read_npz_f32(paths, n, key, out, elems, bad);
+}
+
 int emcid_delta_update(int h, int d, int n, const double* resid, const double* adj_k, float* dW, void* stream) {
   EMCID_CHECK(h > 0 && d > 0 && n > 0 && resid && adj_k && dW, EMCID_ERR_INVALID, "emcid_delta_update: bad argument");
   DgemmParams p;

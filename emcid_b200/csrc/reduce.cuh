@@ -10,6 +10,8 @@
 #pragma once
 
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "mom2.cuh"
 
@@ -286,6 +288,77 @@ inline int fixed_random_subset(long long n_items, long long seed, long long* out
   }
   for (long long i = 0; i < n_out; ++i) out[i] = x[i];
   free(x);
+  return EMCID_OK;
+}
+
+// ---- the v* cache files of an edit (host) ---------------------------------------------------------------------
+// An edit of n concepts starts by reading n files `cache_name + "source_{src}_dest_{dst}.npz"`, each holding one small
+// array `v_star` (emcid/emcid_main.py:873-907: numpy.savez(file, v_star=...)).  Read one by one with numpy that is
+// 90 us per file of zipfile machinery; a lean Python reader still costs 10 ms per 1000 files, all of it under the GIL next
+// to the tokenisation of the prompts.  This reads them in C (the host thread that calls it through ctypes holds no GIL):
+// the first member of the archive must be the stored (uncompressed) `<key>.npy`, little-endian float32, C order, with
+// exactly `elems` elements; sizes come from the npy header (numpy streams members with zip64 placeholders in the local
+// header).  Returns EMCID_OK, or EMCID_ERR_INVALID with *bad = index of the first file that is missing or different —
+// the caller falls back to its general reader for the error message or the unusual layout.
+inline int read_npz_f32(const char* const* paths, int n, const char* key, float* out, long long elems, int* bad) {
+  EMCID_CHECK(paths && key && out && elems > 0 && n >= 0, EMCID_ERR_INVALID, "read_npz_f32: bad argument");
+  const size_t klen = strlen(key);
+  const size_t want = static_cast<size_t>(elems) * sizeof(float);
+  unsigned char head[8192];                    // a 768- or 1280-wide v* file fits: one open / read / close per file
+  for (int i = 0; i < n; ++i) {
+    if (bad) *bad = i;
+    const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return set_error(EMCID_ERR_INVALID, "read_npz_f32: cannot open %s", paths[i]);
+    const ssize_t got_s = read(fd, head, sizeof(head));
+    const size_t got = got_s > 0 ? static_cast<size_t>(got_s) : 0;
+    int ok = 0;
+    size_t data_off = 0;
+    do {
+      if (got < 30 + klen + 4 + 12) break;
+      if (!(head[0] == 'P' && head[1] == 'K' && head[2] == 3 && head[3] == 4)) break;
+      if (head[8] != 0 || head[9] != 0) break;                                   // compression method: stored
+      const size_t nlen = head[26] | (head[27] << 8), xlen = head[28] | (head[29] << 8);
+      if (nlen != klen + 4 || memcmp(head + 30, key, klen) != 0 || memcmp(head + 30 + klen, ".npy", 4) != 0) break;
+      size_t o = 30 + nlen + xlen;
+      if (o + 12 > got || memcmp(head + o, "\x93NUMPY", 6) != 0) break;
+      const int major = head[o + 6];
+      size_t hlen, hstart;
+      if (major == 1) { hlen = head[o + 8] | (head[o + 9] << 8); hstart = o + 10; }
+      else { hlen = head[o + 8] | (head[o + 9] << 8) | (head[o + 10] << 16) | (static_cast<size_t>(head[o + 11]) << 24); hstart = o + 12; }
+      if (hstart + hlen > got) break;
+      char text[768];
+      if (hlen >= sizeof(text)) break;
+      memcpy(text, head + hstart, hlen);
+      text[hlen] = 0;
+      if (!strstr(text, "'descr': '<f4'") || !strstr(text, "'fortran_order': False")) break;
+      const char* sh = strstr(text, "'shape': (");
+      if (!sh) break;
+      long long prod = 1;
+      const char* q = sh + 10;
+      while (*q && *q != ')') {
+        if (*q >= '0' && *q <= '9') { prod *= strtoll(q, const_cast<char**>(&q), 10); continue; }
+        ++q;
+      }
+      if (*q != ')' || prod != elems) break;
+      data_off = hstart + hlen;
+      ok = 1;
+    } while (0);
+    if (ok) {
+      float* dst = out + static_cast<size_t>(i) * elems;
+      const size_t in_head = got > data_off ? got - data_off : 0;
+      const size_t take = in_head < want ? in_head : want;
+      memcpy(dst, head + data_off, take);
+      size_t have = take;
+      while (ok && have < want) {                // the rest straight into the destination
+        const ssize_t r = pread(fd, reinterpret_cast<unsigned char*>(dst) + have, want - have,
+                                static_cast<off_t>(data_off + have));
+        if (r <= 0) ok = 0; else have += static_cast<size_t>(r);
+      }
+    }
+    close(fd);
+    if (!ok) return set_error(EMCID_ERR_INVALID, "read_npz_f32: %s is not a plain float32 '%s' archive of %lld elements", paths[i], key, elems);
+  }
+  if (bad) *bad = -1;
   return EMCID_OK;
 }
 

@@ -221,6 +221,13 @@ int emcid_solve_layers(int device, int batch, int d, int h, int n, const float* 
                        const double* inv_layers_left, double* adj_k, double* resid, float* dW,
                        int refine_steps, void* workspace, size_t workspace_bytes, int* status_dev, void* stream);
 
+/* The v* cache files of an edit (host; emcid/emcid_main.py:873-907 reads them one by one with numpy.load):
+ * out[i * elems .. (i + 1) * elems) = the float32 array `key` of paths[i], for archives whose first member is the stored
+ * `<key>.npy` (what numpy.savez(file, v_star=...) writes).  EMCID_ERR_INVALID with *bad = index of the first file that is
+ * missing or laid out differently (the caller falls back to a general reader); *bad = -1 on success.  Holds no
+ * interpreter lock: bindings call it from a helper thread while the prompts are being tokenised. */
+int emcid_read_npz_f32(const char* const* paths, int n, const char* key, float* out, long long elems, int* bad);
+
 /* dW [h x d] fp32 = float(resid [h x n] * adj_k [d x n]^T), both fp64 row-major on the device: the product
  * apply_emcid_to_text_encoder forms from the deltas (emcid/emcid_main.py:802-809: `upd = adj_k @ resid.T` in fp64, then
  * `.float()`, transposed to the weight's shape) on the DMMA GEMM of the solver. */

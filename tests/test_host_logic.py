@@ -388,6 +388,51 @@ def test_fast_npz_reader_equals_numpy_load(tmp_path):
         emcid_main._read_npz_array(tmp_path / "plain.npz", "absent")
 
 
+def test_library_vstar_reader_equals_the_general_one(tmp_path):
+    """emcid_read_npz_f32 on its helper thread gives what the Python reader gives; files it does not take (another dtype, a
+    compressed archive, a truncated or missing file) fall back to the general reader and its error wording."""
+    from types import SimpleNamespace
+
+    from emcid_b200 import emcid_main
+
+    hp = SimpleNamespace(objective="", use_new_compute_z=False)
+    for h in (64, 768, 4096):                                   # 4096: data longer than the reader's first read
+        reqs = rh.make_requests(7)
+        cache = str(tmp_path / f"h{h}_")
+        rh.write_vstar_cache(cache, reqs, h)
+        pre = emcid_main._VstarPrefetch(reqs, hp, cache, "cpu")
+        got = pre()
+        assert pre.rc == 0 and got.dtype == torch.float32
+        assert torch.equal(got, emcid_main._load_vstars(reqs, hp, cache, "cpu"))
+    reqs = rh.make_requests(4)
+    cache = str(tmp_path / "new_")
+    for i, r in enumerate(reqs):                                # use_new_compute_z: [num, h] per request
+        np.savez(cache + f"source_{r['source']}_dest_{r['dest']}.npz",
+                 v_star=np.random.default_rng(i).standard_normal((3, 64)).astype(np.float32))
+    hp_new = SimpleNamespace(objective="", use_new_compute_z=True)
+    assert torch.equal(emcid_main._VstarPrefetch(reqs, hp_new, cache, "cpu")(),
+                       emcid_main._load_vstars(reqs, hp_new, cache, "cpu"))
+    # one file of another dtype / compressed: the general reader answers
+    cache = str(tmp_path / "h64_")
+    reqs = rh.make_requests(7)
+    odd = cache + f"source_{reqs[3]['source']}_dest_{reqs[3]['dest']}.npz"
+    v = np.load(odd)["v_star"]
+    np.savez_compressed(odd, v_star=v)
+    pre = emcid_main._VstarPrefetch(reqs, hp, cache, "cpu")
+    got = pre()
+    assert pre.rc != 0 and torch.equal(got, emcid_main._load_vstars(reqs, hp, cache, "cpu"))
+    with open(odd, "r+b") as f:                                  # truncated: a cache miss that names the file
+        f.truncate(40)
+    with pytest.raises(NotImplementedError, match="unreadable"):
+        emcid_main._VstarPrefetch(reqs, hp, cache, "cpu")()
+    os.remove(odd)
+    with pytest.raises(NotImplementedError, match="v_star cache miss"):
+        emcid_main._VstarPrefetch(reqs, hp, cache, "cpu")()
+    os.remove(cache + f"source_{reqs[0]['source']}_dest_{reqs[0]['dest']}.npz")
+    with pytest.raises(NotImplementedError, match="v_star cache miss"):     # the first file: at construction
+        emcid_main._VstarPrefetch(reqs, hp, cache, "cpu")
+
+
 def test_factor_cache_policy(monkeypatch):
     """Host logic of the cached-factorisation path of the edit loop (emcid_main._solve_one_layer): narrow edits go through
     one factor per (encoder, layer, lambda, edit_weight), a replaced COV_CACHE tensor rebuilds it, wide edits and
