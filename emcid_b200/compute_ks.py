@@ -31,7 +31,9 @@ def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name
     """(fc2 input [P, d], fc2 output [P, h]) at lookup[p][0] of every prompt through the library, or None when
     this model / module / mask is not covered.  `token` identifies the prompt set: consecutive calls with the same
     token at increasing layers, between which only fc2 of the previous layer changed (the edit loop), continue from
-    the previous call's state instead of re-running the layers below."""
+    the previous call's state instead of re-running the layers below.  `lookup=None` only LAUNCHES the forward up to
+    act(fc1) of the layer (see prefetch_keys): the call that follows with the looked-up positions, same token and layer,
+    gathers its rows from the state this one leaves behind."""
     m = _FC2_NAME.match(module_name)
     if m is None or not text_encoder.device.type == "cuda":
         return None
@@ -44,22 +46,26 @@ def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name
     max_pos = tm.embeddings.position_embedding.weight.shape[0]
     # the packed form of the prompts and the looked-up rows depend on the prompt set only: once per edit, not per layer
     hit = _PACKED.get("last")
-    if token is not None and hit is not None and hit[0] == token and hit[1] is enc["input_ids"]:
-        packed, rows = hit[2], hit[3]
-    else:
+    if token is None or hit is None or hit[0] != token or hit[1] is not enc["input_ids"]:
         packed = clip_forward.pack_batch({"input_ids": enc["input_ids"], "attention_mask": enc["attention_mask"]}, max_pos)
-        rows = None
-        if packed is not None and packed[4] > 0:
-            cu = packed[2]
-            first = torch.tensor([row[0] for row in lookup], dtype=torch.int32, device=cu.device)
-            if bool((first < cu[1:] - cu[:-1]).all()):
-                rows = cu[:-1] + first
-            # else: a looked-up position beyond a prompt's valid tokens (subjects "", " ", "[EOS]" with ragged prompts: the
-            # LAST COLUMN of the padded batch, causal_trace.py:1063-1064): that pad row does not exist in the packed forward
-        _PACKED["last"] = (token, enc["input_ids"], packed, rows)
-    if packed is None or rows is None:
+        hit = _PACKED["last"] = [token, enc["input_ids"], packed, None, False]       # ..., rows, rows looked up
+    packed = hit[2]
+    if packed is None or packed[4] <= 0:
         return None
     ids, pos, cu, S, T = packed
+    if lookup is None:
+        rows = torch.zeros(1, dtype=torch.int32, device=cu.device)
+    else:
+        if not hit[4]:
+            first = torch.tensor([row[0] for row in lookup], dtype=torch.int32, device=cu.device)
+            if bool((first < cu[1:] - cu[:-1]).all()):
+                hit[3] = cu[:-1] + first
+            # else: a looked-up position beyond a prompt's valid tokens (subjects "", " ", "[EOS]" with ragged prompts: the
+            # LAST COLUMN of the padded batch, causal_trace.py:1063-1064): that pad row does not exist in the packed forward
+            hit[4] = True
+        rows = hit[3]
+        if rows is None:
+            return None
     prev_token = getattr(_native_keys, "_last_token", None)
     # once per edit (a new prompt set): compare content checksums too — writes through `.data` do not bump `_version`
     native = clip_forward.key_encoder(text_encoder, T, S, layer, verify=token is None or token != prev_token)
@@ -68,16 +74,27 @@ def _native_keys(text_encoder, enc: Dict[str, torch.Tensor], lookup, module_name
         return None
     resume = -1
     prev = native.keys_token
-    if token is not None and prev is not None and prev[0] == token and prev[1] < layer and prev[2] == T:
+    if token is not None and prev is not None and prev[0] == token and prev[1] <= layer and prev[2] == T:
         changed = native.last_sync
         # fc2.weight / fc2.bias are source tensors 14 and 15 of a layer (NativeClipTextEncoder._layer_tensors)
         # the saved state depends on the embeddings, on layers below prev[1] and on everything of layer prev[1] but its fc2
         if all(isinstance(k, int) and (k > prev[1] or (k == prev[1] and set(v) <= {14, 15})) for k, v in changed.items()):
             resume = prev[1]
-    LAST_PATH["resumed_from"] = resume
+    if lookup is not None:
+        LAST_PATH["resumed_from"] = resume
     out = native.forward_keys(ids, pos, cu, S, T, layer, rows, resume_layer=resume)
     native.keys_token = (token, layer, T) if token is not None else None
     return out
+
+
+def prefetch_keys(text_encoder, enc, module_name: str, token) -> bool:
+    """Launches the library forward of the tokenised prompts up to act(fc1) of `module_name`'s layer BEFORE the positions
+    of the subject tokens are known: the host-side search for them (find_token_range over every prompt, 7 ms per 1000
+    requests) then runs beside the device's pass through the layers below the first edited one instead of in front of it.
+    The keys call that follows (same token and layer) only gathers its rows.  False when the library does not cover
+    this model / module / mask — nothing was launched and the caller's path is unchanged."""
+    with torch.no_grad():
+        return _native_keys(text_encoder, enc, None, module_name, token=token) is not None
 
 
 def last_hidden_at_words(text_encoder, tok, requests: List[Dict]) -> torch.Tensor:
@@ -179,11 +196,15 @@ def _prompts_and_subjects(requests: List[Dict]):
     return prompts, subjects, counts
 
 
-def prepare_lookup(tok, requests: List[Dict], num_fact_token: int, device):
+def prepare_lookup(tok, requests: List[Dict], num_fact_token: int, device, after_tokenise=None):
     """Tokenised source prompts, the looked-up token positions of every prompt and the prompts-per-request counts
-    (compute_z.py:2284-2300).  Independent of the layer: the edit loop computes it once per edit."""
+    (compute_z.py:2284-2300).  Independent of the layer: the edit loop computes it once per edit.  `after_tokenise(enc,
+    serial)` (one looked-up token per prompt only) is called between the tokenisation and the look-up, see prefetch_keys."""
     prompts, subjects, counts = _prompts_and_subjects(requests)
     enc = tokenize_prompts(prompts, tok, device)
+    serial = next(_SERIAL)
+    if after_tokenise is not None and num_fact_token == 1:
+        after_tokenise(enc, serial)
     # token ids as host lists: find_token_range walks them one by one (a device tensor would cost a sync per token)
     pieces: Dict[int, str] = {}
     if num_fact_token == 1:
@@ -195,7 +216,7 @@ def prepare_lookup(tok, requests: List[Dict], num_fact_token: int, device):
         for ids, w, n_valid in zip(enc["input_ids"].tolist(), subjects, enc["attention_mask"].sum(1).tolist()):
             eos = int(n_valid) - 1
             lookup.append([find_token_range(tok, ids, w, pieces)[-1] - 1] + list(range(eos, eos + extra + 1)))
-    return enc, lookup, counts, next(_SERIAL)
+    return enc, lookup, counts, serial
 
 
 def get_module_input_output_at_words(text_encoder, tok, requests: List[Dict], module_name: str,

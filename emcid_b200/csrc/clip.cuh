@@ -714,8 +714,34 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(H->dh));
   int si = 0;
+  // keys of layer keys_layer: k_out = the key rows of f = act(fc1), z_out = fc2 of those rows; leaves the resumable state
+  auto gather_keys = [&](const ClipLayer& Ly) -> int {
+    uint16_t* g_hi = H->ft_hi;   // compact [n_keys x dp] copy of the key rows
+    uint16_t* g_lo = H->ft_lo;
+    clip_gather_keys_kernel<<<n_keys < sms * 8 ? n_keys : sms * 8, 256, 0, stream>>>(
+        H->f_hi, H->f_lo, H->dp, key_rows, n_keys, T, H->d, H->dp, k_out, g_hi, g_lo);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    H->launches += 1;
+    CUtensorMap mg_hi, mg_lo;
+    GemmOutMaps om_z = {};
+    int r;
+    if ((r = make_tmap_2d(&mg_hi, g_hi, n_keys, H->d, H->dp, 128, 2)) ||
+        (r = make_tmap_2d(&mg_lo, g_lo, n_keys, H->d, H->dp, 128, 2)) ||
+        (use_tma_epi && (r = make_tmap_2d(&om_z.c, z_out, n_keys, H->h, H->h, 128, 4, 0, 64))))
+      return r;
+    if ((r = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, stream,
+                         use_tma_epi ? &om_z : nullptr, CLIP_TAG_FC2)))
+      return r;
+    H->keys_state_layer = keys_layer;
+    H->keys_state_tokens = T;
+    return EMCID_OK;
+  };
   for (int l = resume_layer < 0 ? 0 : resume_layer; l < run_layers; ++l) {
     const ClipLayer& Ly = (*H->layers)[l];
+    if (l == resume_layer && l == keys_layer) {
+      if ((rc = gather_keys(Ly))) return rc;
+      break;
+    }
     if (l == resume_layer) {
       // hres = h + attn(h) of this layer and f = act(fc1(LN2 hres)) are where the previous call left them
       if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, stream, pm_res,
@@ -786,23 +812,7 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     }
     if (is_last) break;
     if (l == keys_layer) {
-      uint16_t* g_hi = H->ft_hi;   // compact [n_keys x dp] copy of the key rows
-      uint16_t* g_lo = H->ft_lo;
-      clip_gather_keys_kernel<<<n_keys < sms * 8 ? n_keys : sms * 8, 256, 0, stream>>>(
-          H->f_hi, H->f_lo, H->dp, key_rows, n_keys, T, H->d, H->dp, k_out, g_hi, g_lo);
-      EMCID_CUDA_CHECK(cudaGetLastError());
-      H->launches += 1;
-      CUtensorMap mg_hi, mg_lo;
-      GemmOutMaps om_z = {};
-      if ((rc = make_tmap_2d(&mg_hi, g_hi, n_keys, H->d, H->dp, 128, 2)) ||
-          (rc = make_tmap_2d(&mg_lo, g_lo, n_keys, H->d, H->dp, 128, 2)) ||
-          (use_tma_epi && (rc = make_tmap_2d(&om_z.c, z_out, n_keys, H->h, H->h, 128, 4, 0, 64))))
-        return rc;
-      if ((rc = clip_linear(H, mg_hi, mg_lo, Ly.fc2, n_keys, ACT_NONE, nullptr, z_out, H->h, nullptr, nullptr, 0, stream,
-                            use_tma_epi ? &om_z : nullptr, CLIP_TAG_FC2)))
-        return rc;
-      H->keys_state_layer = l;
-      H->keys_state_tokens = T;
+      if ((rc = gather_keys(Ly))) return rc;
       break;
     }
     if ((rc = clip_linear(H, mf_hi, mf_lo, Ly.fc2, T, ACT_NONE, H->hres, H->hres, H->h, nullptr, nullptr, 0, stream, pm_res,

@@ -35,13 +35,30 @@ struct DgemmParams {
   // split_k > 1 -> grid.z = batches * split_k, slice z of the K range writes alpha * (partial product) to
   // C + z * c_split (plain stores, deterministic); Cin / Cin32 / C32 / beta are ignored and the caller reduces the slices.
   int split_k; long long c_split;
+  // persist > 0: that many CTAs walk the (x, y, z) tile space in a grid-stride loop instead of one CTA per tile — a
+  // product that runs BESIDE a latency chain on another stream (M64 next to the factorisation) then holds `persist` CTA
+  // slots for its whole duration instead of flooding every SM in front of the chain's short, dependent launches.
+  int persist;
+  int batches_z;   // filled by launch_dgemm_nt: batches * split_k (the z extent of the tile space)
 };
 
-// slices so that about 2 x `sms` CTAs run (two are resident per SM), each with at least 256 of K
-inline int dgemm_pick_split(int tiles, int K, int sms) {
-  int s = tiles > 0 ? 2 * sms / tiles : 1;
-  if (s > K / 256) s = K / 256;
-  return s < 1 ? 1 : s;
+// K slices per output tile.  Two CTAs are resident per SM, so `tiles * s` CTAs run in ceil(tiles * s / (2 sms)) waves, the
+// last one partly empty: the residual of a 1000-concept single-layer solve has 384 tiles on 296 slots — two waves, the
+// second 30 % full (measured 1.12 ms for 19.3 GFLOP = 17 TFLOP/s).  Take the smallest s (each slice at least 256 of K, at
+// most `max_s` slices) whose waves are >= 90 % full, else the fullest.
+inline int dgemm_pick_split(int tiles, int K, int sms, int max_s = 8) {
+  if (tiles <= 0) return 1;
+  const int slots = 2 * sms;
+  if (max_s > K / 256) max_s = K / 256;
+  int best = 1;
+  double best_fill = 0.0;
+  for (int s = 1; s <= max_s; ++s) {
+    const long long ctas = static_cast<long long>(tiles) * s;
+    const double fill = static_cast<double>(ctas) / static_cast<double>((ctas + slots - 1) / slots * slots);
+    if (fill >= 0.9) return s;
+    if (fill > best_fill + 1e-9) { best_fill = fill; best = s; }
+  }
+  return best;
 }
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
@@ -53,10 +70,19 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 __global__ void __launch_bounds__(DG_THREADS, 2) dgemm_nt_kernel(const DgemmParams p) {
   __shared__ double As[DG_BK][DG_LDA];
   __shared__ double Bs[DG_BK][DG_LDB];
-  const int bm = blockIdx.y * DG_BM, bn = blockIdx.x * DG_BN;
-  if (p.lower && bn > bm + DG_BM - 1) return;
   const int split = p.split_k > 1 ? p.split_k : 1;
-  const int batch = blockIdx.z / split, kz = blockIdx.z - batch * split;
+  const int tiles_x = (p.N + DG_BN - 1) / DG_BN, tiles_y = (p.M + DG_BM - 1) / DG_BM;
+  const long long n_items = p.persist > 0 ? static_cast<long long>(tiles_x) * tiles_y * p.batches_z : 1;
+  for (long long item = p.persist > 0 ? blockIdx.x : 0; item < n_items; item += p.persist > 0 ? gridDim.x : 1) {
+  int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+  if (p.persist > 0) {
+    bx = static_cast<int>(item % tiles_x);
+    by = static_cast<int>((item / tiles_x) % tiles_y);
+    bz = static_cast<int>(item / (static_cast<long long>(tiles_x) * tiles_y));
+  }
+  const int bm = by * DG_BM, bn = bx * DG_BN;
+  if (p.lower && bn > bm + DG_BM - 1) continue;
+  const int batch = bz / split, kz = bz - batch * split;
   const int k_chunk = ((p.K + split - 1) / split + DG_BK - 1) / DG_BK * DG_BK;
   const int k_begin = kz * k_chunk, k_end = min(p.K, k_begin + k_chunk);
   const double* A = p.A + batch * p.a_batch;
@@ -145,10 +171,15 @@ __global__ void __launch_bounds__(DG_THREADS, 2) dgemm_nt_kernel(const DgemmPara
       }
     }
   }
+  __syncthreads();   // persistent mode: the next item's staging stores must not overtake this item's last fragment loads
+  }
 }
 
-inline int launch_dgemm_nt(const DgemmParams& p, int batches, cudaStream_t stream) {
-  dim3 grid((p.N + DG_BN - 1) / DG_BN, (p.M + DG_BM - 1) / DG_BM, batches * (p.split_k > 1 ? p.split_k : 1));
+inline int launch_dgemm_nt(const DgemmParams& p_in, int batches, cudaStream_t stream) {
+  DgemmParams p = p_in;
+  p.batches_z = batches * (p.split_k > 1 ? p.split_k : 1);
+  dim3 grid((p.N + DG_BN - 1) / DG_BN, (p.M + DG_BM - 1) / DG_BM, p.batches_z);
+  if (p.persist > 0) grid = dim3(p.persist, 1, 1);
   dgemm_nt_kernel<<<grid, DG_THREADS, 0, stream>>>(p);
   EMCID_CUDA_CHECK(cudaGetLastError());
   return EMCID_OK;

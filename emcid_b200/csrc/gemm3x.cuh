@@ -93,7 +93,8 @@ struct GemmParams {
                                //    operand A is then read from HBM once, not once per N tile); 0: along M
   int k_tri;                   // triangular operand: skip the k-blocks that are known zeros.  1: B is lower triangular
                                // (k < n0 + BLOCK_N); 2: B is upper triangular (k >= n0); 3: A is lower triangular
-                               // (k < m0 + BLOCK_M).  Tile-level only (not with stream-K).
+                               // (k < m0 + BLOCK_M); 4: A is upper triangular (k >= m0).  Tile-level only (not with
+                               // stream-K).
   int chunk_kblocks;           // k-blocks accumulated in TMEM between register folds
   const int* dyn_n;            // optional device scalar overriding N (fc1: number of valid tokens)
   const int* dyn_k;            // optional device scalar overriding K (SYRK: number of valid tokens)
@@ -214,6 +215,7 @@ struct Sched {
     if (k_tri == 1) { const int e = (u.n0 + block_n + block_k - 1) / block_k; if (e < u.kb1) u.kb1 = e; }
     else if (k_tri == 2) { u.kb0 = u.n0 / block_k; }
     else if (k_tri == 3) { const int e = (u.m0 + block_m + block_k - 1) / block_k; if (e < u.kb1) u.kb1 = e; }
+    else if (k_tri == 4) { u.kb0 = u.m0 / block_k; }
     tile += tile_step;
     return true;
   }

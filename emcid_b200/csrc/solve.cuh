@@ -56,9 +56,9 @@ inline double solve_adapt_tol(double dflt) {
   static const double env = [] { const char* e = getenv("EMCID_SOLVE_TOL"); return e ? atof(e) : 0.0; }();
   return env > 0.0 ? env * (dflt / SOLVE_ADAPT_TOL) : dflt;
 }
-// capacity of the split-K slice buffer: dgemm_pick_split keeps slices * tiles <= 2 x #SMs (<= 320), a tile is 64 x 128, and
-// the lower-triangular G product covers at most twice its tile count in matrix elements (both uses clamp to it anyway)
-constexpr long long SOLVE_SPLIT_ELEMS = 2LL * 160 * 128 * 128;
+// capacity of the split-K slice buffer (doubles): three slices of a 1024 x 5120 right-hand side block (both uses clamp
+// their slice count to it)
+constexpr long long SOLVE_SPLIT_ELEMS = 3LL * 1024 * 5120;
 
 // ---- diagonal block: potrf + inverse, fp64 in shared memory, register-blocked ----------------------------------------
 // M32: [B][d x d] fp32.  Writes L_kk (symmetric fill) into the LL planes' diagonal block, Linv_kk / Linv_kk^T planes into
@@ -682,7 +682,7 @@ struct FactorCtx {
   int B, dim, sms;
   float *M32, *Mp_hi, *Mp_lo, *LL_hi, *LL_lo, *Li_hi, *Li_lo, *LiT_hi, *LiT_lo;
   float *Lv_hi, *Lv_lo, *LvT_hi, *LvT_lo;   // explicit inverse L^-1 and its transpose (planes)
-  float *Tp_hi, *Tp_lo;                     // [B][dim x 128] scratch of the inverse's block-column step
+  float *Tp_hi, *Tp_lo;                     // [B][dim x 128] scratch of the inverse's block-row step (T^T)
   PlaneMaps mMp, mLL, mLi, mLiT, mLv, mLvT, mTp;
 };
 
@@ -720,10 +720,13 @@ inline int factor_clear(const FactorCtx& f, cudaStream_t stream) {
   return EMCID_OK;
 }
 
-// side stream + events for the look-ahead of the factorisation (one set per device and host thread, never destroyed)
+// side streams + events of the factorisation (one set per device and host thread, never destroyed):
+//   stream / fork / join      the look-ahead's "rest of the trailing update"
+//   inv / inv_fork / inv_join the explicit inverse, one block row behind the factorisation
+//   aux / aux_fork / aux_join work the solve only needs after the factorisation (the fp64 matrix of the refinement)
 struct SolveSide {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t stream = nullptr, inv = nullptr, aux = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, inv_fork = nullptr, inv_join = nullptr, aux_fork = nullptr, aux_join = nullptr;
 };
 
 inline int solve_side(int device, SolveSide** out) {
@@ -732,11 +735,25 @@ inline int solve_side(int device, SolveSide** out) {
   SolveSide& s = sides[device];
   if (!s.stream) {
     EMCID_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    EMCID_CUDA_CHECK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
-    EMCID_CUDA_CHECK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    EMCID_CUDA_CHECK(cudaStreamCreateWithFlags(&s.inv, cudaStreamNonBlocking));
+    EMCID_CUDA_CHECK(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&s.fork, &s.join, &s.inv_fork, &s.inv_join, &s.aux_fork, &s.aux_join})
+      EMCID_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
   *out = &s;
   return EMCID_OK;
+}
+
+// Where the fp64 matrix of the refinement is formed.  One or two stacked problems leave most of the device idle during
+// the factorisation: M64 goes to a side stream there, as a persistent launch of sms / 2 CTAs (one per SM on half the SMs:
+// the diagonal-block kernel needs a whole SM to itself, 253 registers x 256 threads).  From three problems on the chain's
+// own GEMMs fill the device and the side product only delays them.  Measured on B200, ms per solve, in front / beside:
+// B = 1: 5.36 / 4.96, B = 2: 7.46 / 7.22 - 7.41, B = 5: 13.83 / 14.3 (profiles/round2/r05b_solve_variants.txt).
+// EMCID_SOLVE_M64_CTAS = n > 0 forces the side stream with n CTAs, < 0 forces "in front of the chain".
+inline int solve_m64_ctas(int sms, int B) {
+  static const int env = [] { const char* e = getenv("EMCID_SOLVE_M64_CTAS"); return e ? atoi(e) : 0; }();
+  if (env != 0) return env < sms - 2 * B - 8 ? env : sms - 2 * B - 8;
+  return B <= 2 ? sms / 2 : -1;
 }
 
 inline bool solve_use_lookahead() {
@@ -751,22 +768,54 @@ inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) 
   const long long dd = static_cast<long long>(d) * d;
   int rc;
   // Blocked right-looking Cholesky of M32 with a one-step look-ahead: the diagonal-block kernel keeps B SMs busy for
-  // ~70 us and sat in front of every trailing update (24 times per d = 3072).  The trailing update of step k is cut in
+  // ~80 us and sat in front of every trailing update (24 times per d = 3072).  The trailing update of step k is cut in
   // two: block column k+1 (all the next diagonal block and panel need) stays on the caller's stream, the rest runs on a
   // side stream next to potrf(k+1) and panel(k+1) and is joined before block column k+2 is touched again.  The side GEMM
   // leaves B SMs free for the diagonal-block CTAs (both kernels take a whole SM's shared memory).
+  //
+  // The explicit inverse X = L^-1 follows ONE BLOCK ROW BEHIND on a second side stream: block row k of L is final once
+  // panel(k-1) has run and X_kk comes out of potrf(k), so
+  //        T^T        = X[0:k, 0:k]^T  L[k, 0:k]^T          (A = X^T planes, upper triangular: k_tri = 4)
+  //        X[k, 0:k]^T = -T^T X_kk^T                         (planes into LvT, transposed planes into Lv)
+  // are issued right behind potrf(k) and run in the shadow of the chain potrf -> panel -> block column, which leaves most
+  // of the device idle (a single d = 3072 factorisation: 126 us per step on the critical path, 3.0 ms in all).  Computed
+  // block column by block column AFTER the factorisation, as it was, the inverse was another 46 dependent launches
+  // (1.6 ms of a 7.0 ms single-layer solve, profiles/round2/r05a_solve1_launch_list.txt); now only its last row is exposed.
   SolveSide* side = nullptr;
   const bool lookahead = solve_use_lookahead() && nblk > 2;
-  if (lookahead) {
+  if (nblk > 1) {
     int device = 0;
     EMCID_CUDA_CHECK(cudaGetDevice(&device));
     if ((rc = solve_side(device, &side))) return rc;
   }
+  auto inverse_row = [&](int k) -> int {   // on side->inv, after potrf(k) (and with it panel(k-1)) on the caller's stream
+    EMCID_CUDA_CHECK(cudaEventRecord(side->inv_fork, stream));
+    EMCID_CUDA_CHECK(cudaStreamWaitEvent(side->inv, side->inv_fork, 0));
+    const int r0 = k * SOLVE_NB;
+    SubGemm g;
+    memset(&g, 0, sizeof(g));
+    g.A = &f.mLvT; g.a_batch_rows = d;
+    g.B = &f.mLL; g.b_row0 = r0; g.b_batch_rows = d;
+    g.M = r0; g.N = SOLVE_NB; g.K = r0; g.k_tri = 4;
+    g.alpha = 1.0f;
+    g.P_hi = f.Tp_hi; g.P_lo = f.Tp_lo; g.ldp = SOLVE_NB; g.p_batch = static_cast<long long>(d) * SOLVE_NB;
+    if (int r = run_subgemm(g, B, sms, side->inv)) return r;
+    memset(&g, 0, sizeof(g));
+    g.A = &f.mTp; g.a_batch_rows = d;
+    g.B = &f.mLi; g.b_row0 = r0; g.b_batch_rows = d;
+    g.M = r0; g.N = SOLVE_NB; g.K = SOLVE_NB;
+    g.alpha = -1.0f;
+    g.P_hi = f.LvT_hi + r0; g.P_lo = f.LvT_lo + r0; g.ldp = d; g.p_batch = dd;
+    const long long off = static_cast<long long>(r0) * d;
+    g.Pt_hi = f.Lv_hi + off; g.Pt_lo = f.Lv_lo + off; g.ldpt = d; g.pt_batch = dd;
+    return run_subgemm(g, B, sms, side->inv);
+  };
   bool pending_join = false;
   for (int k = 0; k < nblk; ++k) {
     potrf_diag_kernel_v2<<<B, 256, potrf_smem_bytes(), stream>>>(f.M32, d, k, f.LL_hi, f.LL_lo, f.Li_hi, f.Li_lo, f.LiT_hi,
                                                                  f.LiT_lo, f.Lv_hi, f.Lv_lo, f.LvT_hi, f.LvT_lo, status_dev);
     EMCID_CUDA_CHECK(cudaGetLastError());
+    if (k > 0 && (rc = inverse_row(k))) return rc;
     const int rem = d - (k + 1) * SOLVE_NB;
     if (rem <= 0) break;
     const long long off_panel = static_cast<long long>(k + 1) * SOLVE_NB * d + static_cast<long long>(k) * SOLVE_NB;
@@ -811,30 +860,9 @@ inline int factor_spd(const FactorCtx& f, int* status_dev, cudaStream_t stream) 
     }
   }
   if (pending_join) EMCID_CUDA_CHECK(cudaStreamWaitEvent(stream, side->join, 0));
-  // explicit inverse, block columns from the right (the diagonal blocks came from potrf_diag_kernel):
-  //        T          = Linv[k+1:, k+1:] L[k+1:, k]        (A lower triangular: k_tri = 3)
-  //        Linv[k+1:, k] = -T Linv_kk                      (planes into Lv, transposed planes into LvT)
-  for (int k = nblk - 2; k >= 0; --k) {
-    const int r0 = (k + 1) * SOLVE_NB, rem = d - r0;
-    SubGemm g;
-    memset(&g, 0, sizeof(g));
-    g.A = &f.mLv; g.a_row0 = r0; g.a_col0 = r0; g.a_batch_rows = d;
-    g.B = &f.mLL; g.b_row0 = k * SOLVE_NB; g.b_col0 = r0; g.b_batch_rows = d;   // upper blocks of LL hold L^T
-    g.M = rem; g.N = SOLVE_NB; g.K = rem; g.k_tri = 3;
-    g.alpha = 1.0f;
-    g.P_hi = f.Tp_hi + static_cast<long long>(r0) * SOLVE_NB; g.P_lo = f.Tp_lo + static_cast<long long>(r0) * SOLVE_NB;
-    g.ldp = SOLVE_NB; g.p_batch = static_cast<long long>(d) * SOLVE_NB;
-    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
-    memset(&g, 0, sizeof(g));
-    g.A = &f.mTp; g.a_row0 = r0; g.a_col0 = 0; g.a_batch_rows = d;
-    g.B = &f.mLiT; g.b_row0 = k * SOLVE_NB; g.b_col0 = 0; g.b_batch_rows = d;
-    g.M = rem; g.N = SOLVE_NB; g.K = SOLVE_NB;
-    g.alpha = -1.0f;
-    const long long off = static_cast<long long>(r0) * d + static_cast<long long>(k) * SOLVE_NB;
-    const long long off_t = static_cast<long long>(k) * SOLVE_NB * d + r0;
-    g.P_hi = f.Lv_hi + off; g.P_lo = f.Lv_lo + off; g.ldp = d; g.p_batch = dd;
-    g.Pt_hi = f.LvT_hi + off_t; g.Pt_lo = f.LvT_lo + off_t; g.ldpt = d; g.pt_batch = dd;
-    if ((rc = run_subgemm(g, B, sms, stream))) return rc;
+  if (nblk > 1) {
+    EMCID_CUDA_CHECK(cudaEventRecord(side->inv_join, side->inv));
+    EMCID_CUDA_CHECK(cudaStreamWaitEvent(stream, side->inv_join, 0));
   }
   return EMCID_OK;
 }
@@ -1086,8 +1114,20 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
     g.C = w.f.M32; g.ldc = d; g.c_batch = dd;
     g.P_hi = w.f.Mp_hi; g.P_lo = w.f.Mp_lo; g.ldp = d; g.p_batch = dd;
     if ((rc = run_subgemm(g, B, sms, stream))) return rc;
-    // (forming M64 on a side stream next to the factorisation was considered and dropped: its 2880 long-running
-    // CTAs would sit in front of every short, dependent launch of the Cholesky chain)
+  }
+  // M64 (fp64, full) is only read by the refinement: with one or two stacked problems it is formed on a side stream
+  // BESIDE the factorisation (solve_m64_ctas).  (A plain launch there floods every SM with long-running CTAs in front of
+  // the Cholesky chain's short, dependent launches; in front of the factorisation the product sits on the critical path:
+  // 0.6 ms of a 7.0 ms single-layer solve.)
+  SolveSide* side = nullptr;
+  if ((rc = solve_side(device, &side))) return rc;
+  {
+    const int m64_ctas = solve_m64_ctas(sms, B);
+    cudaStream_t st64 = m64_ctas > 0 ? side->aux : stream;
+    if (m64_ctas > 0) {
+      EMCID_CUDA_CHECK(cudaEventRecord(side->aux_fork, stream));
+      EMCID_CUDA_CHECK(cudaStreamWaitEvent(side->aux, side->aux_fork, 0));
+    }
     DgemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = d; p.N = d; p.K = n;
@@ -1097,13 +1137,17 @@ inline int solve_layers(int device, int B, int d, int h, int n, const float* C32
     p.Cin32 = C32; p.ldcin32 = d; p.cin32_batch = dd;
     p.C = w.M64; p.ldc = d; p.c_batch = dd;
     p.lower = 1;
-    if ((rc = launch_dgemm_nt(p, B, stream))) return rc;
-    mirror64_kernel<<<dim3(d / 32, d / 32, B), dim3(32, 8), 0, stream>>>(w.M64, d);
+    if (m64_ctas > 0) p.persist = m64_ctas;
+    if ((rc = launch_dgemm_nt(p, B, st64))) return rc;
+    mirror64_kernel<<<dim3(d / 32, d / 32, B), dim3(32, 8), 0, st64>>>(w.M64, d);
     EMCID_CUDA_CHECK(cudaGetLastError());
+    EMCID_CUDA_CHECK(cudaEventRecord(side->aux_join, st64));
   }
 
   // 3. blocked right-looking Cholesky of M32 and the explicit inverse of its factor
   if ((rc = factor_spd(w.f, status_dev, stream))) return rc;
+
+  EMCID_CUDA_CHECK(cudaStreamWaitEvent(stream, side->aux_join, 0));
 
   // 4./5. solve + refinement; W holds the current right-hand side (transposed), then the solution
   if ((rc = refined_solve(w.f, w.a, false, refine_steps, stream, SOLVE_ADAPT_TOL, status_dev))) return rc;

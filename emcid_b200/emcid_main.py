@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 from . import nethook
-from .compute_ks import get_module_input_output_at_words, prepare_lookup
+from .compute_ks import get_module_input_output_at_words, prefetch_keys, prepare_lookup
 from .globals import STATS_DIR, XL_STATS_DIR1, XL_STATS_DIR2
 from . import _lib
 from .layer_stats import (get_all_cross_attn_kv_layer_names, layer_stats_cross_attn_kv, layer_stats_text_encoder,
@@ -386,7 +386,10 @@ def _insert_loop(text_encoder, tokenizer, requests, hparams, layers, zs, mom2_up
     import time
 
     t = time.perf_counter()
-    prepared = prepare_lookup(tokenizer, requests, hparams.num_edit_tokens, device)
+    # ... and the device starts on the layers below the first edited one as soon as the token ids exist
+    first_module = hparams.rewrite_module_tmp.format(layers[0])
+    prepared = prepare_lookup(tokenizer, requests, hparams.num_edit_tokens, device,
+                              after_tokenise=lambda enc, serial: prefetch_keys(text_encoder, enc, first_module, serial))
     t = _tick(device, "tokenise_lookup_ms", t)
     _prefetch_covariances(text_encoder, tokenizer, hparams, layers, stat_dir, verbose)
     updates = _DEVICE_UPDATES[id(text_encoder)] = {}

@@ -166,7 +166,9 @@ int emcid_clip_forward(emcid_clip_t* h, const int32_t* ids, const int32_t* posit
  * this handle left behind — a keys call at layer r over the SAME packed tokens, after which only fc2 of layer r was
  * re-uploaded (what the edit loop does between layers, emcid/emcid_main.py:1061): layer r is finished with its new fc2
  * and layers (r, layer] follow, so an L-layer edit costs the layers below the first edited one once plus about one
- * layer per edited layer instead of first + ... + last.  Anything else is EMCID_ERR_INVALID. */
+ * layer per edited layer instead of first + ... + last.  resume_layer = layer: the same layer again with other key rows
+ * — only the gather and fc2 of the gathered rows run (a caller launches the forward first, with any valid row, and works
+ * out which rows it wants while the device is busy).  Anything else is EMCID_ERR_INVALID. */
 int emcid_clip_forward_keys(emcid_clip_t* h, const int32_t* ids, const int32_t* positions, const int32_t* cu_seqlens,
                             int n_captions, int n_tokens, int layer, const int32_t* key_rows, int n_keys, float* k_out,
                             float* z_out, int resume_layer, void* stream);
