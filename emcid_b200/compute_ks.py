@@ -125,13 +125,14 @@ def last_hidden_at_words(text_encoder, tok, requests: List[Dict]) -> torch.Tenso
     return rows_out.reshape(len(counts), c, -1).mean(1)
 
 
-def tokenize_prompts(prompts, tokenizer, device, padding_length=None):
+def _tokenize_on_host(prompts, tokenizer, padding_length=None):
     if padding_length is None:
-        enc = tokenizer(prompts, return_tensors="pt", padding=True, truncation=True)
-    else:
-        enc = tokenizer(prompts, return_tensors="pt", padding="max_length", truncation=True,
-                        max_length=padding_length)
-    return {k: v.to(device) for k, v in enc.items()}
+        return tokenizer(prompts, return_tensors="pt", padding=True, truncation=True)
+    return tokenizer(prompts, return_tensors="pt", padding="max_length", truncation=True, max_length=padding_length)
+
+
+def tokenize_prompts(prompts, tokenizer, device, padding_length=None):
+    return {k: v.to(device) for k, v in _tokenize_on_host(prompts, tokenizer, padding_length).items()}
 
 
 def find_token_range(tokenizer, token_array, substring_orig: str, piece_cache: Optional[Dict[int, str]] = None) -> Tuple[int, int]:
@@ -201,19 +202,22 @@ def prepare_lookup(tok, requests: List[Dict], num_fact_token: int, device, after
     (compute_z.py:2284-2300).  Independent of the layer: the edit loop computes it once per edit.  `after_tokenise(enc,
     serial)` (one looked-up token per prompt only) is called between the tokenisation and the look-up, see prefetch_keys."""
     prompts, subjects, counts = _prompts_and_subjects(requests)
-    enc = tokenize_prompts(prompts, tok, device)
+    host = _tokenize_on_host(prompts, tok)
+    enc = {k: v.to(device) for k, v in host.items()}
     serial = next(_SERIAL)
     if after_tokenise is not None and num_fact_token == 1:
         after_tokenise(enc, serial)
-    # token ids as host lists: find_token_range walks them one by one (a device tensor would cost a sync per token)
+    # find_token_range walks the token ids one by one: host lists, taken from the tokenizer's own host tensors (reading
+    # them back from the device would wait for whatever after_tokenise has just launched there)
     pieces: Dict[int, str] = {}
     if num_fact_token == 1:
-        lookup = [[find_token_range(tok, ids, w, pieces)[-1] - 1] for ids, w in zip(enc["input_ids"].tolist(), subjects)]
+        lookup = [[find_token_range(tok, ids, w, pieces)[-1] - 1] for ids, w in zip(host["input_ids"].tolist(), subjects)]
     else:
         extra = num_fact_token - 2
-        enc = tokenize_prompts(prompts, tok, device, padding_length=len(enc["input_ids"][0]) + extra)
+        host = _tokenize_on_host(prompts, tok, padding_length=len(host["input_ids"][0]) + extra)
+        enc = {k: v.to(device) for k, v in host.items()}
         lookup = []
-        for ids, w, n_valid in zip(enc["input_ids"].tolist(), subjects, enc["attention_mask"].sum(1).tolist()):
+        for ids, w, n_valid in zip(host["input_ids"].tolist(), subjects, host["attention_mask"].sum(1).tolist()):
             eos = int(n_valid) - 1
             lookup.append([find_token_range(tok, ids, w, pieces)[-1] - 1] + list(range(eos, eos + extra + 1)))
     return enc, lookup, counts, serial

@@ -657,9 +657,12 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
   }
   // resume_layer = r >= 0: the previous call on this handle was a keys call at layer r over the SAME packed tokens and only
   // fc2 of layer r has changed since (the edit loop, emcid_main.py:1061): start from that call's state — finish layer r
-  // with its new fc2, then run layers (r, keys_layer] — instead of from the embeddings
+  // with its new fc2, then run layers (r, keys_layer] — instead of from the embeddings.  resume_layer == keys_layer: the
+  // same layer again with other key rows — nothing is recomputed but the gather and fc2 of the gathered rows (the edit
+  // launches the forward of the prompts before it has worked out WHICH rows it wants: the host-side search for the subject
+  // tokens runs beside the device's forward)
   if (resume_layer >= 0) {
-    EMCID_CHECK(keys_layer > resume_layer && H->keys_state_layer == resume_layer && H->keys_state_tokens == T, EMCID_ERR_INVALID,
+    EMCID_CHECK(keys_layer >= resume_layer && H->keys_state_layer == resume_layer && H->keys_state_tokens == T, EMCID_ERR_INVALID,
                 "clip_forward: cannot resume from layer %d (state: layer %d, %d tokens; this call: layer %d, %d tokens)",
                 resume_layer, H->keys_state_layer, H->keys_state_tokens, keys_layer, T);
   }
