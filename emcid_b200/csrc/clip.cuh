@@ -305,7 +305,6 @@ __global__ void __launch_bounds__(128) clip_attention2_kernel(const float* __res
   }
 }
 
-__global__ void clip_add_count_kernel(long long* count, long long n) { *count += n; }
 
 // ---- host ---------------------------------------------------------------------------------------
 
@@ -806,12 +805,10 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
       if ((rc = make_tmap_2d(&fm.a_hi, H->f_hi, T, H->d, H->dp, 64, 2)) || (rc = make_tmap_2d(&fm.a_lo, H->f_lo, T, H->d, H->dp, 64, 2)))
         return rc;
       fm.b_hi = fm.a_hi; fm.b_lo = fm.a_lo;
-      if ((rc = mom2_syrk_slab(A, fm, KIND_F16_MN, 0, T, nullptr, stream, hybrid ? 2 : 1))) return rc;
+      // the block's token count rides on the launch
+      if ((rc = mom2_syrk_slab(A, fm, KIND_F16_MN, 0, T, nullptr, stream, hybrid ? 2 : 1, T))) return rc;
       A->slabs_since_fold += 4;
       if (A->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(A, stream))) return rc;
-      clip_add_count_kernel<<<1, 1, 0, stream>>>(A->count, static_cast<long long>(T));
-      EMCID_CUDA_CHECK(cudaGetLastError());
-      A->launches += 1;
     }
     if (is_last) break;
     if (l == keys_layer) {
@@ -879,12 +876,9 @@ inline int clip_forward_final(ClipHandle* H, const int* ids, const int* pos, con
     if ((rc = make_tmap_2d(&ym.a_hi, H->x_hi, T, H->h, H->hp, 64, 2)) || (rc = make_tmap_2d(&ym.a_lo, H->x_lo, T, H->h, H->hp, 64, 2)))
       return rc;
     ym.b_hi = ym.a_hi; ym.b_lo = ym.a_lo;
-    if ((rc = mom2_syrk_slab(acc, ym, KIND_F16_MN, 0, T, nullptr, stream, 2))) return rc;
+    if ((rc = mom2_syrk_slab(acc, ym, KIND_F16_MN, 0, T, nullptr, stream, 2, T))) return rc;
     acc->slabs_since_fold += 4;
     if (acc->slabs_since_fold >= MOM2_FOLD_EVERY && (rc = mom2_fold(acc, stream))) return rc;
-    clip_add_count_kernel<<<1, 1, 0, stream>>>(acc->count, static_cast<long long>(T));
-    EMCID_CUDA_CHECK(cudaGetLastError());
-    acc->launches += 1;
   }
   if (out) {
     const int R = rows ? n_rows : (n_rows < T ? n_rows : T);

@@ -114,6 +114,8 @@ struct GemmParams {
   const float* bias_col;       // [N], EPI_LINEAR (16-byte aligned)
   int act;
   int lo_fmt;                  // KIND_F16: format of the lo planes (FMT_BF16 default, FMT_F16)
+  long long* count;            // optional device counter: thread 0 of CTA (0, 0) adds count_add (the token count of the
+  long long count_add;         // SYRK's block: instead of a 1-thread kernel of its own)
 };
 
 template <int BLOCK_N, int STAGES, int ROWB = GEMM_ROW_BYTES>
@@ -353,6 +355,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   if (CTA2) cluster_sync();   // the peer's barriers exist before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.count && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.count), static_cast<unsigned long long>(p.count_add));
 
   // Each role derives its own scheduler state after the register re-partition so nothing has to
   // be carried (spilled) across the setmaxnreg boundary.

@@ -12,7 +12,6 @@
 
 #include <map>
 #include <mutex>
-#include <utility>
 
 #include "gemm3x.cuh"
 

@@ -388,11 +388,13 @@ inline bool mom2_deterministic() {
   return e && e[0] == '1';
 }
 
+// count_add: added to the handle's token count by the launch itself
 inline int mom2_syrk_slab(Mom2Handle* H, const GemmOperands& ops, int kind, int col0, int t, const int* dyn_k,
-                          cudaStream_t stream, int streamk_mode = 1) {
+                          cudaStream_t stream, int streamk_mode = 1, long long count_add = 0) {
   if (mom2_deterministic()) streamk_mode = 0;
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  if (count_add) { p.count = H->count; p.count_add = count_add; }
   p.M = H->d; p.N = H->d; p.K = t;
   p.a_col0 = col0; p.b_col0 = col0;
   p.dyn_k = dyn_k;
