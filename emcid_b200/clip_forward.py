@@ -143,6 +143,7 @@ class NativeClipTextEncoder:
         """Forget what was uploaded: the next sync re-uploads everything it needs."""
         self._sig.clear()
         self._sums.clear()
+        self.__dict__.pop("_layer_lists", None)
         self.keys_token = None
 
     def sync_weights(self, model, upto_layer: Optional[int] = None, verify: bool = False) -> int:
@@ -162,8 +163,14 @@ class NativeClipTextEncoder:
         fln = getattr(tm, "final_layer_norm", None)
         if isinstance(fln, torch.nn.LayerNorm) and fln.weight is not None and fln.bias is not None:
             groups["final_norm"] = [fln.weight, fln.bias]
+        # the 16 source tensors of a layer, listed once per verified sync (a replaced Parameter object is picked up there;
+        # between two of them — inside one edit — weights only change in place): 12 layers x 16 attribute walks per call
+        # were 0.8 ms of every 100-concept edit
+        cache = self.__dict__.setdefault("_layer_lists", {})
         for i in range(last + 1):
-            groups[i] = self._layer_tensors(tm.encoder.layers[i])
+            if verify or i not in cache:
+                cache[i] = self._layer_tensors(tm.encoder.layers[i])
+            groups[i] = cache[i]
         stale: Dict[object, list] = {}       # group -> indices of the tensors whose content changed behind the version counter
         if verify:
             with torch.cuda.device(self.device):
@@ -210,8 +217,8 @@ class NativeClipTextEncoder:
                 _lib.check(lib.emcid_clip_update_layer(self._h, i, arr, mask, stream))   # first upload: all 16 bits
                 self._sig[i] = sig
                 n += 1
-            if n:
-                torch.cuda.synchronize(self.device)  # the library copied / split everything: sources may change now
+            # no device synchronisation: the library's copies / splits are queued on the current stream, where every later
+            # write to (or release of) a source tensor is ordered behind them
         return n
 
     def _stream(self) -> int:
