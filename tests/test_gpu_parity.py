@@ -334,6 +334,38 @@ def test_native_key_extraction_resumes_after_fc2_edit(dev, monkeypatch, kind, la
         clip_forward.release_key_encoders()
 
 
+@pytest.mark.parametrize("kind,layer", [("tiny", 1), ("clip-l", 7)])
+def test_prefetched_forward_gathers_the_same_keys(dev, kind, layer):
+    """The edit launches the forward of the prompts before the subject tokens are looked up (compute_ks.prefetch_keys:
+    emcid_clip_forward_keys with a placeholder row) and the keys call that follows only gathers its rows from that state
+    (resume_layer == layer): bit-identical to a keys call that runs the whole forward itself; a weight written between
+    the two calls (anything but fc2 of that layer) voids the state."""
+    from emcid_b200 import clip_forward, compute_ks
+    model = rh.make_clip_text_model(kind, seed=4).to(dev)
+    tok = rh.FakeTokenizer(model.config.vocab_size)
+    reqs = rh.make_requests(9)
+    name = f"text_model.encoder.layers.{layer}.mlp.fc2"
+    try:
+        plain = compute_ks.prepare_lookup(tok, reqs, 1, dev)
+        k0, z0 = compute_ks.get_module_input_output_at_words(model, tok, reqs, name, prepared=plain)
+        assert compute_ks.LAST_PATH["native"] and compute_ks.LAST_PATH["resumed_from"] == -1
+        launched = []
+        pre = compute_ks.prepare_lookup(tok, reqs, 1, dev, after_tokenise=lambda enc, serial: launched.append(
+            compute_ks.prefetch_keys(model, enc, name, serial)))
+        assert launched == [True]
+        k1, z1 = compute_ks.get_module_input_output_at_words(model, tok, reqs, name, prepared=pre)
+        assert compute_ks.LAST_PATH["resumed_from"] == layer
+        assert torch.equal(k0, k1) and torch.equal(z0, z1)
+        pre2 = compute_ks.prepare_lookup(tok, reqs, 1, dev, after_tokenise=lambda enc, serial: compute_ks.prefetch_keys(
+            model, enc, name, serial))
+        with torch.no_grad():
+            model.text_model.encoder.layers[layer].mlp.fc1.bias[...] += 0.03
+        k2, _ = compute_ks.get_module_input_output_at_words(model, tok, reqs, name, prepared=pre2)
+        assert compute_ks.LAST_PATH["resumed_from"] == -1 and not torch.equal(k0, k2)
+    finally:
+        clip_forward.release_key_encoders()
+
+
 @pytest.mark.parametrize("max_pos,heads", [(128, 2), (48, 2), (77, 1)])
 def test_native_forward_other_caption_lengths(dev, max_pos, heads):
     """Head dim 64 with other position limits than CLIP's 77: up to 128 tokens (the 8-chunk attention instantiation, 16 KB
