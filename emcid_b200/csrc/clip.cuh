@@ -521,13 +521,14 @@ inline int clip_linear(ClipHandle* H, const CUtensorMap& x_hi, const CUtensorMap
   // 1.650 / 1.682 / 1.724 M tokens/s, hidden-state error vs fp64 1.26e-6 / 1.78e-6 / 2.35e-6 (HF's own fp32 run: 1.46e-6),
   // mom2 error 1.84e-6 / 2.4e-6 / 3.2e-6 (tolerance 1e-5).  The slack only matters where a tile is short: with K <= 1024
   // (q/k/v, out projection, fc1: 12 k-blocks) two chunks of 2 are a third of the tile and the store phase of the previous
-  // tile (128 activations + fp16 splits per thread) does not fit behind them.  So: chunk 3 for K <= 1024, chunk 2 for
-  // fc2 (K = 3072, 91 % tensor-pipe active anyway, and the longest accumulation).  Same-box A/B (profiles/round2/r04f_ab.txt):
-  // 92.9 -> 90.2 ms per step, mom2 probe error over 1.2 M tokens 2.40e-6 -> 2.88e-6.
-  // EMCID_LINEAR_CHUNK=n sets every layer, EMCID_LINEAR_CHUNK_SHORTK=n the K <= 1024 products.
+  // tile (128 activations + fp16 splits per thread) does not fit behind them.  So: chunk 3 for the products that contract
+  // over the hidden width (K = 768; bigG: 1280), chunk 2 for fc2 (K = 3072 / 5120, 91 % tensor-pipe active anyway, and the
+  // longest accumulation).  Same-box A/Bs: CLIP-L 92.9 -> 90.2 ms per step, mom2 probe error over 1.2 M tokens 2.40e-6 ->
+  // 2.88e-6 (profiles/round2/r04f_ab.txt); bigG 545.5 -> 533.1 ms per step (profiles/round2/r05l_bench_sdxl_text2*.json).
+  // EMCID_LINEAR_CHUNK=n sets every layer, EMCID_LINEAR_CHUNK_SHORTK=n the K <= 2048 products.
   static const int chunk_env = [] { const char* e = getenv("EMCID_LINEAR_CHUNK"); return e ? atoi(e) : 0; }();
   static const int chunk_short = [] { const char* e = getenv("EMCID_LINEAR_CHUNK_SHORTK"); return e ? atoi(e) : 0; }();
-  p.chunk_kblocks = chunk_env > 0 ? chunk_env : (W.K <= 1024 ? (chunk_short > 0 ? chunk_short : 3) : 2);
+  p.chunk_kblocks = chunk_env > 0 ? chunk_env : (W.K <= 2048 ? (chunk_short > 0 ? chunk_short : 3) : 2);
   // token tiles outermost: the activation planes (121-484 MB per block) stream from HBM once while the weight
   // planes (<= 19 MB) stay L2-resident.  EMCID_TILE_ORDER=m restores the M-fastest walk (measured: every N tile
   // re-read the activations from DRAM, 1.1-1.5 GB per launch).
