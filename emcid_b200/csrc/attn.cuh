@@ -1,7 +1,10 @@
 // emcid_b200 — causal self-attention of the CLIP text encoder on tcgen05 (head dim 64, captions <= 128 tokens).
 //
-// One (caption, head) unit at a time per persistent CTA; both products run on the tensor core with the
-// same 3-term fp16 split as every other GEMM of the path:
+// One (caption group, head) unit at a time per persistent CTA — a group is a run of consecutive packed captions with at
+// most `lp` tokens in all (clip.cuh::clip_group_captions_kernel): a full-length caption is a group of its own, short ones
+// (real caption data: a dozen tokens; the prompts of an edit: six) share a tile, and the causal mask becomes block
+// diagonal (row i sees columns [start of i's caption, i]).  Both products run on the tensor core with the same 3-term
+// fp16 split as every other GEMM of the path:
 //   S = Q K^T          A = Q planes [128 x 64], B = K planes [LP x 64]        TMA from the q|k|v planes [T x 3h]
 //   P = softmax(S * dh^-1/2, causal)     fp32 in registers, one query row per thread (TMEM lane)
 //   O = P V            A = P planes [128 x LP] written to swizzled smem by the threads,
@@ -9,7 +12,7 @@
 //                      load along the contiguous token axis of a transposed copy would need 16-byte aligned
 //                      caption starts, which packed captions do not have)
 // Rows of the 128-row tiles beyond the caption belong to the next captions (finite, never stored) or are
-// zero-filled by TMA; columns j > i and j >= L get P = 0.  Replaces the softmax(QK^T)V of
+// zero-filled by TMA; columns j > i, j >= L and j before row i's own caption get P = 0.  Replaces the softmax(QK^T)V of
 // transformers modeling_clip.py::CLIPAttention under the reference's `model(**batch)` (emcid/layer_stats.py:215).
 #pragma once
 
@@ -39,11 +42,16 @@ struct AttnMaps {
   CUtensorMap kv_hi, kv_lo;   // same tensor, box 64 x lp (Q, K and V tiles of one caption)
 };
 
-// NC: 16-column chunks of S a thread keeps in registers (lp <= 16 * NC)
-template <int NC>
+// NC: 16-column chunks of S a thread keeps in registers (lp <= 16 * NC).
+// GROUPED = false: one caption per unit, `offs` = cu_seqlens, n_units_host = captions x heads (the headline's 77-token
+// captions: two never fit a tile, and the grouped instantiation is 9 % slower per launch there — same-box A/B,
+// profiles/round2/r05t_ab_grouped_attention.txt).  GROUPED = true: `offs` = group offsets, their number read from the
+// device (n_grp), tok_start[t] = first token of t's caption; the host picks it when captions average under half a tile.
+template <int NC, bool GROUPED>
 __global__ void __launch_bounds__(ATTN_THREADS, NC <= 5 ? 3 : 2)
-clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restrict__ cu, int n_seqs, int heads, int h,
-                         int lp /* padded caption length: multiple of 16, <= 128 */, float scale,
+clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restrict__ offs, int n_units_host,
+                         const int* __restrict__ n_grp, const int* __restrict__ tok_start, int heads, int h,
+                         int lp /* padded caption / group length: multiple of 16, <= 128 */, float scale,
                          uint16_t* __restrict__ o_hi, uint16_t* __restrict__ o_lo, int ldo) {
   extern __shared__ uint8_t attn_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -73,14 +81,13 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
   const uint32_t s_q = smem_u32(smem);          // Q hi | Q lo
   const uint32_t s_k = s_q + 2 * kt, s_v = s_k + 2 * kt;
   const uint32_t s_p = s_q;                     // P hi kb0 | P hi kb1 | P lo kb0 | P lo kb1 over Q and K
-  const int n_units = n_seqs * heads;
+  const int n_units = GROUPED ? *n_grp * heads : n_units_host;
   const int ksteps2 = lp / 16;                 // k-steps of the second product
   const uint32_t idesc1 = make_idesc(FMT_F16, FMT_F16, 128, static_cast<uint32_t>(lp));
   const uint32_t idesc2 = make_idesc(FMT_F16, FMT_F16, 128, ATTN_DH) | (1u << 16);   // B (= V) is MN-major
 
-  auto issue_loads = [&](int unit) {
-    const int head = unit % heads, seq = unit / heads;
-    const int t0 = cu[seq];
+  auto issue_loads = [&](int unit, int t0) {
+    const int head = unit % heads;
     uint8_t* base = smem;
     mbar_arrive_expect_tx(bar_qk, 4 * kt);
     tma_load_2d(base, &tm.kv_hi, bar_qk, head * ATTN_DH, t0);
@@ -92,14 +99,29 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     tma_load_2d(base + 5 * kt, &tm.kv_lo, bar_v, 2 * h + head * ATTN_DH, t0);
   };
 
-  if (tid == 0 && static_cast<int>(blockIdx.x) < n_units) issue_loads(blockIdx.x);
+  // GROUPED: (t0, L, j0) of a unit — first token and length of its group, first column of row tid's caption inside it —
+  // are fetched one unit ahead (two dependent global loads: read at the top of the unit they stall warp 0, which also
+  // issues the MMAs)
+  int t0 = 0, L = 0, j0 = 0;
+  if (static_cast<int>(blockIdx.x) < n_units) {
+    const int seq = blockIdx.x / heads;
+    t0 = offs[seq];
+    L = offs[seq + 1] - t0;
+    if (L > lp) L = lp;
+    if (GROUPED) j0 = tid < L ? tok_start[t0 + tid] - t0 : 0;
+    if (tid == 0) issue_loads(blockIdx.x, t0);
+  }
   int it = 0;
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
     const uint32_t phase = it & 1;
-    const int head = unit % heads, seq = unit / heads;
-    const int t0 = cu[seq];
-    int L = cu[seq + 1] - t0;
-    if (L > lp) L = lp;
+    const int head = unit % heads;
+    const int nunit = unit + static_cast<int>(gridDim.x);
+    if (!GROUPED) {
+      const int seq = unit / heads;
+      t0 = offs[seq];
+      L = offs[seq + 1] - t0;
+      if (L > lp) L = lp;
+    }
     // ---- S = Q K^T
     if (tid == 0) {
       mbar_wait(bar_qk, phase, 11);
@@ -117,12 +139,18 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     }
     mbar_wait(bar_s, phase, 12);
     tc_fence_after();
+    int nt0 = 0, nt1 = 0;                          // GROUPED: the next unit's group, in flight during the softmax
+    if (GROUPED && nunit < n_units) { const int ns = nunit / heads; nt0 = offs[ns]; nt1 = offs[ns + 1]; }
     // ---- causal softmax of row i = tid (TMEM lane): e = exp(s - max) goes to the swizzled P tiles as fp16 hi/lo
     // planes (unnormalised, in (0, 1]); the 1/sum factor is applied to the output row instead
     float inv = 0.f;
     if (warp * 32 < lp) {                          // warp-uniform; rows >= lp have no P row in the lp-row tiles
       const int i = tid;
       const bool live = i < L;
+      // GROUPED: column j of row i is visible iff j0 <= j <= i — one unsigned compare, (j - j0) <= (i - j0); dead rows
+      // see nothing.  Otherwise j0 = 0 and the compare folds to j <= i.
+      const int jb0 = GROUPED ? (live ? j0 : (1 << 20)) : 0;
+      const unsigned span = GROUPED ? (live ? static_cast<unsigned>(i - j0) : 0u) : static_cast<unsigned>(i);
       float v[NC][16];
 #pragma unroll
       for (int c = 0; c < NC; ++c)
@@ -132,7 +160,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
       for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int u = 0; u < 16; ++u)
-          if (c * 16 < lp && live && c * 16 + u <= i) mx = fmaxf(mx, v[c][u]);
+          if (c * 16 < lp && (GROUPED || live) && static_cast<unsigned>(c * 16 + u - jb0) <= span) mx = fmaxf(mx, v[c][u]);
       mx *= scale;                                 // scale > 0: max(scale * s) = scale * max(s)
       float sum = 0.f;
       const uint32_t prow = s_p + i * 128;
@@ -143,8 +171,9 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
           uint32_t hh[8], ll[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const float pa = (live && c * 16 + 2 * u <= i) ? __expf(fmaf(v[c][2 * u], scale, -mx)) : 0.f;
-            const float pb = (live && c * 16 + 2 * u + 1 <= i) ? __expf(fmaf(v[c][2 * u + 1], scale, -mx)) : 0.f;
+            const int ja = c * 16 + 2 * u, jb = ja + 1;
+            const float pa = ((GROUPED || live) && static_cast<unsigned>(ja - jb0) <= span) ? __expf(fmaf(v[c][2 * u], scale, -mx)) : 0.f;
+            const float pb = ((GROUPED || live) && static_cast<unsigned>(jb - jb0) <= span) ? __expf(fmaf(v[c][2 * u + 1], scale, -mx)) : 0.f;
             sum += pa + pb;
             split_f16x2(pa, pb, hh[u], ll[u]);
           }
@@ -164,6 +193,9 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    int nL = nt1 - nt0;
+    if (nL > lp) nL = lp;
+    const int nj0 = (GROUPED && tid < nL) ? tok_start[nt0 + tid] - nt0 : 0;   // in flight during P V and the output stores
     // ---- O = P V
     if (tid == 0) {
       tc_fence_after();
@@ -186,7 +218,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     mbar_wait(bar_o, phase, 14);
     tc_fence_after();
     // the operands are free again: fetch the next unit while this one's output is written
-    if (tid == 0 && unit + static_cast<int>(gridDim.x) < n_units) issue_loads(unit + gridDim.x);
+    if (tid == 0 && nunit < n_units) issue_loads(nunit, GROUPED ? nt0 : offs[nunit / heads]);
     if (warp * 32 < L) {                           // warp-uniform: tcgen05.ld is warp-collective
       uint16_t* oh = o_hi + static_cast<long long>(t0 + tid) * ldo + head * ATTN_DH;
       uint16_t* ol = o_lo + static_cast<long long>(t0 + tid) * ldo + head * ATTN_DH;
@@ -210,6 +242,7 @@ clip_attention_tc_kernel(const __grid_constant__ AttnMaps tm, const int* __restr
     tc_fence_before();
     __syncthreads();   // all TMEM reads of this unit are done before the next unit's MMAs overwrite S / O
     tc_fence_after();
+    if (GROUPED) { t0 = nt0; L = nL; j0 = nj0; }
   }
   tc_fence_before();
   __syncthreads();

@@ -64,6 +64,7 @@ struct ClipHandle {
   uint16_t *f_hi, *f_lo;       // [cap x dp]   act(fc1)
   uint16_t *ft_hi, *ft_lo;     // [d x tp]     scratch planes: the gathered key rows [n_keys x dp] of the key extraction
   unsigned int* scratch;
+  int *grp, *n_grp, *tok_start; // attention units: group offsets [cap_seqs + 2], their number, [cap] first token of t's caption
   std::vector<void*>* allocs;
   DeviceInfo info;
   long long launches;
@@ -368,7 +369,9 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
       (rc = clip_alloc(H, &H->f_hi, cap * H->dp)) || (rc = clip_alloc(H, &H->f_lo, cap * H->dp)) ||
       (rc = clip_alloc(H, &H->ft_hi, static_cast<size_t>(d) * H->tp)) ||
       (rc = clip_alloc(H, &H->ft_lo, static_cast<size_t>(d) * H->tp)) || (rc = clip_alloc(H, &H->scratch, 64)) ||
-      (rc = clip_alloc(H, &H->qp_hi, cap * 3 * h)) || (rc = clip_alloc(H, &H->qp_lo, cap * 3 * h))) {
+      (rc = clip_alloc(H, &H->qp_hi, cap * 3 * h)) || (rc = clip_alloc(H, &H->qp_lo, cap * 3 * h)) ||
+      (rc = clip_alloc(H, &H->grp, static_cast<size_t>(cap_seqs) + 2)) || (rc = clip_alloc(H, &H->n_grp, 4)) ||
+      (rc = clip_alloc(H, &H->tok_start, cap))) {
     clip_destroy(H);
     return rc;
   }
@@ -407,8 +410,12 @@ inline int clip_create(ClipHandle** out, int device, int L, int h, int heads, in
     H->attn_tc = H->dh == ATTN_DH && max_pos <= 128 && (3 * h) % 8 == 0 && !(e && e[0] == '0');
     if (H->attn_tc) {
       const int lp = (max_pos + 15) & ~15;
-      cudaError_t ce = lp <= 80 ? cudaFuncSetAttribute(clip_attention_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(lp))
-                                : cudaFuncSetAttribute(clip_attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(lp));
+      const int smem = attn_smem_bytes(lp);
+      cudaError_t ce = lp <= 80 ? cudaFuncSetAttribute(clip_attention_tc_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                : cudaFuncSetAttribute(clip_attention_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (ce == cudaSuccess)
+        ce = lp <= 80 ? cudaFuncSetAttribute(clip_attention_tc_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                      : cudaFuncSetAttribute(clip_attention_tc_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (ce != cudaSuccess) {
         clip_destroy(H);
         return set_error(EMCID_ERR_CUDA, "clip_create: attention shared memory %d B: %s", attn_smem_bytes(lp), cudaGetErrorString(ce));
@@ -586,6 +593,27 @@ inline int clip_layernorm(ClipHandle* H, const float* x, int T, const float* w, 
   return set_error(EMCID_ERR_UNSUPPORTED, "clip_layernorm: hidden size %d too large", H->h);
 }
 
+// Attention units of a packed block: greedy runs of consecutive captions with at most `lp` tokens in all (block 0,
+// thread 0: one pass over cu_seqlens, ~40 us for 2500 captions, once per block) and, for every token, the first token of
+// its caption (all blocks).  77-token captions stay alone (two do not fit lp = 80); 15-token captions go five to a tile.
+__global__ void clip_group_captions_kernel(const int* __restrict__ cu, int S, int lp, int* __restrict__ grp,
+                                           int* __restrict__ n_grp, int* __restrict__ tok_start) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int g = 0, g0 = cu[0];
+    grp[0] = g0;
+    for (int s = 1; s <= S; ++s) {          // caption s - 1 = [cu[s - 1], cu[s])
+      const int a = cu[s - 1], b = cu[s];
+      if (b - g0 > lp && a > g0) { grp[++g] = a; g0 = a; }
+    }
+    grp[++g] = cu[S];
+    *n_grp = g;
+  }
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    const int a = cu[s], b = cu[s + 1];
+    for (int t = a; t < b; ++t) tok_start[t] = a;
+  }
+}
+
 // Key extraction: rows `rows[r]` of the act(fc1) planes -> fp32 keys (hi + lo: the 22-bit split is exact to 2^-23) and a
 // compact copy of the planes (operand of the fc2 product on those rows only).
 __global__ void clip_gather_keys_kernel(const uint16_t* __restrict__ f_hi, const uint16_t* __restrict__ f_lo, long long ldf,
@@ -716,6 +744,15 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
     H->launches += 1;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(H->dh));
+  // short captions share attention tiles (attn.cuh) when they average under half a tile (at a mean of 40 tokens, len ~
+  // U{4..77}, grouped and ungrouped measure the same: profiles/round2/r05t_ab_grouped_attention.txt)
+  const bool grouped = attn_tc && static_cast<long long>(T) * 2 <= static_cast<long long>(S) * ((H->max_pos + 15) & ~15);
+  if (grouped) {
+    clip_group_captions_kernel<<<S < 64 * 256 ? (S + 255) / 256 : 64, 256, 0, stream>>>(cu_seqlens, S, (H->max_pos + 15) & ~15,
+                                                                                         H->grp, H->n_grp, H->tok_start);
+    EMCID_CUDA_CHECK(cudaGetLastError());
+    H->launches += 1;
+  }
   int si = 0;
   // keys of layer keys_layer: k_out = the key rows of f = act(fc1), z_out = fc2 of those rows; leaves the resumable state
   auto gather_keys = [&](const ClipLayer& Ly) -> int {
@@ -758,16 +795,16 @@ inline int clip_forward(ClipHandle* H, const int* ids, const int* pos, const int
                             pm_qkv, CLIP_TAG_QKV)))
         return rc;
       ClipProfScope prof_attn(H, stream, CLIP_TAG_ATTN, 0.0);
-      const int units = S * H->heads;
+      const int units = S * H->heads;            // grouped: an upper bound, the kernel reads the number of groups
       const int lp = (H->max_pos + 15) & ~15;
       const int per_sm = attn_ctas_per_sm(lp);   // three resident CTAs per SM for CLIP's 77 tokens
       const int grid = units < per_sm * sms ? units : per_sm * sms;
-      if (lp <= 80)
-        clip_attention_tc_kernel<5><<<grid, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
-            am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
-      else
-        clip_attention_tc_kernel<8><<<grid, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(
-            am, cu_seqlens, S, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp);
+#define EMCID_ATTN_TC(NC, G)                                                                                        \
+  clip_attention_tc_kernel<NC, G><<<grid, ATTN_THREADS, attn_smem_bytes(lp), stream>>>(                             \
+      am, G ? H->grp : cu_seqlens, units, H->n_grp, H->tok_start, H->heads, H->h, lp, scale, H->a_hi, H->a_lo, H->hp)
+      if (lp <= 80) { if (grouped) EMCID_ATTN_TC(5, true); else EMCID_ATTN_TC(5, false); }
+      else { if (grouped) EMCID_ATTN_TC(8, true); else EMCID_ATTN_TC(8, false); }
+#undef EMCID_ATTN_TC
     } else {
     if ((rc = clip_linear(H, mx_hi, mx_lo, Ly.qkv, T, ACT_NONE, nullptr, H->qkv, 3ll * H->h, nullptr, nullptr, 0, stream, pm_qkv)))
       return rc;

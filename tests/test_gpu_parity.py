@@ -251,6 +251,42 @@ def test_native_forward_hidden_states_match_hf(dev, kind, n_caps):
         nat.close()
 
 
+def test_short_captions_share_attention_tiles(dev):
+    """Short captions (real caption data, the prompts of an edit) are grouped several to an attention tile with a block
+    diagonal causal mask (csrc/attn.cuh, clip_group_captions_kernel): 300 captions of 2..12 tokens with a few full-length and
+    one-token ones in between, two layers deep, against an fp64 copy of the HF model; no token may see a neighbouring
+    caption (a leak would show as an error of order 1)."""
+    import copy
+    from emcid_b200 import clip_forward
+    model = rh.make_clip_text_model("clip-l", seed=5, num_hidden_layers=2).to(dev)
+    vocab = model.config.vocab_size
+    g = torch.Generator().manual_seed(12)
+    lens = torch.randint(2, 13, (300,), generator=g).tolist()
+    for at, L in ((0, 77), (17, 1), (18, 77), (19, 76), (150, 1), (151, 1), (299, 77)):
+        lens[at] = L
+    caps = [torch.cat([torch.tensor([vocab - 2]), torch.randint(0, vocab - 2, (max(L - 2, 0),), generator=g),
+                       torch.tensor([vocab - 1])])[:L] for L in lens]
+    batch = {k: v.to(dev) for k, v in _padded(caps).items()}
+    keep = batch["attention_mask"].bool()
+    with torch.no_grad():
+        hs64 = copy.deepcopy(model).double()(**batch, output_hidden_states=True).hidden_states
+        hs32 = model(**batch, output_hidden_states=True).hidden_states
+    ids, pos, cu, S, T = clip_forward.pack_batch(batch, model.config.max_position_embeddings)
+    assert T == sum(lens) and S == len(lens)
+    nat = clip_forward.NativeClipTextEncoder(model, T, S)
+    try:
+        for n in (1, 2):
+            h = nat.forward_hidden(ids, pos, cu, S, T, n)
+            ref = hs64[n][keep]
+            err = float((h.double() - ref).norm() / ref.norm())
+            err_hf = float((hs32[n][keep].double() - ref).norm() / ref.norm())
+            assert err < max(3e-6, 3 * err_hf), (n, err, err_hf)
+            worst = float(((h.double() - ref).norm(dim=1) / ref.norm(dim=1)).max())     # per token: no outlier rows
+            assert worst < 1e-4, worst
+    finally:
+        nat.close()
+
+
 @pytest.mark.parametrize("kind,layer,n_req", [("tiny", 1, 7), ("tiny-gelu", 0, 5), ("clip-l", 9, 40)])
 def test_native_key_extraction_matches_hf(dev, monkeypatch, kind, layer, n_req):
     """Keys (fc2 input) and current outputs (fc2 output) at the last subject token: the library's forward

@@ -1,14 +1,16 @@
-"""End-to-end statistics pass on RAGGED captions (len ~ U{4..77}, the shape of real caption data): tokens/s with loader batches
-of 256 captions regrouped into token-budget blocks (default) vs one block per loader batch (block_tokens=0)."""
+"""End-to-end statistics pass on RAGGED captions (len ~ U{4..W}, W = 77 by default; `probe_ragged.py N W` for shorter ones — real
+caption data averages a dozen tokens): tokens/s with loader batches of 256 captions regrouped into token-budget blocks
+(default) vs one block per loader batch (block_tokens=0)."""
 import json, os, sys, tempfile, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from emcid_b200 import layer_stats, synth
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
+W = int(sys.argv[2]) if len(sys.argv) > 2 else 77
 dev = torch.device("cuda:0")
 model = synth.make_text_encoder("sd-text", seed=0).to(dev)
 names = [f"text_model.encoder.layers.{l}.mlp.fc2" for l in (7, 8, 9, 10, 11)]
-caps = synth.make_caption_ids(N, seed=11, full=False, min_len=4)
+caps = synth.make_caption_ids(N, seed=11, full=False, min_len=4, width=W)
 tokens = sum(len(c) for c in caps)
 layer_stats.get_ccs_filtered_ds = lambda tokenizer: synth.CaptionIdDataset(caps)
 out = {"captions": N, "tokens": tokens, "mean_len": tokens / N}
