@@ -104,6 +104,9 @@ class NativeClipTextEncoder:
         self.last_sync: Dict[object, list] = {}
         self.keys_token = None                # (caller token, layer) of the last forward_keys call, see compute_ks.py
         self.has_final_norm = False
+        self._layer_lists: Dict[int, list] = {}   # the 16 source tensors of every layer, listed once per verified sync
+        self._ring = [{"event": None, "bufs": {}} for _ in range(3)]   # pinned staging sets of _to_device
+        self._ring_at = 0
         self.sync_weights(model, verify=True)
 
     @staticmethod
@@ -143,7 +146,7 @@ class NativeClipTextEncoder:
         """Forget what was uploaded: the next sync re-uploads everything it needs."""
         self._sig.clear()
         self._sums.clear()
-        self.__dict__.pop("_layer_lists", None)
+        self._layer_lists.clear()
         self.keys_token = None
 
     def sync_weights(self, model, upto_layer: Optional[int] = None, verify: bool = False) -> int:
@@ -166,7 +169,7 @@ class NativeClipTextEncoder:
         # the 16 source tensors of a layer, listed once per verified sync (a replaced Parameter object is picked up there;
         # between two of them — inside one edit — weights only change in place): 12 layers x 16 attribute walks per call
         # were 0.8 ms of every 100-concept edit
-        cache = self.__dict__.setdefault("_layer_lists", {})
+        cache = self._layer_lists
         for i in range(last + 1):
             if verify or i not in cache:
                 cache[i] = self._layer_tensors(tm.encoder.layers[i])
@@ -233,10 +236,8 @@ class NativeClipTextEncoder:
         the host queue up to three blocks ahead of the device."""
         if all(t.is_cuda for t in tensors):
             return tuple(t.to(self.device, non_blocking=True) for t in tensors)
-        ring = self.__dict__.setdefault("_ring", [{"event": None, "bufs": {}} for _ in range(3)])
-        at = self.__dict__.get("_ring_at", 0)
-        self._ring_at = (at + 1) % len(ring)
-        slot = ring[at]
+        slot = self._ring[self._ring_at]
+        self._ring_at = (self._ring_at + 1) % len(self._ring)
         if slot["event"] is not None:
             slot["event"].synchronize()
         out = []
