@@ -243,16 +243,6 @@ __device__ __forceinline__ float act_ct(float v) {
   return v;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_QUICK_GELU) {
-    // HF QuickGELUActivation: x * sigmoid(1.702 x)   (transformers/activations.py)
-    return v / (1.0f + expf(-1.702f * v));
-  } else if (act == ACT_GELU_ERF) {
-    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-  }
-  return v;
-}
-
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
