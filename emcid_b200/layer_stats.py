@@ -497,7 +497,8 @@ def _run_pass(model, tokenizer, todo: List[str], files, stats, args, *, sample_s
     collate = packed_collation() if (device.type == "cuda" and accumulator_factory is None) else fixed_width_collation()
     loader = torch.utils.data.DataLoader(
         ds, sampler=FixedSubsetSampler(rest[head_n:]), batch_size=captions_per_batch, collate_fn=collate,
-        num_workers=num_workers, pin_memory=(device.type == "cuda"))
+        num_workers=num_workers if len(rest) > head_n else 0,      # nothing left for workers: do not fork any
+        pin_memory=(device.type == "cuda"))
     batch_count = -(-head_n // captions_per_batch) + -(-(len(rest) - head_n) // captions_per_batch)
     if progress is None:
         progress = lambda x, total=None: x
