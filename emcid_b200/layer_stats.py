@@ -550,6 +550,7 @@ def _run_pass(model, tokenizer, todo: List[str], files, stats, args, *, sample_s
         results, roots = _reduce_results(runner, todo, dist, rank, world, device, broadcast, keep_on_device)
         LAST_PASS_INFO.update(native_forward=runner._native is not None, launches=runner.launches(),
                               fallback_blocks=runner.fallback_blocks, captions=len(my_indices))
+        to_save = []
         for n in todo:
             mom2, count = results[n]
             for name in ([n] if write_also is None else write_also):
@@ -557,7 +558,17 @@ def _run_pass(model, tokenizer, todo: List[str], files, stats, args, *, sample_s
                 sm.count = count
                 sm.mom2 = mom2
                 if not force_recompute and rank == roots[n]:
-                    save_cached_state(files[name], stats[name], args)
+                    to_save.append(name)
+        # the statistics files of this rank's layers, written side by side: one 37.7 MB npz is 60 ms of CRC-32 and file
+        # write (both outside the interpreter lock), five of them in a row 0.3 s behind a 4.6 s pass
+        if len(to_save) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=min(len(to_save), 8)) as pool:
+                list(pool.map(lambda name: save_cached_state(files[name], stats[name], args), to_save))
+        else:
+            for name in to_save:
+                save_cached_state(files[name], stats[name], args)
         if ckpt is not None:
             ckpt.discard()                       # the pass is complete: its statistics files are the durable result
         if dist is not None and world > 1:
