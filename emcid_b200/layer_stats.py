@@ -490,8 +490,8 @@ def _run_pass(model, tokenizer, todo: List[str], files, stats, args, *, sample_s
         done = ckpt.load(runner, todo)
         LAST_PASS_INFO["resumed_from_caption"] = done
     # The first HEAD_CAPTIONS captions of the shard are collated right here, in order, while the loader's worker
-    # processes start up (0.1-0.2 s before their first batch arrives: at 8 GPUs that is a fifth of configs[1]'s 0.6 s
-    # per rank); the workers serve the rest.  Caption order — and with it the checkpoint cursor — is what it was.
+    # processes are forked and collate their first batches; the workers serve the rest.  Caption order — and with it the
+    # checkpoint cursor — is what it was.
     rest = my_indices[done:]
     head_n = min(len(rest), HEAD_CAPTIONS) if num_workers > 0 else 0
     collate = packed_collation() if (device.type == "cuda" and accumulator_factory is None) else fixed_width_collation()
@@ -507,16 +507,21 @@ def _run_pass(model, tokenizer, todo: List[str], files, stats, args, *, sample_s
         runner.capacity_hint = min(int(block_tokens), len(my_indices) * int(runner._max_positions()))
     t_loop = time.perf_counter()
     consumed = done
-    # the loader's worker processes start here and collate their first batches while the weights go to the library (the
-    # encoder used to be built when the first block arrived: 0.1 s of worker start-up, then the upload, one after the other)
-    tail_batches = iter(loader)
+    # Start-up order: the weights go to the library first, the first in-process batches follow (the device has work from
+    # here on), and only then are the loader's worker processes forked — two forks of a process with a CUDA context are
+    # 60 ms during which nothing else happens on the host; behind the first three device blocks they are free.  (Forked
+    # before anything else, start-up was 0.1 s of every pass: a sixth of configs[1]'s 0.6 s per rank at 8 GPUs.)
     if reblock is not None and runner.capacity_hint > 0 and batch_count > 0:
         runner._native_encoder(int(runner.capacity_hint), 1)
+    fork_after = 6 * captions_per_batch
 
     def all_batches():
+        tail_batches = None
         for a in range(0, head_n, captions_per_batch):
+            if tail_batches is None and a >= fork_after:
+                tail_batches = iter(loader)
             yield collate([ds[i] for i in rest[a: min(a + captions_per_batch, head_n)]])
-        yield from tail_batches
+        yield from (tail_batches if tail_batches is not None else iter(loader))
 
     def feed(block):
         nonlocal consumed
